@@ -1,0 +1,60 @@
+/* TEST INFRASTRUCTURE ONLY.  Plain-C CPU restatement of the reference's hot path
+ * (aaspip/pyseistr: dip_cfuns.c, sof3d_cfuns.c, sof_cfuns.c).  Never linked, loaded
+ * or called by the product path (pyseistr_b200/); only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline leg may use it.  Parity is PINNED: tests/test_oracle.py
+ * checks every function below bit-for-bit against oracle/_ref (the unmodified
+ * reference C compiled from /root/reference) and against tests/golden/ fixtures
+ * generated from it (the reference ships no golden vectors of its own).
+ *
+ * All volumes are float32 in the reference's flattened Fortran order
+ * i = i1 + n1*(i2 + n2*i3).
+ */
+#ifndef PST_ORACLE_H
+#define PST_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* B-filter taps: dip_cfuns.c:835-910 */
+void pso_passfilter(int nw, float sigma, float *taps /*[2nw+1]*/);
+void pso_aderfilter(int nw, float sigma, float *taps /*[2nw+1]*/);
+
+/* PWD stencil, left=false, drift=false, nj=1: dip_cfuns.c:1135-1200 (inline), :1399-1465 (xline) */
+void pso_allpass(const float *u, const float *sigma, int n1, int n2, int n3, int nw,
+                 int xline, int der, float *y);
+
+/* N-D triangle smoothing in place, axes with rect<=1 skipped: dip_cfuns.c:458-727 (ps_smooth2) */
+void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3);
+
+/* Smooth division rat ~ num/den (num, den are overwritten): dip_cfuns.c:796-827 + :257-383.
+ * Returns the number of CG iterations executed. */
+int pso_divne(float *num, float *den, float *rat, int n1, int n2, int n3,
+              int r1, int r2, int r3, int liter, float eps);
+
+/* dipc: dip_cfuns.c:1694-1989.  mask may be NULL.  dip_out holds N floats when n3==1,
+ * else 2N (inline then xline).  eps_dv/eps_cg/tol_cg are not parameters because the
+ * reference ignores them. */
+int pso_dip(const float *din, const float *mask, int n1, int n2, int n3, int niter, int liter,
+            int order, int r1, int r2, int r3, float *dip_out);
+
+/* one plane-wave prediction (sof3d_cfuns.c:596-661); two==0: predict1_step from trace1/sig1,
+ * two!=0: predict2_step */
+void pso_predict(int n1, int nw, float eps, int two, int forw1, int forw2, const float *trace1,
+                 const float *trace2, const float *sig1, const float *sig2, float *out);
+
+/* csomean3d / csomf3d: sof3d_cfuns.c:1355-1552, :1554-1752 (option 1 = MF only) */
+int pso_somean3d(const float *din, const float *dipi, const float *dipx, int n1, int n2, int n3,
+                 int ns2, int ns3, int order, float *out);
+int pso_somf3d(const float *din, const float *dipi, const float *dipx, int n1, int n2, int n3,
+               int ns2, int ns3, int nmf, int option, int order, float *out);
+
+/* csomean2d / csomf2d: sof_cfuns.c:1433-1532, :1534-1672 (option 1 = MF only; adj=0) */
+int pso_somean2d(const float *din, const float *dip, int n1, int n2, int n3, int ns, int order,
+                 float eps, float *out);
+int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int ns, int nmf,
+               int option, int order, float eps, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
