@@ -1,0 +1,124 @@
+/* pst_b200 — C-ABI of the B200-native (sm_100a) implementation of pyseistr's 3-D/2-D
+ * structure-oriented filtering hot path.  This is the drop-in boundary: each entry point
+ * replaces one function of the reference's CPython extension modules (the FFI the
+ * reference's Python `*c` wrappers bind), with plain pointers and sizes.
+ *
+ * Conventions
+ *  - every volume is float32 in the reference's flattened Fortran order
+ *    i = i1 + n1*(i2 + n2*i3)  (axis 1 = time/depth is contiguous);
+ *  - `pst_*` entry points take HOST pointers (copies H2D/D2H inside the call, like the
+ *    reference's copy-in/copy-out); `pst_*_dev` take DEVICE pointers on the context's GPU;
+ *  - return 0 on success, <0 on error (PST_E*), message via pst_last_error();
+ *  - there is NO CPU fallback: without a CUDA device every call fails with PST_ENODEV.
+ *  - a context is not re-entrant (one call at a time per context; use one context per
+ *    thread), unlike the reference which is not re-entrant per PROCESS (file-scope statics).
+ */
+#ifndef PST_B200_H
+#define PST_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PST_OK        0
+#define PST_EINVAL   -1   /* bad argument (the reference prints and returns NULL) */
+#define PST_ENODEV   -2   /* no usable CUDA device / wrong architecture */
+#define PST_ENOMEM   -3   /* device or host allocation failed */
+#define PST_ECUDA    -4   /* CUDA runtime error */
+#define PST_EUNSUP   -5   /* parameter combination not implemented on the GPU path */
+#define PST_ECOMM    -6   /* multi-GPU communicator error */
+
+typedef struct pst_ctx pst_ctx;
+
+/* Statistics of the last call on a context (roofline accounting uses EXECUTED counts). */
+typedef struct pst_stats {
+    long long kernel_launches;   /* kernels of this library launched by the last call */
+    long long cg_iterations;     /* shaping-CG iterations executed (all GN iterations, both dips) */
+    long long linesearch_evals;  /* allpass evaluations inside the line search */
+    long long gn_iterations;     /* Gauss-Newton iterations executed */
+    long long smooth_passes;     /* single-axis triangle smoothing passes executed */
+    long long predictions;       /* plane-wave predictions (trace solves) executed */
+    double    device_ms;         /* CUDA-event time of the device part of the last call */
+    double    h2d_bytes, d2h_bytes;
+} pst_stats;
+
+const char *pst_last_error(void);
+const char *pst_version(void);
+int  pst_device_count(void);
+
+/* One context per GPU (device ordinal).  */
+int  pst_ctx_create(int device, pst_ctx **ctx);
+void pst_ctx_destroy(pst_ctx *ctx);
+int  pst_ctx_stats(pst_ctx *ctx, pst_stats *out);
+/* The host-pointer entry points reset the statistics themselves; the *_dev entry points
+ * accumulate, so reset explicitly around a device-resident sequence. */
+int  pst_ctx_reset_stats(pst_ctx *ctx);
+/* Multi-GPU: slab decomposition along n3 over `nranks` processes (one per GPU).  `nccl_id`
+ * is the 128-byte ncclUniqueId created by rank 0 (pst_comm_unique_id) and distributed by
+ * the host side (torch.distributed / MPI / files). */
+int  pst_comm_unique_id(void *id128);
+int  pst_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, pst_ctx **ctx);
+
+/* ---- dip estimation.  Replaces dipcfun.dipc (reference pyseistr/src/dip_cfuns.c:1694-1989,
+ * "Oiiiiiifffiiiii"); called by dip3dc (pyseistr/dip3d.py:59-116) and dip2dc
+ * (pyseistr/dip2d.py:115-221, n3=1).  mask may be NULL (hasmask=0).  eps_dv, eps_cg and
+ * tol_cg are accepted and IGNORED exactly as the reference's C does (divne runs
+ * with eps=1, CG with eps=1, tol=1e-6).  dip_out: n1*n2*n3 floats when n3==1, else
+ * 2*n1*n2*n3 (inline dip then xline dip). */
+int pst_dip(pst_ctx *ctx, const float *din, const float *mask, int n1, int n2, int n3,
+            int niter, int liter, int order, float eps_dv, float eps_cg, float tol_cg,
+            int r1, int r2, int r3, int verb, float *dip_out);
+int pst_dip_dev(pst_ctx *ctx, const float *d_din, const float *d_mask, int n1, int n2, int n3,
+                int niter, int liter, int order, int r1, int r2, int r3, int verb,
+                float *d_dip_out);
+
+/* ---- 3-D structure-oriented mean / median.  Replace sof3dcfun.csomean3d
+ * (sof3d_cfuns.c:1355-1552, "OOOiiiiiifi") and sof3dcfun.csomf3d (:1554-1752,
+ * "OOOiiiiiiiifi"); called by somean3dc (pyseistr/somean3d.py:36-73) and somf3dc
+ * (pyseistr/somf3d.py:54-97).  eps is accepted and IGNORED (the reference overwrites it
+ * with 0.01).  option: 1 = median filter (MF). */
+int pst_somean3d(pst_ctx *ctx, const float *din, const float *dipi, const float *dipx,
+                 int n1, int n2, int n3, int ns2, int ns3, int order, float eps, int verb,
+                 float *out);
+int pst_somf3d(pst_ctx *ctx, const float *din, const float *dipi, const float *dipx,
+               int n1, int n2, int n3, int ns2, int ns3, int nmf, int option, int order,
+               float eps, int verb, float *out);
+int pst_somean3d_dev(pst_ctx *ctx, const float *d_din, const float *d_dipi, const float *d_dipx,
+                     int n1, int n2, int n3, int ns2, int ns3, int order, float *d_out);
+int pst_somf3d_dev(pst_ctx *ctx, const float *d_din, const float *d_dipi, const float *d_dipx,
+                   int n1, int n2, int n3, int ns2, int ns3, int nmf, int option, int order,
+                   float *d_out);
+
+/* ---- 2-D structure-oriented mean / median.  Replace sofcfun.csomean2d
+ * (pyseistr/src/sof_cfuns.c:1433-1532, "OOiiiiiifi") and sofcfun.csomf2d (:1534-1672,
+ * "OOiiiiiiifi"); called by somean2dc (pyseistr/somean2d.py:36-74) and somf2dc
+ * (pyseistr/somf2d.py:60-105).  Here eps IS honoured (regularisation eps*eps). */
+int pst_somean2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n2, int n3,
+                 int ns, int order, int adj, float eps, int verb, float *out);
+int pst_somf2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n2, int n3,
+               int ns, int nmf, int option, int order, float eps, int verb, float *out);
+
+/* ---- building blocks exposed for parity tests and for the smoothing wrapper (SURVEY §8f
+ * rank 1: dipcfun.smoothcf, dip_cfuns.c:2006-2123 with adj=0).  Device pointers. */
+int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1, int n2, int n3,
+                    int order, int xline, int der, float *d_y);
+int pst_smooth3_dev(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3);
+int pst_divne_dev(pst_ctx *ctx, float *d_num, float *d_den, float *d_rat, int n1, int n2, int n3,
+                  int r1, int r2, int r3, int liter, int *iters_run);
+int pst_smooth3(pst_ctx *ctx, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
+                float *out);
+
+/* ---- raw device memory helpers so that a host language without a CUDA binding can keep
+ * volumes resident between calls (bench `value` leg, pipelines dip -> somf). */
+int pst_dev_alloc(pst_ctx *ctx, size_t bytes, void **d_ptr);
+int pst_dev_free(pst_ctx *ctx, void *d_ptr);
+int pst_h2d(pst_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int pst_d2h(pst_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int pst_host_alloc_pinned(size_t bytes, void **h_ptr);
+int pst_host_free_pinned(void *h_ptr);
+int pst_sync(pst_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,171 @@
+"""Drop-in Python entry points of the reference's C variants, running on B200.
+
+Same names, argument order, defaults, return layouts and quirks as the reference's
+``*c`` functions (re-exported by reference pyseistr/__init__.py:81-96); each flattens to
+float32 Fortran order exactly as the reference wrapper does and calls the C-ABI
+(include/pst_b200.h) through ctypes.  No CPU fallback: without the CUDA library or a
+B200 these raise.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+def _F(a):
+    """float32 1-D copy in Fortran order (the reference's ``np.float32(x).flatten(order='F')``)."""
+    return np.ascontiguousarray(np.float32(a).flatten(order="F"))
+
+
+def _p(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _shape3(d):
+    if d.ndim == 2:
+        return d.shape[0], d.shape[1], 1
+    if d.ndim != 3:
+        raise ValueError("expected a 2-D or 3-D array")
+    return d.shape
+
+
+def _ctx(ctx):
+    return ctx if ctx is not None else _lib.default_context()
+
+
+def dip3dc(din, niter=5, liter=10, order=2, eps_dv=0.01, eps_cg=1, tol_cg=0.000001,
+           rect=[5, 5, 5], verb=1, runc=1, mask=None, ctx=None):
+    """3-D local slopes by shaping-regularised PWD (reference pyseistr/dip3d.py:59-116 ->
+    dipcfun.dipc, dip_cfuns.c:1694).  Returns (dip_i, dip_x), float32 (n1,n2,n3) views of one
+    F-ordered (n1,n2,n3,2) array, like the reference.  eps_dv, eps_cg, tol_cg are accepted and
+    ignored exactly as the reference's C ignores them."""
+    din = np.asarray(din)
+    if din.ndim != 3:
+        raise ValueError("dip3dc expects a 3-D array (n1,n2,n3)")
+    n1, n2, n3 = din.shape
+    c = _ctx(ctx)
+    d = _F(din)
+    m = None
+    if mask is not None:
+        mask = np.asarray(mask)
+        if mask.size != din.size:
+            raise ValueError("Mask and Data should have the same dimension")
+        m = _F(mask)
+    out = np.empty(2 * d.size if n3 != 1 else d.size, np.float32)
+    _lib.check(c.lib.pst_dip(c.handle, _p(d), _p(m) if m is not None else None, n1, n2, n3,
+                             int(niter), int(liter), int(order), float(eps_dv), float(eps_cg),
+                             float(tol_cg), int(rect[0]), int(rect[1]), int(rect[2]), int(verb),
+                             _p(out)))
+    if n3 == 1:
+        # the reference's reshape(n1,n2,n3,2) fails for n3 == 1 (dipc returns N floats); we
+        # return the inline dip and a zero xline dip instead of raising.
+        dip = out.reshape(n1, n2, 1, order="F")
+        return dip, np.zeros_like(dip)
+    dip = out.reshape(n1, n2, n3, 2, order="F")
+    return dip[:, :, :, 0], dip[:, :, :, 1]
+
+
+def dip2dc(din, niter=5, liter=20, order=2, eps_dv=0.01, eps_cg=1, tol_cg=0.000001,
+           rect=[10, 10, 1], verb=1, mask=None, ctx=None):
+    """2-D local slope (reference pyseistr/dip2d.py:115-221: the same dipc entry with n3=1).
+    Returns float32 (n1,n2), F-ordered."""
+    din = np.asarray(din)
+    if din.ndim != 2:
+        raise ValueError("dip2dc expects a 2-D array (n1,n2)")
+    n1, n2 = din.shape
+    c = _ctx(ctx)
+    d = _F(din)
+    m = None
+    if mask is not None:
+        mask = np.asarray(mask)
+        if mask.size != din.size:
+            raise ValueError("Mask and Data should have the same dimension")
+        m = _F(mask)
+    out = np.empty(d.size, np.float32)
+    _lib.check(c.lib.pst_dip(c.handle, _p(d), _p(m) if m is not None else None, n1, n2, 1,
+                             int(niter), int(liter), int(order), float(eps_dv), float(eps_cg),
+                             float(tol_cg), int(rect[0]), int(rect[1]), int(rect[2]), int(verb),
+                             _p(out)))
+    return out.reshape(n1, n2, order="F")
+
+
+def somean3dc(dn, dipi, dipx, r1, r2, eps, order, verb=0, ctx=None):
+    """3-D structure-oriented mean (reference pyseistr/somean3d.py:36-73 -> csomean3d,
+    sof3d_cfuns.c:1355).  eps is ignored like the reference (overridden by 0.01);
+    slots falling outside the cube count as zeros and the divisor is always np (Q4)."""
+    dn = np.asarray(dn)
+    n1, n2, n3 = _shape3(dn)
+    c = _ctx(ctx)
+    d, a, b = _F(dn), _F(dipi), _F(dipx)
+    if a.size != d.size or b.size != d.size:
+        raise ValueError("data and slope volumes must have the same size")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_somean3d(c.handle, _p(d), _p(a), _p(b), n1, n2, n3, int(r1), int(r2),
+                                  int(order), float(eps), int(verb), _p(out)))
+    return out.reshape([n1, n2, n3], order="F")
+
+
+def somf3dc(dn, dipi, dipx, r1, r2, eps, order, option=1, verb=1, ctx=None):
+    """3-D structure-oriented median (reference pyseistr/somf3d.py:54-97 -> csomf3d,
+    sof3d_cfuns.c:1554).  The median runs over nmf = 2*r1*r2+1 slots along the flattened slot
+    axis around the centre slot.  option=1 (MF); option=2 (SVMF) raises."""
+    dn = np.asarray(dn)
+    n1, n2, n3 = _shape3(dn)
+    c = _ctx(ctx)
+    d, a, b = _F(dn), _F(dipi), _F(dipx)
+    if a.size != d.size or b.size != d.size:
+        raise ValueError("data and slope volumes must have the same size")
+    out = np.empty_like(d)
+    rmf = 2 * int(r1) * int(r2) + 1
+    _lib.check(c.lib.pst_somf3d(c.handle, _p(d), _p(a), _p(b), n1, n2, n3, int(r1), int(r2), rmf,
+                                int(option), int(order), float(eps), int(verb), _p(out)))
+    return out.reshape([n1, n2, n3], order="F")
+
+
+def somean2dc(dn, dip, ns, order, eps, adj=0, verb=1, ctx=None):
+    """2-D structure-oriented (triangle-weighted, normalised) smoothing (reference
+    pyseistr/somean2d.py:36-74 -> csomean2d, sof_cfuns.c:1433).  eps is honoured."""
+    dn = np.asarray(dn)
+    n1, n2, n3 = _shape3(dn)
+    c = _ctx(ctx)
+    d, a = _F(dn), _F(dip)
+    if a.size != d.size:
+        raise ValueError("data and slope must have the same size")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_somean2d(c.handle, _p(d), _p(a), n1, n2, n3, int(ns), int(order), int(adj),
+                                  float(eps), int(verb), _p(out)))
+    return np.squeeze(out.reshape(n1, n2, n3, order="F"))
+
+
+def somf2dc(dn, dip, ns, order, eps, option=1, verb=1, ctx=None):
+    """2-D structure-oriented median over the 2*ns+1 sprayed slots (reference
+    pyseistr/somf2d.py:60-105 -> csomf2d, sof_cfuns.c:1534)."""
+    dn = np.asarray(dn)
+    n1, n2, n3 = _shape3(dn)
+    c = _ctx(ctx)
+    d, a = _F(dn), _F(dip)
+    if a.size != d.size:
+        raise ValueError("data and slope must have the same size")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_somf2d(c.handle, _p(d), _p(a), n1, n2, n3, int(ns), 2 * int(ns) + 1,
+                                int(option), int(order), float(eps), int(verb), _p(out)))
+    return np.squeeze(out.reshape(n1, n2, n3, order="F"))
+
+
+def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=0, ctx=None):
+    """N-D triangle smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf,
+    dip_cfuns.c:2006-2123).  GPU path: the ps_smooth2 kernel dip3d uses, i.e. adj=0, no
+    derivative, no box, repeat=1; other options raise."""
+    if adj or any(diff) or any(box) or repeat != 1:
+        raise NotImplementedError("smoothc on GPU: adj=0, diff=0, box=0, repeat=1 only")
+    din = np.asarray(din)
+    n1, n2, n3 = _shape3(din)
+    c = _ctx(ctx)
+    d = _F(din)
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_smooth3(c.handle, _p(d), n1, n2, n3, int(rect[0]), int(rect[1]),
+                                 int(rect[2]), _p(out)))
+    return out.reshape(din.shape, order="F")

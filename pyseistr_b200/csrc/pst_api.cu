@@ -1,0 +1,378 @@
+// C-ABI surface of libpst_b200 (include/pst_b200.h): context, arena, deterministic reduction
+// plumbing and the host-pointer entry points that mirror the reference's CPython extension
+// functions (copy in -> compute on the GPU -> copy out).  No CPU fallback anywhere: without a
+// usable sm_100 device every call fails loudly.
+#include "pst_common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[1024] = "";
+
+void pst_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *pst_last_error(void) { return g_err; }
+extern "C" const char *pst_version(void) { return "pst_b200 0.1 (sm_100a)"; }
+
+extern "C" int pst_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- arena -----------------------------------------------------------------------------
+int pst_arena_reserve(pst_ctx *c, size_t bytes)
+{
+    bytes += 1 << 20;
+    if (c->arena && c->arena_size >= bytes) return PST_OK;
+    if (c->arena) { cudaStreamSynchronize(c->stream); cudaFree(c->arena); c->arena = nullptr; c->arena_size = 0; }
+    cudaError_t e = cudaMalloc((void **)&c->arena, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pst_set_error("device workspace of %.2f GB unavailable: %s", bytes / 1e9, cudaGetErrorString(e));
+        return PST_ENOMEM;
+    }
+    c->arena_size = bytes;
+    c->arena_used = 0;
+    return PST_OK;
+}
+
+int pst_arena_alloc(pst_ctx *c, size_t bytes, void **p)
+{
+    const size_t a = (c->arena_used + 255) & ~(size_t)255;
+    if (a + bytes > c->arena_size) {
+        pst_set_error("internal: workspace arena overflow (%zu + %zu > %zu)", a, bytes, c->arena_size);
+        return PST_ENOMEM;
+    }
+    *p = c->arena + a;
+    c->arena_used = a + bytes;
+    return PST_OK;
+}
+
+// ---- reductions ------------------------------------------------------------------------
+__global__ void finish_reduce_kernel(const double *__restrict__ partial, int nblocks, int nv,
+                                     double *__restrict__ rec)
+{
+    // one warp per value; fixed strided order + fixed shuffle tree => reproducible
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= nv) return;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * PST_RED_SLOTS + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) rec[q] = s;
+}
+
+int pst_comm_allreduce_record(pst_ctx *c, double *d_rec, int nv);   // pst_comm.cu
+
+int pst_finish_reduce(pst_ctx *c, int nblocks, int nv, int rec)
+{
+    if (nblocks > c->max_blocks) { pst_set_error("internal: reduction grid too large"); return PST_EINVAL; }
+    finish_reduce_kernel<<<1, 32 * PST_RED_SLOTS, 0, c->stream>>>(c->d_partial, nblocks, nv,
+                                                                   c->d_red + (size_t)rec * PST_RED_SLOTS);
+    c->stats.kernel_launches++;
+    PST_CUDA(cudaGetLastError());
+    if (c->comm) PST_TRY(pst_comm_allreduce_record(c, c->d_red + (size_t)rec * PST_RED_SLOTS, nv));
+    return PST_OK;
+}
+
+int pst_fetch_record(pst_ctx *c, int rec, int nv, double *host_out)
+{
+    PST_CUDA(cudaMemcpyAsync(c->h_red + (size_t)rec * PST_RED_SLOTS, c->d_red + (size_t)rec * PST_RED_SLOTS,
+                             nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < nv; q++) host_out[q] = c->h_red[(size_t)rec * PST_RED_SLOTS + q];
+    return PST_OK;
+}
+
+// ---- context ---------------------------------------------------------------------------
+static int ctx_init(pst_ctx *c, int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        pst_set_error("no CUDA device visible: libpst_b200 has no CPU fallback");
+        return PST_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { pst_set_error("device %d out of range (0..%d)", device, ndev - 1); return PST_ENODEV; }
+    cudaDeviceProp prop;
+    PST_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        pst_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return PST_ENODEV;
+    }
+    PST_CUDA(cudaSetDevice(device));
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    PST_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PST_CUDA(cudaEventCreate(&c->ev0));
+    PST_CUDA(cudaEventCreate(&c->ev1));
+    c->max_blocks = c->sm_count * 32;
+    PST_CUDA(cudaMalloc((void **)&c->d_partial, (size_t)c->max_blocks * PST_RED_SLOTS * sizeof(double)));
+    PST_CUDA(cudaMalloc((void **)&c->d_red, 64 * PST_RED_SLOTS * sizeof(double)));
+    PST_CUDA(cudaMallocHost((void **)&c->h_red, 64 * PST_RED_SLOTS * sizeof(double)));
+    return PST_OK;
+}
+
+void pst_comm_destroy(pst_ctx *c);   // pst_comm.cu
+
+extern "C" int pst_ctx_create(int device, pst_ctx **out)
+{
+    if (!out) { pst_set_error("null out pointer"); return PST_EINVAL; }
+    *out = nullptr;
+    pst_ctx *c = new pst_ctx();
+    int rc = ctx_init(c, device);
+    if (rc != PST_OK) { delete c; return rc; }
+    *out = c;
+    return PST_OK;
+}
+
+extern "C" void pst_ctx_destroy(pst_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) pst_comm_destroy(c);
+    if (c->arena) cudaFree(c->arena);
+    if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_red) cudaFree(c->d_red);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int pst_ctx_stats(pst_ctx *c, pst_stats *out)
+{
+    if (!c || !out) { pst_set_error("null argument"); return PST_EINVAL; }
+    *out = c->stats;
+    return PST_OK;
+}
+
+extern "C" int pst_ctx_reset_stats(pst_ctx *c)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    memset(&c->stats, 0, sizeof(c->stats));
+    return PST_OK;
+}
+
+// ---- raw memory helpers ------------------------------------------------------------------
+extern "C" int pst_dev_alloc(pst_ctx *c, size_t bytes, void **d_ptr)
+{
+    if (!c || !d_ptr) { pst_set_error("null argument"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); pst_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return PST_ENOMEM; }
+    return PST_OK;
+}
+extern "C" int pst_dev_free(pst_ctx *c, void *d_ptr)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    PST_CUDA(cudaFree(d_ptr));
+    return PST_OK;
+}
+extern "C" int pst_h2d(pst_ctx *c, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    return PST_OK;
+}
+extern "C" int pst_d2h(pst_ctx *c, void *h_dst, const void *d_src, size_t bytes)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    return PST_OK;
+}
+extern "C" int pst_host_alloc_pinned(size_t bytes, void **h_ptr)
+{
+    if (!h_ptr) { pst_set_error("null argument"); return PST_EINVAL; }
+    cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); pst_set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return PST_ENOMEM; }
+    return PST_OK;
+}
+extern "C" int pst_host_free_pinned(void *h_ptr)
+{
+    PST_CUDA(cudaFreeHost(h_ptr));
+    return PST_OK;
+}
+extern "C" int pst_sync(pst_ctx *c)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    return PST_OK;
+}
+
+// ---- host-pointer entry points -----------------------------------------------------------
+// Scoped device buffers for one call (outside the arena, which the *_dev calls reset).
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; pst_set_error("cudaMalloc(%.2f GB) failed: %s", bytes / 1e9, cudaGetErrorString(e)); return PST_ENOMEM; }
+        return PST_OK;
+    }
+    float *f() { return (float *)p; }
+};
+
+struct CallTimer {
+    pst_ctx *c;
+    explicit CallTimer(pst_ctx *ctx) : c(ctx)
+    {
+        memset(&c->stats, 0, sizeof(c->stats));
+        cudaEventRecord(c->ev0, c->stream);
+    }
+    void stop()
+    {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stats.device_ms = ms;
+    }
+};
+
+static int up(pst_ctx *c, DevBuf &b, const float *h, size_t n)
+{
+    PST_TRY(b.alloc(n * sizeof(float)));
+    PST_CUDA(cudaMemcpyAsync(b.p, h, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (double)n * sizeof(float);
+    return PST_OK;
+}
+static int down(pst_ctx *c, float *h, const DevBuf &b, size_t n)
+{
+    PST_CUDA(cudaMemcpyAsync(h, b.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (double)n * sizeof(float);
+    return PST_OK;
+}
+
+#define PST_ENTRY(c)                                                        \
+    if (!(c)) { pst_set_error("null context"); return PST_EINVAL; }         \
+    PST_CUDA(cudaSetDevice((c)->device));
+
+extern "C" int pst_dip(pst_ctx *c, const float *din, const float *mask, int n1, int n2, int n3,
+                       int niter, int liter, int order, float eps_dv, float eps_cg, float tol_cg,
+                       int r1, int r2, int r3, int verb, float *dip_out)
+{
+    (void)eps_dv; (void)eps_cg; (void)tol_cg;      // ignored by the reference's C
+    PST_ENTRY(c);
+    if (!din || !dip_out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("dip: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, m, o;
+    PST_TRY(up(c, d, din, n));
+    if (mask) PST_TRY(up(c, m, mask, n));
+    PST_TRY(o.alloc((n3 == 1 ? n : 2 * n) * sizeof(float)));
+    PST_TRY(pst_dip_dev(c, d.f(), mask ? m.f() : nullptr, n1, n2, n3, niter, liter, order, r1, r2, r3, verb, o.f()));
+    PST_TRY(down(c, dip_out, o, n3 == 1 ? n : 2 * n));
+    t.stop();
+    return PST_OK;
+}
+
+extern "C" int pst_somean3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx,
+                            int n1, int n2, int n3, int ns2, int ns3, int order, float eps, int verb,
+                            float *out)
+{
+    (void)eps; (void)verb;                          // eps overridden with 0.01 by the reference (Q2)
+    PST_ENTRY(c);
+    if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean3d: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, a, b, o;
+    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_somean3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, order, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
+extern "C" int pst_somf3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx,
+                          int n1, int n2, int n3, int ns2, int ns3, int nmf, int option, int order,
+                          float eps, int verb, float *out)
+{
+    (void)eps; (void)verb;
+    PST_ENTRY(c);
+    if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somf3d: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, a, b, o;
+    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_somf3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, nmf, option, order, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
+int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                     int order, float eps, float *d_out);
+int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                   int nmf, int option, int order, float eps, float *d_out);
+
+extern "C" int pst_somean2d(pst_ctx *c, const float *din, const float *dip, int n1, int n2, int n3,
+                            int ns, int order, int adj, float eps, int verb, float *out)
+{
+    (void)verb;
+    PST_ENTRY(c);
+    if (!din || !dip || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean2d: null pointer or bad shape"); return PST_EINVAL; }
+    if (adj) { pst_set_error("somean2d: adj=1 (adjoint smoothing) not implemented on the GPU path"); return PST_EUNSUP; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, a, o;
+    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dip, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_somean2d_dev(c, d.f(), a.f(), n1, n2, n3, ns, order, eps, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
+extern "C" int pst_somf2d(pst_ctx *c, const float *din, const float *dip, int n1, int n2, int n3,
+                          int ns, int nmf, int option, int order, float eps, int verb, float *out)
+{
+    (void)verb;
+    PST_ENTRY(c);
+    if (!din || !dip || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somf2d: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, a, o;
+    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dip, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_somf2d_dev(c, d.f(), a.f(), n1, n2, n3, ns, nmf, option, order, eps, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
+extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
+                           float *out)
+{
+    PST_ENTRY(c);
+    if (!x || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smooth3: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d;
+    PST_TRY(up(c, d, x, n));
+    PST_TRY(pst_smooth3_dev(c, d.f(), n1, n2, n3, r1, r2, r3));
+    PST_TRY(down(c, out, d, n));
+    t.stop();
+    return PST_OK;
+}

@@ -1,0 +1,109 @@
+// Shared internals of libpst_b200: context, workspace arena, deterministic reductions.
+// Compiled for sm_100a only, with -fmad=false: the reference's results depend on the
+// order and (non-)contraction of float operations, so every
+// kernel spells out reference-order arithmetic and the compiler may not fuse mul+add.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pst_b200.h"
+
+#define PST_MAXTAP 5          // order (nw) 1 or 2 -> 3 or 5 taps
+#define PST_RED_SLOTS 8       // doubles per reduction record
+
+void pst_set_error(const char *fmt, ...);
+
+#define PST_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            pst_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+                          cudaGetErrorString(e__));                                 \
+            return PST_ECUDA;                                                       \
+        }                                                                           \
+    } while (0)
+
+#define PST_TRY(call)                                                               \
+    do {                                                                            \
+        int r__ = (call);                                                           \
+        if (r__ != PST_OK) return r__;                                              \
+    } while (0)
+
+struct pst_comm;   // multi-GPU communicator (pst_comm.cu)
+
+struct pst_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // reduction plumbing: per-block partials -> one record of PST_RED_SLOTS doubles
+    double *d_partial = nullptr;     // [max_blocks * PST_RED_SLOTS]
+    double *d_red = nullptr;         // [64 * PST_RED_SLOTS] ring of records
+    double *h_red = nullptr;         // pinned mirror
+    int max_blocks = 0;
+    // simple bump arena over one big device allocation, reset per call
+    char *arena = nullptr;
+    size_t arena_size = 0, arena_used = 0;
+    pst_stats stats{};
+    pst_comm *comm = nullptr;        // null for single-GPU contexts
+    int rank = 0, nranks = 1;
+};
+
+// ---- arena ---------------------------------------------------------------------------
+int pst_arena_reserve(pst_ctx *c, size_t bytes);            // (re)allocate if too small
+int pst_arena_alloc(pst_ctx *c, size_t bytes, void **p);    // 256-byte aligned bump
+inline void pst_arena_reset(pst_ctx *c) { c->arena_used = 0; }
+
+template <typename T>
+inline int pst_arena_get(pst_ctx *c, size_t count, T **p)
+{
+    void *v = nullptr;
+    int rc = pst_arena_alloc(c, count * sizeof(T), &v);
+    *p = (T *)v;
+    return rc;
+}
+
+// ---- launch geometry -----------------------------------------------------------------
+inline int pst_grid_for(const pst_ctx *c, size_t n, int threads, int per_thread = 4)
+{
+    size_t want = (n + (size_t)threads * per_thread - 1) / ((size_t)threads * per_thread);
+    size_t cap = (size_t)c->sm_count * 8;          // a multiple of the SM count
+    if (want < 1) want = 1;
+    if (want > cap) want = cap;
+    return (int)want;
+}
+
+// ---- deterministic block reduction of NV doubles --------------------------------------
+// Lanes are combined in a fixed shuffle tree, warps in index order, blocks in index order by
+// pst_finish_reduce: results are run-to-run reproducible (no atomics).
+template <int NV>
+__device__ __forceinline__ void pst_block_reduce(double (&v)[NV], double *partial_out)
+{
+    __shared__ double sh[NV][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sh[q][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double x = lane < nwarp ? sh[q][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) partial_out[(size_t)blockIdx.x * PST_RED_SLOTS + q] = x;
+        }
+    }
+}
+
+// sum the per-block partials into record `rec` (device), optionally fetch to host
+int pst_finish_reduce(pst_ctx *c, int nblocks, int nv, int rec);
+int pst_fetch_record(pst_ctx *c, int rec, int nv, double *host_out);   // syncs the stream

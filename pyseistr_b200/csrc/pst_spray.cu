@@ -1,0 +1,679 @@
+// Plane-wave spray + structure-oriented mean / median on sm_100a.
+//
+// Replaces (reference pyseistr/src/sof3d_cfuns.c): sf_banded_define/solve :159-264,
+// pwd_define/pwd_set :401-498, regularization/predict1_step/predict2_step :548-661,
+// update_init/get_update :980-1054, the spray loops of csomean3d :1455-1521 and csomf3d
+// :1639-1705, the mean :1523-1537 and mf/sf_quantile :1058-1252,:1707-1736; and
+// (pyseistr/src/sof_cfuns.c) pwspray_lop :948-1031, pwsmooth_lop/set :1076-1132,
+// csomean2d :1433-1532, csomf2d :1534-1672.
+//
+// Formulation.  The reference sprays source-by-source into a materialised stack
+// u[n2*n3][np][n1].  Here the same values are produced target-by-target and level-by-level:
+// slot (a,b) at location j holds the prediction of trace j from source j-(a,b); it is one
+// implicit plane-wave prediction from the slot(s) one step closer to the source
+// (SURVEY A.8): (a-sgn a, b) at j-sgn a with the inline dip, (a, b-sgn b) at j-sgn b*n2 with
+// the xline dip.  All targets of one slot are independent: one thread per target trace
+// runs the serial banded LDL' factor/solve along n1.  Volumes are held "trace-minor"
+// ([i3][i1][i2], i2 fastest) so that the 32 lanes of a warp walk n1 in lock step with
+// coalesced accesses.  Only the slots the output needs are computed.
+// Arithmetic follows the reference operation by operation (no FMA), so every sprayed
+// value is bit-identical and the median selection is exact.
+#include "pst_common.cuh"
+
+#include <math.h>
+#include <algorithm>
+
+#define PST_MAXSLOT 81
+
+struct BTabS { double b[PST_MAXTAP]; };
+
+static BTabS make_btab_s(int nw)     // apfilt_init sof3d_cfuns.c:286-303
+{
+    BTabS t{};
+    const int nf = 2 * nw;
+    for (int k = 0; k <= nf; k++) {
+        double bk = 1.0;
+        for (int j = 0; j < nf; j++) {
+            if (j < nf - k) bk *= (k + j + 1.0) / (2 * (2 * j + 1) * (j + 1));
+            else            bk *= 1.0 / (2 * (2 * j + 1));
+        }
+        t.b[k] = bk;
+    }
+    return t;
+}
+
+// passfilter (sof3d_cfuns.c:311-329), taps reversed when forw (pwd_define :414-424)
+template <int NW>
+__device__ __forceinline__ void spray_taps(const BTabS &tb, float p, bool forw, float (&a)[2 * NW + 1])
+{
+    constexpr int NF = 2 * NW;
+    float t[2 * NW + 1];
+#pragma unroll
+    for (int k = 0; k <= NF; k++) {
+        double ak = tb.b[k];
+#pragma unroll
+        for (int j = 0; j < NF; j++) {
+            const float f = (j < NF - k) ? ((float)(NF - j) - p) : ((p + (float)j) + 1.0f);
+            ak *= (double)f;
+        }
+        t[k] = (float)ak;
+    }
+#pragma unroll
+    for (int k = 0; k <= NF; k++) a[k] = forw ? t[NF - k] : t[k];
+}
+
+// regularisation constants in the reference's float/double placement (regularization :548-565)
+struct RegC { float d_in, d_e0, d_e1, o0_in, o0_e, o1, eps2; };
+
+static RegC make_reg(float eps)
+{
+    RegC r;
+    const float eps2 = eps;
+    r.d_in = 6. * eps;
+    r.d_e0 = eps2 + eps;
+    r.d_e1 = eps2 + 5. * eps;
+    r.o0_in = -4. * eps;
+    r.o0_e = -2. * eps;
+    r.o1 = eps;
+    r.eps2 = eps2;
+    return r;
+}
+
+struct PredArgs {
+    // all volumes are chunk-local, trace-minor: elem(zl,k,i2) = (zl*n1 + k)*n2 + i2
+    const float *in1, *in2;     // parent slot volumes
+    const float *sg1, *sg2;     // slope volumes
+    long in1_off, in2_off;      // parent location shift, in elements (+-1 or +-n1*n2)
+    long sg1_off, sg2_off;      // slope location shift (0 = target, else = parent shift)
+    int forw1, forw2;
+    float *out;                 // slot volume being produced
+    float *scr;                 // factor scratch [plane][k][NB+2][i2]
+    int n1, n2, n3;
+    int ze0;                    // global index of chunk-local plane 0
+    int zla, zlb;               // chunk-local plane range to produce
+    int a, b;                   // slot offsets: source = target - (a,b)
+    RegC reg;
+    BTabS tb;
+};
+
+// One thread = one target trace.  Forward sweep: taps -> W'W bands (+regularisation) ->
+// LDL' column k -> rhs -> forward substitution; (d, o[0..NB), b) go to scratch.  Backward
+// sweep: back substitution, result stored to the slot volume.
+template <int NW, bool TWO>
+__global__ void __launch_bounds__(128)
+predict_kernel(const PredArgs A)
+{
+    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 2;
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int zl = A.zla + blockIdx.y;
+    if (i2 >= A.n2) return;
+    const int n1 = A.n1, n2 = A.n2;
+    const long base = (long)zl * n1 * n2 + i2;
+    float *out = A.out + base;
+    // slot stays zero when its source lies outside the cube (csomf3d :1656)
+    const int s2 = i2 - A.a, s3 = (A.ze0 + zl) - A.b;
+    if (s2 < 0 || s2 >= n2 || s3 < 0 || s3 >= A.n3) {
+        for (int k = 0; k < n1; k++) out[(long)k * n2] = 0.f;
+        return;
+    }
+    const float *x1 = A.in1 + base + A.in1_off;
+    const float *g1 = A.sg1 + base + A.sg1_off;
+    const float *x2 = TWO ? A.in2 + base + A.in2_off : nullptr;
+    const float *g2 = TWO ? A.sg2 + base + A.sg2_off : nullptr;
+    float *scr = A.scr + ((long)blockIdx.y * n1 * NC) * n2 + i2;
+    const bool f1 = A.forw1 != 0, f2 = A.forw2 != 0;
+    const RegC rg = A.reg;
+
+    // sliding windows, index c <-> sample i-NW+c
+    float W1[NA][NA], T1[NA], X1[NA];
+    float W2[TWO ? NA : 1][NA], T2[TWO ? NA : 1], X2[TWO ? NA : 1];
+    float O[NB][NB], D[NB], Bh[NB];        // history: index h <-> sample k-1-h
+#pragma unroll
+    for (int c = 0; c < NA; c++) {
+        T1[c] = 0.f; X1[c] = 0.f;
+        if (TWO) { T2[c] = 0.f; X2[c] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < NA; j++) { W1[c][j] = 0.f; if (TWO) W2[c][j] = 0.f; }
+    }
+#pragma unroll
+    for (int h = 0; h < NB; h++) {
+        D[h] = 0.f; Bh[h] = 0.f;
+#pragma unroll
+        for (int m = 0; m < NB; m++) O[h][m] = 0.f;
+    }
+    // Invariant at the top of step i (leading sample kk = i + NW):  X[c] = inp[kk - NW + c] = inp[i + c].
+    // The loop starts at i = -NW so the windows fill before column 0; entries with a negative
+    // sample index are never used (tmp is only formed for kk >= NW).
+    {
+        float t1[NA], t2[NA];
+#pragma unroll
+        for (int c = 0; c < NA; c++) {
+            const int idx = c - NW;
+            t1[c] = (idx >= 0 && idx < n1) ? x1[(long)idx * n2] : 0.f;
+            if (TWO) t2[c] = (idx >= 0 && idx < n1) ? x2[(long)idx * n2] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < NA; c++) { X1[c] = t1[c]; if (TWO) X2[c] = t2[c]; }
+    }
+
+    for (int i = -NW; i < n1; i++) {
+        // ---- leading sample kk = i + NW enters the windows at c = NA-1
+        const int kk = i + NW;
+        {
+            float a1[NA], a2[NA];
+            float tm1 = 0.f, tm2 = 0.f;
+            if (kk < n1) {
+                spray_taps<NW>(A.tb, g1[(long)kk * n2], f1, a1);
+                if (TWO) spray_taps<NW>(A.tb, g2[(long)kk * n2], f2, a2);
+                if (kk >= NW && kk < n1 - NW) {               // pwd_set :481-486
+#pragma unroll
+                    for (int j = 0; j < NA; j++) {
+                        tm1 += a1[j] * X1[j];
+                        if (TWO) tm2 += a2[j] * X2[j];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NA; j++) { a1[j] = 0.f; a2[j] = 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < NA; j++) { W1[NA - 1][j] = a1[j]; if (TWO) W2[NA - 1][j] = a2[j]; }
+            T1[NA - 1] = tm1;
+            if (TWO) T2[NA - 1] = tm2;
+        }
+        if (i >= 0) {
+            // ---- matrix column i: regularisation + W'W (pwd_define :426-444)
+            float dg = rg.d_in;
+            if (i == 0 || i == n1 - 1) dg = rg.d_e0;
+            if (i == 1 || i == n1 - 2) dg = rg.d_e1;
+            float of[NB];
+            of[0] = (i == 0 || i == n1 - 2) ? rg.o0_e : rg.o0_in;
+            of[1] = rg.o1;
+#pragma unroll
+            for (int m = 2; m < NB; m++) of[m] = 0.0f;
+            float rhs1 = 0.f, rhs2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < NA; j++) {
+                const int k = i + j - NW;
+                if (k >= NW && k < n1 - NW) { const float aj = W1[j][j]; dg += aj * aj; }
+            }
+#pragma unroll
+            for (int m = 0; m < NB; m++) {
+#pragma unroll
+                for (int j = m + 1; j < NA; j++) {
+                    const int k = i + j - NW;
+                    if (k >= NW && k < n1 - NW) of[m] += W1[j][j - m - 1] * W1[j][j];
+                }
+            }
+            if (TWO) {
+#pragma unroll
+                for (int j = 0; j < NA; j++) {
+                    const int k = i + j - NW;
+                    if (k >= NW && k < n1 - NW) { const float aj = W2[j][j]; dg += aj * aj; }
+                }
+#pragma unroll
+                for (int m = 0; m < NB; m++) {
+#pragma unroll
+                    for (int j = m + 1; j < NA; j++) {
+                        const int k = i + j - NW;
+                        if (k >= NW && k < n1 - NW) of[m] += W2[j][j - m - 1] * W2[j][j];
+                    }
+                }
+            }
+            // ---- rhs (pwd_set :487-496), end terms (predict1/2_step :611-619,:640-658)
+#pragma unroll
+            for (int j = 0; j < NA; j++) {
+                const int k = i + j - NW;
+                if (k >= NW && k < n1 - NW) {
+                    rhs1 += W1[j][j] * T1[j];
+                    if (TWO) rhs2 += W2[j][j] * T2[j];
+                }
+            }
+            float rhs = TWO ? (rhs1 + rhs2) : rhs1;
+            if (i < 2 || i >= n1 - 2) {
+                // X1[0] = inp[kk - NW] = inp[i]
+                float te;
+                if (TWO) te = (float)(0.5 * (double)(X1[0] + X2[0]));
+                else te = X1[0];
+                rhs += rg.eps2 * te;
+            }
+            // ---- LDL' column (sf_banded_define :169-184)
+            float t = dg;
+#pragma unroll
+            for (int m = 0; m < NB; m++)
+                if (m < i) t -= (O[m][m] * O[m][m]) * D[m];
+            const float dk = t;
+            float ok[NB];
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                float v = of[q];
+#pragma unroll
+                for (int m = 0; m < NB - q - 1; m++)
+                    if (m < i) v -= (O[m][m] * O[m][q + m + 1]) * D[m];
+                ok[q] = (q < n1 - i - 1) ? v / dk : 0.f;
+            }
+            // ---- forward substitution (sf_banded_solve :250-256)
+            float bk = rhs;
+#pragma unroll
+            for (int m = 0; m < NB; m++)
+                if (m < i) bk -= O[m][m] * Bh[m];
+            // ---- spill column to scratch
+            float *sc = scr + (long)i * NC * n2;
+            sc[0] = dk;
+#pragma unroll
+            for (int q = 0; q < NB; q++) sc[(long)(1 + q) * n2] = ok[q];
+            sc[(long)(NB + 1) * n2] = bk;
+            // ---- shift LDL history
+#pragma unroll
+            for (int h = NB - 1; h > 0; h--) {
+                D[h] = D[h - 1]; Bh[h] = Bh[h - 1];
+#pragma unroll
+                for (int m = 0; m < NB; m++) O[h][m] = O[h - 1][m];
+            }
+            D[0] = dk; Bh[0] = bk;
+#pragma unroll
+            for (int m = 0; m < NB; m++) O[0][m] = ok[m];
+        }
+        // ---- shift sample windows; new trailing input for the next leading sample
+#pragma unroll
+        for (int c = 0; c < NA - 1; c++) {
+            T1[c] = T1[c + 1]; X1[c] = X1[c + 1];
+            if (TWO) { T2[c] = T2[c + 1]; X2[c] = X2[c + 1]; }
+#pragma unroll
+            for (int j = 0; j < NA; j++) { W1[c][j] = W1[c + 1][j]; if (TWO) W2[c][j] = W2[c + 1][j]; }
+        }
+        {
+            const int idx = kk + 1 + NW;       // X[NA-1] for the next step = inp[(kk+1) + NW]
+            X1[NA - 1] = (idx < n1) ? x1[(long)idx * n2] : 0.f;
+            if (TWO) X2[NA - 1] = (idx < n1) ? x2[(long)idx * n2] : 0.f;
+        }
+    }
+
+    // ---- back substitution (sf_banded_solve :257-263)
+    float Y[NB];
+#pragma unroll
+    for (int m = 0; m < NB; m++) Y[m] = 0.f;
+    for (int k = n1 - 1; k >= 0; k--) {
+        const float *sc = scr + (long)k * NC * n2;
+        const float dk = sc[0];
+        float t = sc[(long)(NB + 1) * n2] / dk;
+#pragma unroll
+        for (int m = 0; m < NB; m++)
+            if (m < n1 - k - 1) t -= sc[(long)(1 + m) * n2] * Y[m];
+        out[(long)k * n2] = t;
+#pragma unroll
+        for (int m = NB - 1; m > 0; m--) Y[m] = Y[m - 1];
+        Y[0] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// layout changes: [i3][i2][i1] (reference order, i1 fastest) <-> [i3][i1][i2] (trace-minor)
+__global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int rows,
+                                 int cols)
+{
+    // per plane: in is [rows][cols] with cols fastest; out is [cols][rows] with rows fastest
+    __shared__ float tile[32][33];
+    const long plane = (long)rows * cols * blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int rr = r0 + r, cc = c0 + threadIdx.x;
+        if (rr < rows && cc < cols) tile[r][threadIdx.x] = in[plane + (long)rr * cols + cc];
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+        const int cc = c0 + c, rr = r0 + threadIdx.x;
+        if (rr < rows && cc < cols) out[plane + (long)cc * rows + rr] = tile[threadIdx.x][c];
+    }
+}
+
+static int transpose_planes(pst_ctx *c, const float *in, float *out, int rows, int cols, int planes)
+{
+    // grid.z is limited to 65535: loop in batches
+    const int zmax = 32768;
+    for (int z0 = 0; z0 < planes; z0 += zmax) {
+        const int nz = std::min(zmax, planes - z0);
+        dim3 grid((cols + 31) / 32, (rows + 31) / 32, nz), block(32, 8);
+        const long off = (long)rows * cols * z0;
+        transpose_kernel<<<grid, block, 0, c->stream>>>(in + off, out + off, rows, cols);
+        c->stats.kernel_launches++;
+    }
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+struct SlotPtrs { const float *p[PST_MAXSLOT]; };
+
+// mean over all np slots in slot order, / np (csomean3d :1531-1535)
+__global__ void __launch_bounds__(256)
+slot_mean_kernel(SlotPtrs S, int np, float *__restrict__ out, long zoff_out, long zoff_slot, long count)
+{
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
+        float sum = 0;
+        for (int s = 0; s < np; s++) sum = sum + S.p[s][zoff_slot + e];
+        sum = sum / np;
+        out[zoff_out + e] = sum;
+    }
+}
+
+// exact m-th order statistic of nmf slot values (mf + sf_quantile :1058-1084,:1214-1252).
+// Selection by rank counting: O(nmf^2) compares, no data-dependent memory traffic.
+template <int NMF>
+__global__ void __launch_bounds__(256)
+slot_median_kernel(SlotPtrs S, int nmf_rt, float *__restrict__ out, long zoff_out, long zoff_slot, long count)
+{
+    const int nmf = NMF > 0 ? NMF : nmf_rt;
+    const int m = (nmf - 1) / 2;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
+        float v[NMF > 0 ? NMF : PST_MAXSLOT];
+#pragma unroll
+        for (int s = 0; s < nmf; s++) v[s] = S.p[s][zoff_slot + e];
+        float res = v[0];
+#pragma unroll
+        for (int s = 0; s < nmf; s++) {
+            int lt = 0, le = 0;
+#pragma unroll
+            for (int q = 0; q < nmf; q++) { lt += (v[q] < v[s]); le += (v[q] <= v[s]); }
+            if (lt <= m && m < le) res = v[s];
+        }
+        out[zoff_out + e] = res;
+    }
+}
+
+// pwsmooth_lop forward (sof_cfuns.c:1099-1108): out = sum_is u_is * w_is * ws, is ascending;
+// MODE 0: ws = 1 and out -> t (normalisation spray of ones); MODE 1: ws = (t != 0 ? 1/t : 0)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+slot_wsum_kernel(SlotPtrs S, int ns, const float *__restrict__ tnorm, float *__restrict__ out, long count)
+{
+    const int ns2 = 2 * ns + 1;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) {
+        float ws = 1.0f;
+        if (MODE == 1) {
+            const float t = tnorm[e];
+            ws = (0.0f != t) ? (float)(1.0 / (double)t) : 0.0f;
+        }
+        float acc = 0.f;
+        for (int is = 0; is < ns2; is++) {
+            const float w = (float)(ns + 1 - abs(is - ns));
+            acc += S.p[is][e] * w * ws;
+        }
+        out[e] = acc;
+    }
+}
+
+__global__ void fill_kernel_s(float *__restrict__ x, float v, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
+// =======================================================================================
+// host side
+// =======================================================================================
+
+struct SprayPlan {
+    int n1, n2, n3, ns2, ns3, nw;
+    int np2, np3, np;
+    float eps_reg;                 // regularisation (already squared)
+    bool live[PST_MAXSLOT];        // slots that must be produced
+};
+
+static void plan_close_parents(SprayPlan &P)
+{
+    // a live slot needs its parent(s): walk from the farthest level inwards
+    for (int lev = P.ns2 + P.ns3; lev >= 1; lev--)
+        for (int s = 0; s < P.np; s++) {
+            const int a = s % P.np2 - P.ns2, b = s / P.np2 - P.ns3;
+            if (!P.live[s] || abs(a) + abs(b) != lev) continue;
+            if (a != 0) P.live[(b + P.ns3) * P.np2 + (a - (a > 0 ? 1 : -1) + P.ns2)] = true;
+            if (b != 0) P.live[(b - (b > 0 ? 1 : -1) + P.ns3) * P.np2 + (a + P.ns2)] = true;
+        }
+}
+
+template <int NW>
+static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
+{
+    const int threads = A.n2 >= 128 ? 128 : (A.n2 >= 64 ? 64 : 32);
+    dim3 grid((A.n2 + threads - 1) / threads, A.zlb - A.zla);
+    if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
+    else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A);
+    c->stats.kernel_launches++;
+}
+
+typedef int (*chunk_reduce_fn)(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0,
+                               int z0, int z1);
+
+// Spray every live slot for all planes, chunk by chunk along n3, and hand the slot volumes
+// of each chunk to `reduce`.  dT/piT/pxT are full trace-minor volumes.
+static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const float *piT, const float *pxT,
+                     chunk_reduce_fn reduce, void *user)
+{
+    const int n1 = P.n1, n2 = P.n2, n3 = P.n3, ns3 = P.ns3, nw = P.nw;
+    const long plane = (long)n1 * n2;
+    int nlive = 0;
+    for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
+    const int NC = 2 * nw + 2;
+    // chunk height: bound slot + scratch memory to ~6 GB
+    const double bytes_per_plane = (double)plane * 4.0 * (nlive + NC);
+    int cz = (int)(6.0e9 / bytes_per_plane) - 2 * ns3;
+    if (cz < 1) cz = 1;
+    if (cz > n3) cz = n3;
+    const int nzl_max = std::min(n3, cz + 2 * ns3);
+    float *slotbuf[PST_MAXSLOT];
+    const int centre = ns3 * P.np2 + P.ns2;
+    for (int s = 0; s < P.np; s++) {
+        slotbuf[s] = nullptr;
+        if (P.live[s] && s != centre) PST_TRY(pst_arena_get(c, (size_t)plane * nzl_max, &slotbuf[s]));
+    }
+    float *scr;
+    PST_TRY(pst_arena_get(c, (size_t)plane * nzl_max * NC, &scr));
+    const RegC reg = make_reg(P.eps_reg);
+    const BTabS tb = make_btab_s(nw);
+
+    for (int z0 = 0; z0 < n3; z0 += cz) {
+        const int z1 = std::min(n3, z0 + cz);
+        const int ze0 = std::max(0, z0 - ns3), ze1 = std::min(n3, z1 + ns3);
+        float *slot[PST_MAXSLOT];
+        for (int s = 0; s < P.np; s++) slot[s] = slotbuf[s];
+        slot[centre] = const_cast<float *>(dT) + (long)ze0 * plane;
+        const float *pi_c = piT + (long)ze0 * plane, *px_c = pxT ? pxT + (long)ze0 * plane : nullptr;
+        for (int lev = 1; lev <= P.ns2 + ns3; lev++) {
+            for (int s = 0; s < P.np; s++) {
+                const int a = s % P.np2 - P.ns2, b = s / P.np2 - ns3;
+                if (!P.live[s] || abs(a) + abs(b) != lev) continue;
+                int lo = z0 - (b >= 0 ? ns3 - b : 0), hi = z1 + (b <= 0 ? ns3 + b : 0);
+                lo = std::max(lo, ze0); hi = std::min(hi, ze1);
+                if (hi <= lo) continue;
+                PredArgs A{};
+                A.n1 = n1; A.n2 = n2; A.n3 = n3; A.ze0 = ze0; A.zla = lo - ze0; A.zlb = hi - ze0;
+                A.a = a; A.b = b; A.reg = reg; A.tb = tb; A.out = slot[s]; A.scr = scr;
+                int nin = 0;
+                const float *inp[2]; const float *sg[2]; long ioff[2], soff[2]; int fw[2];
+                if (a != 0) {                       // inline parent (get_update bit 1, :1661-1673)
+                    const int sa = a > 0 ? 1 : -1;
+                    inp[nin] = slot[(b + ns3) * P.np2 + (a - sa + P.ns2)];
+                    sg[nin] = pi_c; ioff[nin] = -sa; fw[nin] = a > 0;
+                    soff[nin] = a > 0 ? -1 : 0;     // up: parent-location dip; down: target-location dip
+                    nin++;
+                }
+                if (b != 0) {                       // xline parent (bit 2, :1674-1686)
+                    const int sb = b > 0 ? 1 : -1;
+                    inp[nin] = slot[(b - sb + ns3) * P.np2 + (a + P.ns2)];
+                    sg[nin] = px_c; ioff[nin] = -(long)sb * plane; fw[nin] = b > 0;
+                    soff[nin] = b > 0 ? -plane : 0;
+                    nin++;
+                }
+                A.in1 = inp[0]; A.sg1 = sg[0]; A.in1_off = ioff[0]; A.sg1_off = soff[0]; A.forw1 = fw[0];
+                if (nin == 2) { A.in2 = inp[1]; A.sg2 = sg[1]; A.in2_off = ioff[1]; A.sg2_off = soff[1]; A.forw2 = fw[1]; }
+                if (nw == 1) launch_predict<1>(c, A, nin == 2);
+                else         launch_predict<2>(c, A, nin == 2);
+                c->stats.predictions += (long long)(hi - lo) * n2;
+            }
+        }
+        PST_CUDA(cudaGetLastError());
+        PST_TRY(reduce(c, user, P, slot, ze0, z0, z1));
+    }
+    return PST_OK;
+}
+
+struct ReduceOut { float *outT; int nmf; const float *tnorm; int mode; };
+
+static int reduce_mean(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0, int z0, int z1)
+{
+    ReduceOut *R = (ReduceOut *)user;
+    const long plane = (long)P.n1 * P.n2, count = plane * (z1 - z0);
+    SlotPtrs S{};
+    for (int s = 0; s < P.np; s++) S.p[s] = slot[s];
+    const int grid = pst_grid_for(c, (size_t)count, 256, 2);
+    slot_mean_kernel<<<grid, 256, 0, c->stream>>>(S, P.np, R->outT, plane * z0, plane * (z0 - ze0), count);
+    c->stats.kernel_launches++;
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+static int reduce_median(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0, int z0, int z1)
+{
+    ReduceOut *R = (ReduceOut *)user;
+    const long plane = (long)P.n1 * P.n2, count = plane * (z1 - z0);
+    const int nmf = R->nmf, m = (nmf - 1) / 2, cen = (P.np - 1) / 2;
+    SlotPtrs S{};
+    for (int q = 0; q < nmf; q++) {              // boundary(): edge replication along the slot axis
+        int s = cen - m + q;
+        s = std::max(0, std::min(P.np - 1, s));
+        S.p[q] = slot[s];
+    }
+    const int grid = pst_grid_for(c, (size_t)count, 256, 2);
+    const long zo = plane * z0, zs = plane * (z0 - ze0);
+    switch (nmf) {
+        case 3: slot_median_kernel<3><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        case 5: slot_median_kernel<5><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        case 9: slot_median_kernel<9><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        case 13: slot_median_kernel<13><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        case 17: slot_median_kernel<17><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        case 19: slot_median_kernel<19><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+        default: slot_median_kernel<0><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
+    }
+    c->stats.kernel_launches++;
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+static int reduce_wsum(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0, int z0, int z1)
+{
+    ReduceOut *R = (ReduceOut *)user;
+    const long plane = (long)P.n1 * P.n2, count = plane * (z1 - z0);
+    SlotPtrs S{};
+    for (int s = 0; s < P.np; s++) S.p[s] = slot[s] + plane * (z0 - ze0);
+    const int grid = pst_grid_for(c, (size_t)count, 256, 2);
+    if (R->mode == 0) slot_wsum_kernel<0><<<grid, 256, 0, c->stream>>>(S, P.ns2, nullptr, R->outT + plane * z0, count);
+    else              slot_wsum_kernel<1><<<grid, 256, 0, c->stream>>>(S, P.ns2, R->tnorm + plane * z0, R->outT + plane * z0, count);
+    c->stats.kernel_launches++;
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+static int check_spray_args(int n1, int n2, int n3, int ns2, int ns3, int order)
+{
+    if (n1 < 1 || n2 < 1 || n3 < 1 || ns2 < 0 || ns3 < 0) { pst_set_error("spray: bad dimensions/radii"); return PST_EINVAL; }
+    if (order != 1 && order != 2) { pst_set_error("spray: order=%d unsupported (1 or 2)", order); return PST_EUNSUP; }
+    if (n1 < 2 * order + 2) { pst_set_error("spray: n1=%d too short for order %d", n1, order); return PST_EINVAL; }
+    if ((2 * ns2 + 1) * (2 * ns3 + 1) > PST_MAXSLOT) { pst_set_error("spray: (2ns2+1)(2ns3+1) > %d unsupported", PST_MAXSLOT); return PST_EUNSUP; }
+    return PST_OK;
+}
+
+// kind: 0 = mean (3-D), 1 = median (3-D), 2 = weighted normalised smooth (2-D), 3 = median (2-D)
+static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const float *d_dipi, const float *d_dipx,
+                            int n1, int n2, int n3, int ns2, int ns3, int nmf, int order, float eps_reg,
+                            float *d_out)
+{
+    PST_CUDA(cudaSetDevice(c->device));
+    SprayPlan P{};
+    P.n1 = n1; P.n2 = n2; P.n3 = n3; P.ns2 = ns2; P.ns3 = ns3; P.nw = order;
+    P.np2 = 2 * ns2 + 1; P.np3 = 2 * ns3 + 1; P.np = P.np2 * P.np3;
+    P.eps_reg = eps_reg;
+    const int cen = (P.np - 1) / 2;
+    for (int s = 0; s < P.np; s++) P.live[s] = (kind == 0 || kind == 2);
+    if (kind == 1 || kind == 3) {
+        if (nmf < 1 || nmf > PST_MAXSLOT || (nmf % 2) == 0) { pst_set_error("median length nmf=%d unsupported (odd, <= %d)", nmf, PST_MAXSLOT); return PST_EUNSUP; }
+        const int m = (nmf - 1) / 2;
+        for (int q = cen - m; q <= cen + m; q++) P.live[std::max(0, std::min(P.np - 1, q))] = true;
+    }
+    P.live[cen] = true;
+    plan_close_parents(P);
+    int nlive = 0;
+    for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
+
+    const size_t n = (size_t)n1 * n2 * n3;
+    const long plane = (long)n1 * n2;
+    const int NC = 2 * order + 2;
+    // arena: 3 transposed inputs + transposed output (+ norm volume) + chunk buffers
+    double chunk_planes = 6.0e9 / ((double)plane * 4.0 * (nlive + NC));
+    if (chunk_planes > n3) chunk_planes = n3;
+    const size_t nzl = (size_t)std::min<double>(n3, std::max(1.0, floor(chunk_planes) - 2 * ns3) + 2 * ns3);
+    const size_t need = (5 * n + (size_t)plane * nzl * (nlive + NC)) * sizeof(float) + 64 * 256 + (size_t)nlive * 256;
+    PST_TRY(pst_arena_reserve(c, need));
+    pst_arena_reset(c);
+    float *dT, *piT, *pxT = nullptr, *outT, *tnorm = nullptr;
+    PST_TRY(pst_arena_get(c, n, &dT));
+    PST_TRY(pst_arena_get(c, n, &piT));
+    if (d_dipx) PST_TRY(pst_arena_get(c, n, &pxT));
+    PST_TRY(pst_arena_get(c, n, &outT));
+    PST_TRY(transpose_planes(c, d_din, dT, n2, n1, n3));
+    PST_TRY(transpose_planes(c, d_dipi, piT, n2, n1, n3));
+    if (d_dipx) PST_TRY(transpose_planes(c, d_dipx, pxT, n2, n1, n3));
+    ReduceOut R{outT, nmf, nullptr, 0};
+    if (kind == 0) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_mean, &R));
+    else if (kind == 1 || kind == 3) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_median, &R));
+    else {
+        // pwsmooth_set (sof_cfuns.c:1113-1132): normalisation = smooth of a volume of ones
+        PST_TRY(pst_arena_get(c, n, &tnorm));
+        float *ones = outT;            // reuse: outT is written only by the second pass
+        fill_kernel_s<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(ones, 1.0f, n);
+        c->stats.kernel_launches++;
+        const size_t mark = c->arena_used;
+        ReduceOut R0{tnorm, 0, nullptr, 0};
+        PST_TRY(spray_run(c, P, ones, piT, pxT, reduce_wsum, &R0));
+        c->arena_used = mark;          // chunk buffers are reusable
+        ReduceOut R1{outT, 0, tnorm, 1};
+        PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_wsum, &R1));
+    }
+    PST_TRY(transpose_planes(c, outT, d_out, n1, n2, n3));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+extern "C" int pst_somean3d_dev(pst_ctx *c, const float *d_din, const float *d_dipi, const float *d_dipx,
+                                int n1, int n2, int n3, int ns2, int ns3, int order, float *d_out)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_TRY(check_spray_args(n1, n2, n3, ns2, ns3, order));
+    const float eps = 0.01;                       // caller's eps overridden (sof3d_cfuns.c:1402)
+    return spray_filter_dev(c, 0, d_din, d_dipi, d_dipx, n1, n2, n3, ns2, ns3, 0, order, eps * eps, d_out);
+}
+
+extern "C" int pst_somf3d_dev(pst_ctx *c, const float *d_din, const float *d_dipi, const float *d_dipx,
+                              int n1, int n2, int n3, int ns2, int ns3, int nmf, int option, int order,
+                              float *d_out)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_TRY(check_spray_args(n1, n2, n3, ns2, ns3, order));
+    if (option != 1) { pst_set_error("somf3d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
+    const float eps = 0.01;                       // sof3d_cfuns.c:1586
+    return spray_filter_dev(c, 1, d_din, d_dipi, d_dipx, n1, n2, n3, ns2, ns3, nmf, order, eps * eps, d_out);
+}
+
+int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                     int order, float eps, float *d_out)
+{
+    PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
+    return spray_filter_dev(c, 2, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, 0, order, eps * eps, d_out);
+}
+
+int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                   int nmf, int option, int order, float eps, float *d_out)
+{
+    PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
+    if (option != 1) { pst_set_error("somf2d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
+    return spray_filter_dev(c, 3, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, nmf, order, eps * eps, d_out);
+}

@@ -2,8 +2,8 @@
 
 ``cube`` = sum of Ricker plane events w(t - t0 - px*i2 - py*i3) (one mildly curved),
 normalised to max|d| = 1, plus Gaussian noise; ``erratic`` adds the spiky traces the
-somf3d demo uses (reference demos/test_pyseistr_somf3d.py:20-31).  Pure NumPy, no
-dependency on the oracle or on CUDA.
+somf3d demo uses (reference demos/test_pyseistr_somf3d.py:20-31).  Pure NumPy; needs neither
+the checker nor CUDA.
 """
 import numpy as np
 

@@ -1,0 +1,66 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference C (oracle/_ref, compiled from
+/root/reference by oracle/Makefile).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors or asserting tests of its own, so these
+fixtures — inputs AND reference outputs — are what pins the oracle port and the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from pyseistr_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    assert ref.available(), "build oracle/_ref first: make -C oracle ref"
+    g = {}
+    # ---- 3-D: dip3d (defaults), with mask, low order; somean3d / somf3d on its dips
+    d3 = synth.cube(40, 16, 8, seed=11)
+    di, dx = ref.dip3dc(d3)
+    g["dip3d_default"] = dict(din=d3, dipi=di, dipx=dx, niter=5, liter=10, order=2, rect=[5, 5, 5])
+    di1, dx1 = ref.dip3dc(d3, niter=2, liter=5, order=1, rect=[3, 4, 2])
+    g["dip3d_order1"] = dict(din=d3, dipi=di1, dipx=dx1, niter=2, liter=5, order=1, rect=[3, 4, 2])
+    mask = np.ones_like(d3)
+    rng = np.random.default_rng(5)
+    kill = rng.random((16, 8)) < 0.25
+    dm = d3.copy()
+    dm[:, kill] = 0.0
+    mask[:, kill] = 0.0
+    dim_, dxm = ref.dip3dc(dm, niter=3, liter=6, order=2, rect=[4, 3, 3], mask=mask)
+    g["dip3d_mask"] = dict(din=dm, mask=mask, dipi=dim_, dipx=dxm, niter=3, liter=6, order=2, rect=[4, 3, 3])
+    de = synth.erratic(d3, seed=202122, ntraces=5)
+    for name, (r1, r2, order) in {"r22o2": (2, 2, 2), "r11o1": (1, 1, 1), "r21o2": (2, 1, 2),
+                                  "r12o1": (1, 2, 1), "r33o1": (3, 3, 1)}.items():
+        g["somean3d_" + name] = dict(dn=de, dipi=di, dipx=dx, r1=r1, r2=r2, order=order,
+                                     out=ref.somean3dc(de, di, dx, r1, r2, 0.01, order))
+        g["somf3d_" + name] = dict(dn=de, dipi=di, dipx=dx, r1=r1, r2=r2, order=order,
+                                   out=ref.somf3dc(de, di, dx, r1, r2, 0.01, order))
+    # ---- 2-D: dip2d, somf2d, somean2d
+    d2 = synth.cube(64, 24, 1, seed=12)
+    p2 = ref.dip2dc(d2, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    g["dip2d"] = dict(din=d2, dip=p2, niter=2, liter=10, order=2, rect=[7, 7, 1])
+    d2e = synth.erratic(d2, seed=7, ntraces=3)
+    for name, (ns, order, eps) in {"ns3o2": (3, 2, 0.01), "ns2o1": (2, 1, 0.05), "ns8o2": (8, 2, 0.01)}.items():
+        g["somf2d_" + name] = dict(dn=d2e, dip=p2, ns=ns, order=order, eps=eps,
+                                   out=ref.somf2dc(d2e, p2, ns, order, eps))
+        g["somean2d_" + name] = dict(dn=d2e, dip=p2, ns=ns, order=order, eps=eps,
+                                     out=ref.somean2dc(d2e, p2, ns, order, eps))
+    # ---- smoothing (ps_smooth2 through smoothcf adj=0), incl. a radius larger than an axis
+    xs = synth.cube(30, 12, 6, seed=13)
+    g["smooth_534"] = dict(x=xs, rect=[5, 3, 4], out=ref.smoothc(xs, [5, 3, 4]))
+    g["smooth_big_radius"] = dict(x=xs, rect=[2, 15, 9], out=ref.smoothc(xs, [2, 15, 9]))
+    for k, v in g.items():
+        np.savez_compressed(os.path.join(OUT, k + ".npz"), **{a: np.asarray(b) for a, b in v.items()})
+        print("wrote", k, {a: np.asarray(b).shape for a, b in v.items() if np.asarray(b).ndim})
+
+
+if __name__ == "__main__":
+    main()

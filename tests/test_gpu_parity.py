@@ -1,0 +1,229 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI, against (1) the golden
+fixtures from the compiled reference, (2) the oracle port on fresh seeded inputs, and (3)
+size-independent properties at larger sizes.
+
+Tolerances.  Every float vector operation follows the reference's order without FMA, so the
+building blocks (stencil, smoothing, spray, median) are required to be BIT-EXACT.  dip3d /
+divne contain global sums that the reference accumulates sequentially (double for the CG
+scalars, float for the line-search energies) and the GPU accumulates as double trees: their
+results must agree to relative L2 <= 1e-5 (north-star tolerance); in practice they are
+bit-identical or differ by ~1e-7.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names, rel_l2
+from pyseistr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+_vp = ctypes.c_void_p
+
+
+def _F(a):
+    return np.ascontiguousarray(np.float32(a).flatten(order="F"))
+
+
+class Dev:
+    """tiny RAII helper over pst_dev_alloc / pst_h2d / pst_d2h"""
+
+    def __init__(self, ctx, arr=None, n=None):
+        self.ctx = ctx
+        self.n = arr.size if arr is not None else n
+        self.p = ctx.alloc(4 * self.n)
+        if arr is not None:
+            ctx.h2d(self.p, _F(arr))
+
+    def get(self, shape):
+        out = np.empty(self.n, np.float32)
+        self.ctx.d2h(out, self.p)
+        return out.reshape(shape, order="F")
+
+    def __del__(self):
+        try:
+            self.ctx.free(self.p)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ building blocks: bit-exact
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("xline", [0, 1])
+@pytest.mark.parametrize("der", [0, 1])
+def test_allpass_bit_exact(ctx, port, order, xline, der):
+    from pyseistr_b200 import _lib
+    n1, n2, n3 = 37, 11, 6
+    u = synth.cube(n1, n2, n3, seed=31)
+    sg, _ = synth.smooth_dips(n1, n2, n3, seed=32, amp=1.5)
+    du, ds, dy = Dev(ctx, u), Dev(ctx, sg), Dev(ctx, n=u.size)
+    _lib.check(ctx.lib.pst_allpass_dev(ctx.handle, du.p, ds.p, n1, n2, n3, order, xline, der, dy.p))
+    got = dy.get((n1, n2, n3))
+    want = port.allpass(u, sg, order, xline, der)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape,rect", [((40, 12, 9), (5, 5, 5)), ((33, 7, 5), (3, 4, 2)),
+                                        ((64, 20, 1), (10, 10, 1)), ((30, 12, 6), (2, 15, 9)),
+                                        ((300, 9, 4), (40, 3, 1)), ((17, 5, 3), (1, 1, 1))])
+def test_smooth3_bit_exact(ctx, port, shape, rect):
+    import pyseistr_b200 as ps
+    x = synth.cube(*shape, seed=33)
+    got = ps.smoothc(x, rect=list(rect), ctx=ctx)
+    want = port.smooth3(x, rect).reshape(x.shape, order="F")
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", golden_names("smooth_"))
+def test_smooth_golden(ctx, name):
+    import pyseistr_b200 as ps
+    g = golden(name)
+    assert np.array_equal(ps.smoothc(g["x"], rect=[int(v) for v in g["rect"]], ctx=ctx), g["out"])
+
+
+def test_divne_matches_oracle(ctx, port):
+    from pyseistr_b200 import _lib
+    n1, n2, n3 = 36, 10, 7
+    num = synth.cube(n1, n2, n3, seed=41)
+    den = synth.cube(n1, n2, n3, seed=42) + 0.5
+    dn, dd, dr = Dev(ctx, num), Dev(ctx, den), Dev(ctx, n=num.size)
+    its = ctypes.c_int(0)
+    _lib.check(ctx.lib.pst_divne_dev(ctx.handle, dn.p, dd.p, dr.p, n1, n2, n3, 4, 3, 3, 12, ctypes.byref(its)))
+    got = dr.get((n1, n2, n3))
+    want, it_ref = port.divne(num, den, (4, 3, 3), 12)
+    assert its.value == it_ref
+    assert rel_l2(got, want) <= TOL
+
+
+# ------------------------------------------------------------------ dip estimation
+@pytest.mark.parametrize("name", golden_names("dip3d_"))
+def test_dip3d_golden(ctx, name):
+    import pyseistr_b200 as ps
+    g = golden(name)
+    di, dx = ps.dip3dc(g["din"], int(g["niter"]), int(g["liter"]), int(g["order"]),
+                       rect=[int(v) for v in g["rect"]], verb=0, mask=g.get("mask"), ctx=ctx)
+    assert di.shape == g["dipi"].shape and di.dtype == np.float32
+    assert rel_l2(di, g["dipi"]) <= TOL, rel_l2(di, g["dipi"])
+    assert rel_l2(dx, g["dipx"]) <= TOL, rel_l2(dx, g["dipx"])
+
+
+def test_dip2d_golden(ctx):
+    import pyseistr_b200 as ps
+    g = golden("dip2d")
+    p = ps.dip2dc(g["din"], int(g["niter"]), int(g["liter"]), int(g["order"]), rect=[int(v) for v in g["rect"]],
+                  verb=0, ctx=ctx)
+    assert p.shape == g["dip"].shape
+    assert rel_l2(p, g["dip"]) <= TOL, rel_l2(p, g["dip"])
+
+
+@pytest.mark.parametrize("shape,kw", [((100, 50, 10), dict()),
+                                      ((60, 17, 12), dict(niter=3, liter=7, order=1, rect=[3, 6, 4])),
+                                      ((50, 21, 3), dict(niter=2, liter=5, order=2, rect=[4, 4, 1]))])
+def test_dip3d_vs_oracle(ctx, port, shape, kw):
+    """C1-shaped cube of the reference demo (100x50x10, defaults) and two ragged shapes."""
+    import pyseistr_b200 as ps
+    d = synth.cube(*shape, seed=51)
+    di, dx = ps.dip3dc(d, verb=0, ctx=ctx, **kw)
+    oi, ox = port.dip3dc(d, **kw)
+    assert rel_l2(di, oi) <= TOL, rel_l2(di, oi)
+    assert rel_l2(dx, ox) <= TOL, rel_l2(dx, ox)
+    st = ctx.stats()
+    assert st["kernel_launches"] > 0 and st["cg_iterations"] > 0
+
+
+def test_dip3d_ignores_eps_and_tol_like_reference(ctx):
+    """eps_dv, eps_cg, tol_cg do not change the reference's C result."""
+    import pyseistr_b200 as ps
+    d = synth.cube(40, 12, 6, seed=52)
+    a = ps.dip3dc(d, 2, 5, 2, 0.01, 1, 1e-6, [3, 3, 3], 0, ctx=ctx)
+    b = ps.dip3dc(d, 2, 5, 2, 5.0, 7, 0.5, [3, 3, 3], 0, ctx=ctx)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_dip3d_constant_and_zero_input(ctx):
+    import pyseistr_b200 as ps
+    z = np.zeros((30, 8, 5), np.float32)
+    di, dx = ps.dip3dc(z, verb=0, ctx=ctx)
+    assert not di.any() and not dx.any()
+
+
+# ------------------------------------------------------------------ spray: bit-exact
+@pytest.mark.parametrize("name", golden_names("somean3d_") + golden_names("somf3d_"))
+def test_spray3d_golden_bit_exact(ctx, name):
+    import pyseistr_b200 as ps
+    g = golden(name)
+    fn = ps.somean3dc if name.startswith("somean") else ps.somf3dc
+    out = fn(g["dn"], g["dipi"], g["dipx"], int(g["r1"]), int(g["r2"]), 0.01, int(g["order"]), verb=0, ctx=ctx)
+    assert out.shape == g["out"].shape
+    assert np.array_equal(out, g["out"]), rel_l2(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("somean2d_") + golden_names("somf2d_"))
+def test_spray2d_golden_bit_exact(ctx, name):
+    import pyseistr_b200 as ps
+    g = golden(name)
+    fn = ps.somean2dc if name.startswith("somean") else ps.somf2dc
+    out = fn(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]), verb=0, ctx=ctx)
+    assert np.array_equal(out, g["out"]), rel_l2(out, g["out"])
+
+
+@pytest.mark.parametrize("shape,r1,r2,order", [((100, 50, 10), 2, 2, 2), ((31, 5, 4), 2, 2, 1),
+                                               ((40, 3, 9), 1, 2, 2), ((25, 140, 2), 2, 1, 2)])
+def test_spray3d_vs_oracle_bit_exact(ctx, port, shape, r1, r2, order):
+    """Edge cases: axes shorter than the spray diameter, one-plane halos, wide n2 (several
+    thread blocks per plane)."""
+    import pyseistr_b200 as ps
+    d = synth.erratic(synth.cube(*shape, seed=61))
+    pi, px = synth.smooth_dips(*shape, seed=62, amp=0.8)
+    assert np.array_equal(ps.somf3dc(d, pi, px, r1, r2, 0.01, order, verb=0, ctx=ctx),
+                          port.somf3dc(d, pi, px, r1, r2, 0.01, order))
+    assert np.array_equal(ps.somean3dc(d, pi, px, r1, r2, 0.01, order, ctx=ctx),
+                          port.somean3dc(d, pi, px, r1, r2, 0.01, order))
+
+
+def test_spray_on_2d_input_like_reference(ctx, port):
+    """somf3dc/somean3dc accept a 2-D panel (n3=1), reference somf3d.py:85-88."""
+    import pyseistr_b200 as ps
+    d = synth.cube(48, 20, 1, seed=63)
+    p, _ = synth.smooth_dips(48, 20, 1, seed=64)
+    z = np.zeros_like(p)
+    got = ps.somf3dc(d, p, z, 2, 2, 0.01, 2, verb=0, ctx=ctx)
+    assert got.shape == (48, 20, 1)
+    assert np.array_equal(got, port.somf3dc(d, p, z, 2, 2, 0.01, 2))
+
+
+def test_somf3d_option2_is_refused_not_faked(ctx):
+    import pyseistr_b200 as ps
+    d = synth.cube(20, 6, 4, seed=65)
+    with pytest.raises(ps.PstError) as e:
+        ps.somf3dc(d, 0 * d, 0 * d, 1, 1, 0.01, 1, option=2, verb=0, ctx=ctx)
+    assert e.value.code == -5
+
+
+# ------------------------------------------------------------------ properties at scale
+def test_pipeline_properties_at_scale(ctx):
+    """200x128x64 (the survey's proxy cube; the oracle needs ~30 s there so properties are used
+    instead): determinism, median of a constant-dip plane wave keeps the plane wave, r=1 median
+    is independent of dipx (Q3), all-ones mean gives 1 / 6/9 / 4/9 (Q4)."""
+    import pyseistr_b200 as ps
+    n1, n2, n3 = 200, 128, 64
+    d = synth.cube(n1, n2, n3, seed=71)
+    di, dx = ps.dip3dc(d, verb=0, ctx=ctx)
+    di2, dx2 = ps.dip3dc(d, verb=0, ctx=ctx)
+    assert np.array_equal(di, di2) and np.array_equal(dx, dx2)          # run-to-run reproducible
+    assert np.isfinite(di).all() and np.abs(di).max() < 4.0
+    a = ps.somf3dc(d, di, dx, 1, 1, 0.01, 2, verb=0, ctx=ctx)
+    b = ps.somf3dc(d, di, 0 * dx + 0.25, 1, 1, 0.01, 2, verb=0, ctx=ctx)
+    assert np.array_equal(a, b)
+    ones = np.ones((n1, 16, 8), np.float32)
+    z = np.zeros_like(ones)
+    m = ps.somean3dc(ones, z, z, 1, 1, 0.01, 1, ctx=ctx)
+    assert np.allclose(m[5:-5, 5, 4], 1.0, atol=1e-4)
+    assert np.allclose(m[5:-5, 0, 4], 6.0 / 9.0, atol=1e-4)
+    assert np.allclose(m[5:-5, 0, 0], 4.0 / 9.0, atol=1e-4)
+    # filtering reduces the erratic noise energy
+    de = synth.erratic(d, ntraces=40)
+    f = ps.somf3dc(de, di, dx, 2, 2, 0.01, 2, verb=0, ctx=ctx)
+    assert np.linalg.norm(f - d) < 0.7 * np.linalg.norm(de - d)

@@ -1,0 +1,102 @@
+"""CPU suite: the oracle restatement (oracle/pst_oracle.c) is pinned bit-for-bit against the
+golden fixtures generated from the unmodified reference C, and — when oracle/_ref is present
+(build container, or shipped prebuilt to the GPU box) — against the compiled reference on
+fresh seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+from pyseistr_b200 import synth
+
+
+@pytest.mark.parametrize("name", golden_names("dip3d_"))
+def test_port_dip3d_matches_golden(port, name):
+    g = golden(name)
+    mask = g.get("mask")
+    di, dx = port.dip3dc(g["din"], int(g["niter"]), int(g["liter"]), int(g["order"]),
+                         rect=[int(v) for v in g["rect"]], mask=mask)
+    assert np.array_equal(di, g["dipi"])
+    assert np.array_equal(dx, g["dipx"])
+
+
+def test_port_dip2d_matches_golden(port):
+    g = golden("dip2d")
+    p = port.dip2dc(g["din"], int(g["niter"]), int(g["liter"]), int(g["order"]), rect=[int(v) for v in g["rect"]])
+    assert np.array_equal(p, g["dip"])
+
+
+@pytest.mark.parametrize("name", golden_names("somean3d_") + golden_names("somf3d_"))
+def test_port_spray3d_matches_golden(port, name):
+    g = golden(name)
+    fn = port.somean3dc if name.startswith("somean") else port.somf3dc
+    out = fn(g["dn"], g["dipi"], g["dipx"], int(g["r1"]), int(g["r2"]), 0.01, int(g["order"]))
+    assert np.array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("somean2d_") + golden_names("somf2d_"))
+def test_port_spray2d_matches_golden(port, name):
+    g = golden(name)
+    fn = port.somean2dc if name.startswith("somean") else port.somf2dc
+    out = fn(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]))
+    assert np.array_equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("smooth_"))
+def test_port_smooth_matches_golden(port, name):
+    g = golden(name)
+    assert np.array_equal(port.smooth3(g["x"], [int(v) for v in g["rect"]]), g["out"])
+
+
+def test_port_filters_closed_form(port):
+    """nw=1 taps have the closed form [(1-p)(2-p)/12, (2+p)(2-p)/6, (1+p)(2+p)/12]."""
+    for p in (-0.7, 0.0, 0.3, 1.2):
+        a = port.passfilter(1, p)
+        want = np.array([(1 - p) * (2 - p) / 12, (2 + p) * (2 - p) / 6, (1 + p) * (2 + p) / 12])
+        assert np.allclose(a, want, rtol=1e-6)
+        assert abs(a.sum() - 1.0) < 1e-6          # allpass: taps sum to one
+        d = port.aderfilter(1, p)
+        h = 1e-3                                   # aderfilter = -(d/dp) passfilter
+        fd = (port.passfilter(1, p + h).astype(np.float64) - port.passfilter(1, p - h)) / (2 * h)
+        assert np.allclose(d, -fd, atol=2e-4)
+
+
+def test_reference_quirks(port):
+    """Q3/Q4 of SURVEY: r=1 median ignores dipx; all-ones + zero dip gives 1, 6/9, 4/9."""
+    d = synth.cube(24, 9, 7, seed=4)
+    pi, px = synth.smooth_dips(24, 9, 7, seed=2)
+    a = port.somf3dc(d, pi, px, 1, 1, 0.01, 1)
+    b = port.somf3dc(d, pi, 0 * px + 0.3, 1, 1, 0.01, 1)
+    assert np.array_equal(a, b)
+    ones = np.ones((12, 5, 5), np.float32)
+    z = np.zeros_like(ones)
+    m = port.somean3dc(ones, z, z, 1, 1, 0.01, 1)
+    assert np.allclose(m[:, 2, 2], 1.0, atol=1e-4)
+    assert np.allclose(m[:, 0, 2], 6.0 / 9.0, atol=1e-4)
+    assert np.allclose(m[:, 0, 0], 4.0 / 9.0, atol=1e-4)
+
+
+def _ref_or_skip():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    return ref
+
+
+def test_port_vs_compiled_reference_3d(port):
+    ref = _ref_or_skip()
+    d = synth.cube(48, 14, 9, seed=21)
+    ri, rx = ref.dip3dc(d, niter=3, liter=8, order=2, rect=[4, 5, 3])
+    pi, px = port.dip3dc(d, niter=3, liter=8, order=2, rect=[4, 5, 3])
+    assert np.array_equal(ri, pi) and np.array_equal(rx, px)
+    de = synth.erratic(d)
+    assert np.array_equal(ref.somf3dc(de, ri, rx, 2, 2, 0.01, 2), port.somf3dc(de, ri, rx, 2, 2, 0.01, 2))
+    assert np.array_equal(ref.somean3dc(de, ri, rx, 1, 2, 0.01, 2), port.somean3dc(de, ri, rx, 1, 2, 0.01, 2))
+
+
+def test_port_vs_compiled_reference_2d(port):
+    ref = _ref_or_skip()
+    d = synth.cube(70, 30, 1, seed=22)
+    rp = ref.dip2dc(d, 2, 8, 1, 0.01, 1, 1e-6, [6, 9, 1])
+    assert np.array_equal(rp, port.dip2dc(d, 2, 8, 1, 0.01, 1, 1e-6, [6, 9, 1]))
+    assert np.array_equal(ref.somf2dc(d, rp, 4, 2, 0.01), port.somf2dc(d, rp, 4, 2, 0.01))
+    assert np.array_equal(ref.somean2dc(d, rp, 4, 1, 0.02), port.somean2dc(d, rp, 4, 1, 0.02))
