@@ -40,7 +40,20 @@ typedef struct pst_stats {
     long long predictions;       /* plane-wave predictions (trace solves) executed */
     double    device_ms;         /* CUDA-event time of the device part of the last call */
     double    h2d_bytes, d2h_bytes;
+    /* per kernel class (PST_K_*), filled only while profiling is on (pst_ctx_set_profile):
+     * CUDA-event time on the launching stream around every launch, and launch counts */
+    double    class_ms[8];
+    long long class_launches[8];
 } pst_stats;
+
+#define PST_K_ALLPASS   0   /* PWD stencil (+ fused line-search update, sum of squares) */
+#define PST_K_TRI1      1   /* triangle smoothing, axis 1 (contiguous lines, shared-memory tile) */
+#define PST_K_TRI2      2   /* triangle smoothing, axis 2 (strided lines) */
+#define PST_K_TRI3      3   /* triangle smoothing, axis 3 (strided lines) */
+#define PST_K_CGVEC     4   /* fused CG / divne vector kernels with double reductions */
+#define PST_K_PREDICT   5   /* plane-wave prediction: banded LDL' factor + solve per trace */
+#define PST_K_SLOTRED   6   /* mean / median / weighted sum over the sprayed slots */
+#define PST_K_OTHER     7   /* transposes, fills, final reductions */
 
 const char *pst_last_error(void);
 const char *pst_version(void);
@@ -53,6 +66,11 @@ int  pst_ctx_stats(pst_ctx *ctx, pst_stats *out);
 /* The host-pointer entry points reset the statistics themselves; the *_dev entry points
  * accumulate, so reset explicitly around a device-resident sequence. */
 int  pst_ctx_reset_stats(pst_ctx *ctx);
+/* Per-launch CUDA-event timing by kernel class (off by default; costs two event records per launch). */
+int  pst_ctx_set_profile(pst_ctx *ctx, int on);
+/* CUDA-event stopwatch on the context's stream (torch.cuda.Event cannot see this stream). */
+int  pst_timer_start(pst_ctx *ctx);
+int  pst_timer_stop(pst_ctx *ctx, double *elapsed_ms);
 /* Multi-GPU: slab decomposition along n3 over `nranks` processes (one per GPU).  `nccl_id`
  * is the 128-byte ncclUniqueId created by rank 0 (pst_comm_unique_id) and distributed by
  * the host side (torch.distributed / MPI / files). */

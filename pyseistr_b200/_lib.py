@@ -31,10 +31,18 @@ class Stats(ctypes.Structure):
                 ("linesearch_evals", ctypes.c_longlong), ("gn_iterations", ctypes.c_longlong),
                 ("smooth_passes", ctypes.c_longlong), ("predictions", ctypes.c_longlong),
                 ("device_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
-                ("d2h_bytes", ctypes.c_double)]
+                ("d2h_bytes", ctypes.c_double), ("class_ms", ctypes.c_double * 8),
+                ("class_launches", ctypes.c_longlong * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+KERNEL_CLASSES = ("allpass", "tri_axis1", "tri_axis2", "tri_axis3", "cg_vec", "predict", "slot_reduce", "other")
 
 
 # name -> (restype, argtypes); every symbol include/pst_b200.h declares
@@ -46,6 +54,9 @@ SIGNATURES = {
     "pst_ctx_destroy": (None, [_vp]),
     "pst_ctx_stats": (_i, [_vp, ctypes.POINTER(Stats)]),
     "pst_ctx_reset_stats": (_i, [_vp]),
+    "pst_ctx_set_profile": (_i, [_vp, _i]),
+    "pst_timer_start": (_i, [_vp]),
+    "pst_timer_stop": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "pst_comm_unique_id": (_i, [_vp]),
     "pst_ctx_create_dist": (_i, [_i, _i, _i, _vp, ctypes.POINTER(_vp)]),
     "pst_dip": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i, _i, _fp]),
@@ -128,6 +139,17 @@ class Context:
 
     def sync(self):
         check(self.lib.pst_sync(self._h))
+
+    def set_profile(self, on):
+        check(self.lib.pst_ctx_set_profile(self._h, int(bool(on))))
+
+    def timer_start(self):
+        check(self.lib.pst_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double(0.0)
+        check(self.lib.pst_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def alloc(self, nbytes):
         p = _vp()

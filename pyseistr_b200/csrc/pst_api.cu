@@ -75,9 +75,11 @@ int pst_comm_allreduce_record(pst_ctx *c, double *d_rec, int nv);   // pst_comm.
 int pst_finish_reduce(pst_ctx *c, int nblocks, int nv, int rec)
 {
     if (nblocks > c->max_blocks) { pst_set_error("internal: reduction grid too large"); return PST_EINVAL; }
-    finish_reduce_kernel<<<1, 32 * PST_RED_SLOTS, 0, c->stream>>>(c->d_partial, nblocks, nv,
-                                                                   c->d_red + (size_t)rec * PST_RED_SLOTS);
-    c->stats.kernel_launches++;
+    {
+        KTimer kt(c, PST_K_OTHER);
+        finish_reduce_kernel<<<1, 32 * PST_RED_SLOTS, 0, c->stream>>>(c->d_partial, nblocks, nv,
+                                                                       c->d_red + (size_t)rec * PST_RED_SLOTS);
+    }
     PST_CUDA(cudaGetLastError());
     if (c->comm) PST_TRY(pst_comm_allreduce_record(c, c->d_red + (size_t)rec * PST_RED_SLOTS, nv));
     return PST_OK;
@@ -114,6 +116,8 @@ static int ctx_init(pst_ctx *c, int device)
     PST_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PST_CUDA(cudaEventCreate(&c->ev0));
     PST_CUDA(cudaEventCreate(&c->ev1));
+    PST_CUDA(cudaEventCreate(&c->tm0));
+    PST_CUDA(cudaEventCreate(&c->tm1));
     c->max_blocks = c->sm_count * 32;
     PST_CUDA(cudaMalloc((void **)&c->d_partial, (size_t)c->max_blocks * PST_RED_SLOTS * sizeof(double)));
     PST_CUDA(cudaMalloc((void **)&c->d_red, 64 * PST_RED_SLOTS * sizeof(double)));
@@ -146,6 +150,9 @@ extern "C" void pst_ctx_destroy(pst_ctx *c)
     if (c->h_red) cudaFreeHost(c->h_red);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
+    for (auto &e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -153,6 +160,8 @@ extern "C" void pst_ctx_destroy(pst_ctx *c)
 extern "C" int pst_ctx_stats(pst_ctx *c, pst_stats *out)
 {
     if (!c || !out) { pst_set_error("null argument"); return PST_EINVAL; }
+    cudaSetDevice(c->device);
+    pst_prof_resolve(c);
     *out = c->stats;
     return PST_OK;
 }
@@ -160,7 +169,60 @@ extern "C" int pst_ctx_stats(pst_ctx *c, pst_stats *out)
 extern "C" int pst_ctx_reset_stats(pst_ctx *c)
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    cudaSetDevice(c->device);
+    pst_prof_resolve(c);
     memset(&c->stats, 0, sizeof(c->stats));
+    return PST_OK;
+}
+
+void pst_prof_resolve(pst_ctx *c)
+{
+    if (c->prof_used == 0) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t s = 0; s < c->prof_used; s += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[s], c->prof_ev[s + 1]) == cudaSuccess) {
+            const int k = c->prof_cls[s / 2];
+            c->stats.class_ms[k] += ms;
+            c->stats.class_launches[k]++;
+        }
+    }
+    c->prof_used = 0;
+}
+
+extern "C" int pst_ctx_set_profile(pst_ctx *c, int on)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    if (on && c->prof_ev.empty()) {
+        const size_t pairs = 4096;
+        c->prof_ev.resize(2 * pairs);
+        c->prof_cls.resize(pairs);
+        for (auto &e : c->prof_ev) PST_CUDA(cudaEventCreate(&e));
+    }
+    if (!on) pst_prof_resolve(c);
+    c->prof = on != 0;
+    return PST_OK;
+}
+
+extern "C" int pst_timer_start(pst_ctx *c)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    PST_CUDA(cudaEventRecord(c->tm0, c->stream));
+    return PST_OK;
+}
+
+extern "C" int pst_timer_stop(pst_ctx *c, double *elapsed_ms)
+{
+    if (!c || !elapsed_ms) { pst_set_error("null argument"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    PST_CUDA(cudaEventRecord(c->tm1, c->stream));
+    PST_CUDA(cudaEventSynchronize(c->tm1));
+    float ms = 0.f;
+    PST_CUDA(cudaEventElapsedTime(&ms, c->tm0, c->tm1));
+    *elapsed_ms = ms;
     return PST_OK;
 }
 
@@ -235,6 +297,7 @@ struct CallTimer {
     pst_ctx *c;
     explicit CallTimer(pst_ctx *ctx) : c(ctx)
     {
+        pst_prof_resolve(c);
         memset(&c->stats, 0, sizeof(c->stats));
         cudaEventRecord(c->ev0, c->stream);
     }

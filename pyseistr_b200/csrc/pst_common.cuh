@@ -48,9 +48,35 @@ struct pst_ctx {
     char *arena = nullptr;
     size_t arena_size = 0, arena_used = 0;
     pst_stats stats{};
+    // per-launch profiling (pst_ctx_set_profile): pool of event pairs, resolved lazily
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;    // 2 events per timed launch
+    std::vector<int> prof_cls;
+    size_t prof_used = 0;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     pst_comm *comm = nullptr;        // null for single-GPU contexts
     int rank = 0, nranks = 1;
 };
+
+// ---- per-launch profiling -----------------------------------------------------------------
+void pst_prof_resolve(pst_ctx *c);                       // sync + accumulate pending pairs
+struct KTimer {                                          // RAII around one kernel launch
+    pst_ctx *c; size_t slot; bool on;
+    KTimer(pst_ctx *ctx, int cls) : c(ctx), slot(0), on(ctx->prof)
+    {
+        c->stats.kernel_launches++;
+        if (!on) return;
+        if (c->prof_used + 2 > c->prof_ev.size()) pst_prof_resolve(c);
+        slot = c->prof_used;
+        c->prof_used += 2;
+        c->prof_cls[slot / 2] = cls;
+        cudaEventRecord(c->prof_ev[slot], c->stream);
+    }
+    ~KTimer() { if (on) cudaEventRecord(c->prof_ev[slot + 1], c->stream); }
+};
+
+// wrap the launch statement(s) of ONE kernel: counts it and, when profiling, times it
+#define PST_LAUNCH(c, cls, ...) do { KTimer kt__((c), (cls)); __VA_ARGS__; } while (0)
 
 // ---- arena ---------------------------------------------------------------------------
 int pst_arena_reserve(pst_ctx *c, size_t bytes);            // (re)allocate if too small

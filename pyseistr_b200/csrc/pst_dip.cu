@@ -434,18 +434,18 @@ static size_t tri_scratch_floats(const DipGeom &g)
     return m > a3 ? m : a3;
 }
 
-static int tri_lines_launch(pst_ctx *c, float *x, float *scr, long nlines, long na, long sa, long sb,
+static int tri_lines_launch(pst_ctx *c, int cls, float *x, float *scr, long nlines, long na, long sa, long sb,
                             long d, int nx, int nb)
 {
     const float wt = (float)(1.0 / ((double)nb * nb));       // ps_triangle_init :421
     const float w2 = (float)(2. * wt);
     const int threads = 128;
     const long blocks = (nlines + threads - 1) / threads;
-    if (nb <= nx)
-        tri_lines_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, w2);
-    else
-        tri_lines_literal_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, w2);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, cls,
+        if (nb <= nx)
+            tri_lines_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, w2);
+        else
+            tri_lines_literal_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, w2));
     c->stats.smooth_passes++;
     PST_CUDA(cudaGetLastError());
     return PST_OK;
@@ -471,16 +471,15 @@ int pst_smooth3_inplace(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3
             long blocks = (nlines + LPC - 1) / LPC;
             const long cap = (long)c->sm_count * 16;
             if (blocks > cap) blocks = cap;
-            tri_axis1_kernel<LPC><<<(unsigned)blocks, 128, smem, c->stream>>>(x, nlines, n1, r1, wt, w2, pitch);
-            c->stats.kernel_launches++;
+            PST_LAUNCH(c, PST_K_TRI1, (tri_axis1_kernel<LPC><<<(unsigned)blocks, 128, smem, c->stream>>>(x, nlines, n1, r1, wt, w2, pitch)));
             c->stats.smooth_passes++;
             PST_CUDA(cudaGetLastError());
         } else {
-            PST_TRY(tri_lines_launch(c, x, scr, nlines, nlines, n1, 0, 1, n1, r1));
+            PST_TRY(tri_lines_launch(c, PST_K_TRI1, x, scr, nlines, nlines, n1, 0, 1, n1, r1));
         }
     }
-    if (r2 > 1) PST_TRY(tri_lines_launch(c, x, scr, (long)n1 * n3, n1, 1, (long)n1 * n2, n1, n2, r2));
-    if (r3 > 1) PST_TRY(tri_lines_launch(c, x, scr, (long)n1 * n2, (long)n1 * n2, 1, 0, (long)n1 * n2, n3, r3));
+    if (r2 > 1) PST_TRY(tri_lines_launch(c, PST_K_TRI2, x, scr, (long)n1 * n3, n1, 1, (long)n1 * n2, n1, n2, r2));
+    if (r3 > 1) PST_TRY(tri_lines_launch(c, PST_K_TRI3, x, scr, (long)n1 * n2, (long)n1 * n2, 1, 0, (long)n1 * n2, n3, r3));
     return PST_OK;
 }
 
@@ -495,13 +494,13 @@ static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, cons
     const long cap = (long)c->sm_count * 8;
     if (blocks > cap) blocks = cap;
     const int threads = n1 >= 256 ? 256 : (n1 >= 128 ? 128 : 64);
-    if (ls)
-        allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, tb, c->d_partial);
-    else if (der)
-        allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial);
-    else
-        allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_ALLPASS,
+        if (ls)
+            allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, tb, c->d_partial);
+        else if (der)
+            allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial);
+        else
+            allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial));
     PST_CUDA(cudaGetLastError());
     return pst_finish_reduce(c, (int)blocks, 1, rec);
 }
@@ -532,18 +531,15 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     double h[PST_RED_SLOTS];
     if (iters_run) *iters_run = 0;
 
-    divne_prescale_kernel<<<grid, threads, 0, c->stream>>>(num, den, mask, eps_div, n, c->d_partial);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_CGVEC, (divne_prescale_kernel<<<grid, threads, 0, c->stream>>>(num, den, mask, eps_div, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) {
-        fill_kernel<<<grid, threads, 0, c->stream>>>(rat, 0.f, n);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rat, 0.f, n)));
         return PST_OK;
     }
     const double norm = sqrt((double)n / h[0]);
-    divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_CGVEC, (divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) return PST_OK;               // zero residual: p = x = 0 (:299-303)
@@ -553,29 +549,27 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     bool pending = false;
     int iter;
     for (iter = 0; iter < liter; iter++) {
-        if (pending)
-            cg_head_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, a_pending, eps, w.tmp, n);
-        else
-            cg_head_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, 0.f, eps, w.tmp, n);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_CGVEC,
+            if (pending)
+                cg_head_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, a_pending, eps, w.tmp, n);
+            else
+                cg_head_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, 0.f, eps, w.tmp, n));
         pending = false;
         PST_TRY(pst_smooth3_inplace(c, w.tmp, w.scr, g.n1, g.n2, g.n3, g.r1, g.r2, g.r3));
-        cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_CGVEC, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
         PST_TRY(pst_finish_reduce(c, grid, 1, 1));
         PST_TRY(pst_smooth3_inplace(c, w.tmp, w.scr, g.n1, g.n2, g.n3, g.r1, g.r2, g.r3));
         PST_TRY(pst_fetch_record(c, 1, 1, h));
         gn = h[0];
         if (iter == 0) {
             g0 = gn;
-            cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial);
+            PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
         } else {
             alpha = gn / gnp;
             const double dg = gn / g0;
             if (alpha < tol || dg < tol) break;
-            cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, (float)alpha, n, c->d_partial);
+            PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, (float)alpha, n, c->d_partial)));
         }
-        c->stats.kernel_launches++;
         PST_TRY(pst_finish_reduce(c, grid, 3, 2));
         PST_TRY(pst_fetch_record(c, 2, 3, h));
         beta = h[0] + (double)eps * (h[1] - h[2]);
@@ -586,8 +580,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         c->stats.cg_iterations++;
     }
     if (pending) {      // only the model x (= rat) is consumed after the last iteration
-        cg_tail_kernel<<<grid, threads, 0, c->stream>>>(rat, w.sx, a_pending, n);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_CGVEC, (cg_tail_kernel<<<grid, threads, 0, c->stream>>>(rat, w.sx, a_pending, n)));
     }
     if (iters_run) *iters_run = iter;
     PST_CUDA(cudaGetLastError());
@@ -669,9 +662,9 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
         PST_TRY(pst_arena_get(c, n, &m_in));
         PST_TRY(pst_arena_get(c, n, &m_x));
         const int grid = (int)min((long)n2 * n3, (long)c->sm_count * 8);
-        if (order == 1) mask_kernel<1><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3);
-        else            mask_kernel<2><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_OTHER,
+            if (order == 1) mask_kernel<1><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3);
+            else            mask_kernel<2><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3));
     }
     const int ndip = (n3 == 1) ? 1 : 2;
     PST_CUDA(cudaMemsetAsync(d_dip_out, 0, ndip * n * sizeof(float), c->stream));

@@ -335,8 +335,7 @@ static int transpose_planes(pst_ctx *c, const float *in, float *out, int rows, i
         const int nz = std::min(zmax, planes - z0);
         dim3 grid((cols + 31) / 32, (rows + 31) / 32, nz), block(32, 8);
         const long off = (long)rows * cols * z0;
-        transpose_kernel<<<grid, block, 0, c->stream>>>(in + off, out + off, rows, cols);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_OTHER, (transpose_kernel<<<grid, block, 0, c->stream>>>(in + off, out + off, rows, cols)));
     }
     PST_CUDA(cudaGetLastError());
     return PST_OK;
@@ -436,9 +435,9 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 {
     const int threads = A.n2 >= 128 ? 128 : (A.n2 >= 64 ? 64 : 32);
     dim3 grid((A.n2 + threads - 1) / threads, A.zlb - A.zla);
-    if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
-    else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_PREDICT,
+        if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
+        else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A));
 }
 
 typedef int (*chunk_reduce_fn)(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0,
@@ -526,8 +525,7 @@ static int reduce_mean(pst_ctx *c, void *user, const SprayPlan &P, float *const 
     SlotPtrs S{};
     for (int s = 0; s < P.np; s++) S.p[s] = slot[s];
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
-    slot_mean_kernel<<<grid, 256, 0, c->stream>>>(S, P.np, R->outT, plane * z0, plane * (z0 - ze0), count);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_SLOTRED, (slot_mean_kernel<<<grid, 256, 0, c->stream>>>(S, P.np, R->outT, plane * z0, plane * (z0 - ze0), count)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -545,6 +543,7 @@ static int reduce_median(pst_ctx *c, void *user, const SprayPlan &P, float *cons
     }
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
     const long zo = plane * z0, zs = plane * (z0 - ze0);
+    KTimer kt(c, PST_K_SLOTRED);
     switch (nmf) {
         case 3: slot_median_kernel<3><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
         case 5: slot_median_kernel<5><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
@@ -554,7 +553,6 @@ static int reduce_median(pst_ctx *c, void *user, const SprayPlan &P, float *cons
         case 19: slot_median_kernel<19><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
         default: slot_median_kernel<0><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
     }
-    c->stats.kernel_launches++;
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -566,9 +564,9 @@ static int reduce_wsum(pst_ctx *c, void *user, const SprayPlan &P, float *const 
     SlotPtrs S{};
     for (int s = 0; s < P.np; s++) S.p[s] = slot[s] + plane * (z0 - ze0);
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
-    if (R->mode == 0) slot_wsum_kernel<0><<<grid, 256, 0, c->stream>>>(S, P.ns2, nullptr, R->outT + plane * z0, count);
-    else              slot_wsum_kernel<1><<<grid, 256, 0, c->stream>>>(S, P.ns2, R->tnorm + plane * z0, R->outT + plane * z0, count);
-    c->stats.kernel_launches++;
+    PST_LAUNCH(c, PST_K_SLOTRED,
+        if (R->mode == 0) slot_wsum_kernel<0><<<grid, 256, 0, c->stream>>>(S, P.ns2, nullptr, R->outT + plane * z0, count);
+        else              slot_wsum_kernel<1><<<grid, 256, 0, c->stream>>>(S, P.ns2, R->tnorm + plane * z0, R->outT + plane * z0, count));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -629,8 +627,7 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
         // pwsmooth_set (sof_cfuns.c:1113-1132): normalisation = smooth of a volume of ones
         PST_TRY(pst_arena_get(c, n, &tnorm));
         float *ones = outT;            // reuse: outT is written only by the second pass
-        fill_kernel_s<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(ones, 1.0f, n);
-        c->stats.kernel_launches++;
+        PST_LAUNCH(c, PST_K_OTHER, (fill_kernel_s<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(ones, 1.0f, n)));
         const size_t mark = c->arena_used;
         ReduceOut R0{tnorm, 0, nullptr, 0};
         PST_TRY(spray_run(c, P, ones, piT, pxT, reduce_wsum, &R0));

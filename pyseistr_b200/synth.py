@@ -61,3 +61,47 @@ def smooth_dips(n1, n2, n3=1, seed=1, amp=0.6, dtype=np.float32):
     if n3 == 1:
         return pi_[:, :, 0], px_[:, :, 0]
     return pi_, px_
+
+
+def cube_big(n1, n2, n3, seed=0, noise=0.05, nevents=4, threads=None, out=None):
+    """Same family of cubes as ``cube`` but generated plane-chunk by plane-chunk in float32 on a
+    thread pool, for bench-sized volumes (1e9 voxels).  Writes into ``out`` (any float32
+    Fortran-ordered (n1,n2,n3) array, e.g. a pinned buffer) when given."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(seed)
+    ev = []
+    for k in range(nevents):
+        ev.append(dict(f=rng.uniform(0.04, 0.1), px=rng.uniform(-0.5, 0.5), py=rng.uniform(-0.5, 0.5),
+                       t0=rng.uniform(0.2, 0.8) * n1,
+                       curv=0.0 if k else rng.uniform(-0.2, 0.2) / max(n2, 2),
+                       amp=rng.uniform(0.5, 1.0) * rng.choice([-1.0, 1.0])))
+    if out is None:
+        out = np.empty((n1, n2, n3), dtype=np.float32, order="F")
+    t = np.arange(n1, dtype=np.float32)[:, None]
+    x = (np.arange(n2, dtype=np.float32) - n2 / 2)[None, :]
+    threads = threads or min(32, os.cpu_count() or 1)
+
+    def plane(i3):
+        acc = np.zeros((n1, n2), np.float32)
+        for e in ev:
+            tau = t - np.float32(e["t0"]) - np.float32(e["px"]) * x - np.float32(e["py"] * (i3 - n3 / 2)) \
+                - np.float32(e["curv"]) * x * x
+            a = (np.float32(np.pi * e["f"]) * tau) ** 2
+            acc += np.float32(e["amp"]) * (1.0 - 2.0 * a) * np.exp(-a)
+        if noise:
+            acc += np.float32(noise) * np.random.default_rng([seed, i3]).standard_normal((n1, n2), dtype=np.float32)
+        out[:, :, i3] = acc
+        return float(np.abs(acc).max())
+
+    with ThreadPoolExecutor(threads) as ex:
+        mx = max(ex.map(plane, range(n3)))
+    if mx > 0:
+        scale = np.float32(1.0 / mx)
+
+        def norm(i3):
+            out[:, :, i3] *= scale
+
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(norm, range(n3)))
+    return out
