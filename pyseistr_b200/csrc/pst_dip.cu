@@ -12,6 +12,7 @@
 #include "pst_common.cuh"
 
 #include <math.h>
+#include <algorithm>
 
 struct BTab { double b[PST_MAXTAP]; };
 
@@ -292,6 +293,416 @@ tri_axis1_kernel(float *x, long nlines, int nx, int nb, float wt, float w2, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// G2, main path: shared-memory tile kernel for any axis.  A CTA owns W whole lines:
+//   phase 1 (all threads)  tile <- t_k, built from coalesced global loads with deep MLP;
+//   phase 2 (W threads)    the two serial running sums, in shared memory (the only serial part);
+//   phase 3 (all threads)  fold, optional fused CG epilogue, coalesced store.
+// HBM traffic is the compulsory read + write (8 B/voxel); several CTAs per SM overlap the
+// phases.  CONTIG: axis 1, tile[w][pitch] (pitch = 4 mod 32 words: conflict-free 128-bit
+// accesses for the serial threads).  Strided axes: tile[k][16], lanes on adjacent lines.
+// The epilogue of the LAST smoothed axis absorbs the CG vector work that follows the shaping
+// operator in ps_conjgrad (:318-361), so gx/gr never touch HBM.
+enum { EPI_NONE = 0, EPI_GP = 1, EPI_DIR_FIRST = 2, EPI_DIR = 3 };
+
+struct TriArgs {
+    const float *src;
+    float *dst;
+    long ngroups;          // tiles
+    long na, sb, d;        // strided: fastest line-index extent, outer line stride, element stride
+    long nlines;           // contiguous: number of lines
+    int nx, nb, W, pitch;
+    float wt, w2;
+    // epilogue operands
+    const float *p, *w;
+    float *gp, *sp, *sx, *sr;
+    float eps, alpha;
+    double *partial;
+};
+
+__device__ __forceinline__ float tri_fold(const float *col, int stride, int i, int nx, int nb)
+{
+    float v = col[(size_t)(i + nb) * stride];
+    if (i >= nx - nb) v = v + col[(size_t)(nb + nx + (nx - 1 - i)) * stride];
+    if (i < nb) v = v + col[(size_t)(nb - 1 - i) * stride];
+    return v;
+}
+
+// epilogue operands of one element, loaded ahead of use so that U elements' loads are in flight
+struct EpiIn { float p, gp, w, sp, sx, sr; };
+
+template <int EPI>
+__device__ __forceinline__ void tri_epi_load(const TriArgs &A, long gi, EpiIn &e)
+{
+    if (EPI == EPI_GP) e.p = A.p[gi];
+    if (EPI == EPI_DIR_FIRST || EPI == EPI_DIR) { e.gp = A.gp[gi]; e.w = A.w[gi]; }
+    if (EPI == EPI_DIR) { e.sp = A.sp[gi]; e.sx = A.sx[gi]; e.sr = A.sr[gi]; }
+}
+
+template <int EPI>
+__device__ __forceinline__ void tri_epi_apply(const TriArgs &A, long gi, float v, const EpiIn &e, double (&acc)[3])
+{
+    if (EPI == EPI_NONE) {
+        A.dst[gi] = v;
+    } else if (EPI == EPI_GP) {                 // gp = eps*p + S(gx)   (:303,:318)
+        float g = A.eps * e.p;
+        g += v;
+        A.gp[gi] = g;
+        acc[0] += (double)g * (double)g;
+    } else {                                    // gx = S(gp); gr = gx*w; s = g (+ alpha*s)  (:319-361)
+        const float gxi = 0.f + v;
+        const float gri = 0.f + gxi * e.w;
+        float a, b, c;
+        if (EPI == EPI_DIR_FIRST) { a = e.gp; b = gxi; c = gri; }
+        else {
+            a = e.gp + A.alpha * e.sp;
+            b = gxi + A.alpha * e.sx;
+            c = gri + A.alpha * e.sr;
+        }
+        A.sp[gi] = a; A.sx[gi] = b; A.sr[gi] = c;
+        acc[0] += (double)c * (double)c;
+        acc[1] += (double)a * (double)a;
+        acc[2] += (double)b * (double)b;
+    }
+}
+
+struct EpiIn4 { float4 p, gp, w, sp, sx, sr; };
+
+template <int EPI>
+__device__ __forceinline__ void tri_epi_load4(const TriArgs &A, long gi, EpiIn4 &e)
+{
+    if (EPI == EPI_GP) e.p = *reinterpret_cast<const float4 *>(A.p + gi);
+    if (EPI == EPI_DIR_FIRST || EPI == EPI_DIR) {
+        e.gp = *reinterpret_cast<const float4 *>(A.gp + gi);
+        e.w = *reinterpret_cast<const float4 *>(A.w + gi);
+    }
+    if (EPI == EPI_DIR) {
+        e.sp = *reinterpret_cast<const float4 *>(A.sp + gi);
+        e.sx = *reinterpret_cast<const float4 *>(A.sx + gi);
+        e.sr = *reinterpret_cast<const float4 *>(A.sr + gi);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void tri_epi_lane(const TriArgs &A, float v, float p, float gp, float w, float sp,
+                                             float sx, float sr, float &o0, float &o1, float &o2, double (&acc)[3])
+{
+    if (EPI == EPI_NONE) {
+        o0 = v;
+    } else if (EPI == EPI_GP) {
+        float g = A.eps * p;
+        g += v;
+        o0 = g;
+        acc[0] += (double)g * (double)g;
+    } else {
+        const float gxi = 0.f + v;
+        const float gri = 0.f + gxi * w;
+        float a, b, c;
+        if (EPI == EPI_DIR_FIRST) { a = gp; b = gxi; c = gri; }
+        else { a = gp + A.alpha * sp; b = gxi + A.alpha * sx; c = gri + A.alpha * sr; }
+        o0 = a; o1 = b; o2 = c;
+        acc[0] += (double)c * (double)c;
+        acc[1] += (double)a * (double)a;
+        acc[2] += (double)b * (double)b;
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void tri_epi_apply4(const TriArgs &A, long gi, float4 v, const EpiIn4 &e, double (&acc)[3])
+{
+    float4 o0, o1, o2;
+    tri_epi_lane<EPI>(A, v.x, e.p.x, e.gp.x, e.w.x, e.sp.x, e.sx.x, e.sr.x, o0.x, o1.x, o2.x, acc);
+    tri_epi_lane<EPI>(A, v.y, e.p.y, e.gp.y, e.w.y, e.sp.y, e.sx.y, e.sr.y, o0.y, o1.y, o2.y, acc);
+    tri_epi_lane<EPI>(A, v.z, e.p.z, e.gp.z, e.w.z, e.sp.z, e.sx.z, e.sr.z, o0.z, o1.z, o2.z, acc);
+    tri_epi_lane<EPI>(A, v.w, e.p.w, e.gp.w, e.w.w, e.sp.w, e.sx.w, e.sr.w, o0.w, o1.w, o2.w, acc);
+    if (EPI == EPI_NONE) *reinterpret_cast<float4 *>(A.dst + gi) = o0;
+    else if (EPI == EPI_GP) *reinterpret_cast<float4 *>(A.gp + gi) = o0;
+    else {
+        *reinterpret_cast<float4 *>(A.sp + gi) = o0;
+        *reinterpret_cast<float4 *>(A.sx + gi) = o1;
+        *reinterpret_cast<float4 *>(A.sr + gi) = o2;
+    }
+}
+
+// t_k for U rows/samples at once: all 3U loads are unconditional (clamped index) and issued
+// before any use; out-of-range taps are masked to zero afterwards (adding +-0 does not change
+// the value the reference computes by skipping the tap).
+template <int U>
+__device__ __forceinline__ void tri_spread_batch(const float *xl, long d, int k0, int kstep, int nx, int nb,
+                                                 float wm, float w2, float (&t)[U])
+{
+    float xa[U], xb[U], xc[U];
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+        const int k = k0 + q * kstep;
+        const int ia = min(k, nx - 1);
+        const int ib = min(max(k - nb, 0), nx - 1);
+        const int ic = min(max(k - 2 * nb, 0), nx - 1);
+        xa[q] = xl[(long)ia * d];
+        xb[q] = xl[(long)ib * d];
+        xc[q] = xl[(long)ic * d];
+    }
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+        const int k = k0 + q * kstep;
+        const float va = (k < nx) ? xa[q] : 0.f;
+        const float vb = (k >= nb && k - nb < nx) ? xb[q] : 0.f;
+        const float vc = (k >= 2 * nb && k - 2 * nb < nx) ? xc[q] : 0.f;
+        float v = 0.f;
+        v = v + wm * va;
+        v = v + w2 * vb;
+        v = v + wm * vc;
+        t[q] = v;
+    }
+}
+
+__device__ __forceinline__ float tri_t(float va, float vb, float vc, float wm, float w2)
+{
+    float v = 0.f;
+    v = v + wm * va;
+    v = v + w2 * vb;
+    v = v + wm * vc;
+    return v;
+}
+
+__device__ __forceinline__ float4 f4sel(bool c, float4 a)
+{
+    return c ? a : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// VEC: 16-byte global accesses (needs n1 % 4 == 0 and 16-byte aligned volumes).
+template <bool CONTIG, int EPI, bool VEC>
+__global__ void __launch_bounds__(128)
+tri_tile_kernel(const TriArgs A)
+{
+    extern __shared__ __align__(16) float tile[];
+    const int nx = A.nx, nb = A.nb, np = nx + 2 * nb, W = A.W, tid = threadIdx.x;
+    const float wm = -A.wt, w2 = A.w2;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const long gpb = CONTIG ? 1 : (A.na + W - 1) / W;
+    constexpr int U = 8;
+    for (long g = blockIdx.x; g < A.ngroups; g += gridDim.x) {
+        long base;
+        int nw;
+        if (CONTIG) {
+            const long l0 = g * W;
+            nw = (int)min((long)W, A.nlines - l0);
+            base = l0 * nx;
+        } else {
+            const long ib = g / gpb, ia0 = (g % gpb) * W;
+            nw = (int)min((long)W, A.na - ia0);
+            base = ia0 + ib * A.sb;
+        }
+        // ---- phase 1: tile <- t_k
+        if (CONTIG && VEC) {
+            // each warp owns lines w = warp, warp+4, ...: the line is loaded ONCE (8 float4 per lane
+            // in flight), parked at row[2nb + j], and t_k is then formed in place in ascending
+            // batches (all reads of a batch precede its writes; later batches only read positions
+            // the earlier ones did not write).
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int w = warp; w < nw; w += 4) {
+                const float *xl = A.src + base + (long)w * nx;
+                float *row = tile + (size_t)w * A.pitch;
+                for (int j0 = 0; j0 < nx; j0 += 1024) {
+                    float4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int j = j0 + 4 * (lane + 32 * q);
+                        v[q] = (j < nx) ? *reinterpret_cast<const float4 *>(xl + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int j = j0 + 4 * (lane + 32 * q);
+                        if (j < nx) {
+                            float *dstp = row + 2 * nb + j;
+                            dstp[0] = v[q].x; dstp[1] = v[q].y; dstp[2] = v[q].z; dstp[3] = v[q].w;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int kb = 0; kb < np; kb += 256) {
+                    float va[8], vb[8], vc[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int k = kb + lane + 32 * q;
+                        va[q] = (k < nx) ? row[k + 2 * nb] : 0.f;
+                        vb[q] = (k >= nb && k - nb < nx) ? row[k + nb] : 0.f;
+                        vc[q] = (k >= 2 * nb && k - 2 * nb < nx) ? row[k] : 0.f;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int k = kb + lane + 32 * q;
+                        if (k < np) row[k] = tri_t(va[q], vb[q], vc[q], wm, w2);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (CONTIG) {
+            for (int w = 0; w < nw; w++) {
+                const float *xl = A.src + base + (long)w * nx;
+                float *row = tile + (size_t)w * A.pitch;
+                for (int k0 = tid; k0 < np; k0 += 128 * U) {
+                    float t[U];
+                    tri_spread_batch<U>(xl, 1, k0, 128, nx, nb, wm, w2, t);
+#pragma unroll
+                    for (int q = 0; q < U; q++) if (k0 + q * 128 < np) row[k0 + q * 128] = t[q];
+                }
+            }
+        } else if (VEC) {
+            // 4 lanes x float4 cover the 16 columns of a row; a warp covers 8 rows per access
+            const int c4 = (tid & 3) * 4, r = tid >> 2;
+            const bool live = c4 < nw;
+            const float *xl = A.src + base + (live ? c4 : 0);
+            constexpr int UV = 4;
+            for (int k0 = r; k0 < np; k0 += 32 * UV) {
+                float4 xa[UV], xb[UV], xc[UV];
+#pragma unroll
+                for (int q = 0; q < UV; q++) {
+                    const int k = k0 + 32 * q;
+                    xa[q] = *reinterpret_cast<const float4 *>(xl + (long)min(k, nx - 1) * A.d);
+                    xb[q] = *reinterpret_cast<const float4 *>(xl + (long)min(max(k - nb, 0), nx - 1) * A.d);
+                    xc[q] = *reinterpret_cast<const float4 *>(xl + (long)min(max(k - 2 * nb, 0), nx - 1) * A.d);
+                }
+#pragma unroll
+                for (int q = 0; q < UV; q++) {
+                    const int k = k0 + 32 * q;
+                    const float4 a4 = f4sel(k < nx, xa[q]);
+                    const float4 b4 = f4sel(k >= nb && k - nb < nx, xb[q]);
+                    const float4 c4v = f4sel(k >= 2 * nb && k - 2 * nb < nx, xc[q]);
+                    float4 t;
+                    t.x = tri_t(a4.x, b4.x, c4v.x, wm, w2);
+                    t.y = tri_t(a4.y, b4.y, c4v.y, wm, w2);
+                    t.z = tri_t(a4.z, b4.z, c4v.z, wm, w2);
+                    t.w = tri_t(a4.w, b4.w, c4v.w, wm, w2);
+                    if (live && k < np) *reinterpret_cast<float4 *>(tile + (size_t)k * 16 + c4) = t;
+                }
+            }
+        } else {
+            const int w = tid & 15, kr = tid >> 4;
+            const float *xl = A.src + base + min(w, nw - 1);
+            for (int k0 = kr; k0 < np; k0 += 8 * U) {
+                float t[U];
+                tri_spread_batch<U>(xl, A.d, k0, 8, nx, nb, wm, w2, t);
+                if (w < nw) {
+#pragma unroll
+                    for (int q = 0; q < U; q++) if (k0 + q * 8 < np) tile[(size_t)(k0 + q * 8) * 16 + w] = t[q];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: serial running sums, one thread per line
+        if (tid < nw) {
+            if (CONTIG) {
+                float *row = tile + (size_t)tid * A.pitch;
+                const int np4 = np & ~3;
+                float s = 0.f;
+                int k = 0;
+                for (; k < np4; k += 4) {
+                    float4 v = *reinterpret_cast<float4 *>(row + k);
+                    s += v.x; v.x = s; s += v.y; v.y = s; s += v.z; v.z = s; s += v.w; v.w = s;
+                    *reinterpret_cast<float4 *>(row + k) = v;
+                }
+                for (; k < np; k++) { s += row[k]; row[k] = s; }
+                s = 0.f;
+                for (k = np - 1; k >= np4; k--) { s += row[k]; row[k] = s; }
+                for (k = np4 - 4; k >= 0; k -= 4) {
+                    float4 v = *reinterpret_cast<float4 *>(row + k);
+                    s += v.w; v.w = s; s += v.z; v.z = s; s += v.y; v.y = s; s += v.x; v.x = s;
+                    *reinterpret_cast<float4 *>(row + k) = v;
+                }
+            } else {
+                float *col = tile + tid;
+                float s = 0.f;
+                int k = 0;
+                for (; k + 8 <= np; k += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k + q) * 16];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k + q) * 16] = s; }
+                }
+                for (; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+                s = 0.f;
+                k = np - 1;
+                for (; k - 7 >= 0; k -= 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k - q) * 16];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k - q) * 16] = s; }
+                }
+                for (; k >= 0; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: fold + epilogue + store (epilogue operands loaded U4 elements ahead)
+        constexpr int U4 = 4;
+        if (CONTIG) {
+            for (int w = 0; w < nw; w++) {
+                const float *row = tile + (size_t)w * A.pitch;
+                const long lb = base + (long)w * nx;
+                for (int i0 = tid; i0 < nx; i0 += 128 * U4) {
+                    EpiIn e[U4];
+#pragma unroll
+                    for (int q = 0; q < U4; q++) tri_epi_load<EPI>(A, lb + min(i0 + q * 128, nx - 1), e[q]);
+#pragma unroll
+                    for (int q = 0; q < U4; q++) {
+                        const int i = i0 + q * 128;
+                        if (i < nx) tri_epi_apply<EPI>(A, lb + i, tri_fold(row, 1, i, nx, nb), e[q], acc);
+                    }
+                }
+            }
+        } else if (VEC) {
+            const int c4 = (tid & 3) * 4, r = tid >> 2;
+            const bool live = c4 < nw;
+            const int cc = live ? c4 : 0;
+            constexpr int UE = 2;
+            for (int i0 = r; i0 < nx; i0 += 32 * UE) {
+                EpiIn4 e[UE];
+#pragma unroll
+                for (int q = 0; q < UE; q++) tri_epi_load4<EPI>(A, base + cc + (long)min(i0 + 32 * q, nx - 1) * A.d, e[q]);
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < UE; q++) {
+                        const int i = i0 + 32 * q;
+                        if (i < nx) {
+                            float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)(i + nb) * 16 + c4);
+                            if (i >= nx - nb) {
+                                const float4 u = *reinterpret_cast<const float4 *>(tile + (size_t)(nb + nx + (nx - 1 - i)) * 16 + c4);
+                                v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
+                            }
+                            if (i < nb) {
+                                const float4 u = *reinterpret_cast<const float4 *>(tile + (size_t)(nb - 1 - i) * 16 + c4);
+                                v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
+                            }
+                            tri_epi_apply4<EPI>(A, base + c4 + (long)i * A.d, v, e[q], acc);
+                        }
+                    }
+                }
+            }
+        } else {
+            const int w = tid & 15, ir = tid >> 4;
+            const int wc = min(w, nw - 1);
+            const float *col = tile + wc;
+            for (int i0 = ir; i0 < nx; i0 += 8 * U4) {
+                EpiIn e[U4];
+#pragma unroll
+                for (int q = 0; q < U4; q++) tri_epi_load<EPI>(A, base + wc + (long)min(i0 + q * 8, nx - 1) * A.d, e[q]);
+                if (w < nw) {
+#pragma unroll
+                    for (int q = 0; q < U4; q++) {
+                        const int i = i0 + q * 8;
+                        if (i < nx) tri_epi_apply<EPI>(A, base + w + (long)i * A.d, tri_fold(col, 16, i, nx, nb), e[q], acc);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (EPI != EPI_NONE) pst_block_reduce<3>(acc, A.partial);
+}
+
+// ---------------------------------------------------------------------------------------
 // G3/G4: streaming kernels of ps_divne and ps_conjgrad with fused double reductions.
 
 // divne step 1 (:802-809): optional mask zeroing (dip3 :1656-1663), num,den *= 1/hypot(den,eps)
@@ -451,36 +862,159 @@ static int tri_lines_launch(pst_ctx *c, int cls, float *x, float *scr, long nlin
     return PST_OK;
 }
 
-// ps_trianglen_lop body (:692-700): axes 1, 2, 3 in turn, in place
+// ---- shaping operator driver ------------------------------------------------------------
+struct EpiSpec {
+    int kind = EPI_NONE;
+    const float *p = nullptr, *w = nullptr;
+    float *gp = nullptr, *sp = nullptr, *sx = nullptr, *sr = nullptr;
+    float eps = 0.f, alpha = 0.f;
+    int rec = -1;                 // reduction record receiving the fused sums
+};
+// called right before the last axis is launched: lets the caller fetch scalars the epilogue
+// needs (alpha) and veto the launch (CG early exit).  Return <0 error, 0 go on, 1 skip.
+typedef int (*late_bind_fn)(void *user, EpiSpec *epi);
+
+struct TilePlan { bool ok; int W, pitch; size_t smem; int ctas_per_sm; };
+
+static TilePlan tile_plan(bool contig, int nx, int nb)
+{
+    TilePlan t{false, 0, 0, 0, 1};
+    if (nb > nx) return t;                       // multiple reflections: literal fallback
+    const int np = nx + 2 * nb;
+    const size_t soft = 74 * 1024, hard = 220 * 1024;
+    if (contig) {
+        int pitch = np;
+        while (pitch % 32 != 4) pitch++;
+        int W = 16;
+        while (W > 1 && (size_t)W * pitch * 4 > soft) W >>= 1;
+        if ((size_t)W * pitch * 4 > soft) {      // even one line is big: allow one CTA per SM
+            W = 16;
+            while (W > 1 && (size_t)W * pitch * 4 > hard) W >>= 1;
+            if ((size_t)W * pitch * 4 > hard) return t;
+        }
+        t.W = W; t.pitch = pitch; t.smem = (size_t)W * pitch * 4;
+    } else {
+        t.W = 16; t.pitch = 16; t.smem = (size_t)np * 16 * 4;
+        if (t.smem > hard) return t;
+    }
+    t.ok = true;
+    t.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (t.smem + 1024)));
+    return t;
+}
+
+template <bool CONTIG, int EPI, bool VEC>
+static int tile_launch_t(pst_ctx *c, int cls, const TriArgs &A, size_t smem, int grid)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        PST_CUDA(cudaFuncSetAttribute(tri_tile_kernel<CONTIG, EPI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        attr_done = true;
+    }
+    PST_LAUNCH(c, cls, (tri_tile_kernel<CONTIG, EPI, VEC><<<grid, 128, smem, c->stream>>>(A)));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+template <bool CONTIG, bool VEC>
+static int tile_launch_e(pst_ctx *c, int cls, int epi, const TriArgs &A, size_t smem, int grid)
+{
+    switch (epi) {
+        case EPI_GP:        return tile_launch_t<CONTIG, EPI_GP, VEC>(c, cls, A, smem, grid);
+        case EPI_DIR_FIRST: return tile_launch_t<CONTIG, EPI_DIR_FIRST, VEC>(c, cls, A, smem, grid);
+        case EPI_DIR:       return tile_launch_t<CONTIG, EPI_DIR, VEC>(c, cls, A, smem, grid);
+        default:            return tile_launch_t<CONTIG, EPI_NONE, VEC>(c, cls, A, smem, grid);
+    }
+}
+
+template <bool CONTIG>
+static int tile_launch(pst_ctx *c, int cls, int epi, bool vec, const TriArgs &A, size_t smem, int grid)
+{
+    return vec ? tile_launch_e<CONTIG, true>(c, cls, epi, A, smem, grid)
+               : tile_launch_e<CONTIG, false>(c, cls, epi, A, smem, grid);
+}
+
+// one axis: src -> dst (dst may alias src).  axis 0/1/2.  epi (may be null) is fused only on
+// the tile path; *fused reports it.
+static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src, float *dst, float *scr,
+                       const EpiSpec *epi, bool *fused)
+{
+    const int nn[3] = {g.n1, g.n2, g.n3}, rr[3] = {g.r1, g.r2, g.r3};
+    const int nx = nn[axis], nb = rr[axis];
+    const int cls = axis == 0 ? PST_K_TRI1 : (axis == 1 ? PST_K_TRI2 : PST_K_TRI3);
+    if (fused) *fused = false;
+    const TilePlan tp = tile_plan(axis == 0, nx, nb);
+    c->stats.smooth_passes++;
+    if (tp.ok) {
+        TriArgs A{};
+        A.src = src; A.dst = dst; A.nx = nx; A.nb = nb; A.W = tp.W; A.pitch = tp.pitch;
+        A.wt = (float)(1.0 / ((double)nb * nb));            // ps_triangle_init :421
+        A.w2 = (float)(2. * A.wt);
+        if (axis == 0) {
+            A.nlines = (long)g.n2 * g.n3;
+            A.ngroups = (A.nlines + tp.W - 1) / tp.W;
+        } else if (axis == 1) {
+            A.na = g.n1; A.sb = (long)g.n1 * g.n2; A.d = g.n1;
+            A.ngroups = ((A.na + 15) / 16) * (long)g.n3;
+        } else {
+            A.na = (long)g.n1 * g.n2; A.sb = 0; A.d = (long)g.n1 * g.n2;
+            A.ngroups = (A.na + 15) / 16;
+        }
+        int kind = EPI_NONE;
+        if (epi && epi->kind != EPI_NONE) {
+            kind = epi->kind;
+            A.p = epi->p; A.w = epi->w; A.gp = epi->gp; A.sp = epi->sp; A.sx = epi->sx; A.sr = epi->sr;
+            A.eps = epi->eps; A.alpha = epi->alpha; A.partial = c->d_partial;
+        }
+        long grid = std::min<long>(A.ngroups, (long)c->sm_count * tp.ctas_per_sm);
+        // 16-byte path: every row/line start must be 16-byte aligned
+        auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
+        const bool vec = (g.n1 % 4 == 0) && al16(src) && al16(dst) && al16(A.p) && al16(A.w) && al16(A.gp) &&
+                         al16(A.sp) && al16(A.sx) && al16(A.sr);
+        if (axis == 0) PST_TRY(tile_launch<true>(c, cls, kind, vec, A, tp.smem, (int)grid));
+        else           PST_TRY(tile_launch<false>(c, cls, kind, vec, A, tp.smem, (int)grid));
+        if (kind != EPI_NONE) {
+            PST_TRY(pst_finish_reduce(c, (int)grid, 3, epi->rec));
+            if (fused) *fused = true;
+        }
+        return PST_OK;
+    }
+    // fallback: in-place line kernels with F staged through global scratch
+    if (dst != src) PST_CUDA(cudaMemcpyAsync(dst, src, g.n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    if (axis == 0) return tri_lines_launch(c, cls, dst, scr, (long)g.n2 * g.n3, (long)g.n2 * g.n3, g.n1, 0, 1, nx, nb);
+    if (axis == 1) return tri_lines_launch(c, cls, dst, scr, (long)g.n1 * g.n3, g.n1, 1, (long)g.n1 * g.n2, g.n1, nx, nb);
+    return tri_lines_launch(c, cls, dst, scr, (long)g.n1 * g.n2, (long)g.n1 * g.n2, 1, 0, (long)g.n1 * g.n2, nx, nb);
+}
+
+// ps_trianglen_lop body (:692-700): tmp <- S(src), axes 1, 2, 3 in turn.  With `epi`, the last
+// smoothed axis applies the epilogue instead of storing to tmp (then *fused = true and tmp is
+// not the result); `late` is invoked just before that last launch.  Returns 1 when `late`
+// vetoed the last axis.
+int pst_shape_apply(pst_ctx *c, const DipGeom &g, const float *src, float *tmp, float *scr,
+                    EpiSpec *epi, late_bind_fn late, void *user, bool *fused)
+{
+    const int rr[3] = {g.r1, g.r2, g.r3};
+    int act[3], na = 0;
+    for (int a = 0; a < 3; a++) if (rr[a] > 1) act[na++] = a;
+    if (fused) *fused = false;
+    if (na == 0) {                                   // S = identity
+        if (late) { int v = late(user, epi); if (v) return v; }
+        if (tmp != src) PST_CUDA(cudaMemcpyAsync(tmp, src, g.n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return PST_OK;
+    }
+    const float *in = src;
+    for (int j = 0; j < na; j++) {
+        const bool last = (j == na - 1);
+        if (last && late) { int v = late(user, epi); if (v) return v; }
+        PST_TRY(smooth_axis(c, g, act[j], in, tmp, scr, last ? epi : nullptr, last ? fused : nullptr));
+        in = tmp;
+    }
+    return PST_OK;
+}
+
 int pst_smooth3_inplace(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3, int r1, int r2, int r3)
 {
-    if (r1 > 1) {
-        const long nlines = (long)n2 * n3;
-        const int np = n1 + 2 * r1;
-        const int pitch = (np % 2) ? np : np + 1;
-        constexpr int LPC = 16;
-        const size_t smem = (size_t)LPC * pitch * sizeof(float);
-        if (r1 <= n1 && smem <= 200 * 1024) {
-            const float wt = (float)(1.0 / ((double)r1 * r1));
-            const float w2 = (float)(2. * wt);
-            static bool attr_done = false;
-            if (!attr_done) {
-                PST_CUDA(cudaFuncSetAttribute(tri_axis1_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_done = true;
-            }
-            long blocks = (nlines + LPC - 1) / LPC;
-            const long cap = (long)c->sm_count * 16;
-            if (blocks > cap) blocks = cap;
-            PST_LAUNCH(c, PST_K_TRI1, (tri_axis1_kernel<LPC><<<(unsigned)blocks, 128, smem, c->stream>>>(x, nlines, n1, r1, wt, w2, pitch)));
-            c->stats.smooth_passes++;
-            PST_CUDA(cudaGetLastError());
-        } else {
-            PST_TRY(tri_lines_launch(c, PST_K_TRI1, x, scr, nlines, nlines, n1, 0, 1, n1, r1));
-        }
-    }
-    if (r2 > 1) PST_TRY(tri_lines_launch(c, PST_K_TRI2, x, scr, (long)n1 * n3, n1, 1, (long)n1 * n2, n1, n2, r2));
-    if (r3 > 1) PST_TRY(tri_lines_launch(c, PST_K_TRI3, x, scr, (long)n1 * n2, (long)n1 * n2, 1, 0, (long)n1 * n2, n3, r3));
-    return PST_OK;
+    DipGeom g{n1, n2, n3, r1, r2, r3, (size_t)n1 * n2 * n3};
+    return pst_shape_apply(c, g, x, x, scr, nullptr, nullptr, nullptr, nullptr);
 }
 
 template <int NW>
@@ -519,6 +1053,22 @@ struct CgWork {
     float *p, *r, *sp, *sx, *sr, *gp, *tmp, *scr;
 };
 
+// scalars of ps_conjgrad that gate the direction update (:330-349): fetched as late as possible
+struct CgLate { pst_ctx *c; double gn, gnp, g0; float tol; int iter; bool stop; };
+
+static int cg_late_bind(void *user, EpiSpec *epi)
+{
+    CgLate *L = (CgLate *)user;
+    double h[PST_RED_SLOTS];
+    PST_TRY(pst_fetch_record(L->c, 1, 1, h));
+    L->gn = h[0];
+    if (L->iter == 0) { L->g0 = L->gn; return 0; }
+    const double alpha = L->gn / L->gnp, dg = L->gn / L->g0;
+    if (alpha < L->tol || dg < L->tol) { L->stop = true; return 1; }
+    epi->alpha = (float)alpha;
+    return 0;
+}
+
 // ps_divne (:796-827) + ps_conjgrad (:257-383, prec=NULL, hasp0=false, eps=1*1, tol=1e-6).
 // num/den are overwritten (den becomes the weight); rat receives the CG model x.
 int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *rat,
@@ -544,7 +1094,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) return PST_OK;               // zero residual: p = x = 0 (:299-303)
 
-    double gn = 0., gnp = 0., g0 = 0., alpha, beta;
+    CgLate L{c, 0., 0., 0., tol, 0, false};
     float a_pending = 0.f;
     bool pending = false;
     int iter;
@@ -555,28 +1105,36 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
             else
                 cg_head_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, 0.f, eps, w.tmp, n));
         pending = false;
-        PST_TRY(pst_smooth3_inplace(c, w.tmp, w.scr, g.n1, g.n2, g.n3, g.r1, g.r2, g.r3));
-        PST_LAUNCH(c, PST_K_CGVEC, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
-        PST_TRY(pst_finish_reduce(c, grid, 1, 1));
-        PST_TRY(pst_smooth3_inplace(c, w.tmp, w.scr, g.n1, g.n2, g.n3, g.r1, g.r2, g.r3));
-        PST_TRY(pst_fetch_record(c, 1, 1, h));
-        gn = h[0];
-        if (iter == 0) {
-            g0 = gn;
-            PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
-        } else {
-            alpha = gn / gnp;
-            const double dg = gn / g0;
-            if (alpha < tol || dg < tol) break;
-            PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, (float)alpha, n, c->d_partial)));
+        // gp = eps*p + S(gx), sum gp^2 -> record 1
+        EpiSpec e1;
+        e1.kind = EPI_GP; e1.p = w.p; e1.gp = w.gp; e1.eps = eps; e1.rec = 1;
+        bool fused = false;
+        PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, &e1, nullptr, nullptr, &fused));
+        if (!fused) {
+            PST_LAUNCH(c, PST_K_CGVEC, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
+            PST_TRY(pst_finish_reduce(c, grid, 1, 1));
         }
-        PST_TRY(pst_finish_reduce(c, grid, 3, 2));
+        // gx = S(gp); direction update fused into the last axis once alpha is known
+        EpiSpec e2;
+        e2.kind = (iter == 0) ? EPI_DIR_FIRST : EPI_DIR;
+        e2.w = den; e2.gp = w.gp; e2.sp = w.sp; e2.sx = w.sx; e2.sr = w.sr; e2.rec = 2;
+        L.iter = iter; L.stop = false;
+        int v = pst_shape_apply(c, g, w.gp, w.tmp, w.scr, &e2, cg_late_bind, &L, &fused);
+        if (v < 0) return v;
+        if (L.stop) break;
+        if (!fused) {
+            if (iter == 0)
+                PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
+            else
+                PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, e2.alpha, n, c->d_partial)));
+            PST_TRY(pst_finish_reduce(c, grid, 3, 2));
+        }
         PST_TRY(pst_fetch_record(c, 2, 3, h));
-        beta = h[0] + (double)eps * (h[1] - h[2]);
-        alpha = -gn / beta;
+        const double beta = h[0] + (double)eps * (h[1] - h[2]);
+        const double alpha = -L.gn / beta;
         a_pending = (float)alpha;
         pending = true;
-        gnp = gn;
+        L.gnp = L.gn;
         c->stats.cg_iterations++;
     }
     if (pending) {      // only the model x (= rat) is consumed after the last iteration
