@@ -464,6 +464,17 @@ __device__ __forceinline__ float tri_t(float va, float vb, float vc, float wm, f
     return v;
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 f4sel(bool c, float4 a)
 {
     return c ? a : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -494,31 +505,22 @@ tri_tile_kernel(const TriArgs A)
         }
         // ---- phase 1: tile <- t_k
         if (CONTIG && VEC) {
-            // each warp owns lines w = warp, warp+4, ...: the line is loaded ONCE (8 float4 per lane
-            // in flight), parked at row[2nb + j], and t_k is then formed in place in ascending
-            // batches (all reads of a batch precede its writes; later batches only read positions
-            // the earlier ones did not write).
+            // each warp owns lines w = warp, warp+4, ...  The whole line is fetched ONCE with
+            // 16-byte cp.async (all requests of all lines in flight together) and parked at
+            // row[xo + j], xo = 2nb rounded up to 4; t_k is then formed in place at row[sh + k],
+            // sh = xo - 2nb, in ascending batches (all reads of a batch precede its writes; later
+            // batches only read positions the earlier ones did not write).
             const int lane = tid & 31, warp = tid >> 5;
+            const int xo = (2 * nb + 3) & ~3, sh = xo - 2 * nb;
             for (int w = warp; w < nw; w += 4) {
                 const float *xl = A.src + base + (long)w * nx;
                 float *row = tile + (size_t)w * A.pitch;
-                for (int j0 = 0; j0 < nx; j0 += 1024) {
-                    float4 v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int j = j0 + 4 * (lane + 32 * q);
-                        v[q] = (j < nx) ? *reinterpret_cast<const float4 *>(xl + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int j = j0 + 4 * (lane + 32 * q);
-                        if (j < nx) {
-                            float *dstp = row + 2 * nb + j;
-                            dstp[0] = v[q].x; dstp[1] = v[q].y; dstp[2] = v[q].z; dstp[3] = v[q].w;
-                        }
-                    }
-                }
-                __syncwarp();
+                for (int j = 4 * lane; j < nx; j += 128) cp_async16(row + xo + j, xl + j);
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            for (int w = warp; w < nw; w += 4) {
+                float *row = tile + (size_t)w * A.pitch + sh;        // row[k + 2nb] = x_k
                 for (int kb = 0; kb < np; kb += 256) {
                     float va[8], vb[8], vc[8];
 #pragma unroll
@@ -549,33 +551,42 @@ tri_tile_kernel(const TriArgs A)
                 }
             }
         } else if (VEC) {
-            // 4 lanes x float4 cover the 16 columns of a row; a warp covers 8 rows per access
+            // 4 lanes x 16 bytes cover the 16 columns of a row.  x rows are fetched ONCE with
+            // cp.async into tile rows [2nb, 2nb+nx); t_k is then formed in place at row k in
+            // ascending batches of 128 rows (reads of a batch, barrier, writes, barrier).
             const int c4 = (tid & 3) * 4, r = tid >> 2;
             const bool live = c4 < nw;
-            const float *xl = A.src + base + (live ? c4 : 0);
+            if (live) {
+                const float *xl = A.src + base + c4;
+                for (int j = r; j < nx; j += 32) cp_async16(tile + (size_t)(j + 2 * nb) * 16 + c4, xl + (long)j * A.d);
+            }
+            cp_async_wait_all();
+            __syncthreads();
             constexpr int UV = 4;
-            for (int k0 = r; k0 < np; k0 += 32 * UV) {
-                float4 xa[UV], xb[UV], xc[UV];
+            for (int kb = 0; kb < np; kb += 32 * UV) {
+                float4 ta[UV], tb[UV], tc[UV];
 #pragma unroll
                 for (int q = 0; q < UV; q++) {
-                    const int k = k0 + 32 * q;
-                    xa[q] = *reinterpret_cast<const float4 *>(xl + (long)min(k, nx - 1) * A.d);
-                    xb[q] = *reinterpret_cast<const float4 *>(xl + (long)min(max(k - nb, 0), nx - 1) * A.d);
-                    xc[q] = *reinterpret_cast<const float4 *>(xl + (long)min(max(k - 2 * nb, 0), nx - 1) * A.d);
+                    const int k = kb + r + 32 * q;
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ta[q] = (k < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(k + 2 * nb) * 16 + c4) : z;
+                    tb[q] = (k >= nb && k - nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(k + nb) * 16 + c4) : z;
+                    tc[q] = (k >= 2 * nb && k - 2 * nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)k * 16 + c4) : z;
                 }
+                __syncthreads();
 #pragma unroll
                 for (int q = 0; q < UV; q++) {
-                    const int k = k0 + 32 * q;
-                    const float4 a4 = f4sel(k < nx, xa[q]);
-                    const float4 b4 = f4sel(k >= nb && k - nb < nx, xb[q]);
-                    const float4 c4v = f4sel(k >= 2 * nb && k - 2 * nb < nx, xc[q]);
-                    float4 t;
-                    t.x = tri_t(a4.x, b4.x, c4v.x, wm, w2);
-                    t.y = tri_t(a4.y, b4.y, c4v.y, wm, w2);
-                    t.z = tri_t(a4.z, b4.z, c4v.z, wm, w2);
-                    t.w = tri_t(a4.w, b4.w, c4v.w, wm, w2);
-                    if (live && k < np) *reinterpret_cast<float4 *>(tile + (size_t)k * 16 + c4) = t;
+                    const int k = kb + r + 32 * q;
+                    if (k < np) {
+                        float4 t;
+                        t.x = tri_t(ta[q].x, tb[q].x, tc[q].x, wm, w2);
+                        t.y = tri_t(ta[q].y, tb[q].y, tc[q].y, wm, w2);
+                        t.z = tri_t(ta[q].z, tb[q].z, tc[q].z, wm, w2);
+                        t.w = tri_t(ta[q].w, tb[q].w, tc[q].w, wm, w2);
+                        *reinterpret_cast<float4 *>(tile + (size_t)k * 16 + c4) = t;
+                    }
                 }
+                __syncthreads();
             }
         } else {
             const int w = tid & 15, kr = tid >> 4;
@@ -590,56 +601,86 @@ tri_tile_kernel(const TriArgs A)
             }
         }
         __syncthreads();
-        // ---- phase 2: serial running sums, one thread per line
+        // ---- phase 2: serial running sums, one thread per line.  The next chunk is loaded into
+        // registers before the dependent FADD chain of the current one (software pipelining), so
+        // the shared-memory latency is off the critical path: ~4 cycles per element.
         if (tid < nw) {
             if (CONTIG) {
-                float *row = tile + (size_t)tid * A.pitch;
-                const int np4 = np & ~3;
+                float *row = tile + (size_t)tid * A.pitch + ((VEC) ? (((2 * nb + 3) & ~3) - 2 * nb) : 0);
+                // row may be misaligned by sh floats: peel to a 16-byte boundary
+                const int mis = (int)((((uintptr_t)row) >> 2) & 3);
+                const int head = mis ? min(4 - mis, np) : 0;
                 float s = 0.f;
                 int k = 0;
-                for (; k < np4; k += 4) {
-                    float4 v = *reinterpret_cast<float4 *>(row + k);
-                    s += v.x; v.x = s; s += v.y; v.y = s; s += v.z; v.z = s; s += v.w; v.w = s;
-                    *reinterpret_cast<float4 *>(row + k) = v;
+                for (; k < head; k++) { s += row[k]; row[k] = s; }
+                const int nq = (np - head) >> 2;             // full float4 groups
+                float4 *r4 = reinterpret_cast<float4 *>(row + head);
+                if (nq > 0) {
+                    float4 cur = r4[0];
+                    for (int q = 0; q < nq; q++) {
+                        const float4 nxt = (q + 1 < nq) ? r4[q + 1] : cur;
+                        s += cur.x; cur.x = s; s += cur.y; cur.y = s; s += cur.z; cur.z = s; s += cur.w; cur.w = s;
+                        r4[q] = cur;
+                        cur = nxt;
+                    }
                 }
-                for (; k < np; k++) { s += row[k]; row[k] = s; }
+                for (k = head + 4 * nq; k < np; k++) { s += row[k]; row[k] = s; }
                 s = 0.f;
-                for (k = np - 1; k >= np4; k--) { s += row[k]; row[k] = s; }
-                for (k = np4 - 4; k >= 0; k -= 4) {
-                    float4 v = *reinterpret_cast<float4 *>(row + k);
-                    s += v.w; v.w = s; s += v.z; v.z = s; s += v.y; v.y = s; s += v.x; v.x = s;
-                    *reinterpret_cast<float4 *>(row + k) = v;
+                for (k = np - 1; k >= head + 4 * nq; k--) { s += row[k]; row[k] = s; }
+                if (nq > 0) {
+                    float4 cur = r4[nq - 1];
+                    for (int q = nq - 1; q >= 0; q--) {
+                        const float4 nxt = (q > 0) ? r4[q - 1] : cur;
+                        s += cur.w; cur.w = s; s += cur.z; cur.z = s; s += cur.y; cur.y = s; s += cur.x; cur.x = s;
+                        r4[q] = cur;
+                        cur = nxt;
+                    }
                 }
+                for (k = head - 1; k >= 0; k--) { s += row[k]; row[k] = s; }
             } else {
                 float *col = tile + tid;
                 float s = 0.f;
-                int k = 0;
-                for (; k + 8 <= np; k += 8) {
-                    float v[8];
+                const int nc = np >> 3;                      // full chunks of 8
+                if (nc > 0) {
+                    float cur[8], nxt[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k + q) * 16];
+                    for (int q = 0; q < 8; q++) cur[q] = col[(size_t)q * 16];
+                    for (int ch = 0; ch < nc; ch++) {
+                        const int kn = (ch + 1 < nc) ? (ch + 1) * 8 : ch * 8;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k + q) * 16] = s; }
+                        for (int q = 0; q < 8; q++) nxt[q] = col[(size_t)(kn + q) * 16];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { s += cur[q]; col[(size_t)(ch * 8 + q) * 16] = s; }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+                    }
                 }
-                for (; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+                for (int k = nc * 8; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
                 s = 0.f;
-                k = np - 1;
-                for (; k - 7 >= 0; k -= 8) {
-                    float v[8];
+                for (int k = np - 1; k >= nc * 8; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+                if (nc > 0) {
+                    float cur[8], nxt[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k - q) * 16];
+                    for (int q = 0; q < 8; q++) cur[q] = col[(size_t)((nc - 1) * 8 + q) * 16];
+                    for (int ch = nc - 1; ch >= 0; ch--) {
+                        const int kn = (ch > 0) ? (ch - 1) * 8 : 0;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k - q) * 16] = s; }
+                        for (int q = 0; q < 8; q++) nxt[q] = col[(size_t)(kn + q) * 16];
+#pragma unroll
+                        for (int q = 7; q >= 0; q--) { s += cur[q]; col[(size_t)(ch * 8 + q) * 16] = s; }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+                    }
                 }
-                for (; k >= 0; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
             }
         }
         __syncthreads();
         // ---- phase 3: fold + epilogue + store (epilogue operands loaded U4 elements ahead)
         constexpr int U4 = 4;
         if (CONTIG) {
+            const int sh3 = VEC ? (((2 * nb + 3) & ~3) - 2 * nb) : 0;
             for (int w = 0; w < nw; w++) {
-                const float *row = tile + (size_t)w * A.pitch;
+                const float *row = tile + (size_t)w * A.pitch + sh3;
                 const long lb = base + (long)w * nx;
                 for (int i0 = tid; i0 < nx; i0 += 128 * U4) {
                     EpiIn e[U4];
@@ -883,7 +924,7 @@ static TilePlan tile_plan(bool contig, int nx, int nb)
     const int np = nx + 2 * nb;
     const size_t soft = 74 * 1024, hard = 220 * 1024;
     if (contig) {
-        int pitch = np;
+        int pitch = np + 3;                       // room for the 16-byte alignment shift of the VEC path
         while (pitch % 32 != 4) pitch++;
         int W = 16;
         while (W > 1 && (size_t)W * pitch * 4 > soft) W >>= 1;
