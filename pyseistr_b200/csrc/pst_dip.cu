@@ -485,7 +485,10 @@ template <bool CONTIG, int EPI, bool VEC>
 __global__ void __launch_bounds__(128)
 tri_tile_kernel(const TriArgs A)
 {
-    extern __shared__ __align__(16) float tile[];
+    extern __shared__ __align__(16) float tile_raw[];
+    // leading pad: 8 rows (strided) / 4 floats (contiguous) so that the pipelined serial loops may
+    // prefetch one chunk beyond either end of a line without guards
+    float *const tile = tile_raw + (CONTIG ? 4 : 8 * 16);
     const int nx = A.nx, nb = A.nb, np = nx + 2 * nb, W = A.W, tid = threadIdx.x;
     const float wm = -A.wt, w2 = A.w2;
     double acc[3] = {0.0, 0.0, 0.0};
@@ -551,40 +554,41 @@ tri_tile_kernel(const TriArgs A)
                 }
             }
         } else if (VEC) {
-            // 4 lanes x 16 bytes cover the 16 columns of a row.  x rows are fetched ONCE with
-            // cp.async into tile rows [2nb, 2nb+nx); t_k is then formed in place at row k in
-            // ascending batches of 128 rows (reads of a batch, barrier, writes, barrier).
-            const int c4 = (tid & 3) * 4, r = tid >> 2;
-            const bool live = c4 < nw;
-            if (live) {
-                const float *xl = A.src + base + c4;
-                for (int j = r; j < nx; j += 32) cp_async16(tile + (size_t)(j + 2 * nb) * 16 + c4, xl + (long)j * A.d);
+            // x rows are fetched ONCE with 16-byte cp.async into tile rows [2nb, 2nb+nx) in
+            // row-major layout A (elem(k,w) at k*16+w).  t_k is then formed in place, batch by
+            // batch in ascending k, and written in layout B (elem(k,w) at ((k>>2)*16+w)*4+(k&3)):
+            // four consecutive k of a line are contiguous, so the serial phase moves 16 bytes per
+            // shared-memory instruction.  A group of 4 rows occupies the same 64 floats in both
+            // layouts, so a batch only overwrites rows that no later batch reads.
+            {
+                const int c4 = (tid & 3) * 4, r = tid >> 2;
+                if (c4 < nw) {
+                    const float *xl = A.src + base + c4;
+                    for (int j = r; j < nx; j += 32) cp_async16(tile + (size_t)(j + 2 * nb) * 16 + c4, xl + (long)j * A.d);
+                }
             }
             cp_async_wait_all();
             __syncthreads();
-            constexpr int UV = 4;
-            for (int kb = 0; kb < np; kb += 32 * UV) {
-                float4 ta[UV], tb[UV], tc[UV];
+            const int ng = (np + 3) >> 2;                    // groups of 4 rows
+            for (int gb = 0; gb < ng; gb += 32) {            // 32 groups = 128 rows per batch
+                float t[4][4];
 #pragma unroll
-                for (int q = 0; q < UV; q++) {
-                    const int k = kb + r + 32 * q;
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ta[q] = (k < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(k + 2 * nb) * 16 + c4) : z;
-                    tb[q] = (k >= nb && k - nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(k + nb) * 16 + c4) : z;
-                    tc[q] = (k >= 2 * nb && k - 2 * nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)k * 16 + c4) : z;
+                for (int j = 0; j < 4; j++) {
+                    const int it = tid + 128 * j, w = it & 15, g = gb + (it >> 4);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int k = 4 * g + e;
+                        const float va = (k < nx) ? tile[(size_t)(k + 2 * nb) * 16 + w] : 0.f;
+                        const float vb = (k >= nb && k - nb < nx) ? tile[(size_t)(k + nb) * 16 + w] : 0.f;
+                        const float vc = (k >= 2 * nb && k - 2 * nb < nx) ? tile[(size_t)k * 16 + w] : 0.f;
+                        t[j][e] = tri_t(va, vb, vc, wm, w2);
+                    }
                 }
                 __syncthreads();
 #pragma unroll
-                for (int q = 0; q < UV; q++) {
-                    const int k = kb + r + 32 * q;
-                    if (k < np) {
-                        float4 t;
-                        t.x = tri_t(ta[q].x, tb[q].x, tc[q].x, wm, w2);
-                        t.y = tri_t(ta[q].y, tb[q].y, tc[q].y, wm, w2);
-                        t.z = tri_t(ta[q].z, tb[q].z, tc[q].z, wm, w2);
-                        t.w = tri_t(ta[q].w, tb[q].w, tc[q].w, wm, w2);
-                        *reinterpret_cast<float4 *>(tile + (size_t)k * 16 + c4) = t;
-                    }
+                for (int j = 0; j < 4; j++) {
+                    const int it = tid + 128 * j, w = it & 15, g = gb + (it >> 4);
+                    if (g < ng) *reinterpret_cast<float4 *>(tile + ((size_t)g * 16 + w) * 4) = make_float4(t[j][0], t[j][1], t[j][2], t[j][3]);
                 }
                 __syncthreads();
             }
@@ -601,77 +605,117 @@ tri_tile_kernel(const TriArgs A)
             }
         }
         __syncthreads();
-        // ---- phase 2: serial running sums, one thread per line.  The next chunk is loaded into
-        // registers before the dependent FADD chain of the current one (software pipelining), so
-        // the shared-memory latency is off the critical path: ~4 cycles per element.
+        // ---- phase 2: serial running sums, one thread per line.  Hand-scheduled: the loads of the
+        // next chunk and the (delayed) stores of finished sums are interleaved with the dependent
+        // FADD chain, so the chain's 4-cycle latency is the only thing on the critical path.  The
+        // tile carries 16 pad elements per line at both ends, so the prefetch never needs a guard.
         if (tid < nw) {
             if (CONTIG) {
                 float *row = tile + (size_t)tid * A.pitch + ((VEC) ? (((2 * nb + 3) & ~3) - 2 * nb) : 0);
-                // row may be misaligned by sh floats: peel to a 16-byte boundary
                 const int mis = (int)((((uintptr_t)row) >> 2) & 3);
                 const int head = mis ? min(4 - mis, np) : 0;
                 float s = 0.f;
                 int k = 0;
                 for (; k < head; k++) { s += row[k]; row[k] = s; }
-                const int nq = (np - head) >> 2;             // full float4 groups
+                const int nq = (np - head) >> 2;             // aligned float4 groups
                 float4 *r4 = reinterpret_cast<float4 *>(row + head);
-                if (nq > 0) {
-                    float4 cur = r4[0];
+                {
+                    float4 cur = r4[0], done = cur;
                     for (int q = 0; q < nq; q++) {
-                        const float4 nxt = (q + 1 < nq) ? r4[q + 1] : cur;
-                        s += cur.x; cur.x = s; s += cur.y; cur.y = s; s += cur.z; cur.z = s; s += cur.w; cur.w = s;
-                        r4[q] = cur;
+                        const float4 nxt = r4[q + 1];        // pad makes q+1 == nq readable
+                        s += cur.x; cur.x = s;
+                        if (q > 0) r4[q - 1] = done;
+                        s += cur.y; cur.y = s;
+                        s += cur.z; cur.z = s;
+                        s += cur.w; cur.w = s;
+                        done = cur;
                         cur = nxt;
                     }
+                    if (nq > 0) r4[nq - 1] = done;
                 }
                 for (k = head + 4 * nq; k < np; k++) { s += row[k]; row[k] = s; }
                 s = 0.f;
                 for (k = np - 1; k >= head + 4 * nq; k--) { s += row[k]; row[k] = s; }
                 if (nq > 0) {
-                    float4 cur = r4[nq - 1];
+                    float4 cur = r4[nq - 1], done = cur;
                     for (int q = nq - 1; q >= 0; q--) {
-                        const float4 nxt = (q > 0) ? r4[q - 1] : cur;
-                        s += cur.w; cur.w = s; s += cur.z; cur.z = s; s += cur.y; cur.y = s; s += cur.x; cur.x = s;
-                        r4[q] = cur;
+                        const float4 nxt = r4[q - 1];        // q-1 == -1 reads the leading pad
+                        s += cur.w; cur.w = s;
+                        if (q < nq - 1) r4[q + 1] = done;
+                        s += cur.z; cur.z = s;
+                        s += cur.y; cur.y = s;
+                        s += cur.x; cur.x = s;
+                        done = cur;
                         cur = nxt;
                     }
+                    r4[0] = done;
                 }
                 for (k = head - 1; k >= 0; k--) { s += row[k]; row[k] = s; }
+            } else if (VEC) {
+                // layout B: one float4 = rows 4g..4g+3 of this line.  Rows >= np of the last group
+                // hold t = 0 (forward) and are skipped in the backward sum.
+                float4 *col = reinterpret_cast<float4 *>(tile) + tid;
+                const int ng = (np + 3) >> 2, nfull = np >> 2;
+                float s = 0.f;
+                {
+                    float4 cur = col[0], done = cur;
+                    for (int g = 0; g < ng; g++) {
+                        const float4 nxt = col[(size_t)(g + 1) * 16];     // trailing pad is readable
+                        s += cur.x; cur.x = s;
+                        if (g > 0) col[(size_t)(g - 1) * 16] = done;
+                        s += cur.y; cur.y = s;
+                        s += cur.z; cur.z = s;
+                        s += cur.w; cur.w = s;
+                        done = cur;
+                        cur = nxt;
+                    }
+                    col[(size_t)(ng - 1) * 16] = done;
+                }
+                s = 0.f;
+                if (ng > nfull) {                                         // partial last group
+                    float4 v = col[(size_t)nfull * 16];
+                    const int rem = np & 3;
+                    if (rem > 2) { s += v.z; v.z = s; }
+                    if (rem > 1) { s += v.y; v.y = s; }
+                    s += v.x; v.x = s;
+                    col[(size_t)nfull * 16] = v;
+                }
+                if (nfull > 0) {
+                    float4 cur = col[(size_t)(nfull - 1) * 16], done = cur;
+                    for (int g = nfull - 1; g >= 0; g--) {
+                        const float4 nxt = col[((long)g - 1) * 16];       // g-1 == -1 reads the leading pad
+                        s += cur.w; cur.w = s;
+                        if (g < nfull - 1) col[(size_t)(g + 1) * 16] = done;
+                        s += cur.z; cur.z = s;
+                        s += cur.y; cur.y = s;
+                        s += cur.x; cur.x = s;
+                        done = cur;
+                        cur = nxt;
+                    }
+                    col[0] = done;
+                }
             } else {
                 float *col = tile + tid;
                 float s = 0.f;
-                const int nc = np >> 3;                      // full chunks of 8
-                if (nc > 0) {
-                    float cur[8], nxt[8];
+                int k = 0;
+                for (; k + 8 <= np; k += 8) {
+                    float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) cur[q] = col[(size_t)q * 16];
-                    for (int ch = 0; ch < nc; ch++) {
-                        const int kn = (ch + 1 < nc) ? (ch + 1) * 8 : ch * 8;
+                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k + q) * 16];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) nxt[q] = col[(size_t)(kn + q) * 16];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) { s += cur[q]; col[(size_t)(ch * 8 + q) * 16] = s; }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-                    }
+                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k + q) * 16] = s; }
                 }
-                for (int k = nc * 8; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+                for (; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
                 s = 0.f;
-                for (int k = np - 1; k >= nc * 8; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
-                if (nc > 0) {
-                    float cur[8], nxt[8];
+                k = np - 1;
+                for (; k - 7 >= 0; k -= 8) {
+                    float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) cur[q] = col[(size_t)((nc - 1) * 8 + q) * 16];
-                    for (int ch = nc - 1; ch >= 0; ch--) {
-                        const int kn = (ch > 0) ? (ch - 1) * 8 : 0;
+                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k - q) * 16];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) nxt[q] = col[(size_t)(kn + q) * 16];
-#pragma unroll
-                        for (int q = 7; q >= 0; q--) { s += cur[q]; col[(size_t)(ch * 8 + q) * 16] = s; }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-                    }
+                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k - q) * 16] = s; }
                 }
+                for (; k >= 0; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
             }
         }
         __syncthreads();
@@ -698,6 +742,11 @@ tri_tile_kernel(const TriArgs A)
             const bool live = c4 < nw;
             const int cc = live ? c4 : 0;
             constexpr int UE = 2;
+            // layout B read of 4 adjacent columns of row k
+            auto rowB = [&](int k) {
+                const float *q = tile + ((size_t)(k >> 2) * 16 + c4) * 4 + (k & 3);
+                return make_float4(q[0], q[4], q[8], q[12]);
+            };
             for (int i0 = r; i0 < nx; i0 += 32 * UE) {
                 EpiIn4 e[UE];
 #pragma unroll
@@ -707,13 +756,13 @@ tri_tile_kernel(const TriArgs A)
                     for (int q = 0; q < UE; q++) {
                         const int i = i0 + 32 * q;
                         if (i < nx) {
-                            float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)(i + nb) * 16 + c4);
+                            float4 v = rowB(i + nb);
                             if (i >= nx - nb) {
-                                const float4 u = *reinterpret_cast<const float4 *>(tile + (size_t)(nb + nx + (nx - 1 - i)) * 16 + c4);
+                                const float4 u = rowB(nb + nx + (nx - 1 - i));
                                 v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
                             }
                             if (i < nb) {
-                                const float4 u = *reinterpret_cast<const float4 *>(tile + (size_t)(nb - 1 - i) * 16 + c4);
+                                const float4 u = rowB(nb - 1 - i);
                                 v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
                             }
                             tri_epi_apply4<EPI>(A, base + c4 + (long)i * A.d, v, e[q], acc);
@@ -924,18 +973,18 @@ static TilePlan tile_plan(bool contig, int nx, int nb)
     const int np = nx + 2 * nb;
     const size_t soft = 74 * 1024, hard = 220 * 1024;
     if (contig) {
-        int pitch = np + 3;                       // room for the 16-byte alignment shift of the VEC path
+        int pitch = np + 8;                       // alignment shift of the VEC path (<=3) + prefetch pad
         while (pitch % 32 != 4) pitch++;
         int W = 16;
-        while (W > 1 && (size_t)W * pitch * 4 > soft) W >>= 1;
-        if ((size_t)W * pitch * 4 > soft) {      // even one line is big: allow one CTA per SM
+        while (W > 1 && ((size_t)W * pitch + 8) * 4 > soft) W >>= 1;
+        if (((size_t)W * pitch + 8) * 4 > soft) {      // even one line is big: allow one CTA per SM
             W = 16;
-            while (W > 1 && (size_t)W * pitch * 4 > hard) W >>= 1;
-            if ((size_t)W * pitch * 4 > hard) return t;
+            while (W > 1 && ((size_t)W * pitch + 8) * 4 > hard) W >>= 1;
+            if (((size_t)W * pitch + 8) * 4 > hard) return t;
         }
-        t.W = W; t.pitch = pitch; t.smem = (size_t)W * pitch * 4;
+        t.W = W; t.pitch = pitch; t.smem = ((size_t)W * pitch + 8) * 4;
     } else {
-        t.W = 16; t.pitch = 16; t.smem = (size_t)np * 16 * 4;
+        t.W = 16; t.pitch = 16; t.smem = (size_t)(np + 16) * 16 * 4;
         if (t.smem > hard) return t;
     }
     t.ok = true;
