@@ -480,15 +480,12 @@ __device__ __forceinline__ float4 f4sel(bool c, float4 a)
     return c ? a : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// VEC: 16-byte global accesses (needs n1 % 4 == 0 and 16-byte aligned volumes).
-template <bool CONTIG, int EPI, bool VEC>
+// ---- generic (scalar) tile kernel: any n1, any alignment ---------------------------------
+template <bool CONTIG, int EPI>
 __global__ void __launch_bounds__(128)
 tri_tile_kernel(const TriArgs A)
 {
-    extern __shared__ __align__(16) float tile_raw[];
-    // leading pad: 8 rows (strided) / 4 floats (contiguous) so that the pipelined serial loops may
-    // prefetch one chunk beyond either end of a line without guards
-    float *const tile = tile_raw + (CONTIG ? 4 : 8 * 16);
+    extern __shared__ __align__(16) float tile[];
     const int nx = A.nx, nb = A.nb, np = nx + 2 * nb, W = A.W, tid = threadIdx.x;
     const float wm = -A.wt, w2 = A.w2;
     double acc[3] = {0.0, 0.0, 0.0};
@@ -507,42 +504,7 @@ tri_tile_kernel(const TriArgs A)
             base = ia0 + ib * A.sb;
         }
         // ---- phase 1: tile <- t_k
-        if (CONTIG && VEC) {
-            // each warp owns lines w = warp, warp+4, ...  The whole line is fetched ONCE with
-            // 16-byte cp.async (all requests of all lines in flight together) and parked at
-            // row[xo + j], xo = 2nb rounded up to 4; t_k is then formed in place at row[sh + k],
-            // sh = xo - 2nb, in ascending batches (all reads of a batch precede its writes; later
-            // batches only read positions the earlier ones did not write).
-            const int lane = tid & 31, warp = tid >> 5;
-            const int xo = (2 * nb + 3) & ~3, sh = xo - 2 * nb;
-            for (int w = warp; w < nw; w += 4) {
-                const float *xl = A.src + base + (long)w * nx;
-                float *row = tile + (size_t)w * A.pitch;
-                for (int j = 4 * lane; j < nx; j += 128) cp_async16(row + xo + j, xl + j);
-            }
-            cp_async_wait_all();
-            __syncwarp();
-            for (int w = warp; w < nw; w += 4) {
-                float *row = tile + (size_t)w * A.pitch + sh;        // row[k + 2nb] = x_k
-                for (int kb = 0; kb < np; kb += 256) {
-                    float va[8], vb[8], vc[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int k = kb + lane + 32 * q;
-                        va[q] = (k < nx) ? row[k + 2 * nb] : 0.f;
-                        vb[q] = (k >= nb && k - nb < nx) ? row[k + nb] : 0.f;
-                        vc[q] = (k >= 2 * nb && k - 2 * nb < nx) ? row[k] : 0.f;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int k = kb + lane + 32 * q;
-                        if (k < np) row[k] = tri_t(va[q], vb[q], vc[q], wm, w2);
-                    }
-                    __syncwarp();
-                }
-            }
-        } else if (CONTIG) {
+        if (CONTIG) {
             for (int w = 0; w < nw; w++) {
                 const float *xl = A.src + base + (long)w * nx;
                 float *row = tile + (size_t)w * A.pitch;
@@ -552,45 +514,6 @@ tri_tile_kernel(const TriArgs A)
 #pragma unroll
                     for (int q = 0; q < U; q++) if (k0 + q * 128 < np) row[k0 + q * 128] = t[q];
                 }
-            }
-        } else if (VEC) {
-            // x rows are fetched ONCE with 16-byte cp.async into tile rows [2nb, 2nb+nx) in
-            // row-major layout A (elem(k,w) at k*16+w).  t_k is then formed in place, batch by
-            // batch in ascending k, and written in layout B (elem(k,w) at ((k>>2)*16+w)*4+(k&3)):
-            // four consecutive k of a line are contiguous, so the serial phase moves 16 bytes per
-            // shared-memory instruction.  A group of 4 rows occupies the same 64 floats in both
-            // layouts, so a batch only overwrites rows that no later batch reads.
-            {
-                const int c4 = (tid & 3) * 4, r = tid >> 2;
-                if (c4 < nw) {
-                    const float *xl = A.src + base + c4;
-                    for (int j = r; j < nx; j += 32) cp_async16(tile + (size_t)(j + 2 * nb) * 16 + c4, xl + (long)j * A.d);
-                }
-            }
-            cp_async_wait_all();
-            __syncthreads();
-            const int ng = (np + 3) >> 2;                    // groups of 4 rows
-            for (int gb = 0; gb < ng; gb += 32) {            // 32 groups = 128 rows per batch
-                float t[4][4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int it = tid + 128 * j, w = it & 15, g = gb + (it >> 4);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int k = 4 * g + e;
-                        const float va = (k < nx) ? tile[(size_t)(k + 2 * nb) * 16 + w] : 0.f;
-                        const float vb = (k >= nb && k - nb < nx) ? tile[(size_t)(k + nb) * 16 + w] : 0.f;
-                        const float vc = (k >= 2 * nb && k - 2 * nb < nx) ? tile[(size_t)k * 16 + w] : 0.f;
-                        t[j][e] = tri_t(va, vb, vc, wm, w2);
-                    }
-                }
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int it = tid + 128 * j, w = it & 15, g = gb + (it >> 4);
-                    if (g < ng) *reinterpret_cast<float4 *>(tile + ((size_t)g * 16 + w) * 4) = make_float4(t[j][0], t[j][1], t[j][2], t[j][3]);
-                }
-                __syncthreads();
             }
         } else {
             const int w = tid & 15, kr = tid >> 4;
@@ -605,126 +528,37 @@ tri_tile_kernel(const TriArgs A)
             }
         }
         __syncthreads();
-        // ---- phase 2: serial running sums, one thread per line.  Hand-scheduled: the loads of the
-        // next chunk and the (delayed) stores of finished sums are interleaved with the dependent
-        // FADD chain, so the chain's 4-cycle latency is the only thing on the critical path.  The
-        // tile carries 16 pad elements per line at both ends, so the prefetch never needs a guard.
+        // ---- phase 2: serial running sums, one thread per line
         if (tid < nw) {
-            if (CONTIG) {
-                float *row = tile + (size_t)tid * A.pitch + ((VEC) ? (((2 * nb + 3) & ~3) - 2 * nb) : 0);
-                const int mis = (int)((((uintptr_t)row) >> 2) & 3);
-                const int head = mis ? min(4 - mis, np) : 0;
-                float s = 0.f;
-                int k = 0;
-                for (; k < head; k++) { s += row[k]; row[k] = s; }
-                const int nq = (np - head) >> 2;             // aligned float4 groups
-                float4 *r4 = reinterpret_cast<float4 *>(row + head);
-                {
-                    float4 cur = r4[0], done = cur;
-                    for (int q = 0; q < nq; q++) {
-                        const float4 nxt = r4[q + 1];        // pad makes q+1 == nq readable
-                        s += cur.x; cur.x = s;
-                        if (q > 0) r4[q - 1] = done;
-                        s += cur.y; cur.y = s;
-                        s += cur.z; cur.z = s;
-                        s += cur.w; cur.w = s;
-                        done = cur;
-                        cur = nxt;
-                    }
-                    if (nq > 0) r4[nq - 1] = done;
-                }
-                for (k = head + 4 * nq; k < np; k++) { s += row[k]; row[k] = s; }
-                s = 0.f;
-                for (k = np - 1; k >= head + 4 * nq; k--) { s += row[k]; row[k] = s; }
-                if (nq > 0) {
-                    float4 cur = r4[nq - 1], done = cur;
-                    for (int q = nq - 1; q >= 0; q--) {
-                        const float4 nxt = r4[q - 1];        // q-1 == -1 reads the leading pad
-                        s += cur.w; cur.w = s;
-                        if (q < nq - 1) r4[q + 1] = done;
-                        s += cur.z; cur.z = s;
-                        s += cur.y; cur.y = s;
-                        s += cur.x; cur.x = s;
-                        done = cur;
-                        cur = nxt;
-                    }
-                    r4[0] = done;
-                }
-                for (k = head - 1; k >= 0; k--) { s += row[k]; row[k] = s; }
-            } else if (VEC) {
-                // layout B: one float4 = rows 4g..4g+3 of this line.  Rows >= np of the last group
-                // hold t = 0 (forward) and are skipped in the backward sum.
-                float4 *col = reinterpret_cast<float4 *>(tile) + tid;
-                const int ng = (np + 3) >> 2, nfull = np >> 2;
-                float s = 0.f;
-                {
-                    float4 cur = col[0], done = cur;
-                    for (int g = 0; g < ng; g++) {
-                        const float4 nxt = col[(size_t)(g + 1) * 16];     // trailing pad is readable
-                        s += cur.x; cur.x = s;
-                        if (g > 0) col[(size_t)(g - 1) * 16] = done;
-                        s += cur.y; cur.y = s;
-                        s += cur.z; cur.z = s;
-                        s += cur.w; cur.w = s;
-                        done = cur;
-                        cur = nxt;
-                    }
-                    col[(size_t)(ng - 1) * 16] = done;
-                }
-                s = 0.f;
-                if (ng > nfull) {                                         // partial last group
-                    float4 v = col[(size_t)nfull * 16];
-                    const int rem = np & 3;
-                    if (rem > 2) { s += v.z; v.z = s; }
-                    if (rem > 1) { s += v.y; v.y = s; }
-                    s += v.x; v.x = s;
-                    col[(size_t)nfull * 16] = v;
-                }
-                if (nfull > 0) {
-                    float4 cur = col[(size_t)(nfull - 1) * 16], done = cur;
-                    for (int g = nfull - 1; g >= 0; g--) {
-                        const float4 nxt = col[((long)g - 1) * 16];       // g-1 == -1 reads the leading pad
-                        s += cur.w; cur.w = s;
-                        if (g < nfull - 1) col[(size_t)(g + 1) * 16] = done;
-                        s += cur.z; cur.z = s;
-                        s += cur.y; cur.y = s;
-                        s += cur.x; cur.x = s;
-                        done = cur;
-                        cur = nxt;
-                    }
-                    col[0] = done;
-                }
-            } else {
-                float *col = tile + tid;
-                float s = 0.f;
-                int k = 0;
-                for (; k + 8 <= np; k += 8) {
-                    float v[8];
+            float *col = CONTIG ? tile + (size_t)tid * A.pitch : tile + tid;
+            const int st = CONTIG ? 1 : 16;
+            float s = 0.f;
+            int k = 0;
+            for (; k + 8 <= np; k += 8) {
+                float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k + q) * 16];
+                for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k + q) * st];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k + q) * 16] = s; }
-                }
-                for (; k < np; k++) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
-                s = 0.f;
-                k = np - 1;
-                for (; k - 7 >= 0; k -= 8) {
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k - q) * 16];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k - q) * 16] = s; }
-                }
-                for (; k >= 0; k--) { s += col[(size_t)k * 16]; col[(size_t)k * 16] = s; }
+                for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k + q) * st] = s; }
             }
+            for (; k < np; k++) { s += col[(size_t)k * st]; col[(size_t)k * st] = s; }
+            s = 0.f;
+            k = np - 1;
+            for (; k - 7 >= 0; k -= 8) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = col[(size_t)(k - q) * st];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { s += v[q]; col[(size_t)(k - q) * st] = s; }
+            }
+            for (; k >= 0; k--) { s += col[(size_t)k * st]; col[(size_t)k * st] = s; }
         }
         __syncthreads();
         // ---- phase 3: fold + epilogue + store (epilogue operands loaded U4 elements ahead)
         constexpr int U4 = 4;
         if (CONTIG) {
-            const int sh3 = VEC ? (((2 * nb + 3) & ~3) - 2 * nb) : 0;
             for (int w = 0; w < nw; w++) {
-                const float *row = tile + (size_t)w * A.pitch + sh3;
+                const float *row = tile + (size_t)w * A.pitch;
                 const long lb = base + (long)w * nx;
                 for (int i0 = tid; i0 < nx; i0 += 128 * U4) {
                     EpiIn e[U4];
@@ -734,39 +568,6 @@ tri_tile_kernel(const TriArgs A)
                     for (int q = 0; q < U4; q++) {
                         const int i = i0 + q * 128;
                         if (i < nx) tri_epi_apply<EPI>(A, lb + i, tri_fold(row, 1, i, nx, nb), e[q], acc);
-                    }
-                }
-            }
-        } else if (VEC) {
-            const int c4 = (tid & 3) * 4, r = tid >> 2;
-            const bool live = c4 < nw;
-            const int cc = live ? c4 : 0;
-            constexpr int UE = 2;
-            // layout B read of 4 adjacent columns of row k
-            auto rowB = [&](int k) {
-                const float *q = tile + ((size_t)(k >> 2) * 16 + c4) * 4 + (k & 3);
-                return make_float4(q[0], q[4], q[8], q[12]);
-            };
-            for (int i0 = r; i0 < nx; i0 += 32 * UE) {
-                EpiIn4 e[UE];
-#pragma unroll
-                for (int q = 0; q < UE; q++) tri_epi_load4<EPI>(A, base + cc + (long)min(i0 + 32 * q, nx - 1) * A.d, e[q]);
-                if (live) {
-#pragma unroll
-                    for (int q = 0; q < UE; q++) {
-                        const int i = i0 + 32 * q;
-                        if (i < nx) {
-                            float4 v = rowB(i + nb);
-                            if (i >= nx - nb) {
-                                const float4 u = rowB(nb + nx + (nx - 1 - i));
-                                v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
-                            }
-                            if (i < nb) {
-                                const float4 u = rowB(nb - 1 - i);
-                                v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
-                            }
-                            tri_epi_apply4<EPI>(A, base + c4 + (long)i * A.d, v, e[q], acc);
-                        }
                     }
                 }
             }
@@ -783,6 +584,309 @@ tri_tile_kernel(const TriArgs A)
                     for (int q = 0; q < U4; q++) {
                         const int i = i0 + q * 8;
                         if (i < nx) tri_epi_apply<EPI>(A, base + w + (long)i * A.d, tri_fold(col, 16, i, nx, nb), e[q], acc);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (EPI != EPI_NONE) pst_block_reduce<3>(acc, A.partial);
+}
+
+// serial running sums over NG float4 groups spaced `gs` float4 apart (forward then backward);
+// hand-scheduled so the next group's load and the previous group's store overlap the FADD chain.
+// One readable pad group must exist before group 0 and after group ng-1.  Rows >= np in the
+// last group hold t = 0 (forward) and are skipped by the backward sum.
+__device__ __forceinline__ void tri_serial_v4(float4 *col, int gs, int np)
+{
+    const int ng = (np + 3) >> 2, nfull = np >> 2;
+    float s = 0.f;
+    {
+        float4 cur = col[0], done = cur;
+        for (int g = 0; g < ng; g++) {
+            const float4 nxt = col[(size_t)(g + 1) * gs];
+            s += cur.x; cur.x = s;
+            if (g > 0) col[(size_t)(g - 1) * gs] = done;
+            s += cur.y; cur.y = s;
+            s += cur.z; cur.z = s;
+            s += cur.w; cur.w = s;
+            done = cur;
+            cur = nxt;
+        }
+        col[(size_t)(ng - 1) * gs] = done;
+    }
+    s = 0.f;
+    if (ng > nfull) {
+        float4 v = col[(size_t)nfull * gs];
+        const int rem = np & 3;
+        if (rem > 2) { s += v.z; v.z = s; }
+        if (rem > 1) { s += v.y; v.y = s; }
+        s += v.x; v.x = s;
+        col[(size_t)nfull * gs] = v;
+    }
+    if (nfull > 0) {
+        float4 cur = col[(size_t)(nfull - 1) * gs], done = cur;
+        for (int g = nfull - 1; g >= 0; g--) {
+            const float4 nxt = col[((long)g - 1) * gs];
+            s += cur.w; cur.w = s;
+            if (g < nfull - 1) col[(size_t)(g + 1) * gs] = done;
+            s += cur.z; cur.z = s;
+            s += cur.y; cur.y = s;
+            s += cur.x; cur.x = s;
+            done = cur;
+            cur = nxt;
+        }
+        col[0] = done;
+    }
+}
+
+// ---- strided axes, 16-byte path (n1 % 4 == 0, 16-byte aligned volumes) -------------------
+// Shared-memory tile of 16 lines in groups of 4 rows; one group = 64 floats + 4 pad (pitch 68:
+// consecutive groups start 4 banks apart).  Layout A (row-major inside a group, elem(k,c) at
+// 68(k>>2) + 16(k&3) + c) receives x via cp.async; layout B (k-minor, elem(k,c) at
+// 68(k>>2) + 4c + (k&3)) holds t / F / B.  Both layouts keep a group in the same 64 floats, so
+// t can be formed in place batch by batch in ascending k.  Lane mapping for the transposing
+// phases: a quarter-warp = 8 consecutive groups of one 4-column block => every 128-bit shared
+// access is conflict-free.
+#define TRI_GP 68
+template <int EPI>
+__global__ void __launch_bounds__(128)
+tri_tile_strided_v4_kernel(const TriArgs A)
+{
+    extern __shared__ __align__(16) float tile_raw[];
+    float *const tile = tile_raw + TRI_GP;                    // one pad group in front
+    const int nx = A.nx, nb = A.nb, np = nx + 2 * nb, tid = threadIdx.x;
+    const int ng = (np + 3) >> 2;
+    const float wm = -A.wt, w2 = A.w2;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const long gpb = (A.na + 15) / 16;
+    const int lane = tid & 31, wq = tid >> 5;
+    const int tc4 = (lane >> 3) * 4, tgl = 8 * wq + (lane & 7);   // transposing phases: columns, group-in-batch
+    for (long g0 = blockIdx.x; g0 < A.ngroups; g0 += gridDim.x) {
+        const long ib = g0 / gpb, ia0 = (g0 % gpb) * 16;
+        const int nw = (int)min((long)16, A.na - ia0);
+        const long base = ia0 + ib * A.sb;
+        // ---- phase 1a: x rows -> layout A at rows [2nb, 2nb+nx)
+        {
+            const int c4 = (tid & 3) * 4, r = tid >> 2;
+            if (c4 < nw) {
+                const float *xl = A.src + base + c4;
+                for (int j = r; j < nx; j += 32) {
+                    const int row = j + 2 * nb;
+                    cp_async16(tile + (size_t)(row >> 2) * TRI_GP + (row & 3) * 16 + c4, xl + (long)j * A.d);
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // ---- phase 1b: t_k in place, layout A -> layout B, 32 groups per batch
+        for (int gb = 0; gb < ng; gb += 32) {
+            const int g = gb + tgl;
+            float4 t[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = 4 * g + e;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ra = k + 2 * nb, rb = k + nb;
+                const float4 xa = (k < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(ra >> 2) * TRI_GP + (ra & 3) * 16 + tc4) : z;
+                const float4 xb = (k >= nb && k - nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)(rb >> 2) * TRI_GP + (rb & 3) * 16 + tc4) : z;
+                const float4 xc = (k >= 2 * nb && k - 2 * nb < nx) ? *reinterpret_cast<const float4 *>(tile + (size_t)g * TRI_GP + e * 16 + tc4) : z;
+                t[e].x = tri_t(xa.x, xb.x, xc.x, wm, w2);
+                t[e].y = tri_t(xa.y, xb.y, xc.y, wm, w2);
+                t[e].z = tri_t(xa.z, xb.z, xc.z, wm, w2);
+                t[e].w = tri_t(xa.w, xb.w, xc.w, wm, w2);
+            }
+            __syncthreads();
+            if (g < ng) {
+                float *q = tile + (size_t)g * TRI_GP + tc4 * 4;
+                *reinterpret_cast<float4 *>(q + 0) = make_float4(t[0].x, t[1].x, t[2].x, t[3].x);
+                *reinterpret_cast<float4 *>(q + 4) = make_float4(t[0].y, t[1].y, t[2].y, t[3].y);
+                *reinterpret_cast<float4 *>(q + 8) = make_float4(t[0].z, t[1].z, t[2].z, t[3].z);
+                *reinterpret_cast<float4 *>(q + 12) = make_float4(t[0].w, t[1].w, t[2].w, t[3].w);
+            }
+            __syncthreads();
+        }
+        // ---- phase 2
+        if (tid < nw) tri_serial_v4(reinterpret_cast<float4 *>(tile) + tid, TRI_GP / 4, np);
+        __syncthreads();
+        // ---- phase 3: layout B -> rows of 4 columns, fold, epilogue, 16-byte stores
+        {
+            const bool live = tc4 < nw;
+            const int cc = live ? tc4 : 0;
+            auto rowB = [&](int k) {                          // scalar gather, only for reflections
+                const float *q = tile + (size_t)(k >> 2) * TRI_GP + tc4 * 4 + (k & 3);
+                return make_float4(q[0], q[4], q[8], q[12]);
+            };
+            for (int gb = 0; gb < ng; gb += 32) {
+                const int g = gb + tgl;
+                float4 cB[4];
+                {
+                    const float *q = tile + (size_t)min(g, ng - 1) * TRI_GP + tc4 * 4;
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; e2++) cB[e2] = *reinterpret_cast<const float4 *>(q + 4 * e2);
+                }
+                const float4 rw[4] = {make_float4(cB[0].x, cB[1].x, cB[2].x, cB[3].x), make_float4(cB[0].y, cB[1].y, cB[2].y, cB[3].y),
+                                      make_float4(cB[0].z, cB[1].z, cB[2].z, cB[3].z), make_float4(cB[0].w, cB[1].w, cB[2].w, cB[3].w)};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {                 // two rows at a time: bounded registers
+                    EpiIn4 ein[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int i = min(max(4 * g + 2 * h + e - nb, 0), nx - 1);
+                        tri_epi_load4<EPI>(A, base + cc + (long)i * A.d, ein[e]);
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int i = 4 * g + 2 * h + e - nb;
+                            if (i >= 0 && i < nx) {
+                                float4 v = rw[2 * h + e];
+                                if (i >= nx - nb) {
+                                    const float4 u = rowB(nb + nx + (nx - 1 - i));
+                                    v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
+                                }
+                                if (i < nb) {
+                                    const float4 u = rowB(nb - 1 - i);
+                                    v.x = v.x + u.x; v.y = v.y + u.y; v.z = v.z + u.z; v.w = v.w + u.w;
+                                }
+                                tri_epi_apply4<EPI>(A, base + tc4 + (long)i * A.d, v, ein[e], acc);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (EPI != EPI_NONE) pst_block_reduce<3>(acc, A.partial);
+}
+
+// ---- contiguous axis, 16-byte path ---------------------------------------------------------
+// unaligned 4-float read from shared memory as two aligned 16-byte loads + a uniform select
+__device__ __forceinline__ float4 lds_f4_unaligned(const float *p)
+{
+    const int m = (int)((((uintptr_t)p) >> 2) & 3);
+    const float4 *q = reinterpret_cast<const float4 *>(p - m);
+    const float4 lo = q[0];
+    if (m == 0) return lo;
+    const float4 hi = q[1];
+    if (m == 1) return make_float4(lo.y, lo.z, lo.w, hi.x);
+    if (m == 2) return make_float4(lo.z, lo.w, hi.x, hi.y);
+    return make_float4(lo.w, hi.x, hi.y, hi.z);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(128)
+tri_tile_contig_v4_kernel(const TriArgs A)
+{
+    extern __shared__ __align__(16) float tile_raw[];
+    float *const tile = tile_raw + 4;                         // 4 floats of pad before row 0
+    const int nx = A.nx, nb = A.nb, np = nx + 2 * nb, W = A.W, tid = threadIdx.x;
+    const float wm = -A.wt, w2 = A.w2;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const int lane = tid & 31, warp = tid >> 5;
+    // x_j is parked at rowbase[xo + j] (16-byte aligned for cp.async); t_k / F_k / B_k live at
+    // rowbase[sh + k] with sh = xo - 2nb, i.e. R[k] with R = rowbase + sh and x_k = R[k + 2nb].
+    const int xo = (2 * nb + 3) & ~3, sh = xo - 2 * nb;
+    for (long g = blockIdx.x; g < A.ngroups; g += gridDim.x) {
+        const long l0 = g * W;
+        const int nw = (int)min((long)W, A.nlines - l0);
+        const long base = l0 * nx;
+        // ---- phase 1: each warp owns lines w = warp, warp+4, ...
+        for (int w = warp; w < nw; w += 4) {
+            const float *xl = A.src + base + (long)w * nx;
+            float *row = tile + (size_t)w * A.pitch;
+            for (int j = 4 * lane; j < nx; j += 128) cp_async16(row + xo + j, xl + j);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        for (int w = warp; w < nw; w += 4) {
+            float *R = tile + (size_t)w * A.pitch + sh;
+            for (int kb = 0; kb < np; kb += 256) {            // ascending batches, reads before writes
+                float va[8], vb[8], vc[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int k = kb + lane + 32 * q;
+                    va[q] = (k < nx) ? R[k + 2 * nb] : 0.f;
+                    vb[q] = (k >= nb && k - nb < nx) ? R[k + nb] : 0.f;
+                    vc[q] = (k >= 2 * nb && k - 2 * nb < nx) ? R[k] : 0.f;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int k = kb + lane + 32 * q;
+                    if (k < np) R[k] = tri_t(va[q], vb[q], vc[q], wm, w2);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: the running sums start at R[0]; peel to a 16-byte boundary
+        if (tid < nw) {
+            float *R = tile + (size_t)tid * A.pitch + sh;
+            const int head = sh ? min(4 - sh, np) : 0;        // rowbase is 16-byte aligned
+            float s = 0.f;
+            for (int k = 0; k < head; k++) { s += R[k]; R[k] = s; }
+            const int nq = (np - head) >> 2;
+            float4 *r4 = reinterpret_cast<float4 *>(R + head);
+            if (nq > 0) {
+                float4 cur = r4[0], done = cur;
+                for (int q = 0; q < nq; q++) {
+                    const float4 nxt = r4[q + 1];
+                    s += cur.x; cur.x = s;
+                    if (q > 0) r4[q - 1] = done;
+                    s += cur.y; cur.y = s;
+                    s += cur.z; cur.z = s;
+                    s += cur.w; cur.w = s;
+                    done = cur;
+                    cur = nxt;
+                }
+                r4[nq - 1] = done;
+            }
+            for (int k = head + 4 * nq; k < np; k++) { s += R[k]; R[k] = s; }
+            s = 0.f;
+            for (int k = np - 1; k >= head + 4 * nq; k--) { s += R[k]; R[k] = s; }
+            if (nq > 0) {
+                float4 cur = r4[nq - 1], done = cur;
+                for (int q = nq - 1; q >= 0; q--) {
+                    const float4 nxt = r4[q - 1];
+                    s += cur.w; cur.w = s;
+                    if (q < nq - 1) r4[q + 1] = done;
+                    s += cur.z; cur.z = s;
+                    s += cur.y; cur.y = s;
+                    s += cur.x; cur.x = s;
+                    done = cur;
+                    cur = nxt;
+                }
+                r4[0] = done;
+            }
+            for (int k = head - 1; k >= 0; k--) { s += R[k]; R[k] = s; }
+        }
+        __syncthreads();
+        // ---- phase 3: 4 outputs per thread, 16-byte global accesses
+        for (int w = 0; w < nw; w++) {
+            const float *R = tile + (size_t)w * A.pitch + sh;
+            const long lb = base + (long)w * nx;
+            for (int i0 = 4 * tid; i0 < nx; i0 += 4 * 128 * 2) {
+                EpiIn4 ein[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) tri_epi_load4<EPI>(A, lb + min(i0 + 512 * q, nx - 4), ein[q]);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int i = i0 + 512 * q;
+                    if (i < nx) {
+                        float4 v = lds_f4_unaligned(R + nb + i);
+                        if (i + 3 >= nx - nb || i < nb) {      // reflections touch this quad
+                            float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const int ii = i + e;
+                                if (ii >= nx - nb) vv[e] = vv[e] + R[nb + nx + (nx - 1 - ii)];
+                                if (ii < nb) vv[e] = vv[e] + R[nb - 1 - ii];
+                            }
+                            v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        }
+                        tri_epi_apply4<EPI>(A, lb + i, v, ein[q], acc);
                     }
                 }
             }
@@ -966,25 +1070,29 @@ typedef int (*late_bind_fn)(void *user, EpiSpec *epi);
 
 struct TilePlan { bool ok; int W, pitch; size_t smem; int ctas_per_sm; };
 
-static TilePlan tile_plan(bool contig, int nx, int nb)
+static TilePlan tile_plan(bool contig, bool vec, int nx, int nb)
 {
     TilePlan t{false, 0, 0, 0, 1};
     if (nb > nx) return t;                       // multiple reflections: literal fallback
     const int np = nx + 2 * nb;
     const size_t soft = 74 * 1024, hard = 220 * 1024;
     if (contig) {
-        int pitch = np + 8;                       // alignment shift of the VEC path (<=3) + prefetch pad
+        int pitch = np + 8;                       // alignment shift of the 16-byte path (<=3) + prefetch pad
         while (pitch % 32 != 4) pitch++;
         int W = 16;
         while (W > 1 && ((size_t)W * pitch + 8) * 4 > soft) W >>= 1;
-        if (((size_t)W * pitch + 8) * 4 > soft) {      // even one line is big: allow one CTA per SM
+        if (((size_t)W * pitch + 8) * 4 > soft) {   // even one line is big: allow one CTA per SM
             W = 16;
             while (W > 1 && ((size_t)W * pitch + 8) * 4 > hard) W >>= 1;
             if (((size_t)W * pitch + 8) * 4 > hard) return t;
         }
         t.W = W; t.pitch = pitch; t.smem = ((size_t)W * pitch + 8) * 4;
+    } else if (vec) {
+        t.W = 16; t.pitch = 16;
+        t.smem = (size_t)(((np + 3) >> 2) + 2) * TRI_GP * 4;
+        if (t.smem > hard) return t;
     } else {
-        t.W = 16; t.pitch = 16; t.smem = (size_t)(np + 16) * 16 * 4;
+        t.W = 16; t.pitch = 16; t.smem = (size_t)np * 16 * 4;
         if (t.smem > hard) return t;
     }
     t.ok = true;
@@ -992,35 +1100,36 @@ static TilePlan tile_plan(bool contig, int nx, int nb)
     return t;
 }
 
-template <bool CONTIG, int EPI, bool VEC>
-static int tile_launch_t(pst_ctx *c, int cls, const TriArgs &A, size_t smem, int grid)
+template <typename K>
+static int tile_launch_k(pst_ctx *c, int cls, K kern, bool *attr_done, const TriArgs &A, size_t smem, int grid)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        PST_CUDA(cudaFuncSetAttribute(tri_tile_kernel<CONTIG, EPI, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        attr_done = true;
+    if (!*attr_done) {
+        PST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        *attr_done = true;
     }
-    PST_LAUNCH(c, cls, (tri_tile_kernel<CONTIG, EPI, VEC><<<grid, 128, smem, c->stream>>>(A)));
+    PST_LAUNCH(c, cls, (kern<<<grid, 128, smem, c->stream>>>(A)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
 
-template <bool CONTIG, bool VEC>
-static int tile_launch_e(pst_ctx *c, int cls, int epi, const TriArgs &A, size_t smem, int grid)
+template <int EPI>
+static int tile_launch_epi(pst_ctx *c, int cls, bool contig, bool vec, const TriArgs &A, size_t smem, int grid)
 {
-    switch (epi) {
-        case EPI_GP:        return tile_launch_t<CONTIG, EPI_GP, VEC>(c, cls, A, smem, grid);
-        case EPI_DIR_FIRST: return tile_launch_t<CONTIG, EPI_DIR_FIRST, VEC>(c, cls, A, smem, grid);
-        case EPI_DIR:       return tile_launch_t<CONTIG, EPI_DIR, VEC>(c, cls, A, smem, grid);
-        default:            return tile_launch_t<CONTIG, EPI_NONE, VEC>(c, cls, A, smem, grid);
-    }
+    static bool d0 = false, d1 = false, d2 = false, d3 = false;
+    if (vec) return contig ? tile_launch_k(c, cls, tri_tile_contig_v4_kernel<EPI>, &d0, A, smem, grid)
+                           : tile_launch_k(c, cls, tri_tile_strided_v4_kernel<EPI>, &d1, A, smem, grid);
+    return contig ? tile_launch_k(c, cls, tri_tile_kernel<true, EPI>, &d2, A, smem, grid)
+                  : tile_launch_k(c, cls, tri_tile_kernel<false, EPI>, &d3, A, smem, grid);
 }
 
-template <bool CONTIG>
-static int tile_launch(pst_ctx *c, int cls, int epi, bool vec, const TriArgs &A, size_t smem, int grid)
+static int tile_launch(pst_ctx *c, int cls, int epi, bool contig, bool vec, const TriArgs &A, size_t smem, int grid)
 {
-    return vec ? tile_launch_e<CONTIG, true>(c, cls, epi, A, smem, grid)
-               : tile_launch_e<CONTIG, false>(c, cls, epi, A, smem, grid);
+    switch (epi) {
+        case EPI_GP:        return tile_launch_epi<EPI_GP>(c, cls, contig, vec, A, smem, grid);
+        case EPI_DIR_FIRST: return tile_launch_epi<EPI_DIR_FIRST>(c, cls, contig, vec, A, smem, grid);
+        case EPI_DIR:       return tile_launch_epi<EPI_DIR>(c, cls, contig, vec, A, smem, grid);
+        default:            return tile_launch_epi<EPI_NONE>(c, cls, contig, vec, A, smem, grid);
+    }
 }
 
 // one axis: src -> dst (dst may alias src).  axis 0/1/2.  epi (may be null) is fused only on
@@ -1032,7 +1141,12 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     const int nx = nn[axis], nb = rr[axis];
     const int cls = axis == 0 ? PST_K_TRI1 : (axis == 1 ? PST_K_TRI2 : PST_K_TRI3);
     if (fused) *fused = false;
-    const TilePlan tp = tile_plan(axis == 0, nx, nb);
+    // 16-byte path: every row/line start must be 16-byte aligned
+    auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
+    const bool has_epi = epi && epi->kind != EPI_NONE;
+    const bool vec = (g.n1 % 4 == 0) && al16(src) && al16(dst) &&
+                     (!has_epi || (al16(epi->p) && al16(epi->w) && al16(epi->gp) && al16(epi->sp) && al16(epi->sx) && al16(epi->sr)));
+    const TilePlan tp = tile_plan(axis == 0, vec, nx, nb);
     c->stats.smooth_passes++;
     if (tp.ok) {
         TriArgs A{};
@@ -1056,12 +1170,7 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
             A.eps = epi->eps; A.alpha = epi->alpha; A.partial = c->d_partial;
         }
         long grid = std::min<long>(A.ngroups, (long)c->sm_count * tp.ctas_per_sm);
-        // 16-byte path: every row/line start must be 16-byte aligned
-        auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
-        const bool vec = (g.n1 % 4 == 0) && al16(src) && al16(dst) && al16(A.p) && al16(A.w) && al16(A.gp) &&
-                         al16(A.sp) && al16(A.sx) && al16(A.sr);
-        if (axis == 0) PST_TRY(tile_launch<true>(c, cls, kind, vec, A, tp.smem, (int)grid));
-        else           PST_TRY(tile_launch<false>(c, cls, kind, vec, A, tp.smem, (int)grid));
+        PST_TRY(tile_launch(c, cls, kind, axis == 0, vec, A, tp.smem, (int)grid));
         if (kind != EPI_NONE) {
             PST_TRY(pst_finish_reduce(c, (int)grid, 3, epi->rec));
             if (fused) *fused = true;
