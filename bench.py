@@ -42,9 +42,6 @@ UNIT = "Mvoxels/s"
 DEFAULT_SHAPE = (1000, 1024, 1024)
 DIP_KW = dict(niter=5, liter=10, order=2, rect=(5, 5, 5))
 SOMF_KW = dict(r1=2, r2=2, order=2, option=1)
-CLASS_BYTES_PER_VOXEL = {            # algorithmic bytes per voxel per launch
-    "allpass": 12.0, "tri_axis1": 8.0, "tri_axis2": 8.0, "tri_axis3": 8.0,
-}
 
 
 # --------------------------------------------------------------------------- helpers
@@ -349,30 +346,28 @@ def main():
     if rank != 0:
         return 0
 
-    # ---- roofline of the dominant kernel class (live CUDA-event timing per launch)
+    # ---- roofline of the dominant kernel class: CUDA events around every launch of the class
+    # during the timed steps (on the library's stream); algorithmic bytes counted by the library
+    # per launch
     peak, peak_src = load_peaks()
-    cls_ms = dict(zip(_lib.KERNEL_CLASSES, st["class_ms"]))
-    cls_n = dict(zip(_lib.KERNEL_CLASSES, st["class_launches"]))
-    dom = max(cls_ms, key=lambda k: cls_ms[k])
-    roof = {"bound": "hbm", "kernel_class": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-            "traffic": None}
-    if dom in CLASS_BYTES_PER_VOXEL and cls_n[dom] > 0:
-        bytes_per_launch = CLASS_BYTES_PER_VOXEL[dom] * N
-        avg_ms = cls_ms[dom] / cls_n[dom]
-        roof["achieved"] = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        roof["frac"] = roof["achieved"] / peak
-        roof["avg_launch_ms"] = avg_ms
-        roof["launches"] = cls_n[dom]
-        roof["algorithmic_bytes_per_launch"] = bytes_per_launch
-    else:
-        roof.update({"achieved": None, "frac": None})
+    names = _lib.KERNEL_CLASSES
+    cls_ms = dict(zip(names, st["class_ms"]))
+    cls_n = dict(zip(names, st["class_launches"]))
+    cls_b = dict(zip(names, st["class_bytes"]))
+    hbm = [k for k in names if cls_n[k] > 0 and cls_b[k] > 0 and k not in ("predict", "other", "slot_reduce")]
+    dom = max(hbm, key=lambda k: cls_ms[k])
     total_cls = sum(cls_ms.values()) or 1.0
-    roof["share_of_step"] = cls_ms[dom] / total_cls
-    roof["class_ms_per_step"] = {k: v / args.steps for k, v in cls_ms.items()}
-    roof["class_launches_per_step"] = {k: v / args.steps for k, v in cls_n.items()}
-    for k, b in CLASS_BYTES_PER_VOXEL.items():
-        if cls_n.get(k):
-            roof.setdefault("class_gbs", {})[k] = b * N / (cls_ms[k] / cls_n[k] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel_class": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "achieved": cls_b[dom] / (cls_ms[dom] * 1e-3) / 1e9,
+            "traffic": None,
+            "avg_launch_ms": cls_ms[dom] / cls_n[dom], "launches": cls_n[dom],
+            "algorithmic_bytes_per_launch": cls_b[dom] / cls_n[dom],
+            "share_of_step": cls_ms[dom] / total_cls}
+    roof["frac"] = roof["achieved"] / peak
+    roof["classes"] = {k: {"ms_per_step": cls_ms[k] / args.steps, "launches_per_step": cls_n[k] / args.steps,
+                           "algorithmic_GBps": (cls_b[k] / (cls_ms[k] * 1e-3) / 1e9) if cls_ms[k] > 0 and cls_b[k] > 0 else None,
+                           "share": cls_ms[k] / total_cls}
+                       for k in names if cls_n[k] > 0}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -42,18 +42,23 @@ typedef struct pst_stats {
     double    h2d_bytes, d2h_bytes;
     /* per kernel class (PST_K_*), filled only while profiling is on (pst_ctx_set_profile):
      * CUDA-event time on the launching stream around every launch, and launch counts */
-    double    class_ms[8];
-    long long class_launches[8];
+    double    class_ms[12];
+    long long class_launches[12];
+    double    class_bytes[12];   /* ALGORITHMIC bytes (compulsory reads + writes) of those launches */
 } pst_stats;
 
 #define PST_K_ALLPASS   0   /* PWD stencil (+ fused line-search update, sum of squares) */
 #define PST_K_TRI1      1   /* triangle smoothing, axis 1 (contiguous lines, shared-memory tile) */
 #define PST_K_TRI2      2   /* triangle smoothing, axis 2 (strided lines) */
 #define PST_K_TRI3      3   /* triangle smoothing, axis 3 (strided lines) */
-#define PST_K_CGVEC     4   /* fused CG / divne vector kernels with double reductions */
+#define PST_K_CGVEC     4   /* divne pre-scaling / CG set-up vector kernels with double reductions */
 #define PST_K_PREDICT   5   /* plane-wave prediction: banded LDL' factor + solve per trace */
 #define PST_K_SLOTRED   6   /* mean / median / weighted sum over the sprayed slots */
 #define PST_K_OTHER     7   /* transposes, fills, final reductions */
+#define PST_K_CGHEAD    8   /* CG: p,x,r += a*s of the previous iteration + gradient head gx = -eps x + w r */
+#define PST_K_CGGP      9   /* CG: gp = eps p + S(gx), sum gp^2 */
+#define PST_K_CGDIR    10   /* CG: gr = w gx, direction update s = g + alpha s, three dots */
+#define PST_K_NCLASS   12
 
 const char *pst_last_error(void);
 const char *pst_version(void);

@@ -31,8 +31,8 @@ class Stats(ctypes.Structure):
                 ("linesearch_evals", ctypes.c_longlong), ("gn_iterations", ctypes.c_longlong),
                 ("smooth_passes", ctypes.c_longlong), ("predictions", ctypes.c_longlong),
                 ("device_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
-                ("d2h_bytes", ctypes.c_double), ("class_ms", ctypes.c_double * 8),
-                ("class_launches", ctypes.c_longlong * 8)]
+                ("d2h_bytes", ctypes.c_double), ("class_ms", ctypes.c_double * 12),
+                ("class_launches", ctypes.c_longlong * 12), ("class_bytes", ctypes.c_double * 12)]
 
     def as_dict(self):
         d = {}
@@ -42,7 +42,8 @@ class Stats(ctypes.Structure):
         return d
 
 
-KERNEL_CLASSES = ("allpass", "tri_axis1", "tri_axis2", "tri_axis3", "cg_vec", "predict", "slot_reduce", "other")
+KERNEL_CLASSES = ("allpass", "tri_axis1", "tri_axis2", "tri_axis3", "cg_setup", "predict", "slot_reduce", "other",
+                  "cg_head", "cg_gp", "cg_dir", "reserved")
 
 
 # name -> (restype, argtypes); every symbol include/pst_b200.h declares

@@ -12,6 +12,7 @@
 #include "pst_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 struct BTab { double b[PST_MAXTAP]; };
@@ -312,6 +313,7 @@ struct TriArgs {
     long nlines;           // contiguous: number of lines
     int nx, nb, W, pitch;
     float wt, w2;
+    double bytes;          // algorithmic bytes of this launch (profiling only)
     // epilogue operands
     const float *p, *w;
     float *gp, *sp, *sx, *sr;
@@ -974,9 +976,9 @@ cg_tail_kernel(float *__restrict__ x, const float *__restrict__ sx, float a, siz
         x[i] += a * sx[i];
 }
 
-// gp = eps*p + S(gx)  (:303,:318); tmp <- gp as the input of the second shaping; partial gp.gp
+// gp = eps*p + S(gx)  (:303,:318); partial gp.gp.  (The second shaping call reads gp out of place.)
 __global__ void __launch_bounds__(256)
-cg_gp_kernel(const float *__restrict__ p, float *__restrict__ tmp, float *__restrict__ gp,
+cg_gp_kernel(const float *__restrict__ p, const float *__restrict__ tmp, float *__restrict__ gp,
              float eps, size_t n, double *__restrict__ partial)
 {
     double acc[1] = {0.0};
@@ -984,7 +986,6 @@ cg_gp_kernel(const float *__restrict__ p, float *__restrict__ tmp, float *__rest
         float g = eps * p[i];
         g += tmp[i];
         gp[i] = g;
-        tmp[i] = g;
         acc[0] += (double)g * (double)g;
     }
     pst_block_reduce<1>(acc, partial);
@@ -1046,7 +1047,7 @@ static int tri_lines_launch(pst_ctx *c, int cls, float *x, float *scr, long nlin
     const float w2 = (float)(2. * wt);
     const int threads = 128;
     const long blocks = (nlines + threads - 1) / threads;
-    PST_LAUNCH(c, cls,
+    PST_LAUNCHB(c, cls, 8.0 * (double)nlines * nx,
         if (nb <= nx)
             tri_lines_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, w2);
         else
@@ -1103,11 +1104,12 @@ static TilePlan tile_plan(bool contig, bool vec, int nx, int nb)
 template <typename K>
 static int tile_launch_k(pst_ctx *c, int cls, K kern, bool *attr_done, const TriArgs &A, size_t smem, int grid)
 {
+    const double bytes = A.bytes;
     if (!*attr_done) {
         PST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         *attr_done = true;
     }
-    PST_LAUNCH(c, cls, (kern<<<grid, 128, smem, c->stream>>>(A)));
+    PST_LAUNCHB(c, cls, bytes, (kern<<<grid, 128, smem, c->stream>>>(A)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -1163,8 +1165,10 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
             A.na = (long)g.n1 * g.n2; A.sb = 0; A.d = (long)g.n1 * g.n2;
             A.ngroups = (A.na + 15) / 16;
         }
+        A.bytes = 8.0 * (double)g.n;
         int kind = EPI_NONE;
         if (epi && epi->kind != EPI_NONE) {
+            A.bytes += (epi->kind == EPI_GP ? 4.0 : (epi->kind == EPI_DIR ? 28.0 : 16.0)) * (double)g.n;
             kind = epi->kind;
             A.p = epi->p; A.w = epi->w; A.gp = epi->gp; A.sp = epi->sp; A.sx = epi->sx; A.sr = epi->sr;
             A.eps = epi->eps; A.alpha = epi->alpha; A.partial = c->d_partial;
@@ -1227,7 +1231,7 @@ static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, cons
     const long cap = (long)c->sm_count * 8;
     if (blocks > cap) blocks = cap;
     const int threads = n1 >= 256 ? 256 : (n1 >= 128 ? 128 : 64);
-    PST_LAUNCH(c, PST_K_ALLPASS,
+    PST_LAUNCHB(c, PST_K_ALLPASS, (ls ? 20.0 : 12.0) * (double)n1 * n2 * n3,
         if (ls)
             allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, tb, c->d_partial);
         else if (der)
@@ -1253,7 +1257,7 @@ struct CgWork {
 };
 
 // scalars of ps_conjgrad that gate the direction update (:330-349): fetched as late as possible
-struct CgLate { pst_ctx *c; double gn, gnp, g0; float tol; int iter; bool stop; };
+struct CgLate { pst_ctx *c; double gn, gnp, g0; float tol; int iter; bool stop; float alpha; };
 
 static int cg_late_bind(void *user, EpiSpec *epi)
 {
@@ -1264,7 +1268,8 @@ static int cg_late_bind(void *user, EpiSpec *epi)
     if (L->iter == 0) { L->g0 = L->gn; return 0; }
     const double alpha = L->gn / L->gnp, dg = L->gn / L->g0;
     if (alpha < L->tol || dg < L->tol) { L->stop = true; return 1; }
-    epi->alpha = (float)alpha;
+    L->alpha = (float)alpha;
+    if (epi) epi->alpha = L->alpha;
     return 0;
 }
 
@@ -1280,7 +1285,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     double h[PST_RED_SLOTS];
     if (iters_run) *iters_run = 0;
 
-    PST_LAUNCH(c, PST_K_CGVEC, (divne_prescale_kernel<<<grid, threads, 0, c->stream>>>(num, den, mask, eps_div, n, c->d_partial)));
+    PST_LAUNCHB(c, PST_K_CGVEC, 16.0 * (double)n, (divne_prescale_kernel<<<grid, threads, 0, c->stream>>>(num, den, mask, eps_div, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) {
@@ -1288,17 +1293,21 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         return PST_OK;
     }
     const double norm = sqrt((double)n / h[0]);
-    PST_LAUNCH(c, PST_K_CGVEC, (divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial)));
+    PST_LAUNCHB(c, PST_K_CGVEC, 24.0 * (double)n, (divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) return PST_OK;               // zero residual: p = x = 0 (:299-303)
 
-    CgLate L{c, 0., 0., 0., tol, 0, false};
+    // A/B switch.  Measured on B200 at 1000x1024x1024 (round 1): fusing the CG vector work into the
+    // epilogue of the last smoothing pass costs more than it saves (4.83 s unfused vs 5.15 s fused per
+    // step): the streaming kernels run at ~5.5 TB/s, the tile kernel's phase 3 does not.  Default: off.
+    static const bool fuse = []() { const char *e = getenv("PST_FUSE_EPILOGUE"); return e && e[0] == '1'; }();
+    CgLate L{c, 0., 0., 0., tol, 0, false, 0.f};
     float a_pending = 0.f;
     bool pending = false;
     int iter;
     for (iter = 0; iter < liter; iter++) {
-        PST_LAUNCH(c, PST_K_CGVEC,
+        PST_LAUNCHB(c, PST_K_CGHEAD, (pending ? 44.0 : 16.0) * (double)n,
             if (pending)
                 cg_head_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, a_pending, eps, w.tmp, n);
             else
@@ -1308,9 +1317,9 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         EpiSpec e1;
         e1.kind = EPI_GP; e1.p = w.p; e1.gp = w.gp; e1.eps = eps; e1.rec = 1;
         bool fused = false;
-        PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, &e1, nullptr, nullptr, &fused));
+        PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, fuse ? &e1 : nullptr, nullptr, nullptr, &fused));
         if (!fused) {
-            PST_LAUNCH(c, PST_K_CGVEC, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
+            PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
             PST_TRY(pst_finish_reduce(c, grid, 1, 1));
         }
         // gx = S(gp); direction update fused into the last axis once alpha is known
@@ -1318,14 +1327,14 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         e2.kind = (iter == 0) ? EPI_DIR_FIRST : EPI_DIR;
         e2.w = den; e2.gp = w.gp; e2.sp = w.sp; e2.sx = w.sx; e2.sr = w.sr; e2.rec = 2;
         L.iter = iter; L.stop = false;
-        int v = pst_shape_apply(c, g, w.gp, w.tmp, w.scr, &e2, cg_late_bind, &L, &fused);
+        int v = pst_shape_apply(c, g, w.gp, w.tmp, w.scr, fuse ? &e2 : nullptr, cg_late_bind, &L, &fused);
         if (v < 0) return v;
         if (L.stop) break;
         if (!fused) {
             if (iter == 0)
-                PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
+                PST_LAUNCHB(c, PST_K_CGDIR, 24.0 * (double)n, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
             else
-                PST_LAUNCH(c, PST_K_CGVEC, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, e2.alpha, n, c->d_partial)));
+                PST_LAUNCHB(c, PST_K_CGDIR, 36.0 * (double)n, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, L.alpha, n, c->d_partial)));
             PST_TRY(pst_finish_reduce(c, grid, 3, 2));
         }
         PST_TRY(pst_fetch_record(c, 2, 3, h));
@@ -1337,7 +1346,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         c->stats.cg_iterations++;
     }
     if (pending) {      // only the model x (= rat) is consumed after the last iteration
-        PST_LAUNCH(c, PST_K_CGVEC, (cg_tail_kernel<<<grid, threads, 0, c->stream>>>(rat, w.sx, a_pending, n)));
+        PST_LAUNCHB(c, PST_K_CGHEAD, 12.0 * (double)n, (cg_tail_kernel<<<grid, threads, 0, c->stream>>>(rat, w.sx, a_pending, n)));
     }
     if (iters_run) *iters_run = iter;
     PST_CUDA(cudaGetLastError());

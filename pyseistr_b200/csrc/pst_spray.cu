@@ -335,7 +335,7 @@ static int transpose_planes(pst_ctx *c, const float *in, float *out, int rows, i
         const int nz = std::min(zmax, planes - z0);
         dim3 grid((cols + 31) / 32, (rows + 31) / 32, nz), block(32, 8);
         const long off = (long)rows * cols * z0;
-        PST_LAUNCH(c, PST_K_OTHER, (transpose_kernel<<<grid, block, 0, c->stream>>>(in + off, out + off, rows, cols)));
+        PST_LAUNCHB(c, PST_K_OTHER, 8.0 * (double)rows * cols * nz, (transpose_kernel<<<grid, block, 0, c->stream>>>(in + off, out + off, rows, cols)));
     }
     PST_CUDA(cudaGetLastError());
     return PST_OK;
@@ -435,7 +435,7 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 {
     const int threads = A.n2 >= 128 ? 128 : (A.n2 >= 64 ? 64 : 32);
     dim3 grid((A.n2 + threads - 1) / threads, A.zlb - A.zla);
-    PST_LAUNCH(c, PST_K_PREDICT,
+    PST_LAUNCHB(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * A.n2 * (A.zlb - A.zla),
         if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
         else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A));
 }
