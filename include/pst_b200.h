@@ -81,6 +81,10 @@ int  pst_timer_stop(pst_ctx *ctx, double *elapsed_ms);
  * the host side (torch.distributed / MPI / files). */
 int  pst_comm_unique_id(void *id128);
 int  pst_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, pst_ctx **ctx);
+/* The library's slab rule: rank r of G owns global planes [n3*r/G, n3*(r+1)/G).  In a distributed
+ * context every entry point takes the GLOBAL n3 and pointers to this rank's slab (for pst_dip the
+ * output is the slab of the inline dip followed by the slab of the xline dip). */
+int  pst_ctx_slab(pst_ctx *ctx, int n3, int *z0, int *z1);
 
 /* ---- dip estimation.  Replaces dipcfun.dipc (reference pyseistr/src/dip_cfuns.c:1694-1989,
  * "Oiiiiiifffiiiii"); called by dip3dc (pyseistr/dip3d.py:59-116) and dip2dc

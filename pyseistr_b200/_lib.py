@@ -60,6 +60,7 @@ SIGNATURES = {
     "pst_timer_stop": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "pst_comm_unique_id": (_i, [_vp]),
     "pst_ctx_create_dist": (_i, [_i, _i, _i, _vp, ctypes.POINTER(_vp)]),
+    "pst_ctx_slab": (_i, [_vp, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "pst_dip": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i, _i, _fp]),
     "pst_dip_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pst_somean3d": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _fp]),
@@ -120,11 +121,24 @@ def check(rc):
 class Context:
     """One GPU context (stream, workspace arena, reduction buffers)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None):
+        """Single-GPU context, or (nranks > 1) one rank of an n3-slab decomposition; nccl_id is the
+        128-byte id from ``unique_id()`` on rank 0, distributed by the caller."""
         self._h = _vp()
         self.lib = load()
-        check(self.lib.pst_ctx_create(int(device), ctypes.byref(self._h)))
+        self.rank, self.nranks = int(rank), int(nranks)
+        if self.nranks > 1:
+            buf = ctypes.create_string_buffer(bytes(nccl_id), 128)
+            check(self.lib.pst_ctx_create_dist(int(device), self.rank, self.nranks, buf, ctypes.byref(self._h)))
+        else:
+            check(self.lib.pst_ctx_create(int(device), ctypes.byref(self._h)))
         self.device = device
+
+    def slab(self, n3):
+        """Global plane range [z0, z1) this rank owns."""
+        z0, z1 = _i(0), _i(0)
+        check(self.lib.pst_ctx_slab(self._h, int(n3), ctypes.byref(z0), ctypes.byref(z1)))
+        return z0.value, z1.value
 
     @property
     def handle(self):
@@ -176,6 +190,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def unique_id():
+    """128-byte NCCL id (call on rank 0, broadcast to the other ranks)."""
+    buf = ctypes.create_string_buffer(128)
+    check(load().pst_comm_unique_id(buf))
+    return buf.raw
 
 
 _default_ctx = {}

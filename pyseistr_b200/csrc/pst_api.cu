@@ -328,6 +328,13 @@ static int down(pst_ctx *c, float *h, const DevBuf &b, size_t n)
     return PST_OK;
 }
 
+// planes held by this rank: all of them on a single-GPU context
+static int slab_planes(pst_ctx *c, int n3)
+{
+    if (c->nranks <= 1) return n3;
+    return (int)(((long)n3 * (c->rank + 1)) / c->nranks) - (int)(((long)n3 * c->rank) / c->nranks);
+}
+
 #define PST_ENTRY(c)                                                        \
     if (!(c)) { pst_set_error("null context"); return PST_EINVAL; }         \
     PST_CUDA(cudaSetDevice((c)->device));
@@ -339,12 +346,12 @@ extern "C" int pst_dip(pst_ctx *c, const float *din, const float *mask, int n1, 
     (void)eps_dv; (void)eps_cg; (void)tol_cg;      // ignored by the reference's C
     PST_ENTRY(c);
     if (!din || !dip_out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("dip: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, m, o;
     PST_TRY(up(c, d, din, n));
     if (mask) PST_TRY(up(c, m, mask, n));
-    PST_TRY(o.alloc((n3 == 1 ? n : 2 * n) * sizeof(float)));
+    PST_TRY(o.alloc((n3 == 1 ? n : 2 * n) * sizeof(float)));   /* n = this rank's slab */
     PST_TRY(pst_dip_dev(c, d.f(), mask ? m.f() : nullptr, n1, n2, n3, niter, liter, order, r1, r2, r3, verb, o.f()));
     PST_TRY(down(c, dip_out, o, n3 == 1 ? n : 2 * n));
     t.stop();
@@ -358,7 +365,7 @@ extern "C" int pst_somean3d(pst_ctx *c, const float *din, const float *dipi, con
     (void)eps; (void)verb;                          // eps overridden with 0.01 by the reference (Q2)
     PST_ENTRY(c);
     if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean3d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, a, b, o;
     PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
@@ -376,7 +383,7 @@ extern "C" int pst_somf3d(pst_ctx *c, const float *din, const float *dipi, const
     (void)eps; (void)verb;
     PST_ENTRY(c);
     if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somf3d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, a, b, o;
     PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
@@ -399,7 +406,7 @@ extern "C" int pst_somean2d(pst_ctx *c, const float *din, const float *dip, int 
     PST_ENTRY(c);
     if (!din || !dip || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean2d: null pointer or bad shape"); return PST_EINVAL; }
     if (adj) { pst_set_error("somean2d: adj=1 (adjoint smoothing) not implemented on the GPU path"); return PST_EUNSUP; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, a, o;
     PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dip, n));
@@ -416,7 +423,7 @@ extern "C" int pst_somf2d(pst_ctx *c, const float *din, const float *dip, int n1
     (void)verb;
     PST_ENTRY(c);
     if (!din || !dip || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somf2d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, a, o;
     PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dip, n));
@@ -432,7 +439,7 @@ extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, i
 {
     PST_ENTRY(c);
     if (!x || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smooth3: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d;
     PST_TRY(up(c, d, x, n));

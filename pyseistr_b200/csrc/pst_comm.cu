@@ -1,36 +1,164 @@
-// Multi-GPU plumbing (slab decomposition along n3, one process per GPU).
-// Round-1 state: single-GPU contexts only; the distributed entry points are declared in the
-// C-ABI and report PST_EUNSUP until the NCCL halo / carry exchange lands.
+// Multi-GPU plumbing: n3-slab decomposition, one process per GPU, NCCL over NVLink.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"; if the host process already loaded one —
+// e.g. torch's bundled copy — that instance is reused), so libpst_b200.so has no link-time
+// dependency and single-GPU use never touches it.  Only the few entry points used here are
+// declared; their ABI is stable across NCCL 2.x.
+//
+// What crosses slabs:
+//   * CG / divne / line-search scalars: all-reduce of <= 8 doubles (pst_comm_allreduce_record);
+//   * plane halos (xline stencil, spray inputs, axis-3 smoothing taps): pst_comm_halo_*;
+//   * axis-3 running sums: a carry plane handed rank to rank (pst_comm_send / pst_comm_recv).
 #include "pst_common.cuh"
 
+#include <dlfcn.h>
 #include <string.h>
 
-struct pst_comm { int dummy; };
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };   // ncclDataType_t values (nccl.h)
+enum { ncclSum = 0 };                          // ncclRedOp_t
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.handle) return PST_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // reuse the host process's copy
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { pst_set_error("cannot load libnccl.so.2: %s", dlerror()); return PST_ECOMM; }
+#define PST_SYM(field, name)                                                            \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                         \
+    if (!g_nccl.field) { pst_set_error("libnccl: missing symbol %s", name); return PST_ECOMM; }
+    PST_SYM(GetUniqueId, "ncclGetUniqueId");
+    PST_SYM(CommInitRank, "ncclCommInitRank");
+    PST_SYM(CommDestroy, "ncclCommDestroy");
+    PST_SYM(AllReduce, "ncclAllReduce");
+    PST_SYM(Send, "ncclSend");
+    PST_SYM(Recv, "ncclRecv");
+    PST_SYM(GroupStart, "ncclGroupStart");
+    PST_SYM(GroupEnd, "ncclGroupEnd");
+    PST_SYM(GetErrorString, "ncclGetErrorString");
+#undef PST_SYM
+    g_nccl.handle = h;
+    return PST_OK;
+}
+
+#define PST_NCCL(call)                                                                  \
+    do {                                                                                \
+        ncclResult_t r__ = (call);                                                      \
+        if (r__ != 0) {                                                                 \
+            pst_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
+            return PST_ECOMM;                                                           \
+        }                                                                               \
+    } while (0)
+
+struct pst_comm { ncclComm_t comm = nullptr; };
 
 int pst_comm_allreduce_record(pst_ctx *c, double *d_rec, int nv)
 {
-    (void)c; (void)d_rec; (void)nv;
+    if (!c->comm) return PST_OK;
+    PST_NCCL(g_nccl.AllReduce(d_rec, d_rec, (size_t)nv, ncclFloat64, ncclSum, c->comm->comm, c->stream));
+    return PST_OK;
+}
+
+// point-to-point on the context's stream
+int pst_comm_send(pst_ctx *c, const float *d_buf, size_t count, int peer)
+{
+    PST_NCCL(g_nccl.Send(d_buf, count, ncclFloat32, peer, c->comm->comm, c->stream));
+    return PST_OK;
+}
+int pst_comm_recv(pst_ctx *c, float *d_buf, size_t count, int peer)
+{
+    PST_NCCL(g_nccl.Recv(d_buf, count, ncclFloat32, peer, c->comm->comm, c->stream));
+    return PST_OK;
+}
+
+// Exchange plane halos with both neighbours in one NCCL group:
+//   send_lo (count floats) -> rank-1,   recv_lo <- rank-1   (their send_hi)
+//   send_hi               -> rank+1,   recv_hi <- rank+1   (their send_lo)
+// Edge ranks skip the missing side (their recv buffer is left untouched).
+int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_hi, float *recv_lo,
+                           float *recv_hi, size_t count)
+{
+    if (!c->comm || count == 0) return PST_OK;
+    PST_NCCL(g_nccl.GroupStart());
+    if (c->rank > 0) {
+        PST_NCCL(g_nccl.Send(send_lo, count, ncclFloat32, c->rank - 1, c->comm->comm, c->stream));
+        PST_NCCL(g_nccl.Recv(recv_lo, count, ncclFloat32, c->rank - 1, c->comm->comm, c->stream));
+    }
+    if (c->rank < c->nranks - 1) {
+        PST_NCCL(g_nccl.Send(send_hi, count, ncclFloat32, c->rank + 1, c->comm->comm, c->stream));
+        PST_NCCL(g_nccl.Recv(recv_hi, count, ncclFloat32, c->rank + 1, c->comm->comm, c->stream));
+    }
+    PST_NCCL(g_nccl.GroupEnd());
     return PST_OK;
 }
 
 void pst_comm_destroy(pst_ctx *c)
 {
-    delete c->comm;
+    if (c->comm) {
+        if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
+        delete c->comm;
+    }
     c->comm = nullptr;
 }
 
 extern "C" int pst_comm_unique_id(void *id128)
 {
     if (!id128) { pst_set_error("null argument"); return PST_EINVAL; }
-    memset(id128, 0, 128);
-    pst_set_error("multi-GPU communicator not built in this version");
-    return PST_EUNSUP;
+    PST_TRY(nccl_load());
+    ncclUniqueId id;
+    PST_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return PST_OK;
 }
 
 extern "C" int pst_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, pst_ctx **ctx)
 {
-    (void)nccl_id128;
-    if (nranks == 1 && rank == 0) return pst_ctx_create(device, ctx);
-    pst_set_error("multi-GPU slab decomposition not built in this version (nranks=%d)", nranks);
-    return PST_EUNSUP;
+    if (!ctx) { pst_set_error("null out pointer"); return PST_EINVAL; }
+    if (nranks < 1 || rank < 0 || rank >= nranks) { pst_set_error("bad rank %d / nranks %d", rank, nranks); return PST_EINVAL; }
+    PST_TRY(pst_ctx_create(device, ctx));
+    if (nranks == 1) return PST_OK;
+    pst_ctx *c = *ctx;
+    if (!nccl_id128) { pst_ctx_destroy(c); *ctx = nullptr; pst_set_error("null NCCL id"); return PST_EINVAL; }
+    int rc = nccl_load();
+    if (rc != PST_OK) { pst_ctx_destroy(c); *ctx = nullptr; return rc; }
+    ncclUniqueId id;
+    memcpy(&id, nccl_id128, 128);
+    c->comm = new pst_comm();
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm->comm, nranks, id, rank);
+    if (r != 0) {
+        pst_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete c->comm; c->comm = nullptr;
+        pst_ctx_destroy(c); *ctx = nullptr;
+        return PST_ECOMM;
+    }
+    return PST_OK;
+}
+
+// The library's fixed slab rule: rank r owns global planes [n3*r/G, n3*(r+1)/G).
+extern "C" int pst_ctx_slab(pst_ctx *c, int n3, int *z0, int *z1)
+{
+    if (!c || !z0 || !z1) { pst_set_error("null argument"); return PST_EINVAL; }
+    *z0 = (int)(((long)n3 * c->rank) / c->nranks);
+    *z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+    return PST_OK;
 }

@@ -83,7 +83,7 @@ template <int NW, bool DER, bool LS>
 __global__ void __launch_bounds__(256)
 allpass_kernel(const float *__restrict__ u, const float *__restrict__ p_in,
                const float *__restrict__ dp, float lam, float *__restrict__ p_out,
-               float *__restrict__ y, int n1, int n2, int n3, int xline, BTab tb,
+               float *__restrict__ y, int n1, int n2, int n3, int xline, int n3_live, BTab tb,
                double *__restrict__ partial)
 {
     const long ntr = (long)n2 * n3;
@@ -91,7 +91,7 @@ allpass_kernel(const float *__restrict__ u, const float *__restrict__ p_in,
     double acc2[1] = {0.0};
     for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
         const int i2 = (int)(tr % n2), i3 = (int)(tr / n2);
-        const bool live_tr = xline ? (i3 < n3 - 1) : (i2 < n2 - 1);
+        const bool live_tr = xline ? (i3 < n3_live) : (i2 < n2 - 1);
         const long base = tr * n1;
         for (int i1 = threadIdx.x; i1 < n1; i1 += blockDim.x) {
             const long i = base + i1;
@@ -127,7 +127,7 @@ allpass_kernel(const float *__restrict__ u, const float *__restrict__ p_in,
 // G5: mask32 (both=false, nj=1): footprint of either stencil touches a zero sample
 template <int NW>
 __global__ void mask_kernel(const float *__restrict__ um, unsigned char *__restrict__ m_in,
-                            unsigned char *__restrict__ m_x, int n1, int n2, int n3)
+                            unsigned char *__restrict__ m_x, int n1, int n2, int n3, int n3_live)
 {
     const long ntr = (long)n2 * n3;
     const long pl = (long)n1 * n2;
@@ -139,7 +139,7 @@ __global__ void mask_kernel(const float *__restrict__ um, unsigned char *__restr
             if (i1 >= NW && i1 < n1 - NW) {
                 if (i2 < n2 - 1)
                     for (int s = -NW; s <= NW; s++) a = a || (um[i - s] == 0.f) || (um[i + n1 + s] == 0.f);
-                if (i3 < n3 - 1)
+                if (i3 < n3_live)
                     for (int s = -NW; s <= NW; s++) b = b || (um[i - s] == 0.f) || (um[i + pl + s] == 0.f);
             }
             m_in[i] = a;
@@ -1028,7 +1028,23 @@ __global__ void fill_kernel(float *__restrict__ x, float v, size_t n)
 // host side
 // =======================================================================================
 
-struct DipGeom { int n1, n2, n3, r1, r2, r3; size_t n; };
+// n3 = planes held by this rank (whole cube on a single GPU), n = n1*n2*n3.  In a distributed
+// context the cube has n3g planes in total and this rank owns global planes [z0, z0+n3).
+struct DipGeom {
+    int n1, n2, n3, r1, r2, r3; size_t n;
+    int n3g = 0, z0 = 0; double nglob = 0.0;
+    bool dist = false;
+    // work buffers of the distributed axis-3 pass (arena): halo planes before / after the slab,
+    // carry planes (in / out), see smooth_axis3_dist
+    float *hb = nullptr, *ha = nullptr, *cin = nullptr, *cout = nullptr;
+};
+static DipGeom make_geom(int n1, int n2, int n3, int r1, int r2, int r3)
+{
+    DipGeom g;
+    g.n1 = n1; g.n2 = n2; g.n3 = n3; g.r1 = r1; g.r2 = r2; g.r3 = r3; g.n = (size_t)n1 * n2 * n3;
+    g.n3g = n3; g.z0 = 0; g.nglob = (double)g.n;
+    return g;
+}
 
 static size_t tri_scratch_floats(const DipGeom &g)
 {
@@ -1055,6 +1071,80 @@ static int tri_lines_launch(pst_ctx *c, int cls, float *x, float *scr, long nlin
     c->stats.smooth_passes++;
     PST_CUDA(cudaGetLastError());
     return PST_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Distributed axis-3 smoothing (n3-slabs over ranks): the two running sums run ACROSS ranks in the
+// reference's order, so results stay bit-identical to the single-GPU / reference result.  Rank r
+// owns the extended positions k in [K0, K1) of every line (K0 = z0 + nb, or 0 on rank 0;
+// K1 = z1 + nb, or n3g + 2nb on the last rank).  The running value at the slab edge is handed to
+// the neighbour as a carry plane; lines are processed in chunks so that ranks work concurrently
+// (software pipeline over chunks).  x at global plane j comes from the slab, or from the nb-plane
+// halos received before the pass.
+struct Tri3Args {
+    const float *x;        // slab [nz][L]
+    const float *hb, *ha;  // halos: planes [z0-nb, z0) and [z1, z1+nb)
+    float *F;              // scratch [K1-K0][L]
+    const float *cin;      // carry in  (nullptr = 0)
+    float *cout;           // carry out
+    float *dst;            // fold output [nz][L]
+    long L, l0, l1;        // lines per plane, chunk [l0, l1)
+    int n3g, z0, nz, nb, K0, K1;
+    float wt, w2;
+};
+
+__device__ __forceinline__ float tri3_x(const Tri3Args &A, int j, long l)
+{
+    if (j >= A.z0 && j < A.z0 + A.nz) return A.x[(long)(j - A.z0) * A.L + l];
+    if (j < A.z0) return A.hb[(long)(j - (A.z0 - A.nb)) * A.L + l];
+    return A.ha[(long)(j - (A.z0 + A.nz)) * A.L + l];
+}
+
+__global__ void __launch_bounds__(128)
+tri3_dist_fwd_kernel(const Tri3Args A)
+{
+    const long l = A.l0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= A.l1) return;
+    const float wm = -A.wt;
+    float s = A.cin ? A.cin[l] : 0.f;
+    for (int k = A.K0; k < A.K1; k++) {
+        float t = 0.f;
+        if (k < A.n3g) t = t + wm * tri3_x(A, k, l);
+        if (k >= A.nb && k - A.nb < A.n3g) t = t + A.w2 * tri3_x(A, k - A.nb, l);
+        if (k >= 2 * A.nb && k - 2 * A.nb < A.n3g) t = t + wm * tri3_x(A, k - 2 * A.nb, l);
+        s += t;
+        A.F[(long)(k - A.K0) * A.L + l] = s;
+    }
+    A.cout[l] = s;
+}
+
+__global__ void __launch_bounds__(128)
+tri3_dist_bwd_kernel(const Tri3Args A)
+{
+    const long l = A.l0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= A.l1) return;
+    float s = A.cin ? A.cin[l] : 0.f;
+    for (int k = A.K1 - 1; k >= A.K0; k--) {
+        s += A.F[(long)(k - A.K0) * A.L + l];
+        A.F[(long)(k - A.K0) * A.L + l] = s;
+    }
+    A.cout[l] = s;
+}
+
+// fold2 (:458-484): every term lives on the owning rank (needs slab height >= 2nb)
+__global__ void __launch_bounds__(256)
+tri3_dist_fold_kernel(const Tri3Args A)
+{
+    const long total = (long)A.nz * A.L;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / A.L);
+        const long l = e - (long)i * A.L;
+        const int gi = A.z0 + i;
+        float v = A.F[(long)(gi + A.nb - A.K0) * A.L + l];
+        if (gi >= A.n3g - A.nb) v = v + A.F[(long)(A.nb + A.n3g + (A.n3g - 1 - gi) - A.K0) * A.L + l];
+        if (gi < A.nb) v = v + A.F[(long)(A.nb - 1 - gi - A.K0) * A.L + l];
+        A.dst[e] = v;
+    }
 }
 
 // ---- shaping operator driver ------------------------------------------------------------
@@ -1134,6 +1224,48 @@ static int tile_launch(pst_ctx *c, int cls, int epi, bool contig, bool vec, cons
     }
 }
 
+int pst_comm_send(pst_ctx *c, const float *d_buf, size_t count, int peer);            // pst_comm.cu
+int pst_comm_recv(pst_ctx *c, float *d_buf, size_t count, int peer);
+int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_hi, float *recv_lo,
+                           float *recv_hi, size_t count);
+
+static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, float *dst, float *scr)
+{
+    const int nb = g.r3, nz = g.n3, n3g = g.n3g;
+    const long L = (long)g.n1 * g.n2;
+    const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
+    // nb-plane halos of the CURRENT input (it changes every pass)
+    PST_TRY(pst_comm_halo_exchange(c, src, src + (size_t)(nz - nb) * L, g.hb, g.ha, (size_t)nb * L));
+    Tri3Args A{};
+    A.x = src; A.hb = g.hb; A.ha = g.ha; A.F = scr; A.dst = dst; A.L = L;
+    A.n3g = n3g; A.z0 = g.z0; A.nz = nz; A.nb = nb;
+    A.K0 = first ? 0 : g.z0 + nb;
+    A.K1 = last ? n3g + 2 * nb : g.z0 + nz + nb;
+    A.wt = (float)(1.0 / ((double)nb * nb));
+    A.w2 = (float)(2. * A.wt);
+    // chunks of lines: enough to fill the GPU, few enough to keep NCCL launches cheap
+    const int nchunk = 8;
+    long per = ((L + nchunk - 1) / nchunk + 127) / 128 * 128;
+    const double bytes_half = 8.0 * (double)g.n;
+    for (int pass = 0; pass < 2; pass++) {          // 0: forward (carries flow up), 1: backward (down)
+        const bool has_in = pass == 0 ? !first : !last, has_out = pass == 0 ? !last : !first;
+        const int peer_in = pass == 0 ? c->rank - 1 : c->rank + 1, peer_out = pass == 0 ? c->rank + 1 : c->rank - 1;
+        for (long l0 = 0; l0 < L; l0 += per) {
+            const long l1 = std::min(L, l0 + per);
+            if (has_in) PST_TRY(pst_comm_recv(c, g.cin + l0, (size_t)(l1 - l0), peer_in));
+            A.l0 = l0; A.l1 = l1; A.cin = has_in ? g.cin : nullptr; A.cout = g.cout;
+            const unsigned blocks = (unsigned)((l1 - l0 + 127) / 128);
+            PST_LAUNCHB(c, PST_K_TRI3, bytes_half * (double)(l1 - l0) / (double)L,
+                if (pass == 0) tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A);
+                else           tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A));
+            if (has_out) PST_TRY(pst_comm_send(c, g.cout + l0, (size_t)(l1 - l0), peer_out));
+        }
+    }
+    PST_LAUNCHB(c, PST_K_TRI3, 0.0, (tri3_dist_fold_kernel<<<pst_grid_for(c, g.n, 256), 256, 0, c->stream>>>(A)));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
 // one axis: src -> dst (dst may alias src).  axis 0/1/2.  epi (may be null) is fused only on
 // the tile path; *fused reports it.
 static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src, float *dst, float *scr,
@@ -1143,6 +1275,10 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     const int nx = nn[axis], nb = rr[axis];
     const int cls = axis == 0 ? PST_K_TRI1 : (axis == 1 ? PST_K_TRI2 : PST_K_TRI3);
     if (fused) *fused = false;
+    if (axis == 2 && g.dist) {
+        c->stats.smooth_passes++;
+        return smooth_axis3_dist(c, g, src, dst, scr);
+    }
     // 16-byte path: every row/line start must be 16-byte aligned
     auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
     const bool has_epi = epi && epi->kind != EPI_NONE;
@@ -1216,14 +1352,14 @@ int pst_shape_apply(pst_ctx *c, const DipGeom &g, const float *src, float *tmp, 
 
 int pst_smooth3_inplace(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3, int r1, int r2, int r3)
 {
-    DipGeom g{n1, n2, n3, r1, r2, r3, (size_t)n1 * n2 * n3};
+    DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
     return pst_shape_apply(c, g, x, x, scr, nullptr, nullptr, nullptr, nullptr);
 }
 
 template <int NW>
 static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, const float *dp, float lam,
                              float *p_out, float *y, int n1, int n2, int n3, int xline, bool der,
-                             bool ls, int rec)
+                             bool ls, int rec, int n3_live)
 {
     static const BTab tb = make_btab(NW);
     const long ntr = (long)n2 * n3;
@@ -1233,21 +1369,25 @@ static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, cons
     const int threads = n1 >= 256 ? 256 : (n1 >= 128 ? 128 : 64);
     PST_LAUNCHB(c, PST_K_ALLPASS, (ls ? 20.0 : 12.0) * (double)n1 * n2 * n3,
         if (ls)
-            allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, tb, c->d_partial);
+            allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, n3_live, tb, c->d_partial);
         else if (der)
-            allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial);
+            allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, c->d_partial);
         else
-            allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, tb, c->d_partial));
+            allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, c->d_partial));
     PST_CUDA(cudaGetLastError());
     return pst_finish_reduce(c, (int)blocks, 1, rec);
 }
 
+// n3_live: planes whose next plane exists (xline stencil); -1 = n3 - 1 (whole cube on this GPU).
+// In a distributed context u carries one halo plane behind the slab and n3_live = n3 except on
+// the last rank.
 int pst_allpass_launch(pst_ctx *c, const float *u, const float *p_in, const float *dp, float lam,
                        float *p_out, float *y, int n1, int n2, int n3, int nw, int xline, bool der,
-                       bool ls, int rec)
+                       bool ls, int rec, int n3_live = -1)
 {
-    if (nw == 1) return allpass_launch_nw<1>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec);
-    if (nw == 2) return allpass_launch_nw<2>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec);
+    if (n3_live < 0) n3_live = n3 - 1;
+    if (nw == 1) return allpass_launch_nw<1>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live);
+    if (nw == 2) return allpass_launch_nw<2>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live);
     pst_set_error("order=%d unsupported (1 or 2)", nw);
     return PST_EUNSUP;
 }
@@ -1292,7 +1432,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rat, 0.f, n)));
         return PST_OK;
     }
-    const double norm = sqrt((double)n / h[0]);
+    const double norm = sqrt(g.nglob / h[0]);
     PST_LAUNCHB(c, PST_K_CGVEC, 24.0 * (double)n, (divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
@@ -1356,22 +1496,22 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
 // dip3 (:1619-1691) for one direction.  p holds the initial dip (zeros) and receives the result.
 static int gauss_newton(pst_ctx *c, const DipGeom &g, const float *u, float *p, const unsigned char *mask,
                         int xline, int niter, int liter, int nw, float *u1, float *u2, float *dp,
-                        float *ptrial, const CgWork &w, int verb)
+                        float *ptrial, const CgWork &w, int verb, int n3_live = -1)
 {
     double h[PST_RED_SLOTS];
     float *pcur = p, *pnext = ptrial;
-    PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u2, g.n1, g.n2, g.n3, nw, xline, false, false, 3));
+    PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u2, g.n1, g.n2, g.n3, nw, xline, false, false, 3, n3_live));
     PST_TRY(pst_fetch_record(c, 3, 1, h));
     double usum = h[0];
     for (int iter = 0; iter < niter; iter++) {
-        PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u1, g.n1, g.n2, g.n3, nw, xline, true, false, 4));
+        PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u1, g.n1, g.n2, g.n3, nw, xline, true, false, 4, n3_live));
         int its = 0;
         PST_TRY(pst_divne_run(c, g, u2, u1, dp, mask, w, liter, 1.0f, &its));
         float lam = 1.f;
         double usum2 = 0.;
         int k;
         for (k = 0; k < 8; k++) {
-            PST_TRY(pst_allpass_launch(c, u, pcur, dp, lam, pnext, u2, g.n1, g.n2, g.n3, nw, xline, false, true, 3));
+            PST_TRY(pst_allpass_launch(c, u, pcur, dp, lam, pnext, u2, g.n1, g.n2, g.n3, nw, xline, false, true, 3, n3_live));
             PST_TRY(pst_fetch_record(c, 3, 1, h));
             c->stats.linesearch_evals++;
             usum2 = h[0];
@@ -1396,6 +1536,9 @@ static int check_dip_args(int n1, int n2, int n3, int niter, int liter, int orde
     return PST_OK;
 }
 
+// In a distributed context (pst_ctx_create_dist, nranks > 1) n3 is the GLOBAL number of planes and
+// d_din / d_mask / d_dip_out are this rank's slab (pst_ctx_slab): nz = z1 - z0 planes; d_dip_out
+// holds the slab of the inline dip followed by the slab of the xline dip.
 extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, int n1, int n2, int n3,
                            int niter, int liter, int order, int r1, int r2, int r3, int verb,
                            float *d_dip_out)
@@ -1403,10 +1546,25 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_dip_args(n1, n2, n3, niter, liter, order, r1, r2, r3));
     PST_CUDA(cudaSetDevice(c->device));
-    DipGeom g{n1, n2, n3, r1, r2, r3, (size_t)n1 * n2 * n3};
-    const size_t n = g.n;
-    const size_t scr = tri_scratch_floats(g);
-    const size_t need = (11 * n + scr) * sizeof(float) + 2 * n + 16 * 256;
+    const bool dist = c->comm != nullptr && c->nranks > 1;
+    int z0 = 0, z1 = n3;
+    if (dist) {
+        z0 = (int)(((long)n3 * c->rank) / c->nranks);
+        z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+        const int need_planes = std::max(2 * (r3 > 1 ? r3 : 0), 1);
+        if ((n3 / c->nranks) < need_planes) {
+            pst_set_error("dip: %d planes over %d ranks leaves slabs thinner than 2*r3 = %d", n3, c->nranks, 2 * r3);
+            return PST_EUNSUP;
+        }
+    }
+    const int nz = z1 - z0;
+    DipGeom g = make_geom(n1, n2, nz, r1, r2, r3);
+    g.n3g = n3; g.z0 = z0; g.nglob = (double)n1 * n2 * n3; g.dist = dist;
+    const size_t n = g.n, plane = (size_t)n1 * n2;
+    size_t scr = tri_scratch_floats(g);
+    if (dist) scr = std::max(scr, (size_t)(nz + 2 * r3) * plane);
+    const size_t extra = dist ? (plane * (size_t)(2 * r3 + 2 + 2) + n + plane) : 0;
+    const size_t need = (11 * n + scr + extra) * sizeof(float) + 2 * n + 32 * 256;
     PST_TRY(pst_arena_reserve(c, need));
     pst_arena_reset(c);
     float *u1, *u2, *dp, *ptrial;
@@ -1424,19 +1582,37 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     PST_TRY(pst_arena_get(c, n, &w.gp));
     PST_TRY(pst_arena_get(c, n, &w.tmp));
     PST_TRY(pst_arena_get(c, scr, &w.scr));
+    const float *u = d_din, *um = d_mask;
+    int n3_live = nz - 1;
+    if (dist) {
+        // the xline stencil reads plane i3+1: keep a copy of the slab with the neighbour's first
+        // plane appended (static data: exchanged once per call)
+        float *ue, *dummy;
+        PST_TRY(pst_arena_get(c, n + plane, &ue));
+        PST_TRY(pst_arena_get(c, plane, &dummy));
+        PST_CUDA(cudaMemcpyAsync(ue, d_din, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        PST_TRY(pst_comm_halo_exchange(c, d_din, d_din, dummy, ue + n, plane));
+        u = ue;
+        n3_live = (c->rank == c->nranks - 1) ? nz - 1 : nz;
+        PST_TRY(pst_arena_get(c, plane * (size_t)std::max(r3, 1), &g.hb));
+        PST_TRY(pst_arena_get(c, plane * (size_t)std::max(r3, 1), &g.ha));
+        PST_TRY(pst_arena_get(c, plane, &g.cin));
+        PST_TRY(pst_arena_get(c, plane, &g.cout));
+    }
     if (d_mask) {
+        if (dist) { pst_set_error("dip: mask= is not supported in distributed contexts yet"); return PST_EUNSUP; }
         PST_TRY(pst_arena_get(c, n, &m_in));
         PST_TRY(pst_arena_get(c, n, &m_x));
-        const int grid = (int)min((long)n2 * n3, (long)c->sm_count * 8);
+        const int grid = (int)min((long)n2 * nz, (long)c->sm_count * 8);
         PST_LAUNCH(c, PST_K_OTHER,
-            if (order == 1) mask_kernel<1><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3);
-            else            mask_kernel<2><<<grid, 128, 0, c->stream>>>(d_mask, m_in, m_x, n1, n2, n3));
+            if (order == 1) mask_kernel<1><<<grid, 128, 0, c->stream>>>(um, m_in, m_x, n1, n2, nz, n3_live);
+            else            mask_kernel<2><<<grid, 128, 0, c->stream>>>(um, m_in, m_x, n1, n2, nz, n3_live));
     }
     const int ndip = (n3 == 1) ? 1 : 2;
     PST_CUDA(cudaMemsetAsync(d_dip_out, 0, ndip * n * sizeof(float), c->stream));
-    PST_TRY(gauss_newton(c, g, d_din, d_dip_out, m_in, 0, niter, liter, order, u1, u2, dp, ptrial, w, verb));
+    PST_TRY(gauss_newton(c, g, u, d_dip_out, m_in, 0, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
     if (ndip == 2)
-        PST_TRY(gauss_newton(c, g, d_din, d_dip_out + n, m_x, 1, niter, liter, order, u1, u2, dp, ptrial, w, verb));
+        PST_TRY(gauss_newton(c, g, u, d_dip_out + n, m_x, 1, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -1457,7 +1633,7 @@ extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, i
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smooth3: bad arguments"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
-    DipGeom g{n1, n2, n3, r1, r2, r3, (size_t)n1 * n2 * n3};
+    DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
     const size_t scr = tri_scratch_floats(g);
     PST_TRY(pst_arena_reserve(c, scr * sizeof(float) + 4096));
     pst_arena_reset(c);
@@ -1474,7 +1650,7 @@ extern "C" int pst_divne_dev(pst_ctx *c, float *d_num, float *d_den, float *d_ra
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("divne: bad arguments"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
-    DipGeom g{n1, n2, n3, r1, r2, r3, (size_t)n1 * n2 * n3};
+    DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
     const size_t n = g.n, scr = tri_scratch_floats(g);
     PST_TRY(pst_arena_reserve(c, (7 * n + scr) * sizeof(float) + 16 * 256));
     pst_arena_reset(c);

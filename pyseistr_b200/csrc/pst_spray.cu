@@ -416,6 +416,10 @@ struct SprayPlan {
     int np2, np3, np;
     float eps_reg;                 // regularisation (already squared)
     bool live[PST_MAXSLOT];        // slots that must be produced
+    // plane bookkeeping (global plane indices; n3 above is the GLOBAL extent): the trace-minor
+    // input volumes hold planes [zs0, zs1); outputs are produced for planes [zt0, zt1).
+    // Single GPU: zs = zt = [0, n3).  Distributed: zt = this rank's slab, zs = slab + ns3 halos.
+    int zs0, zs1, zt0, zt1;
 };
 
 static void plan_close_parents(SprayPlan &P)
@@ -448,7 +452,7 @@ typedef int (*chunk_reduce_fn)(pst_ctx *c, void *user, const SprayPlan &P, float
 static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const float *piT, const float *pxT,
                      chunk_reduce_fn reduce, void *user)
 {
-    const int n1 = P.n1, n2 = P.n2, n3 = P.n3, ns3 = P.ns3, nw = P.nw;
+    const int n1 = P.n1, n2 = P.n2, n3 = P.n3, ns3 = P.ns3, nw = P.nw;   // n3: global extent
     const long plane = (long)n1 * n2;
     int nlive = 0;
     for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
@@ -457,8 +461,8 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     const double bytes_per_plane = (double)plane * 4.0 * (nlive + NC);
     int cz = (int)(6.0e9 / bytes_per_plane) - 2 * ns3;
     if (cz < 1) cz = 1;
-    if (cz > n3) cz = n3;
-    const int nzl_max = std::min(n3, cz + 2 * ns3);
+    if (cz > P.zt1 - P.zt0) cz = P.zt1 - P.zt0;
+    const int nzl_max = std::min(P.zs1 - P.zs0, cz + 2 * ns3);
     float *slotbuf[PST_MAXSLOT];
     const int centre = ns3 * P.np2 + P.ns2;
     for (int s = 0; s < P.np; s++) {
@@ -470,13 +474,13 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     const RegC reg = make_reg(P.eps_reg);
     const BTabS tb = make_btab_s(nw);
 
-    for (int z0 = 0; z0 < n3; z0 += cz) {
-        const int z1 = std::min(n3, z0 + cz);
-        const int ze0 = std::max(0, z0 - ns3), ze1 = std::min(n3, z1 + ns3);
+    for (int z0 = P.zt0; z0 < P.zt1; z0 += cz) {
+        const int z1 = std::min(P.zt1, z0 + cz);
+        const int ze0 = std::max(P.zs0, z0 - ns3), ze1 = std::min(P.zs1, z1 + ns3);
         float *slot[PST_MAXSLOT];
         for (int s = 0; s < P.np; s++) slot[s] = slotbuf[s];
-        slot[centre] = const_cast<float *>(dT) + (long)ze0 * plane;
-        const float *pi_c = piT + (long)ze0 * plane, *px_c = pxT ? pxT + (long)ze0 * plane : nullptr;
+        slot[centre] = const_cast<float *>(dT) + (long)(ze0 - P.zs0) * plane;
+        const float *pi_c = piT + (long)(ze0 - P.zs0) * plane, *px_c = pxT ? pxT + (long)(ze0 - P.zs0) * plane : nullptr;
         for (int lev = 1; lev <= P.ns2 + ns3; lev++) {
             for (int s = 0; s < P.np; s++) {
                 const int a = s % P.np2 - P.ns2, b = s / P.np2 - ns3;
@@ -525,7 +529,7 @@ static int reduce_mean(pst_ctx *c, void *user, const SprayPlan &P, float *const 
     SlotPtrs S{};
     for (int s = 0; s < P.np; s++) S.p[s] = slot[s];
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
-    PST_LAUNCH(c, PST_K_SLOTRED, (slot_mean_kernel<<<grid, 256, 0, c->stream>>>(S, P.np, R->outT, plane * z0, plane * (z0 - ze0), count)));
+    PST_LAUNCH(c, PST_K_SLOTRED, (slot_mean_kernel<<<grid, 256, 0, c->stream>>>(S, P.np, R->outT, plane * (z0 - P.zt0), plane * (z0 - ze0), count)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -542,7 +546,7 @@ static int reduce_median(pst_ctx *c, void *user, const SprayPlan &P, float *cons
         S.p[q] = slot[s];
     }
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
-    const long zo = plane * z0, zs = plane * (z0 - ze0);
+    const long zo = plane * (z0 - P.zt0), zs = plane * (z0 - ze0);
     KTimer kt(c, PST_K_SLOTRED);
     switch (nmf) {
         case 3: slot_median_kernel<3><<<grid, 256, 0, c->stream>>>(S, nmf, R->outT, zo, zs, count); break;
@@ -565,8 +569,8 @@ static int reduce_wsum(pst_ctx *c, void *user, const SprayPlan &P, float *const 
     for (int s = 0; s < P.np; s++) S.p[s] = slot[s] + plane * (z0 - ze0);
     const int grid = pst_grid_for(c, (size_t)count, 256, 2);
     PST_LAUNCH(c, PST_K_SLOTRED,
-        if (R->mode == 0) slot_wsum_kernel<0><<<grid, 256, 0, c->stream>>>(S, P.ns2, nullptr, R->outT + plane * z0, count);
-        else              slot_wsum_kernel<1><<<grid, 256, 0, c->stream>>>(S, P.ns2, R->tnorm + plane * z0, R->outT + plane * z0, count));
+        if (R->mode == 0) slot_wsum_kernel<0><<<grid, 256, 0, c->stream>>>(S, P.ns2, nullptr, R->outT + plane * (z0 - P.zt0), count);
+        else              slot_wsum_kernel<1><<<grid, 256, 0, c->stream>>>(S, P.ns2, R->tnorm + plane * (z0 - P.zt0), R->outT + plane * (z0 - P.zt0), count));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -580,16 +584,32 @@ static int check_spray_args(int n1, int n2, int n3, int ns2, int ns3, int order)
     return PST_OK;
 }
 
-// kind: 0 = mean (3-D), 1 = median (3-D), 2 = weighted normalised smooth (2-D), 3 = median (2-D)
+int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_hi, float *recv_lo,
+                           float *recv_hi, size_t count);                                   // pst_comm.cu
+
+// kind: 0 = mean (3-D), 1 = median (3-D), 2 = weighted normalised smooth (2-D), 3 = median (2-D).
+// Distributed contexts: n3 is the GLOBAL plane count, the pointers are this rank's slab; the
+// ns3-plane halos of din / dipi / dipx are exchanged once and halo sources are sprayed redundantly.
 static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const float *d_dipi, const float *d_dipx,
                             int n1, int n2, int n3, int ns2, int ns3, int nmf, int order, float eps_reg,
                             float *d_out)
 {
     PST_CUDA(cudaSetDevice(c->device));
+    const bool dist = c->comm != nullptr && c->nranks > 1;
+    int z0 = 0, z1 = n3;
+    if (dist) {
+        z0 = (int)(((long)n3 * c->rank) / c->nranks);
+        z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+        if (n3 / c->nranks < std::max(ns3, 1)) { pst_set_error("spray: slabs thinner than the xline spray radius"); return PST_EUNSUP; }
+    }
+    const int nz = z1 - z0;
     SprayPlan P{};
     P.n1 = n1; P.n2 = n2; P.n3 = n3; P.ns2 = ns2; P.ns3 = ns3; P.nw = order;
     P.np2 = 2 * ns2 + 1; P.np3 = 2 * ns3 + 1; P.np = P.np2 * P.np3;
     P.eps_reg = eps_reg;
+    P.zt0 = z0; P.zt1 = z1;
+    P.zs0 = std::max(0, z0 - ns3); P.zs1 = std::min(n3, z1 + ns3);
+    const int ne = P.zs1 - P.zs0;                       // stored planes (slab + halos)
     const int cen = (P.np - 1) / 2;
     for (int s = 0; s < P.np; s++) P.live[s] = (kind == 0 || kind == 2);
     if (kind == 1 || kind == 3) {
@@ -602,32 +622,41 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     int nlive = 0;
     for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
 
-    const size_t n = (size_t)n1 * n2 * n3;
     const long plane = (long)n1 * n2;
+    const size_t n = (size_t)plane * nz, nex = (size_t)plane * ne;
     const int NC = 2 * order + 2;
-    // arena: 3 transposed inputs + transposed output (+ norm volume) + chunk buffers
     double chunk_planes = 6.0e9 / ((double)plane * 4.0 * (nlive + NC));
-    if (chunk_planes > n3) chunk_planes = n3;
-    const size_t nzl = (size_t)std::min<double>(n3, std::max(1.0, floor(chunk_planes) - 2 * ns3) + 2 * ns3);
-    const size_t need = (5 * n + (size_t)plane * nzl * (nlive + NC)) * sizeof(float) + 64 * 256 + (size_t)nlive * 256;
+    if (chunk_planes > nz) chunk_planes = nz;
+    const size_t nzl = (size_t)std::min<double>(ne, std::max(1.0, floor(chunk_planes) - 2 * ns3) + 2 * ns3);
+    const size_t need = (4 * nex + 2 * n + (size_t)plane * nzl * (nlive + NC)) * sizeof(float) + 64 * 256 + (size_t)nlive * 256;
     PST_TRY(pst_arena_reserve(c, need));
     pst_arena_reset(c);
     float *dT, *piT, *pxT = nullptr, *outT, *tnorm = nullptr;
-    PST_TRY(pst_arena_get(c, n, &dT));
-    PST_TRY(pst_arena_get(c, n, &piT));
-    if (d_dipx) PST_TRY(pst_arena_get(c, n, &pxT));
+    PST_TRY(pst_arena_get(c, nex, &dT));
+    PST_TRY(pst_arena_get(c, nex, &piT));
+    if (d_dipx) PST_TRY(pst_arena_get(c, nex, &pxT));
     PST_TRY(pst_arena_get(c, n, &outT));
-    PST_TRY(transpose_planes(c, d_din, dT, n2, n1, n3));
-    PST_TRY(transpose_planes(c, d_dipi, piT, n2, n1, n3));
-    if (d_dipx) PST_TRY(transpose_planes(c, d_dipx, pxT, n2, n1, n3));
+    const size_t off = (size_t)plane * (z0 - P.zs0);    // slab position inside the stored range
+    PST_TRY(transpose_planes(c, d_din, dT + off, n2, n1, nz));
+    PST_TRY(transpose_planes(c, d_dipi, piT + off, n2, n1, nz));
+    if (d_dipx) PST_TRY(transpose_planes(c, d_dipx, pxT + off, n2, n1, nz));
+    if (dist && ns3 > 0) {
+        const size_t cnt = (size_t)plane * ns3;
+        float *vols[3] = {dT, piT, pxT};
+        for (float *v : vols) {
+            if (!v) continue;
+            PST_TRY(pst_comm_halo_exchange(c, v + off, v + off + n - cnt, v, v + off + n, cnt));
+        }
+    }
     ReduceOut R{outT, nmf, nullptr, 0};
     if (kind == 0) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_mean, &R));
     else if (kind == 1 || kind == 3) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_median, &R));
     else {
         // pwsmooth_set (sof_cfuns.c:1113-1132): normalisation = smooth of a volume of ones
         PST_TRY(pst_arena_get(c, n, &tnorm));
-        float *ones = outT;            // reuse: outT is written only by the second pass
-        PST_LAUNCH(c, PST_K_OTHER, (fill_kernel_s<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(ones, 1.0f, n)));
+        float *ones;
+        PST_TRY(pst_arena_get(c, nex, &ones));
+        PST_LAUNCH(c, PST_K_OTHER, (fill_kernel_s<<<pst_grid_for(c, nex, 256), 256, 0, c->stream>>>(ones, 1.0f, nex)));
         const size_t mark = c->arena_used;
         ReduceOut R0{tnorm, 0, nullptr, 0};
         PST_TRY(spray_run(c, P, ones, piT, pxT, reduce_wsum, &R0));
@@ -635,7 +664,7 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
         ReduceOut R1{outT, 0, tnorm, 1};
         PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_wsum, &R1));
     }
-    PST_TRY(transpose_planes(c, outT, d_out, n1, n2, n3));
+    PST_TRY(transpose_planes(c, outT, d_out, n1, n2, nz));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
