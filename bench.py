@@ -245,28 +245,33 @@ def main():
 
     import pyseistr_b200 as ps
     from pyseistr_b200 import _lib, synth
+    from pyseistr_b200 import dist as pd
 
-    ctx = ps.Context(local)
-    lib = ctx.lib
     n1, n2, n3g = parse_shape(args)
-    # N > 1 (round 1): the cube is cut into `world` n3-slabs processed independently (no halo /
-    # carry exchange yet, so slab edges differ from the single-GPU result).
-    z0 = (n3g * rank) // world
-    z1 = (n3g * (rank + 1)) // world
+    # N > 1: the cube is cut into n3-slabs, one per rank; the library exchanges halos, carry planes
+    # of the axis-3 running sums and all-reduces the CG scalars over NCCL.
+    if world > 1:
+        pd.check_slabs(n3g, world, r3=DIP_KW["rect"][2], ns3=SOMF_KW["r2"])
+        ctx = pd.context_from_torch(dist, local)
+        z0, z1 = ctx.slab(n3g)
+    else:
+        ctx = ps.Context(local)
+        z0, z1 = 0, n3g
+    lib = ctx.lib
     n3 = z1 - z0
     N = n1 * n2 * n3
     Nglobal = n1 * n2 * n3g
 
-    # ---- synthetic input in pinned host memory
+    # ---- synthetic input in pinned host memory (each rank generates its slab of the same cube)
     h_in, _p1 = pinned_array(lib, N)
     cube = h_in.reshape((n1, n2, n3), order="F")
-    full_seed = 7
-    if world == 1:
-        synth.cube_big(n1, n2, n3, seed=full_seed, out=cube)
-    else:
-        tmp = synth.cube_big(n1, n2, n3, seed=full_seed + rank)
-        cube[...] = tmp
-        del tmp
+    _, mx = synth.cube_big(n1, n2, n3g, seed=7, out=cube, z0=z0, z1=z1, normalise=False)
+    if dist is not None:
+        import torch
+        t = torch.tensor([mx], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mx = float(t.item())
+    synth.scale_by(cube, mx)
     h_dip, _p2 = pinned_array(lib, 2 * N)
     h_out, _p3 = pinned_array(lib, N)
 
@@ -282,9 +287,9 @@ def main():
     rmf = 2 * SOMF_KW["r1"] * SOMF_KW["r2"] + 1
 
     def step_dev():
-        _lib.check(lib.pst_dip_dev(ctx.handle, d_in, None, n1, n2, n3, DIP_KW["niter"], DIP_KW["liter"],
+        _lib.check(lib.pst_dip_dev(ctx.handle, d_in, None, n1, n2, n3g, DIP_KW["niter"], DIP_KW["liter"],
                                    DIP_KW["order"], *DIP_KW["rect"], 0, d_dip))
-        _lib.check(lib.pst_somf3d_dev(ctx.handle, d_in, d_dip, d_dipx, n1, n2, n3, SOMF_KW["r1"], SOMF_KW["r2"],
+        _lib.check(lib.pst_somf3d_dev(ctx.handle, d_in, d_dip, d_dipx, n1, n2, n3g, SOMF_KW["r1"], SOMF_KW["r2"],
                                       rmf, SOMF_KW["option"], SOMF_KW["order"], d_out))
 
     def barrier():
@@ -321,9 +326,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         def step_e2e():
-            _lib.check(lib.pst_dip(ctx.handle, P(h_in), None, n1, n2, n3, DIP_KW["niter"], DIP_KW["liter"],
+            _lib.check(lib.pst_dip(ctx.handle, P(h_in), None, n1, n2, n3g, DIP_KW["niter"], DIP_KW["liter"],
                                    DIP_KW["order"], 0.01, 1.0, 1e-6, *DIP_KW["rect"], 0, P(h_dip)))
-            _lib.check(lib.pst_somf3d(ctx.handle, P(h_in), P(h_dip), P(h_dip, N), n1, n2, n3, SOMF_KW["r1"],
+            _lib.check(lib.pst_somf3d(ctx.handle, P(h_in), P(h_dip), P(h_dip, N), n1, n2, n3g, SOMF_KW["r1"],
                                       SOMF_KW["r2"], rmf, SOMF_KW["option"], SOMF_KW["order"], 0.01, 0, P(h_out)))
         ctx.free(d_out); ctx.free(d_dip); ctx.free(d_in)
         step_e2e()                                   # warm-up (allocations, page mapping)
@@ -374,7 +379,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name((n1, n2, n3g)),
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent n3-slabs (no halo exchange yet)",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"{world} n3-slabs, NCCL: halos (xline stencil, spray), carry planes (axis-3 running sums), "
+                   f"all-reduced CG scalars",
                    "l2_policy": "inputs (4 B x voxels per volume) are far larger than the 126 MB L2",
                    "executed": {"cg_iterations_per_step": st["cg_iterations"] / args.steps,
                                 "gn_iterations_per_step": st["gn_iterations"] / args.steps,
@@ -387,6 +394,9 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if world > 1:
+        # the class timers above are rank 0's; N = its slab
+        roof["note"] = "per-launch times and bytes are rank 0's slab"
     if not args.no_cpu_baseline and world == 1:
         shape = tuple(int(v) for v in args.cpu_shape.split(","))
         nproc = os.cpu_count() or 1

@@ -63,10 +63,13 @@ def smooth_dips(n1, n2, n3=1, seed=1, amp=0.6, dtype=np.float32):
     return pi_, px_
 
 
-def cube_big(n1, n2, n3, seed=0, noise=0.05, nevents=4, threads=None, out=None):
+def cube_big(n1, n2, n3, seed=0, noise=0.05, nevents=4, threads=None, out=None, z0=0, z1=None,
+             normalise=True):
     """Same family of cubes as ``cube`` but generated plane-chunk by plane-chunk in float32 on a
     thread pool, for bench-sized volumes (1e9 voxels).  Writes into ``out`` (any float32
-    Fortran-ordered (n1,n2,n3) array, e.g. a pinned buffer) when given."""
+    Fortran-ordered array, e.g. a pinned buffer) when given.  ``z0:z1`` selects a slab of planes
+    of the same global cube (multi-GPU ranks generate only their slab); returns (array, max|d|)
+    when ``normalise`` is False so the caller can normalise with the global maximum."""
     import os
     from concurrent.futures import ThreadPoolExecutor
     rng = np.random.default_rng(seed)
@@ -76,8 +79,9 @@ def cube_big(n1, n2, n3, seed=0, noise=0.05, nevents=4, threads=None, out=None):
                        t0=rng.uniform(0.2, 0.8) * n1,
                        curv=0.0 if k else rng.uniform(-0.2, 0.2) / max(n2, 2),
                        amp=rng.uniform(0.5, 1.0) * rng.choice([-1.0, 1.0])))
+    z1 = n3 if z1 is None else z1
     if out is None:
-        out = np.empty((n1, n2, n3), dtype=np.float32, order="F")
+        out = np.empty((n1, n2, z1 - z0), dtype=np.float32, order="F")
     t = np.arange(n1, dtype=np.float32)[:, None]
     x = (np.arange(n2, dtype=np.float32) - n2 / 2)[None, :]
     threads = threads or min(32, os.cpu_count() or 1)
@@ -91,17 +95,28 @@ def cube_big(n1, n2, n3, seed=0, noise=0.05, nevents=4, threads=None, out=None):
             acc += np.float32(e["amp"]) * (1.0 - 2.0 * a) * np.exp(-a)
         if noise:
             acc += np.float32(noise) * np.random.default_rng([seed, i3]).standard_normal((n1, n2), dtype=np.float32)
-        out[:, :, i3] = acc
+        out[:, :, i3 - z0] = acc
         return float(np.abs(acc).max())
 
     with ThreadPoolExecutor(threads) as ex:
-        mx = max(ex.map(plane, range(n3)))
-    if mx > 0:
-        scale = np.float32(1.0 / mx)
+        mx = max(ex.map(plane, range(z0, z1)))
+    if not normalise:
+        return out, mx
+    scale_by(out, mx, threads)
+    return out
 
-        def norm(i3):
-            out[:, :, i3] *= scale
 
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(norm, range(n3)))
+def scale_by(out, mx, threads=None):
+    """out /= mx, plane by plane on a thread pool (second half of ``cube_big``)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    if mx <= 0:
+        return out
+    scale = np.float32(1.0 / mx)
+
+    def norm(i3):
+        out[:, :, i3] *= scale
+
+    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(norm, range(out.shape[2])))
     return out
