@@ -176,7 +176,7 @@ def run_reference_cpu(shape, nproc, steps):
     return vals, kind
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, real_stdout):
     if rank != 0:
         return 0
     nproc = os.cpu_count() or 1
@@ -201,7 +201,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(real_stdout, line)
     return 0
 
 
@@ -218,6 +218,21 @@ def workload_name(shape):
 
 
 def main():
+    # everything but the final JSON line goes to stderr (NCCL prints its version to stdout)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def emit(real_stdout, line):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -234,7 +249,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return reference_arm(args, rank, world, real_stdout)
 
     dist = None
     if world > 1:
@@ -349,6 +364,9 @@ def main():
                "path": "pst_dip(host)->pst_somf3d(host): H2D din; D2H dipi,dipx; H2D din,dipi,dipx; D2H out"}
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel class: CUDA events around every launch of the class
@@ -408,7 +426,10 @@ def main():
         except Exception as e:      # the checker is optional for the number, never for the product
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": nproc, "kind": "unavailable",
                                     "sample": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(real_stdout, line)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -89,6 +89,17 @@ int pst_comm_recv(pst_ctx *c, float *d_buf, size_t count, int peer)
     return PST_OK;
 }
 
+// one NCCL group with an optional send and an optional receive (null pointer = skip)
+int pst_comm_sendrecv(pst_ctx *c, const float *send, size_t nsend, int peer_out, float *recv, size_t nrecv, int peer_in)
+{
+    if ((!send || nsend == 0) && (!recv || nrecv == 0)) return PST_OK;
+    PST_NCCL(g_nccl.GroupStart());
+    if (send && nsend) PST_NCCL(g_nccl.Send(send, nsend, ncclFloat32, peer_out, c->comm->comm, c->stream));
+    if (recv && nrecv) PST_NCCL(g_nccl.Recv(recv, nrecv, ncclFloat32, peer_in, c->comm->comm, c->stream));
+    PST_NCCL(g_nccl.GroupEnd());
+    return PST_OK;
+}
+
 // Exchange plane halos with both neighbours in one NCCL group:
 //   send_lo (count floats) -> rank-1,   recv_lo <- rank-1   (their send_hi)
 //   send_hi               -> rank+1,   recv_hi <- rank+1   (their send_lo)

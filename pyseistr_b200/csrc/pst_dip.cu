@@ -1118,33 +1118,35 @@ tri3_dist_fwd_kernel(const Tri3Args A)
     A.cout[l] = s;
 }
 
+// backward sum fused with fold2 (:458-484): y_i = (B_{i+nb} + B_{nb+n3g+(n3g-1-i)}[i >= n3g-nb])
+// + B_{nb-1-i}[i < nb].  Every term lives on the owning rank (slab height >= 2nb): the right-pad
+// values (last rank, visited first) are parked in their target rows, the left-pad values
+// (rank 0, visited last) are added in place.
 __global__ void __launch_bounds__(128)
 tri3_dist_bwd_kernel(const Tri3Args A)
 {
     const long l = A.l0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= A.l1) return;
+    const int nb = A.nb, n3g = A.n3g;
     float s = A.cin ? A.cin[l] : 0.f;
-    for (int k = A.K1 - 1; k >= A.K0; k--) {
+    int k = A.K1 - 1;
+    for (; k >= nb + n3g && k >= A.K0; k--) {               // right pad (last rank only)
         s += A.F[(long)(k - A.K0) * A.L + l];
-        A.F[(long)(k - A.K0) * A.L + l] = s;
+        const int gi = n3g - 1 - (k - nb - n3g);
+        A.dst[(long)(gi - A.z0) * A.L + l] = s;
+    }
+    for (; k >= nb && k >= A.K0; k--) {                     // middle: global plane gi = k - nb
+        s += A.F[(long)(k - A.K0) * A.L + l];
+        const int gi = k - nb;
+        float v = s;
+        if (gi >= n3g - nb) v = v + A.dst[(long)(gi - A.z0) * A.L + l];
+        A.dst[(long)(gi - A.z0) * A.L + l] = v;
+    }
+    for (; k >= A.K0; k--) {                                // left pad (rank 0 only)
+        s += A.F[(long)(k - A.K0) * A.L + l];
+        A.dst[(long)(nb - 1 - k - A.z0) * A.L + l] += s;
     }
     A.cout[l] = s;
-}
-
-// fold2 (:458-484): every term lives on the owning rank (needs slab height >= 2nb)
-__global__ void __launch_bounds__(256)
-tri3_dist_fold_kernel(const Tri3Args A)
-{
-    const long total = (long)A.nz * A.L;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int i = (int)(e / A.L);
-        const long l = e - (long)i * A.L;
-        const int gi = A.z0 + i;
-        float v = A.F[(long)(gi + A.nb - A.K0) * A.L + l];
-        if (gi >= A.n3g - A.nb) v = v + A.F[(long)(A.nb + A.n3g + (A.n3g - 1 - gi) - A.K0) * A.L + l];
-        if (gi < A.nb) v = v + A.F[(long)(A.nb - 1 - gi - A.K0) * A.L + l];
-        A.dst[e] = v;
-    }
 }
 
 // ---- shaping operator driver ------------------------------------------------------------
@@ -1226,6 +1228,7 @@ static int tile_launch(pst_ctx *c, int cls, int epi, bool contig, bool vec, cons
 
 int pst_comm_send(pst_ctx *c, const float *d_buf, size_t count, int peer);            // pst_comm.cu
 int pst_comm_recv(pst_ctx *c, float *d_buf, size_t count, int peer);
+int pst_comm_sendrecv(pst_ctx *c, const float *send, size_t nsend, int peer_out, float *recv, size_t nrecv, int peer_in);
 int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_hi, float *recv_lo,
                            float *recv_hi, size_t count);
 
@@ -1250,18 +1253,20 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     for (int pass = 0; pass < 2; pass++) {          // 0: forward (carries flow up), 1: backward (down)
         const bool has_in = pass == 0 ? !first : !last, has_out = pass == 0 ? !last : !first;
         const int peer_in = pass == 0 ? c->rank - 1 : c->rank + 1, peer_out = pass == 0 ? c->rank + 1 : c->rank - 1;
+        if (has_in) PST_TRY(pst_comm_recv(c, g.cin, (size_t)std::min(L, per), peer_in));
         for (long l0 = 0; l0 < L; l0 += per) {
             const long l1 = std::min(L, l0 + per);
-            if (has_in) PST_TRY(pst_comm_recv(c, g.cin + l0, (size_t)(l1 - l0), peer_in));
             A.l0 = l0; A.l1 = l1; A.cin = has_in ? g.cin : nullptr; A.cout = g.cout;
             const unsigned blocks = (unsigned)((l1 - l0 + 127) / 128);
             PST_LAUNCHB(c, PST_K_TRI3, bytes_half * (double)(l1 - l0) / (double)L,
                 if (pass == 0) tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A);
                 else           tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A));
-            if (has_out) PST_TRY(pst_comm_send(c, g.cout + l0, (size_t)(l1 - l0), peer_out));
+            // one NCCL group: hand this chunk's carry on, and receive the next chunk's
+            const long n0 = l0 + per, n1c = std::min(L, n0 + per);
+            PST_TRY(pst_comm_sendrecv(c, has_out ? g.cout + l0 : nullptr, (size_t)(l1 - l0), peer_out,
+                                      (has_in && n0 < L) ? g.cin + n0 : nullptr, (size_t)std::max(0L, n1c - n0), peer_in));
         }
     }
-    PST_LAUNCHB(c, PST_K_TRI3, 0.0, (tri3_dist_fold_kernel<<<pst_grid_for(c, g.n, 256), 256, 0, c->stream>>>(A)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
