@@ -125,6 +125,17 @@ int pst_somean2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n
 int pst_somf2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n2, int n3,
                int ns, int nmf, int option, int order, float eps, int verb, float *out);
 
+/* ---- 3-D structure-oriented interpolation (PWD-residual CG).  Replaces soint3dcfun.csoint3d
+ * (pyseistr/src/soint3d_cfuns.c:2405-2508, "OOOOiiiiiiiiiifi"); called by soint3dc
+ * (pyseistr/soint3d.py:65-108).  GPU path: njs = 1, drift = 0, var = 0 (others: PST_EUNSUP).
+ * hasmask=1: known samples are mask != 0, else din != 0.  seed is unused when var = 0. */
+int pst_soint3d(pst_ctx *ctx, const float *din, const float *mask, const float *dipi, const float *dipx,
+                int n1, int n2, int n3, int nw, int nj1, int nj2, int niter, int drift, int seed,
+                int hasmask, float var, int verb, float *out);
+int pst_soint3d_dev(pst_ctx *ctx, const float *d_din, const float *d_mask, const float *d_dipi,
+                    const float *d_dipx, int n1, int n2, int n3, int nw, int nj1, int nj2, int niter,
+                    int drift, int seed, int hasmask, float var, int verb, float *d_out);
+
 /* ---- building blocks exposed for parity tests and for the smoothing wrapper (SURVEY §8f
  * rank 1: dipcfun.smoothcf, dip_cfuns.c:2006-2123 with adj=0).  Device pointers. */
 int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1, int n2, int n3,

@@ -145,3 +145,12 @@ def somf2dc(dn, dip, ns, order, eps, option=1, verb=0):
     if rc:
         raise ValueError("oracle: unsupported somf2d option")
     return np.squeeze(out.reshape(n1, n2, n3, order="F"))
+
+
+def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=(1, 1), drift=0, seed=202223, hasmask=1, var=0, verb=0):
+    n1, n2, n3 = _shape3(din)
+    d, a, b = _F(din), _F(dipi), _F(dipx)
+    m = _F(mask) if hasmask else None
+    out = np.zeros_like(d)
+    lib().pso_soint3d(_p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, n3, int(order), int(niter), _p(out))
+    return out.reshape(n1, n2, n3, order="F")

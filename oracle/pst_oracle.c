@@ -701,3 +701,98 @@ int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int n
     free(u); predictor_free(P);
     return 0;
 }
+
+/* ------------------------------------------------------------------ PWD-residual interpolation */
+
+/* allpass3_lop :625-729 (drift=false, nj=1): y[0:N] = inline PWD of x, y[N:2N] = xline PWD;
+ * adjoint scatters in the same loop order. */
+static void pwd3_lop(int adj, int add, int n1, int n2, int n3, int nw, const float *pp, const float *qq,
+                     float *xx, float *yy)
+{
+    size_t n = (size_t)n1 * n2 * n3;
+    float flt[MAXTAP];
+    if (!add) {
+        if (adj) memset(xx, 0, n * sizeof(float));
+        else     memset(yy, 0, 2 * n * sizeof(float));
+    }
+    for (int iz = 0; iz < n3; iz++)
+        for (int iy = 0; iy < n2 - 1; iy++)
+            for (int ix = nw; ix < n1 - nw; ix++) {
+                long i = ix + (long)n1 * (iy + (long)n2 * iz);
+                pso_passfilter(nw, pp[i], flt);
+                for (int iw = 0; iw <= 2 * nw; iw++) {
+                    int is = iw - nw;
+                    if (adj) { xx[i + n1 + is] += yy[i] * flt[iw]; xx[i - is] -= yy[i] * flt[iw]; }
+                    else     yy[i] += (xx[i + n1 + is] - xx[i - is]) * flt[iw];
+                }
+            }
+    long pl = (long)n1 * n2;
+    for (int iz = 0; iz < n3 - 1; iz++)
+        for (int iy = 0; iy < n2; iy++)
+            for (int ix = nw; ix < n1 - nw; ix++) {
+                long i = ix + (long)n1 * (iy + (long)n2 * iz);
+                pso_passfilter(nw, qq[i], flt);
+                for (int iw = 0; iw <= 2 * nw; iw++) {
+                    int is = iw - nw;
+                    if (adj) { xx[i + pl + is] += yy[i + n] * flt[iw]; xx[i - is] -= yy[i + n] * flt[iw]; }
+                    else     yy[i + n] += (xx[i + pl + is] - xx[i - is]) * flt[iw];
+                }
+            }
+}
+
+static float sumsq_f(size_t n, const float *x)       /* ps_cblas_snrm2 :805-818: float sum of squares */
+{
+    float s = 0.0;
+    for (size_t i = 0; i < n; i++) s += x[i] * x[i];
+    return s;
+}
+
+int pso_soint3d(const float *din, const float *mask, const float *dipi, const float *dipx,
+                int n1, int n2, int n3, int order, int niter, float *out)
+{
+    size_t n = (size_t)n1 * n2 * n3, ny = 2 * n;
+    float *x = out, *g = falloc(n), *rr = falloc(ny), *gg = falloc(ny), *S = falloc(n), *Ss = falloc(ny);
+    unsigned char *known = (unsigned char *)malloc(n);
+    for (size_t i = 0; i < n; i++) known[i] = mask ? (mask[i] != 0.f) : (din[i] != 0.f);
+    /* ps_solver :1018-1040: rr = -dat (dat = 0 when var = 0); x = x0; rr += L x */
+    for (size_t i = 0; i < ny; i++) rr[i] = -0.0f;
+    memcpy(x, din, n * sizeof(float));
+    pwd3_lop(0, 1, n1, n2, n3, order, dipi, dipx, x, rr);
+    float dpr0 = sumsq_f(ny, rr), dpg0 = 1.f, dpr, dpg;
+    int first = 1;
+    for (int iter = 0; iter < niter; iter++) {
+        pwd3_lop(1, 0, n1, n2, n3, order, dipi, dipx, g, rr);
+        for (size_t i = 0; i < n; i++) if (known[i]) g[i] = 0.0;
+        pwd3_lop(0, 0, n1, n2, n3, order, dipi, dipx, g, gg);
+        if (iter == 0) { dpg0 = sumsq_f(n, g); dpr = 1.; dpg = 1.; }
+        else { dpr = sumsq_f(ny, rr) / dpr0; dpg = sumsq_f(n, g) / dpg0; }
+        if (dpr < 1.e-12f || dpg < 1.e-12f) break;
+        /* ps_cgstep :826-877 */
+        double alfa, beta;
+        if (first) {
+            first = 0;
+            memset(S, 0, n * sizeof(float)); memset(Ss, 0, ny * sizeof(float));
+            beta = 0.0;
+            alfa = ddot(ny, gg, gg);
+            if (alfa <= 0.) continue;
+            alfa = -ddot(ny, gg, rr) / alfa;
+        } else {
+            double gdg = ddot(ny, gg, gg), sds = ddot(ny, Ss, Ss), gds = ddot(ny, gg, Ss);
+            if (gdg == 0. || sds == 0.) continue;
+            double determ = 1.0 - (gds / gdg) * (gds / sds);
+            if (determ > 1.e-12f) determ *= gdg * sds; else determ = gdg * sds * 1.e-12f;
+            double gdr = -ddot(ny, gg, rr), sdr = -ddot(ny, Ss, rr);
+            alfa = (sds * gdr - gds * sdr) / determ;
+            beta = (-gds * gdr + gdg * sdr) / determ;
+        }
+        float fb = (float)beta, fa = (float)alfa;
+        for (size_t i = 0; i < n; i++) S[i] *= fb;
+        for (size_t i = 0; i < n; i++) S[i] += fa * g[i];
+        for (size_t i = 0; i < ny; i++) Ss[i] *= fb;
+        for (size_t i = 0; i < ny; i++) Ss[i] += fa * gg[i];
+        for (size_t i = 0; i < n; i++) x[i] += S[i];
+        for (size_t i = 0; i < ny; i++) rr[i] += Ss[i];
+    }
+    free(g); free(rr); free(gg); free(S); free(Ss); free(known);
+    return 0;
+}

@@ -54,6 +54,12 @@ int pso_somean2d(const float *din, const float *dip, int n1, int n2, int n3, int
 int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int ns, int nmf,
                int option, int order, float eps, float *out);
 
+/* csoint3d: soint3d_cfuns.c:2405-2508 with var=0, drift=0, nj1=nj2=1 (PWD-residual CG interpolation:
+ * allpass3_lop :625-729, ps_solver :894-1174 with known mask and x0, ps_cgstep :826-877).
+ * mask may be NULL (hasmask=0: known = data != 0). */
+int pso_soint3d(const float *din, const float *mask, const float *dipi, const float *dipx,
+                int n1, int n2, int n3, int order, int niter, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,6 +155,27 @@ def somf2dc(dn, dip, ns, order, eps, option=1, verb=1, ctx=None):
     return np.squeeze(out.reshape(n1, n2, n3, order="F"))
 
 
+def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=[1, 1], drift=0, seed=202223, hasmask=1, var=0,
+             verb=1, ctx=None):
+    """3-D structure-oriented interpolation: CG on the inline + xline PWD residual with the known
+    samples held fixed (reference pyseistr/soint3d.py:65-108 -> csoint3d, soint3d_cfuns.c:2405).
+    GPU path: njs=[1,1], drift=0, var=0; anything else raises (PST_EUNSUP)."""
+    din = np.asarray(din)
+    n1, n2, n3 = _shape3(din)
+    c = _ctx(ctx)
+    d, a, b = _F(din), _F(dipi), _F(dipx)
+    m = _F(mask) if mask is not None else None
+    if a.size != d.size or b.size != d.size or (m is not None and m.size != d.size):
+        raise ValueError("data, mask and slope volumes must have the same size")
+    if hasmask and m is None:
+        raise ValueError("hasmask=1 needs a mask")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_soint3d(c.handle, _p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, n3,
+                                 int(order), int(njs[0]), int(njs[1]), int(niter), int(drift), int(seed),
+                                 int(hasmask), float(var), int(verb), _p(out)))
+    return out.reshape(n1, n2, n3, order="F")
+
+
 def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=0, ctx=None):
     """N-D triangle smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf,
     dip_cfuns.c:2006-2123).  GPU path: the ps_smooth2 kernel dip3d uses, i.e. adj=0, no

@@ -434,6 +434,27 @@ extern "C" int pst_somf2d(pst_ctx *c, const float *din, const float *dip, int n1
     return PST_OK;
 }
 
+extern "C" int pst_soint3d(pst_ctx *c, const float *din, const float *mask, const float *dipi, const float *dipx,
+                           int n1, int n2, int n3, int nw, int nj1, int nj2, int niter, int drift, int seed,
+                           int hasmask, float var, int verb, float *out)
+{
+    PST_ENTRY(c);
+    if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("soint3d: null pointer or bad shape"); return PST_EINVAL; }
+    if (hasmask && !mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, m, a, b, o;
+    PST_TRY(up(c, d, din, n));
+    if (hasmask) PST_TRY(up(c, m, mask, n));
+    PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_soint3d_dev(c, d.f(), hasmask ? m.f() : nullptr, a.f(), b.f(), n1, n2, n3, nw, nj1, nj2, niter, drift, seed,
+                            hasmask, var, verb, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
 extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
                            float *out)
 {

@@ -1672,3 +1672,260 @@ extern "C" int pst_divne_dev(pst_ctx *c, float *d_num, float *d_den, float *d_ra
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
 }
+
+// =======================================================================================
+// soint3dc: structure-oriented interpolation by minimising the 3-D PWD residual with CG.
+// Replaces (reference pyseistr/src/soint3d_cfuns.c) allpass3_lop :625-729, ps_cgstep :826-877,
+// ps_solver :894-1174 (options actually used: "known", "x0") and the csoint3d driver :2405-2508.
+// The adjoint, a scatter in the reference, is evaluated as a gather that adds the contributions
+// of every target in the reference's own order (source index ascending, inline operator before
+// xline), so the vectors stay bit-identical; the five CG dots are double tree reductions.
+// =======================================================================================
+
+// taps of the inline / xline B-filters at every voxel, stored tap-major ([w][N]) : the slopes are
+// fixed during the solve, so passfilter (20 double multiplies) runs once per voxel, not per iteration
+template <int NW>
+__global__ void __launch_bounds__(256)
+pwd3_taps_kernel(const float *__restrict__ pp, const float *__restrict__ qq, float *__restrict__ fi,
+                 float *__restrict__ fx, size_t n, BTab tb)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float a[2 * NW + 1];
+        pst_passfilter<NW>(tb, pp[i], a);
+#pragma unroll
+        for (int w = 0; w <= 2 * NW; w++) fi[(size_t)w * n + i] = a[w];
+        pst_passfilter<NW>(tb, qq[i], a);
+#pragma unroll
+        for (int w = 0; w <= 2 * NW; w++) fx[(size_t)w * n + i] = a[w];
+    }
+}
+
+// forward: y[0:N] (+)= inline PWD of x, y[N:2N] (+)= xline PWD.  DOTS: also the five dots of
+// ps_cgstep (:853-863) of the freshly computed gg with Ss and rr.
+template <int NW, bool ADD, bool DOTS>
+__global__ void __launch_bounds__(256)
+pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const float *__restrict__ fx,
+                float *__restrict__ y, const float *__restrict__ Ss, const float *__restrict__ rr,
+                int n1, int n2, int n3, double *__restrict__ partial)
+{
+    const size_t n = (size_t)n1 * n2 * n3;
+    const long pl = (long)n1 * n2;
+    double acc[5] = {0., 0., 0., 0., 0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int i1 = (int)(i % n1), i2 = (int)((i / n1) % n2), i3 = (int)(i / pl);
+        float yi = ADD ? y[i] : 0.f, yx = ADD ? y[i + n] : 0.f;
+        if (i1 >= NW && i1 < n1 - NW) {
+            if (i2 < n2 - 1) {
+#pragma unroll
+                for (int w = 0; w <= 2 * NW; w++) { const int s = w - NW; yi += (x[i + n1 + s] - x[i - s]) * fi[(size_t)w * n + i]; }
+            }
+            if (i3 < n3 - 1) {
+#pragma unroll
+                for (int w = 0; w <= 2 * NW; w++) { const int s = w - NW; yx += (x[i + pl + s] - x[i - s]) * fx[(size_t)w * n + i]; }
+            }
+        }
+        y[i] = yi;
+        y[i + n] = yx;
+        if (DOTS) {
+            const float s0 = Ss[i], s1 = Ss[i + n], r0 = rr[i], r1 = rr[i + n];
+            acc[0] += (double)yi * yi + (double)yx * yx;          // gg.gg
+            acc[1] += (double)s0 * s0 + (double)s1 * s1;          // Ss.Ss
+            acc[2] += (double)yi * s0 + (double)yx * s1;          // gg.Ss
+            acc[3] += (double)yi * r0 + (double)yx * r1;          // gg.rr
+            acc[4] += (double)s0 * r0 + (double)s1 * r1;          // Ss.rr
+        }
+    }
+    if (DOTS) pst_block_reduce<5>(acc, partial);
+}
+
+// adjoint as a gather, then the known-sample mask (ps_solver :1062-1066); partial of g.g
+template <int NW>
+__global__ void __launch_bounds__(256)
+pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, const float *__restrict__ fx,
+                const unsigned char *__restrict__ known, float *__restrict__ g, int n1, int n2, int n3,
+                double *__restrict__ partial)
+{
+    const size_t n = (size_t)n1 * n2 * n3;
+    const long pl = (long)n1 * n2;
+    double acc[1] = {0.};
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        const int j1 = (int)(j % n1), j2 = (int)((j / n1) % n2), j3 = (int)(j / pl);
+        float v = 0.f;
+        // inline operator: "+" targets of sources in trace j2-1 (source index ascending = shift descending)
+        if (j2 >= 1) {
+#pragma unroll
+            for (int s = NW; s >= -NW; s--) {
+                const int ix = j1 - s;
+                if (ix >= NW && ix < n1 - NW) { const size_t i = j - n1 - s; v += yy[i] * fi[(size_t)(s + NW) * n + i]; }
+            }
+        }
+        if (j2 <= n2 - 2) {
+#pragma unroll
+            for (int s = -NW; s <= NW; s++) {
+                const int ix = j1 + s;
+                if (ix >= NW && ix < n1 - NW) { const size_t i = j + s; v -= yy[i] * fi[(size_t)(s + NW) * n + i]; }
+            }
+        }
+        // xline operator
+        if (j3 >= 1) {
+#pragma unroll
+            for (int s = NW; s >= -NW; s--) {
+                const int ix = j1 - s;
+                if (ix >= NW && ix < n1 - NW) { const size_t i = j - pl - s; v += yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
+            }
+        }
+        if (j3 <= n3 - 2) {
+#pragma unroll
+            for (int s = -NW; s <= NW; s++) {
+                const int ix = j1 + s;
+                if (ix >= NW && ix < n1 - NW) { const size_t i = j + s; v -= yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
+            }
+        }
+        if (known[j]) v = 0.0f;
+        g[j] = v;
+        acc[0] += (double)v * v;
+    }
+    pst_block_reduce<1>(acc, partial);
+}
+
+// ps_cgstep tail (:865-875): S = beta S + alfa g; Ss = beta Ss + alfa gg; x += S; rr += Ss; partial rr.rr
+__global__ void __launch_bounds__(256)
+cgstep_update_kernel(float *__restrict__ x, float *__restrict__ S, const float *__restrict__ g,
+                     float *__restrict__ rr, float *__restrict__ Ss, const float *__restrict__ gg,
+                     float alfa, float beta, size_t n, double *__restrict__ partial)
+{
+    double acc[1] = {0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = S[i];
+        s *= beta;
+        s += alfa * g[i];
+        S[i] = s;
+        x[i] += s;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const size_t k = i + h * n;
+            float t = Ss[k];
+            t *= beta;
+            t += alfa * gg[k];
+            Ss[k] = t;
+            const float r = rr[k] + t;
+            rr[k] = r;
+            acc[0] += (double)r * r;
+        }
+    }
+    pst_block_reduce<1>(acc, partial);
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float *__restrict__ v, size_t n, double *__restrict__ partial)
+{
+    double acc[1] = {0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc[0] += (double)v[i] * v[i];
+    pst_block_reduce<1>(acc, partial);
+}
+
+__global__ void known_kernel(const float *__restrict__ ref, unsigned char *__restrict__ known, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        known[i] = (ref[i] != 0.f);
+}
+
+template <int NW>
+static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, const float *d_pp, const float *d_qq,
+                       int n1, int n2, int n3, int niter, int verb, float *d_out)
+{
+    static const BTab tb = make_btab(NW);
+    constexpr int NA = 2 * NW + 1;
+    const size_t n = (size_t)n1 * n2 * n3;
+    PST_TRY(pst_arena_reserve(c, (size_t)(2 * NA + 8) * n * sizeof(float) + n + 64 * 256));
+    pst_arena_reset(c);
+    float *fi, *fx, *g, *S, *rr, *gg, *Ss;
+    unsigned char *known;
+    PST_TRY(pst_arena_get(c, NA * n, &fi));
+    PST_TRY(pst_arena_get(c, NA * n, &fx));
+    PST_TRY(pst_arena_get(c, n, &g));
+    PST_TRY(pst_arena_get(c, n, &S));
+    PST_TRY(pst_arena_get(c, 2 * n, &rr));
+    PST_TRY(pst_arena_get(c, 2 * n, &gg));
+    PST_TRY(pst_arena_get(c, 2 * n, &Ss));
+    PST_TRY(pst_arena_get(c, n, &known));
+    float *x = d_out;
+    const int threads = 256, grid = pst_grid_for(c, n, threads);
+    double h[PST_RED_SLOTS];
+    PST_LAUNCHB(c, PST_K_OTHER, 48.0 * (double)n, (pwd3_taps_kernel<NW><<<grid, threads, 0, c->stream>>>(d_pp, d_qq, fi, fx, n, tb)));
+    PST_LAUNCH(c, PST_K_OTHER, (known_kernel<<<grid, threads, 0, c->stream>>>(d_mask ? d_mask : d_din, known, n)));
+    // ps_solver :1018-1040 with dat = 0 (var = 0): rr = -0; x = x0 = data; rr += L x
+    PST_CUDA(cudaMemcpyAsync(x, d_din, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
+    PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
+                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, c->d_partial)));
+    PST_CUDA(cudaMemsetAsync(S, 0, n * sizeof(float), c->stream));
+    PST_CUDA(cudaMemsetAsync(Ss, 0, 2 * n * sizeof(float), c->stream));
+    // dpr0 = rr.rr (:1042)
+    PST_LAUNCH(c, PST_K_OTHER, (sumsq_kernel<<<grid, threads, 0, c->stream>>>(rr, 2 * n, c->d_partial)));
+    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_TRY(pst_fetch_record(c, 8, 1, h));
+    const double dpr0 = h[0];
+    double dpg0 = 1., rr2 = dpr0;
+    bool first = true;
+    for (int iter = 0; iter < niter; iter++) {
+        PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 13.0) * (double)n,
+                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, c->d_partial)));
+        PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+        PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 28.0) * (double)n,
+                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, c->d_partial)));
+        PST_TRY(pst_finish_reduce(c, grid, 5, 9));
+        PST_TRY(pst_fetch_record(c, 8, 1, h));
+        const double g2 = h[0];
+        double dpr, dpg;
+        if (iter == 0) { dpg0 = g2; dpr = 1.; dpg = 1.; }
+        else { dpr = rr2 / dpr0; dpg = g2 / dpg0; }
+        if (verb) printf("[pst] soint3d iteration %d res %g grad %g\n", iter + 1, dpr, dpg);
+        if (dpr < 1.e-12 || dpg < 1.e-12) break;             // TOLERANCE (:889)
+        PST_TRY(pst_fetch_record(c, 9, 5, h));
+        const double gdg = h[0], sds = h[1], gds = h[2], ggr = h[3], ssr = h[4];
+        double alfa, beta;
+        if (first) {                                          // forget (:838-846)
+            first = false;
+            beta = 0.0;
+            if (gdg <= 0.) continue;
+            alfa = -ggr / gdg;
+        } else {
+            if (gdg == 0. || sds == 0.) continue;
+            double determ = 1.0 - (gds / gdg) * (gds / sds);
+            const double EPS = (double)1.e-12f;
+            if (determ > EPS) determ *= gdg * sds; else determ = gdg * sds * EPS;
+            const double gdr = -ggr, sdr = -ssr;
+            alfa = (sds * gdr - gds * sdr) / determ;
+            beta = (-gds * gdr + gdg * sdr) / determ;
+        }
+        PST_LAUNCHB(c, PST_K_CGDIR, 60.0 * (double)n,
+                    (cgstep_update_kernel<<<grid, threads, 0, c->stream>>>(x, S, g, rr, Ss, gg, (float)alfa, (float)beta, n, c->d_partial)));
+        PST_TRY(pst_finish_reduce(c, grid, 1, 10));
+        PST_TRY(pst_fetch_record(c, 10, 1, h));
+        rr2 = h[0];
+        c->stats.cg_iterations++;
+    }
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+extern "C" int pst_soint3d_dev(pst_ctx *c, const float *d_din, const float *d_mask, const float *d_dipi,
+                               const float *d_dipx, int n1, int n2, int n3, int nw, int nj1, int nj2, int niter,
+                               int drift, int seed, int hasmask, float var, int verb, float *d_out)
+{
+    (void)seed;
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    if (n1 < 1 || n2 < 1 || n3 < 1 || niter < 0) { pst_set_error("soint3d: bad dimensions"); return PST_EINVAL; }
+    if (nw != 1 && nw != 2) { pst_set_error("soint3d: order=%d unsupported (1 or 2)", nw); return PST_EUNSUP; }
+    if (n1 < 2 * nw + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
+    if (nj1 != 1 || nj2 != 1 || drift != 0) { pst_set_error("soint3d: njs != 1 / drift are not implemented on the GPU path"); return PST_EUNSUP; }
+    if (var != 0.f) { pst_set_error("soint3d: var != 0 (random right-hand side) is not implemented on the GPU path"); return PST_EUNSUP; }
+    if (c->comm && c->nranks > 1) { pst_set_error("soint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
+    if (hasmask && !d_mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    const float *m = hasmask ? d_mask : nullptr;
+    if (nw == 1) return soint3d_run<1>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, verb, d_out);
+    return soint3d_run<2>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, verb, d_out);
+}

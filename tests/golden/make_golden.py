@@ -43,6 +43,16 @@ def main():
                                      out=ref.somean3dc(de, di, dx, r1, r2, 0.01, order))
         g["somf3d_" + name] = dict(dn=de, dipi=di, dipx=dx, r1=r1, r2=r2, order=order,
                                    out=ref.somf3dc(de, di, dx, r1, r2, 0.01, order))
+    # ---- soint3d (PWD-residual CG interpolation of 50 % missing traces)
+    dc = synth.cube(40, 16, 8, seed=11, noise=0.0)
+    pi_, px_ = ref.dip3dc(dc)
+    keep = np.random.default_rng(9).random((16, 8)) > 0.5
+    mk = np.zeros_like(dc)
+    mk[:, keep] = 1
+    d0 = dc * mk
+    for name, (order, niter, hasmask) in {"o2n20": (2, 20, 1), "o1n8": (1, 8, 1), "o2n6nomask": (2, 6, 0)}.items():
+        g["soint3d_" + name] = dict(din=d0, mask=mk, dipi=pi_, dipx=px_, order=order, niter=niter, hasmask=hasmask,
+                                    out=ref.soint3dc(d0, mk, pi_, px_, order=order, niter=niter, hasmask=hasmask))
     # ---- 2-D: dip2d, somf2d, somean2d
     d2 = synth.cube(64, 24, 1, seed=12)
     p2 = ref.dip2dc(d2, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])

@@ -202,6 +202,43 @@ def test_somf3d_option2_is_refused_not_faked(ctx):
     assert e.value.code == -5
 
 
+# ------------------------------------------------------------------ interpolation
+@pytest.mark.parametrize("name", golden_names("soint3d_"))
+def test_soint3d_golden(ctx, name):
+    """Vectors are reference-ordered (bit-identical operators, gather adjoint in scatter order); the five
+    CG dots are double trees instead of sequential doubles: relative L2 <= 1e-5."""
+    import pyseistr_b200 as ps
+    g = golden(name)
+    out = ps.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=int(g["order"]), niter=int(g["niter"]),
+                      hasmask=int(g["hasmask"]), verb=0, ctx=ctx)
+    assert out.shape == g["out"].shape
+    assert rel_l2(out, g["out"]) <= TOL, rel_l2(out, g["out"])
+
+
+def test_soint3d_vs_oracle_and_recovers_plane_waves(ctx, port):
+    import pyseistr_b200 as ps
+    d = synth.cube(64, 20, 12, seed=81, noise=0.0)
+    pi, px = port.dip3dc(d, 3, 8, 2, rect=(4, 4, 3))
+    keep = np.random.default_rng(82).random((20, 12)) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    d0 = d * mask
+    got = ps.soint3dc(d0, mask, pi, px, order=2, niter=25, verb=0, ctx=ctx)
+    want = port.soint3dc(d0, mask, pi, px, order=2, niter=25)
+    assert rel_l2(got, want) <= TOL, rel_l2(got, want)
+    assert np.array_equal(got[:, keep], d0[:, keep])                      # known traces untouched
+    assert np.linalg.norm(got - d) < 0.25 * np.linalg.norm(d0 - d)        # missing traces filled in
+
+
+def test_soint3d_unsupported_options_refused(ctx):
+    import pyseistr_b200 as ps
+    d = synth.cube(20, 6, 4, seed=83)
+    for kw in (dict(var=0.1), dict(drift=1), dict(njs=[2, 1])):
+        with pytest.raises(ps.PstError) as e:
+            ps.soint3dc(d, np.ones_like(d), 0 * d, 0 * d, niter=2, verb=0, ctx=ctx, **kw)
+        assert e.value.code == -5
+
+
 # ------------------------------------------------------------------ properties at scale
 def test_pipeline_properties_at_scale(ctx):
     """200x128x64 (the survey's proxy cube; the oracle needs ~30 s there so properties are used

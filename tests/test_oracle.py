@@ -41,6 +41,14 @@ def test_port_spray2d_matches_golden(port, name):
     assert np.array_equal(out, g["out"])
 
 
+@pytest.mark.parametrize("name", golden_names("soint3d_"))
+def test_port_soint3d_matches_golden(port, name):
+    g = golden(name)
+    out = port.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=int(g["order"]), niter=int(g["niter"]),
+                        hasmask=int(g["hasmask"]))
+    assert np.array_equal(out, g["out"])
+
+
 @pytest.mark.parametrize("name", golden_names("smooth_"))
 def test_port_smooth_matches_golden(port, name):
     g = golden(name)
