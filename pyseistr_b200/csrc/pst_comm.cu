@@ -28,6 +28,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -51,6 +52,7 @@ static int nccl_load()
     PST_SYM(AllReduce, "ncclAllReduce");
     PST_SYM(Send, "ncclSend");
     PST_SYM(Recv, "ncclRecv");
+    PST_SYM(AllGather, "ncclAllGather");
     PST_SYM(GroupStart, "ncclGroupStart");
     PST_SYM(GroupEnd, "ncclGroupEnd");
     PST_SYM(GetErrorString, "ncclGetErrorString");
@@ -68,7 +70,18 @@ static int nccl_load()
         }                                                                               \
     } while (0)
 
-struct pst_comm { ncclComm_t comm = nullptr; };
+// Peer-memory mailbox of the axis-3 carry pipeline: every rank owns one
+// device buffer [carry_fwd[L] | carry_bwd[L] | flag_fwd[nblk] | flag_bwd[nblk] | err], exported with
+// CUDA IPC; rank r writes its outgoing carries straight into the neighbour's buffer over NVLink and
+// then raises the neighbour's per-CTA flag (release at system scope).
+struct pst_comm {
+    ncclComm_t comm = nullptr;
+    char *mbox = nullptr;            // my mailbox (device)
+    char *mbox_prev = nullptr;       // rank-1's mailbox, mapped (null on rank 0)
+    char *mbox_next = nullptr;       // rank+1's mailbox, mapped (null on the last rank)
+    size_t mbox_L = 0, mbox_bytes = 0;
+    unsigned epoch = 0;
+};
 
 int pst_comm_allreduce_record(pst_ctx *c, double *d_rec, int nv)
 {
@@ -124,6 +137,9 @@ int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_h
 void pst_comm_destroy(pst_ctx *c)
 {
     if (c->comm) {
+        if (c->comm->mbox_prev) cudaIpcCloseMemHandle(c->comm->mbox_prev);
+        if (c->comm->mbox_next) cudaIpcCloseMemHandle(c->comm->mbox_next);
+        if (c->comm->mbox) cudaFree(c->comm->mbox);
         if (c->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->comm);
         delete c->comm;
     }
@@ -171,5 +187,77 @@ extern "C" int pst_ctx_slab(pst_ctx *c, int n3, int *z0, int *z1)
     if (!c || !z0 || !z1) { pst_set_error("null argument"); return PST_EINVAL; }
     *z0 = (int)(((long)n3 * c->rank) / c->nranks);
     *z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+    return PST_OK;
+}
+
+// ---- carry mailboxes ---------------------------------------------------------------------
+static size_t mbox_layout(size_t L, size_t *off_cb, size_t *off_ff, size_t *off_fb, size_t *off_err)
+{
+    const size_t nblk = (L + 127) / 128;
+    size_t o = 0;
+    o += L * sizeof(float);                 *off_cb = o;
+    o += L * sizeof(float);                 *off_ff = o;
+    o += nblk * sizeof(unsigned);           *off_fb = o;
+    o += nblk * sizeof(unsigned);           *off_err = o;
+    o += 64;
+    return (o + 255) & ~(size_t)255;
+}
+
+// Collective: make sure every rank's mailbox can hold L carries per direction and that the
+// neighbours' mailboxes are mapped.  Returns the pointers the kernels need.
+int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v)
+{
+    pst_comm *m = c->comm;
+    size_t ocb, off, ofb, oerr;
+    if (m->mbox_L < L) {
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        if (m->mbox_prev) { cudaIpcCloseMemHandle(m->mbox_prev); m->mbox_prev = nullptr; }
+        if (m->mbox_next) { cudaIpcCloseMemHandle(m->mbox_next); m->mbox_next = nullptr; }
+        if (m->mbox) { cudaFree(m->mbox); m->mbox = nullptr; }
+        m->mbox_bytes = mbox_layout(L, &ocb, &off, &ofb, &oerr);
+        PST_CUDA(cudaMalloc((void **)&m->mbox, m->mbox_bytes));
+        PST_CUDA(cudaMemset(m->mbox, 0, m->mbox_bytes));
+        m->mbox_L = L;
+        m->epoch = 0;
+        // exchange IPC handles through NCCL (all-gather of 64-byte handles)
+        cudaIpcMemHandle_t mine;
+        PST_CUDA(cudaIpcGetMemHandle(&mine, m->mbox));
+        char *d_h = nullptr;
+        PST_CUDA(cudaMalloc((void **)&d_h, sizeof(mine) * (size_t)(c->nranks + 1)));
+        PST_CUDA(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        PST_NCCL(g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0 /* ncclInt8 */, m->comm, c->stream));
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+        PST_CUDA(cudaMemcpy(all.data(), d_h + sizeof(mine), sizeof(mine) * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+        PST_CUDA(cudaFree(d_h));
+        if (c->rank > 0)
+            PST_CUDA(cudaIpcOpenMemHandle((void **)&m->mbox_prev, all[(size_t)c->rank - 1], cudaIpcMemLazyEnablePeerAccess));
+        if (c->rank < c->nranks - 1)
+            PST_CUDA(cudaIpcOpenMemHandle((void **)&m->mbox_next, all[(size_t)c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
+    }
+    mbox_layout(m->mbox_L, &ocb, &off, &ofb, &oerr);
+    v->cf_in = (float *)m->mbox;                        // written by rank-1
+    v->cb_in = (float *)(m->mbox + ocb);                // written by rank+1
+    v->ff_in = (unsigned *)(m->mbox + off);
+    v->fb_in = (unsigned *)(m->mbox + ofb);
+    v->err = (unsigned *)(m->mbox + oerr);
+    v->cf_out = m->mbox_next ? (float *)m->mbox_next : nullptr;
+    v->ff_out = m->mbox_next ? (unsigned *)(m->mbox_next + off) : nullptr;
+    v->cb_out = m->mbox_prev ? (float *)(m->mbox_prev + ocb) : nullptr;
+    v->fb_out = m->mbox_prev ? (unsigned *)(m->mbox_prev + ofb) : nullptr;
+    v->epoch = ++m->epoch;
+    return PST_OK;
+}
+
+// after a call: did any kernel give up waiting for a neighbour?
+int pst_comm_check(pst_ctx *c)
+{
+    if (!c->comm || !c->comm->mbox) return PST_OK;
+    size_t ocb, off, ofb, oerr;
+    mbox_layout(c->comm->mbox_L, &ocb, &off, &ofb, &oerr);
+    unsigned e = 0;
+    PST_CUDA(cudaMemcpyAsync(&e, c->comm->mbox + oerr, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    if (e) { pst_set_error("axis-3 carry pipeline: timed out waiting for a neighbour rank"); return PST_ECOMM; }
     return PST_OK;
 }

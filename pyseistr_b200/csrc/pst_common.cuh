@@ -34,6 +34,16 @@ void pst_set_error(const char *fmt, ...);
 
 struct pst_comm;   // multi-GPU communicator (pst_comm.cu)
 
+// what the distributed axis-3 kernels need from the carry mailboxes (pst_comm.cu)
+struct pst_mailbox_view {
+    float *cf_in, *cb_in;            // my mailbox: forward carries from rank-1, backward carries from rank+1
+    unsigned *ff_in, *fb_in;         // per-CTA flags raised by the producer (value = epoch)
+    float *cf_out, *cb_out;          // neighbours' mailboxes (peer memory): rank+1's cf, rank-1's cb
+    unsigned *ff_out, *fb_out;
+    unsigned *err;                   // set when a wait times out
+    unsigned epoch;
+};
+
 struct pst_ctx {
     int device = 0;
     int sm_count = 148;

@@ -1085,8 +1085,11 @@ struct Tri3Args {
     const float *x;        // slab [nz][L]
     const float *hb, *ha;  // halos: planes [z0-nb, z0) and [z1, z1+nb)
     float *F;              // scratch [K1-K0][L]
-    const float *cin;      // carry in  (nullptr = 0)
-    float *cout;           // carry out
+    // carry pipeline: incoming carries + per-CTA flag in MY mailbox (nullptr = edge rank, carry 0);
+    // outgoing carries + flag in the NEIGHBOUR's mailbox (peer memory over NVLink; nullptr = edge)
+    const float *cin; const unsigned *fin;
+    float *cout; unsigned *fout;
+    unsigned *err; unsigned epoch;
     float *dst;            // fold output [nz][L]
     long L, l0, l1;        // lines per plane, chunk [l0, l1)
     int n3g, z0, nz, nb, K0, K1;
@@ -1100,22 +1103,51 @@ __device__ __forceinline__ float tri3_x(const Tri3Args &A, int j, long l)
     return A.ha[(long)(j - (A.z0 + A.nz)) * A.L + l];
 }
 
+// consumer side of the carry hand-off: one thread spins (acquire, system scope) on this CTA's
+// flag, with a generous timeout so that a failed neighbour cannot hang the GPU
+__device__ __forceinline__ void tri3_wait(const unsigned *flag, unsigned epoch, unsigned *err)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == epoch) break;
+            if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+}
+// producer side: carries were stored to the neighbour's mailbox by all threads
+__device__ __forceinline__ void tri3_signal(unsigned *flag, unsigned epoch)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
 __global__ void __launch_bounds__(128)
 tri3_dist_fwd_kernel(const Tri3Args A)
 {
-    const long l = A.l0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= A.l1) return;
+    const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.cin) tri3_wait(A.fin + blockIdx.x, A.epoch, A.err);
+    const bool live = l < A.L;
     const float wm = -A.wt;
-    float s = A.cin ? A.cin[l] : 0.f;
-    for (int k = A.K0; k < A.K1; k++) {
-        float t = 0.f;
-        if (k < A.n3g) t = t + wm * tri3_x(A, k, l);
-        if (k >= A.nb && k - A.nb < A.n3g) t = t + A.w2 * tri3_x(A, k - A.nb, l);
-        if (k >= 2 * A.nb && k - 2 * A.nb < A.n3g) t = t + wm * tri3_x(A, k - 2 * A.nb, l);
-        s += t;
-        A.F[(long)(k - A.K0) * A.L + l] = s;
+    float s = 0.f;
+    if (live) {
+        if (A.cin) s = __ldcv(A.cin + l);
+        for (int k = A.K0; k < A.K1; k++) {
+            float t = 0.f;
+            if (k < A.n3g) t = t + wm * tri3_x(A, k, l);
+            if (k >= A.nb && k - A.nb < A.n3g) t = t + A.w2 * tri3_x(A, k - A.nb, l);
+            if (k >= 2 * A.nb && k - 2 * A.nb < A.n3g) t = t + wm * tri3_x(A, k - 2 * A.nb, l);
+            s += t;
+            A.F[(long)(k - A.K0) * A.L + l] = s;
+        }
+        if (A.cout) A.cout[l] = s;
     }
-    A.cout[l] = s;
+    if (A.cout) tri3_signal(A.fout + blockIdx.x, A.epoch);
 }
 
 // backward sum fused with fold2 (:458-484): y_i = (B_{i+nb} + B_{nb+n3g+(n3g-1-i)}[i >= n3g-nb])
@@ -1125,28 +1157,32 @@ tri3_dist_fwd_kernel(const Tri3Args A)
 __global__ void __launch_bounds__(128)
 tri3_dist_bwd_kernel(const Tri3Args A)
 {
-    const long l = A.l0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= A.l1) return;
+    const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.cin) tri3_wait(A.fin + blockIdx.x, A.epoch, A.err);
+    const bool live = l < A.L;
     const int nb = A.nb, n3g = A.n3g;
-    float s = A.cin ? A.cin[l] : 0.f;
-    int k = A.K1 - 1;
-    for (; k >= nb + n3g && k >= A.K0; k--) {               // right pad (last rank only)
-        s += A.F[(long)(k - A.K0) * A.L + l];
-        const int gi = n3g - 1 - (k - nb - n3g);
-        A.dst[(long)(gi - A.z0) * A.L + l] = s;
+    if (live) {
+        float s = A.cin ? __ldcv(A.cin + l) : 0.f;
+        int k = A.K1 - 1;
+        for (; k >= nb + n3g && k >= A.K0; k--) {               // right pad (last rank only)
+            s += A.F[(long)(k - A.K0) * A.L + l];
+            const int gi = n3g - 1 - (k - nb - n3g);
+            A.dst[(long)(gi - A.z0) * A.L + l] = s;
+        }
+        for (; k >= nb && k >= A.K0; k--) {                     // middle: global plane gi = k - nb
+            s += A.F[(long)(k - A.K0) * A.L + l];
+            const int gi = k - nb;
+            float v = s;
+            if (gi >= n3g - nb) v = v + A.dst[(long)(gi - A.z0) * A.L + l];
+            A.dst[(long)(gi - A.z0) * A.L + l] = v;
+        }
+        for (; k >= A.K0; k--) {                                // left pad (rank 0 only)
+            s += A.F[(long)(k - A.K0) * A.L + l];
+            A.dst[(long)(nb - 1 - k - A.z0) * A.L + l] += s;
+        }
+        if (A.cout) A.cout[l] = s;
     }
-    for (; k >= nb && k >= A.K0; k--) {                     // middle: global plane gi = k - nb
-        s += A.F[(long)(k - A.K0) * A.L + l];
-        const int gi = k - nb;
-        float v = s;
-        if (gi >= n3g - nb) v = v + A.dst[(long)(gi - A.z0) * A.L + l];
-        A.dst[(long)(gi - A.z0) * A.L + l] = v;
-    }
-    for (; k >= A.K0; k--) {                                // left pad (rank 0 only)
-        s += A.F[(long)(k - A.K0) * A.L + l];
-        A.dst[(long)(nb - 1 - k - A.z0) * A.L + l] += s;
-    }
-    A.cout[l] = s;
+    if (A.cout) tri3_signal(A.fout + blockIdx.x, A.epoch);
 }
 
 // ---- shaping operator driver ------------------------------------------------------------
@@ -1232,6 +1268,9 @@ int pst_comm_sendrecv(pst_ctx *c, const float *send, size_t nsend, int peer_out,
 int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_hi, float *recv_lo,
                            float *recv_hi, size_t count);
 
+int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v);                      // pst_comm.cu
+int pst_comm_check(pst_ctx *c);
+
 static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, float *dst, float *scr)
 {
     const int nb = g.r3, nz = g.n3, n3g = g.n3g;
@@ -1239,34 +1278,25 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
     // nb-plane halos of the CURRENT input (it changes every pass)
     PST_TRY(pst_comm_halo_exchange(c, src, src + (size_t)(nz - nb) * L, g.hb, g.ha, (size_t)nb * L));
+    pst_mailbox_view mb;
+    PST_TRY(pst_comm_mailbox(c, (size_t)L, &mb));
     Tri3Args A{};
-    A.x = src; A.hb = g.hb; A.ha = g.ha; A.F = scr; A.dst = dst; A.L = L;
+    A.x = src; A.hb = g.hb; A.ha = g.ha; A.F = scr; A.dst = dst; A.L = L; A.l0 = 0; A.l1 = L;
     A.n3g = n3g; A.z0 = g.z0; A.nz = nz; A.nb = nb;
     A.K0 = first ? 0 : g.z0 + nb;
     A.K1 = last ? n3g + 2 * nb : g.z0 + nz + nb;
     A.wt = (float)(1.0 / ((double)nb * nb));
     A.w2 = (float)(2. * A.wt);
-    // chunks of lines: enough to fill the GPU, few enough to keep NCCL launches cheap
-    const int nchunk = 8;
-    long per = ((L + nchunk - 1) / nchunk + 127) / 128 * 128;
-    const double bytes_half = 8.0 * (double)g.n;
-    for (int pass = 0; pass < 2; pass++) {          // 0: forward (carries flow up), 1: backward (down)
-        const bool has_in = pass == 0 ? !first : !last, has_out = pass == 0 ? !last : !first;
-        const int peer_in = pass == 0 ? c->rank - 1 : c->rank + 1, peer_out = pass == 0 ? c->rank + 1 : c->rank - 1;
-        if (has_in) PST_TRY(pst_comm_recv(c, g.cin, (size_t)std::min(L, per), peer_in));
-        for (long l0 = 0; l0 < L; l0 += per) {
-            const long l1 = std::min(L, l0 + per);
-            A.l0 = l0; A.l1 = l1; A.cin = has_in ? g.cin : nullptr; A.cout = g.cout;
-            const unsigned blocks = (unsigned)((l1 - l0 + 127) / 128);
-            PST_LAUNCHB(c, PST_K_TRI3, bytes_half * (double)(l1 - l0) / (double)L,
-                if (pass == 0) tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A);
-                else           tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A));
-            // one NCCL group: hand this chunk's carry on, and receive the next chunk's
-            const long n0 = l0 + per, n1c = std::min(L, n0 + per);
-            PST_TRY(pst_comm_sendrecv(c, has_out ? g.cout + l0 : nullptr, (size_t)(l1 - l0), peer_out,
-                                      (has_in && n0 < L) ? g.cin + n0 : nullptr, (size_t)std::max(0L, n1c - n0), peer_in));
-        }
-    }
+    A.err = mb.err; A.epoch = mb.epoch;
+    const unsigned blocks = (unsigned)((L + 127) / 128);
+    // forward sums: carries flow rank -> rank+1, CTA by CTA, through the neighbour's mailbox
+    A.cin = first ? nullptr : mb.cf_in;  A.fin = mb.ff_in;
+    A.cout = last ? nullptr : mb.cf_out; A.fout = mb.ff_out;
+    PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+    // backward sums (+ fold): carries flow rank -> rank-1
+    A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;
+    A.cout = first ? nullptr : mb.cb_out; A.fout = mb.fb_out;
+    PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -1618,6 +1648,7 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     PST_TRY(gauss_newton(c, g, u, d_dip_out, m_in, 0, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
     if (ndip == 2)
         PST_TRY(gauss_newton(c, g, u, d_dip_out + n, m_x, 1, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
+    if (dist) PST_TRY(pst_comm_check(c));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
