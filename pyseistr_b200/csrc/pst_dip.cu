@@ -1137,13 +1137,31 @@ tri3_dist_fwd_kernel(const Tri3Args A)
     float s = 0.f;
     if (live) {
         if (A.cin) s = __ldcv(A.cin + l);
-        for (int k = A.K0; k < A.K1; k++) {
-            float t = 0.f;
-            if (k < A.n3g) t = t + wm * tri3_x(A, k, l);
-            if (k >= A.nb && k - A.nb < A.n3g) t = t + A.w2 * tri3_x(A, k - A.nb, l);
-            if (k >= 2 * A.nb && k - 2 * A.nb < A.n3g) t = t + wm * tri3_x(A, k - 2 * A.nb, l);
-            s += t;
-            A.F[(long)(k - A.K0) * A.L + l] = s;
+        // loads of U steps are issued together, ahead of the dependent FADD chain: the latency of a
+        // CTA is what every downstream rank waits for (pipeline fill), so it must be short
+        constexpr int U = 8;
+        for (int k0 = A.K0; k0 < A.K1; k0 += U) {
+            float va[U], vb[U], vc[U];
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                const int k = k0 + q;
+                const bool in = k < A.K1;
+                va[q] = (in && k < A.n3g) ? tri3_x(A, k, l) : 0.f;
+                vb[q] = (in && k >= A.nb && k - A.nb < A.n3g) ? tri3_x(A, k - A.nb, l) : 0.f;
+                vc[q] = (in && k >= 2 * A.nb && k - 2 * A.nb < A.n3g) ? tri3_x(A, k - 2 * A.nb, l) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                const int k = k0 + q;
+                if (k < A.K1) {
+                    float t = 0.f;
+                    t = t + wm * va[q];
+                    t = t + A.w2 * vb[q];
+                    t = t + wm * vc[q];
+                    s += t;
+                    A.F[(long)(k - A.K0) * A.L + l] = s;
+                }
+            }
         }
         if (A.cout) A.cout[l] = s;
     }
@@ -1169,7 +1187,22 @@ tri3_dist_bwd_kernel(const Tri3Args A)
             const int gi = n3g - 1 - (k - nb - n3g);
             A.dst[(long)(gi - A.z0) * A.L + l] = s;
         }
-        for (; k >= nb && k >= A.K0; k--) {                     // middle: global plane gi = k - nb
+        const int kmid = max(nb, A.K0);                        // middle: global plane gi = k - nb
+        constexpr int U = 8;
+        for (; k - (U - 1) >= kmid; k -= U) {
+            float f[U];
+#pragma unroll
+            for (int q = 0; q < U; q++) f[q] = A.F[(long)(k - q - A.K0) * A.L + l];
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                s += f[q];
+                const int gi = k - q - nb;
+                float v = s;
+                if (gi >= n3g - nb) v = v + A.dst[(long)(gi - A.z0) * A.L + l];
+                A.dst[(long)(gi - A.z0) * A.L + l] = v;
+            }
+        }
+        for (; k >= kmid; k--) {
             s += A.F[(long)(k - A.K0) * A.L + l];
             const int gi = k - nb;
             float v = s;
