@@ -387,6 +387,14 @@ def _main(real_stdout):
             "algorithmic_bytes_per_launch": cls_b[dom] / cls_n[dom],
             "share_of_step": cls_ms[dom] / total_cls}
     roof["frac"] = roof["achieved"] / peak
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    # capture of that kernel (profiles/r01_*_ncu_summary.md), as a ratio to its algorithmic bytes
+    ncu_ratio = {"cg_head": (3.670121 + 2.059249) / (44 * 0.131072), "cg_dir": (3.145735 + 1.533136) / (36 * 0.131072),
+                 "tri_axis1": (1.048597 + 0.992547) / 2.097152, "tri_axis2": (1.048627 + 0.994858) / 2.097152,
+                 "tri_axis3": (1.051120 + 0.997099) / 2.097152}
+    if dom in ncu_ratio:
+        roof["traffic"] = ncu_ratio[dom] * roof["algorithmic_bytes_per_launch"]
+        roof["traffic_source"] = "ncu --set full capture scaled by voxel count, see profiles/"
     roof["classes"] = {k: {"ms_per_step": cls_ms[k] / args.steps, "launches_per_step": cls_n[k] / args.steps,
                            "algorithmic_GBps": (cls_b[k] / (cls_ms[k] * 1e-3) / 1e9) if cls_ms[k] > 0 and cls_b[k] > 0 else None,
                            "share": cls_ms[k] / total_cls}
