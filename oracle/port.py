@@ -38,6 +38,11 @@ def _shape3(d):
     return (d.shape[0], d.shape[1], 1) if d.ndim == 2 else d.shape
 
 
+def set_dot_mode(mode):
+    """0 = reference (sequential double dots); 1 = blocked association (sensitivity probe)."""
+    lib().pso_set_dot_mode(int(mode))
+
+
 def passfilter(nw, sigma):
     a = np.zeros(2 * nw + 1, np.float32)
     lib().pso_passfilter(ctypes.c_int(nw), ctypes.c_float(sigma), _p(a))

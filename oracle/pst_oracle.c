@@ -170,10 +170,26 @@ void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3)
 
 /* ------------------------------------------------------------------ shaping CG + divne */
 
+/* Sensitivity probe (not reference behaviour): mode 1 sums the same exact double products in
+ * blocks of 4096 and then the block sums — a different ASSOCIATION of the same double additions,
+ * like any parallel reduction.  Used only to measure how much the reference's OWN result moves
+ * when the last bits of its dot products move (tests/test_oracle.py). */
+static int g_dot_mode = 0;
+void pso_set_dot_mode(int mode) { g_dot_mode = mode; }
+
 static double ddot(size_t n, const float *a, const float *b)   /* ps_cblas_dsdot :122-137 */
 {
     double s = 0.;
-    for (size_t i = 0; i < n; i++) s += (double)a[i] * b[i];
+    if (g_dot_mode == 0) {
+        for (size_t i = 0; i < n; i++) s += (double)a[i] * b[i];
+        return s;
+    }
+    for (size_t i0 = 0; i0 < n; i0 += 4096) {
+        double t = 0.;
+        size_t i1 = i0 + 4096 < n ? i0 + 4096 : n;
+        for (size_t i = i0; i < i1; i++) t += (double)a[i] * b[i];
+        s += t;
+    }
     return s;
 }
 

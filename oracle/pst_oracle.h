@@ -15,6 +15,10 @@
 extern "C" {
 #endif
 
+/* sensitivity probe: 0 = the reference's sequential double dot products (default), 1 = the same
+ * products summed in blocks (see pst_oracle.c) */
+void pso_set_dot_mode(int mode);
+
 /* B-filter taps: dip_cfuns.c:835-910 */
 void pso_passfilter(int nw, float sigma, float *taps /*[2nw+1]*/);
 void pso_aderfilter(int nw, float sigma, float *taps /*[2nw+1]*/);

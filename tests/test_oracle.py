@@ -108,3 +108,15 @@ def test_port_vs_compiled_reference_2d(port):
     assert np.array_equal(rp, port.dip2dc(d, 2, 8, 1, 0.01, 1, 1e-6, [6, 9, 1]))
     assert np.array_equal(ref.somf2dc(d, rp, 4, 2, 0.01), port.somf2dc(d, rp, 4, 2, 0.01))
     assert np.array_equal(ref.somean2dc(d, rp, 4, 1, 0.02), port.somean2dc(d, rp, 4, 1, 0.02))
+
+
+def test_dot_association_probe_is_inert_on_small_cases(port):
+    """The sensitivity probe re-associates the double dot products; on the small well-conditioned
+    fixtures it must not change a single bit (so tolerances widened by it stay honest)."""
+    g = golden("dip3d_default")
+    port.set_dot_mode(1)
+    try:
+        di, dx = port.dip3dc(g["din"], int(g["niter"]), int(g["liter"]), int(g["order"]), rect=[int(v) for v in g["rect"]])
+    finally:
+        port.set_dot_mode(0)
+    assert np.array_equal(di, g["dipi"]) and np.array_equal(dx, g["dipx"])
