@@ -159,3 +159,19 @@ def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=(1, 1), drift=0, see
     out = np.zeros_like(d)
     lib().pso_soint3d(_p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, n3, int(order), int(niter), _p(out))
     return out.reshape(n1, n2, n3, order="F")
+
+
+def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, order2=1, verb=0):
+    n1, n2, n3 = _shape3(din)
+    d, a, b, m = _F(din), _F(dipi), _F(dipx), _F(mask)
+    out = np.zeros_like(d)
+    lib().pso_sint3d(_p(d), _p(a), _p(b), _p(m), n1, n2, n3, int(niter), int(ns1), int(ns2), int(order1), int(order2),
+                     ctypes.c_float(eps), _p(out))
+    return out.reshape(n1, n2, n3, order="F")
+
+
+def predict_adj(trace, sig, nw, forw, eps=1e-4):
+    t = _F(trace).copy()
+    s = _F(sig)
+    lib().pso_predict_adj(t.size, int(nw), ctypes.c_float(eps), int(forw), _p(t), _p(s))
+    return t

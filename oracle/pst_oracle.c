@@ -812,3 +812,208 @@ int pso_soint3d(const float *din, const float *mask, const float *dipi, const fl
     free(g); free(rr); free(gg); free(S); free(Ss); free(known);
     return 0;
 }
+
+/* ------------------------------------------------------------------ spray-operator interpolation */
+
+/* pwd_set(adj=true) soint3d_cfuns.c (same as sof3d_cfuns.c:460-478): inp = W'(W ... )' applied in
+ * the scatter order of the reference */
+static void wtw_apply_adj(predictor *P, float **a, float *io, float *tmp)
+{
+    int n = P->n1, nw = P->nw, na = 2 * nw + 1;
+    for (int i = 0; i < n; i++) tmp[i] = 0.f;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < na; j++) {
+            int k = i + j - nw;
+            if (k >= nw && k < n - nw) tmp[k] += a[j][k] * io[i];
+        }
+    for (int i = 0; i < n; i++) io[i] = 0.f;
+    for (int i = nw; i < n - nw; i++)
+        for (int j = 0; j < na; j++) io[i + j - nw] += a[j][i] * tmp[i];
+}
+
+/* predict_step(adj=true) soint3d_cfuns.c:1777-1804: solve first, then the adjoint of W'W */
+static void predict_adj(predictor *P, int forw, float *trace, const float *sg)
+{
+    int n1 = P->n1;
+    float eps2 = P->eps;
+    reg_fill(P);
+    wtw_add(P, forw, sg, P->a1);
+    ldl_factor(P);
+    ldl_solve(P, trace);
+    float t0 = trace[0], t1 = trace[1], t2 = trace[n1 - 2], t3 = trace[n1 - 1];
+    wtw_apply_adj(P, P->a1, trace, P->t1);
+    trace[0] += eps2 * t0; trace[1] += eps2 * t1; trace[n1 - 2] += eps2 * t2; trace[n1 - 1] += eps2 * t3;
+}
+
+void pso_predict_adj(int n1, int nw, float eps, int forw, float *trace, const float *sig)
+{
+    predictor *P = predictor_new(n1, nw, eps);
+    predict_adj(P, forw, trace, sig);
+    predictor_free(P);
+}
+
+/* pwspray_lop(adj=true, add=true) :1963-2003 on one [n2][n1] panel: u1 += spray'(u) */
+static void spray2_adj(predictor *P, const float *u, const float *dip, int n1, int n2, int ns, float *u1)
+{
+    int ns2 = 2 * ns + 1;
+    float *tr = falloc(n1);
+    for (int i = 0; i < n2; i++) {
+        for (int k = 0; k < n1; k++) tr[k] = 0.0f;
+        for (int is = ns - 1; is >= 0; is--) {
+            int ip = i + is + 1;
+            if (ip >= n2) continue;
+            const float *src = u + ((size_t)ip * ns2 + ns + is + 1) * n1;
+            for (int k = 0; k < n1; k++) tr[k] += src[k];
+            predict_adj(P, 1, tr, dip + (size_t)(ip - 1) * n1);
+        }
+        for (int k = 0; k < n1; k++) { u1[(size_t)i * n1 + k] += tr[k]; tr[k] = 0.0f; }
+        for (int is = ns - 1; is >= 0; is--) {
+            int ip = i - is - 1;
+            if (ip < 0) continue;
+            const float *src = u + ((size_t)ip * ns2 + ns - is - 1) * n1;
+            for (int k = 0; k < n1; k++) tr[k] += src[k];
+            predict_adj(P, 0, tr, dip + (size_t)ip * n1);
+        }
+        for (int k = 0; k < n1; k++) {
+            u1[(size_t)i * n1 + k] += tr[k];
+            tr[k] = u[((size_t)i * ns2 + ns) * n1 + k];
+            u1[(size_t)i * n1 + k] += tr[k];
+        }
+    }
+    free(tr);
+}
+
+typedef struct { predictor *P; int n1, n2, ns; float *u, *w1, *t; } smoother2;
+
+/* pwsmooth_set :2117-2132 (normalisation by the smooth of ones) */
+static void smoother2_set(smoother2 *s, const float *dip)
+{
+    size_t n12 = (size_t)s->n1 * s->n2;
+    for (size_t i = 0; i < n12; i++) s->w1[i] = 1.0f;
+    spray2(s->P, s->w1, dip, s->n1, s->n2, s->ns, s->u);
+    smooth2_apply(s->u, s->w1, s->n1, s->n2, s->ns, s->t);
+    for (size_t i = 0; i < n12; i++) s->w1[i] = (0.0f != s->t[i]) ? (float)(1.0 / s->t[i]) : 0.0f;
+}
+
+/* pwsmooth_lop :2079-2110: forward writes `out` (no add); adjoint ACCUMULATES into `in` when add */
+static void smoother2_fwd(smoother2 *s, const float *dip, const float *in, float *out)
+{
+    spray2(s->P, in, dip, s->n1, s->n2, s->ns, s->u);
+    smooth2_apply(s->u, s->w1, s->n1, s->n2, s->ns, out);
+}
+static void smoother2_adj(smoother2 *s, const float *dip, int add, float *in, const float *out)
+{
+    int ns2 = 2 * s->ns + 1;
+    size_t n12 = (size_t)s->n1 * s->n2;
+    if (!add) memset(in, 0, n12 * sizeof(float));
+    for (int i2 = 0; i2 < s->n2; i2++)
+        for (int k = 0; k < s->n1; k++) {
+            float ws = s->w1[(size_t)i2 * s->n1 + k];
+            for (int is = 0; is < ns2; is++) {
+                float w = (float)(s->ns + 1 - abs(is - s->ns));
+                s->u[((size_t)i2 * ns2 + is) * s->n1 + k] = out[(size_t)i2 * s->n1 + k] * w * ws;
+            }
+        }
+    spray2_adj(s->P, s->u, dip, s->n1, s->n2, s->ns, in);
+}
+
+typedef struct {
+    int n1, n2, n3, ns1, ns2, o1, o2; float eps;
+    const float *idip; float *xdipT;              /* xline slopes as [n2][n3][n1] */
+    float *itmp, *itmp2, *xtmp;
+} smoother3;
+
+/* pwsmooth3_lop :2231-2300 */
+static void smoother3_apply(smoother3 *S, int adj, int add, float *trace, float *smooth)
+{
+    int n1 = S->n1, n2 = S->n2, n3 = S->n3;
+    size_t n = (size_t)n1 * n2 * n3, n12 = (size_t)n1 * n2, n13 = (size_t)n1 * n3;
+    if (!add) { if (adj) memset(trace, 0, n * sizeof(float)); else memset(smooth, 0, n * sizeof(float)); }
+    smoother2 sa = { predictor_new(n1, S->o1, S->eps * S->eps), n1, n2, S->ns1, falloc(n12 * (2 * S->ns1 + 1)), falloc(n12), falloc(n12) };
+    smoother2 sb = { predictor_new(n1, S->o2, S->eps * S->eps), n1, n3, S->ns2, falloc(n13 * (2 * S->ns2 + 1)), falloc(n13), falloc(n13) };
+    if (adj) {
+        for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+            memcpy(S->xtmp + ((size_t)i2 * n3 + i3) * n1, smooth + ((size_t)i3 * n2 + i2) * n1, n1 * sizeof(float));
+        for (int i2 = 0; i2 < n2; i2++) {
+            smoother2_set(&sb, S->xdipT + i2 * n13);
+            smoother2_adj(&sb, S->xdipT + i2 * n13, 0, S->itmp2 + i2 * n13, S->xtmp + i2 * n13);
+        }
+        for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+            memcpy(S->itmp + ((size_t)i3 * n2 + i2) * n1, S->itmp2 + ((size_t)i2 * n3 + i3) * n1, n1 * sizeof(float));
+        for (int i3 = 0; i3 < n3; i3++) {
+            smoother2_set(&sa, S->idip + i3 * n12);
+            smoother2_adj(&sa, S->idip + i3 * n12, 1, trace + i3 * n12, S->itmp + i3 * n12);
+        }
+    } else {
+        for (int i3 = 0; i3 < n3; i3++) {
+            smoother2_set(&sa, S->idip + i3 * n12);
+            smoother2_fwd(&sa, S->idip + i3 * n12, trace + i3 * n12, S->itmp + i3 * n12);
+        }
+        for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+            memcpy(S->itmp2 + ((size_t)i2 * n3 + i3) * n1, S->itmp + ((size_t)i3 * n2 + i2) * n1, n1 * sizeof(float));
+        for (int i2 = 0; i2 < n2; i2++) {
+            smoother2_set(&sb, S->xdipT + i2 * n13);
+            smoother2_fwd(&sb, S->xdipT + i2 * n13, S->itmp2 + i2 * n13, S->xtmp + i2 * n13);
+        }
+        for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++) for (int k = 0; k < n1; k++)
+            smooth[k + (size_t)n1 * (i2 + (size_t)n2 * i3)] += S->xtmp[((size_t)i2 * n3 + i3) * n1 + k];
+    }
+    predictor_free(sa.P); free(sa.u); free(sa.w1); free(sa.t);
+    predictor_free(sb.P); free(sb.u); free(sb.w1); free(sb.t);
+}
+
+/* csint3d :2510-2640 */
+int pso_sint3d(const float *din, const float *dipi, const float *dipx, const float *mask,
+               int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, float eps,
+               float *out)
+{
+    size_t n = (size_t)n1 * n2 * n3;
+    unsigned char *known = (unsigned char *)malloc(n);
+    float lam = 0.;
+    for (size_t i = 0; i < n; i++) { if (mask[i] != 0.) { known[i] = 1; lam += 1.; } else known[i] = 0; }
+    lam = sqrtf(lam / n);
+    smoother3 S = { n1, n2, n3, ns1, ns2, order1, order2, eps, dipi, falloc(n), falloc(n), falloc(n), falloc(n) };
+    for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+        memcpy(S.xdipT + ((size_t)i2 * n3 + i3) * n1, dipx + ((size_t)i3 * n2 + i2) * n1, n1 * sizeof(float));
+    /* ps_conjgrad(NULL, mask, pwsmooth3, p = copy of data, x = mm, dat = mm, niter), hasp0 = true */
+    const float ceps = lam * lam, tol = 10 * 1.19209290e-07F;
+    float *p = falloc(n), *x = out, *r = falloc(n), *sp = falloc(n), *sx = falloc(n), *sr = falloc(n);
+    float *gp = falloc(n), *gx = falloc(n), *gr = falloc(n);
+    memcpy(p, din, n * sizeof(float));
+    for (size_t i = 0; i < n; i++) r[i] = -din[i];
+    smoother3_apply(&S, 0, 0, p, x);                                   /* x = S p */
+    for (size_t i = 0; i < n; i++) if (known[i]) r[i] += x[i];         /* r += L x */
+    double gn, gnp = 0., alpha, beta, g0 = 0., dg;
+    if (ddot(n, r, r) != 0.) {
+        for (int iter = 0; iter < niter; iter++) {
+            for (size_t i = 0; i < n; i++) { gp[i] = ceps * p[i]; gx[i] = -ceps * x[i]; }
+            for (size_t i = 0; i < n; i++) if (known[i]) gx[i] += r[i];       /* L' r, add */
+            smoother3_apply(&S, 1, 1, gp, gx);                                 /* gp += S' gx */
+            smoother3_apply(&S, 0, 0, gp, gx);                                 /* gx  = S gp */
+            for (size_t i = 0; i < n; i++) { gr[i] = 0.f; if (known[i]) gr[i] += gx[i]; }
+            gn = ddot(n, gp, gp);
+            if (iter == 0) {
+                g0 = gn;
+                memcpy(sp, gp, n * sizeof(float)); memcpy(sx, gx, n * sizeof(float)); memcpy(sr, gr, n * sizeof(float));
+            } else {
+                alpha = gn / gnp; dg = gn / g0;
+                if (alpha < tol || dg < tol) break;
+                float a = (float)alpha;
+                for (size_t i = 0; i < n; i++) {
+                    float t;
+                    t = gp[i] + a * sp[i]; gp[i] = sp[i]; sp[i] = t;
+                    t = gx[i] + a * sx[i]; gx[i] = sx[i]; sx[i] = t;
+                    t = gr[i] + a * sr[i]; gr[i] = sr[i]; sr[i] = t;
+                }
+            }
+            beta = ddot(n, sr, sr) + ceps * (ddot(n, sp, sp) - ddot(n, sx, sx));
+            alpha = -gn / beta;
+            float a = (float)alpha;
+            for (size_t i = 0; i < n; i++) { p[i] += a * sp[i]; x[i] += a * sx[i]; r[i] += a * sr[i]; }
+            gnp = gn;
+        }
+    }
+    free(p); free(r); free(sp); free(sx); free(sr); free(gp); free(gx); free(gr); free(known);
+    free(S.xdipT); free(S.itmp); free(S.itmp2); free(S.xtmp);
+    return 0;
+}

@@ -64,6 +64,15 @@ int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int n
 int pso_soint3d(const float *din, const float *mask, const float *dipi, const float *dipx,
                 int n1, int n2, int n3, int order, int niter, float *out);
 
+/* csint3d: soint3d_cfuns.c:2510-2640 (shaping CG, L = known-data mask :1350-1372, S = pwsmooth3_lop
+ * :2231-2300 = inline 2-D pwsmooth o transpose o xline 2-D pwsmooth, adjoint spray :1963-2003,
+ * predict_step(adj) :1777-1804; ps_conjgrad with hasp0 = true, eps = lam^2, tol = 10*FLT_EPSILON). */
+int pso_sint3d(const float *din, const float *dipi, const float *dipx, const float *mask,
+               int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, float eps,
+               float *out);
+/* one adjoint prediction step in place (unit-test hook): predict_step(adj=true) :1777-1804 */
+void pso_predict_adj(int n1, int nw, float eps, int forw, float *trace, const float *sig);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,13 @@ def main():
     for name, (order, niter, hasmask) in {"o2n20": (2, 20, 1), "o1n8": (1, 8, 1), "o2n6nomask": (2, 6, 0)}.items():
         g["soint3d_" + name] = dict(din=d0, mask=mk, dipi=pi_, dipx=px_, order=order, niter=niter, hasmask=hasmask,
                                     out=ref.soint3dc(d0, mk, pi_, px_, order=order, niter=niter, hasmask=hasmask))
+    # ---- sint3d (spray-operator shaping CG interpolation), same decimated cube
+    for name, (niter, ns1, ns2, o1, o2) in {"n6s11o11": (6, 1, 1, 1, 1), "n5s22o22": (5, 2, 2, 2, 2),
+                                            "n4s32o21": (4, 3, 2, 2, 1)}.items():
+        g["sint3d_" + name] = dict(din=d0, mask=mk, dipi=pi_, dipx=px_, niter=niter, ns1=ns1, ns2=ns2, order1=o1,
+                                   order2=o2, eps=0.01,
+                                   out=ref.sint3dc(d0, mk, pi_, px_, niter=niter, eps=0.01, ns1=ns1, ns2=ns2,
+                                                   order1=o1, order2=o2))
     # ---- 2-D: dip2d, somf2d, somean2d
     d2 = synth.cube(64, 24, 1, seed=12)
     p2 = ref.dip2dc(d2, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
@@ -67,7 +74,10 @@ def main():
     xs = synth.cube(30, 12, 6, seed=13)
     g["smooth_534"] = dict(x=xs, rect=[5, 3, 4], out=ref.smoothc(xs, [5, 3, 4]))
     g["smooth_big_radius"] = dict(x=xs, rect=[2, 15, 9], out=ref.smoothc(xs, [2, 15, 9]))
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for k, v in g.items():
+        if not k.startswith(only):
+            continue
         np.savez_compressed(os.path.join(OUT, k + ".npz"), **{a: np.asarray(b) for a, b in v.items()})
         print("wrote", k, {a: np.asarray(b).shape for a, b in v.items() if np.asarray(b).ndim})
 

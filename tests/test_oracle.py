@@ -49,6 +49,14 @@ def test_port_soint3d_matches_golden(port, name):
     assert np.array_equal(out, g["out"])
 
 
+@pytest.mark.parametrize("name", golden_names("sint3d_"))
+def test_port_sint3d_matches_golden(port, name):
+    g = golden(name)
+    out = port.sint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], niter=int(g["niter"]), eps=float(g["eps"]),
+                       ns1=int(g["ns1"]), ns2=int(g["ns2"]), order1=int(g["order1"]), order2=int(g["order2"]))
+    assert np.array_equal(out, g["out"])
+
+
 @pytest.mark.parametrize("name", golden_names("smooth_"))
 def test_port_smooth_matches_golden(port, name):
     g = golden(name)
