@@ -1,0 +1,10 @@
+// Streaming (persistent, warp-specialised, TMA-staged) triangle smoothing of one axis.
+// See pst_tri_stream.cu.  Results are bit-identical to ps_smooth2 (reference dip_cfuns.c:564-580).
+#pragma once
+#include <cuda_runtime.h>
+
+// true when the streaming kernel can run this axis (axis 0/1/2 of an n1 x n2 x n3 volume, radius nb)
+bool pst_tri_stream_ok(int axis, int n1, int n2, int n3, int nb, const void *src, const void *dst);
+// src -> dst (dst may alias src).  Returns 0, or < 0 when the launch could not be set up.
+int pst_tri_stream_launch(cudaStream_t stream, int sm_count, int axis, const float *src, float *dst,
+                          int n1, int n2, int n3, int nb, unsigned *d_err);
