@@ -41,12 +41,27 @@ constexpr int KB = 32;                 // samples (k) per pipeline stage
 constexpr int GP = 132;                // floats per 4-sample group in the t / B rings (132 = 4 mod 32)
 constexpr int TSTAGE = 8 * GP;         // floats per ring stage
 constexpr int NTS = 4;                 // t ring slots
-constexpr int NOS = 4;                 // B ring slots
+#ifndef TS_NOS
+#define TS_NOS 8
+#endif
+#ifndef TS_NXS
+#define TS_NXS 8
+#endif
+#ifndef TS_EARLY
+#define TS_EARLY 1
+#endif
+// PROTOCOL RULE: a ring's slot count must be a multiple of the number of warps that consume it
+// round-robin (each slot is then always waited on by the same warp).  mbarrier waits identify a
+// phase by its PARITY only, so a waiter may never run two phases ahead of a barrier; with, say, 6
+// slots and 4 consumer warps a warp can reach use n+1 of a slot before another warp's use n has
+// completed, and its wait falls through (observed: corrupted tiles and launch failures).
+constexpr int NOS = TS_NOS;            // B ring slots
 constexpr int NBW = 4;                 // builder warps
 constexpr int NSW = 4;                 // storer warps
 constexpr int NWARPS = 12;
 constexpr int NBMAX = 16;
-constexpr int NXS_MAX = 8;
+constexpr int NXS_MAX = TS_NXS;
+static_assert(NTS % NBW == 0 && NXS_MAX % NBW == 0 && NOS % NSW == 0, "ring slots must be a multiple of their consumer warps");
 
 // row pitch of a contiguous-axis x stage: 32 + 2nb samples rounded up to a 16-byte multiple and to
 // an ODD number of 16-byte units so that "lane = line" 128-bit reads are conflict-free.  The box
@@ -86,6 +101,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *b)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_probe(uint64_t *b, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
 }
 // spin with a wall-clock bound: a protocol bug must surface as an error, never as a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity, unsigned *err)
@@ -134,15 +156,19 @@ struct Cursor {
 //   forward chain of the next tile:       Fs += t            -> F_new[slot]
 // REV selects the slot order of this pass (ping-pong).
 template <bool REV, bool FWD, bool BWD>
-__device__ __forceinline__ void chain_stage_fast(float *Fl, const float *T, float *O, int G0, int NG, float &Fs, float &B)
+__device__ __forceinline__ void chain_stage_load(const float *Fl, const float *T, int G0, int NG, float4 (&tv)[8], float4 (&fv)[8])
 {
-    float4 tv[8], fv[8];
 #pragma unroll
     for (int g = 0; g < 8; g++) {
         const int PG = REV ? NG - 1 - (G0 + g) : G0 + g;
         if (BWD) fv[g] = *reinterpret_cast<const float4 *>(Fl + (size_t)PG * 128);
         if (FWD) tv[g] = *reinterpret_cast<const float4 *>(T + g * GP);
     }
+}
+template <bool REV, bool FWD, bool BWD>
+__device__ __forceinline__ void chain_stage_compute(float *Fl, float *O, int G0, int NG, const float4 (&tv)[8], const float4 (&fv)[8],
+                                                    float &Fs, float &B)
+{
 #pragma unroll
     for (int g = 0; g < 8; g++) {
         const int PG = REV ? NG - 1 - (G0 + g) : G0 + g;
@@ -165,7 +191,7 @@ __device__ __forceinline__ void chain_stage_fast(float *Fl, const float *T, floa
 // of the stage is kb = kb_hi - jj.  Right-tail sums are parked in ER until their mirror sample comes
 // by, heads (i < nb) are parked in EH until the left tail completes them; the storers map ring
 // steps kb < nb to sample nb-1-kb and skip kb in [nb, 2nb) and the right tail.
-__device__ __forceinline__ void chain_fold_fix(float *O, float *ER, float *EH, int lane, int kb_hi, int nx, int nb, int L)
+__device__ __noinline__ void chain_fold_fix(float *O, float *ER, float *EH, int lane, int kb_hi, int nx, int nb, int L)
 {
     const int kb_lo = kb_hi - (KB - 1);
     auto at = [&](int kb) -> float * { const int jj = kb_hi - kb; return O + (jj >> 2) * GP + (jj & 3); };
@@ -176,7 +202,8 @@ __device__ __forceinline__ void chain_fold_fix(float *O, float *ER, float *EH, i
 }
 
 // One pass of the chain warp over the NS stages of a line: forward chain of tile p (FWD) fused with
-// the backward chain of tile p-1 (BWD).
+// the backward chain of tile p-1 (BWD).  The barrier state of stage q+1 is probed while the FADD
+// chains of stage q run, so a ready stage costs no wait latency.
 template <bool REV, bool FWD, bool BWD>
 __device__ __forceinline__ void chain_pass(float *Fl, const float *Tr, float *Or, float *ER, float *EH, int lane,
                                            uint64_t *full_t, uint64_t *empty_t, uint64_t *full_o, uint64_t *empty_o,
@@ -185,20 +212,28 @@ __device__ __forceinline__ void chain_pass(float *Fl, const float *Tr, float *Or
     const int NG = NS * (KB / 4);
     float Fs = 0.f, B = 0.f;
     int kb_hi = L - 1;
+    bool rt = false, ro = false;
     for (int q = 0; q < NS; q++, kb_hi -= KB) {
-        if (FWD) mbar_wait(full_t + ct.slot, ct.par, err);
-        if (BWD) mbar_wait(empty_o + co.slot, co.par ^ 1u, err);
+        if (FWD && !rt) mbar_wait(full_t + ct.slot, ct.par, err);
+        if (BWD && !ro) mbar_wait(empty_o + co.slot, co.par ^ 1u, err);
         const float *T = Tr + ct.slot * TSTAGE + 4 * lane;
         float *O = Or + co.slot * TSTAGE + 4 * lane;
-        chain_stage_fast<REV, FWD, BWD>(Fl, T, O, q * (KB / 4), NG, Fs, B);
+        uint64_t *const rel_t = empty_t + ct.slot, *const sig_o = full_o + co.slot;
+        float4 tv[8], fv[8];
+        chain_stage_load<REV, FWD, BWD>(Fl, T, q * (KB / 4), NG, tv, fv);
+        if (FWD) { ct.slot = ct.slot + 1 == NTS ? 0 : ct.slot + 1; ct.par ^= (ct.slot == 0); }
+        if (BWD) { co.slot = co.slot + 1 == NOS ? 0 : co.slot + 1; co.par ^= (co.slot == 0); }
+        if (q + 1 < NS) {
+            if (FWD) rt = mbar_probe(full_t + ct.slot, ct.par);
+            if (BWD) ro = mbar_probe(empty_o + co.slot, co.par ^ 1u);
+        } else { rt = false; ro = false; }
+        chain_stage_compute<REV, FWD, BWD>(Fl, O, q * (KB / 4), NG, tv, fv, Fs, B);
         if (BWD && (kb_hi >= nx || kb_hi - (KB - 1) < 2 * nb)) chain_fold_fix(O, ER, EH, lane, kb_hi, nx, nb, L);
         __syncwarp();
         if (lane == 0) {
-            if (FWD) mbar_arrive(empty_t + ct.slot);
-            if (BWD) mbar_arrive(full_o + co.slot);
+            if (FWD) mbar_arrive(rel_t);
+            if (BWD) mbar_arrive(sig_o);
         }
-        if (FWD) ct.advance(1);
-        if (BWD) co.advance(1);
     }
 }
 
@@ -364,9 +399,11 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                 const float *ol = Or + co.slot * TSTAGE + (lane >> 2) * GP + (lane & 3);
                 float *dl = A.dst + line0 * nx + i;
                 if (valid) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int c = 0; c < nl; c++) dl[(long)c * nx] = ol[4 * c];
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_o + co.slot);
             } else {
                 // lane = line: a warp row is 128 contiguous bytes
                 const long ib = tile / A.tilesA;
@@ -375,20 +412,26 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                 float *dtile = A.dst + ib * A.sb + c0 + lane;
                 mbar_wait(full_o + co.slot, co.par, A.err);
                 const float *ol = Or + co.slot * TSTAGE + 4 * lane;
-                const int kb0 = L - 1 - q * KB;                       // backward position of step 0 of the stage
+                float4 o[8];
+#pragma unroll
+                for (int g = 0; g < 8; g++) o[g] = *reinterpret_cast<const float4 *>(ol + g * GP);
+                __syncwarp();
+                if (TS_EARLY && lane == 0) mbar_arrive(empty_o + co.slot);        // slot is in registers: release it before storing
+                const int kb0 = L - 1 - q * KB;                        // backward position of step 0 of the stage
                 if (kb0 < nx + nb && kb0 - (KB - 1) >= 2 * nb) {        // interior stage: every step is a plain sample
                     float *op = dtile + (long)(kb0 - nb) * A.d;
                     const long d = A.d;
+                    if (live) {
 #pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        const float4 o = *reinterpret_cast<const float4 *>(ol + g * GP);
-                        if (live) { op[0] = o.x; op[-d] = o.y; op[-2 * d] = o.z; op[-3 * d] = o.w; }
-                        op -= 4 * d;
+                        for (int g = 0; g < 8; g++) {
+                            op[0] = o[g].x; op[-d] = o[g].y; op[-2 * d] = o[g].z; op[-3 * d] = o[g].w;
+                            op -= 4 * d;
+                        }
                     }
                 } else {
+#pragma unroll
                     for (int g = 0; g < 8; g++) {
-                        const float4 o = *reinterpret_cast<const float4 *>(ol + g * GP);
-                        const float oa[4] = {o.x, o.y, o.z, o.w};
+                        const float oa[4] = {o[g].x, o[g].y, o[g].z, o[g].w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const int kb = kb0 - 4 * g - e;
@@ -402,8 +445,7 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_o + co.slot);
+            if (!CONTIG && !TS_EARLY) { __syncwarp(); if (lane == 0) mbar_arrive(empty_o + co.slot); }
             co.advance(NSW);
         }
     }
@@ -464,7 +506,7 @@ bool pst_tri_stream_ok(int axis, int n1, int n2, int n3, int nb, const void *src
     const int L = nx + 2 * nb, Lp = (L + KB - 1) / KB * KB;
     const int XW = xw_of(nb);
     const int xsf = axis == 0 ? 32 * XW : (KB + 2 * nb) * 32;
-    return smem_bytes(axis == 0, Lp, 3, xsf, nb) <= 226 * 1024;
+    return smem_bytes(axis == 0, Lp, NBW, xsf, nb) <= 226 * 1024;
 }
 
 int pst_tri_stream_launch(cudaStream_t stream, int sm_count, int axis, const float *src, float *dst,
@@ -485,7 +527,7 @@ int pst_tri_stream_launch(cudaStream_t stream, int sm_count, int axis, const flo
     A.XW = xw_of(nb);
     A.xsf = contig ? 32 * A.XW : (KB + 2 * nb) * 32;
     int nxs = NXS_MAX;
-    while (nxs > 3 && smem_bytes(contig, A.Lp, nxs, A.xsf, nb) > 226 * 1024) nxs--;
+    while (nxs > NBW && smem_bytes(contig, A.Lp, nxs, A.xsf, nb) > 226 * 1024) nxs -= NBW;   // multiples of NBW only
     A.nxs = nxs;
     const size_t smem = smem_bytes(contig, A.Lp, nxs, A.xsf, nb);
     if (smem > 226 * 1024) return -1;
