@@ -10,6 +10,7 @@
 // vectors are bit-identical to the reference's; only the global sums (double tree
 // reductions here, sequential sums there) may differ in the last bits of a double.
 #include "pst_common.cuh"
+#include "pst_tri_stream.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1352,8 +1353,17 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     const bool has_epi = epi && epi->kind != EPI_NONE;
     const bool vec = (g.n1 % 4 == 0) && al16(src) && al16(dst) &&
                      (!has_epi || (al16(epi->p) && al16(epi->w) && al16(epi->gp) && al16(epi->sp) && al16(epi->sx) && al16(epi->sr)));
-    const TilePlan tp = tile_plan(axis == 0, vec, nx, nb);
     c->stats.smooth_passes++;
+    // main path: the streaming (persistent, TMA-staged, ping-pong chain) kernel, pst_tri_stream.cu
+    static const bool stream_on = []() { const char *e = getenv("PST_TRI_STREAM"); return !(e && e[0] == '0'); }();
+    if (stream_on && !has_epi && pst_tri_stream_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
+        int rc = 0;
+        PST_LAUNCHB(c, cls, 8.0 * (double)g.n,
+                    rc = pst_tri_stream_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb, nullptr));
+        if (rc != 0) { pst_set_error("pst_tri_stream_launch failed (%d)", rc); return PST_ECUDA; }
+        return PST_OK;
+    }
+    const TilePlan tp = tile_plan(axis == 0, vec, nx, nb);
     if (tp.ok) {
         TriArgs A{};
         A.src = src; A.dst = dst; A.nx = nx; A.nb = nb; A.W = tp.W; A.pitch = tp.pitch;

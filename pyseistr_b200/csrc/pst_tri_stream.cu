@@ -191,13 +191,27 @@ __device__ __forceinline__ void chain_stage_compute(float *Fl, float *O, int G0,
 // of the stage is kb = kb_hi - jj.  Right-tail sums are parked in ER until their mirror sample comes
 // by, heads (i < nb) are parked in EH until the left tail completes them; the storers map ring
 // steps kb < nb to sample nb-1-kb and skip kb in [nb, 2nb) and the right tail.
-__device__ __noinline__ void chain_fold_fix(float *O, float *ER, float *EH, int lane, int kb_hi, int nx, int nb, int L)
+__device__ __noinline__ void chain_fold_fix(float *__restrict__ O, float *__restrict__ ER, float *__restrict__ EH, int lane,
+                                            int kb_hi, int nx, int nb, int L)
 {
     const int kb_lo = kb_hi - (KB - 1);
     auto at = [&](int kb) -> float * { const int jj = kb_hi - kb; return O + (jj >> 2) * GP + (jj & 3); };
-    for (int kb = min(L - 1, kb_hi); kb >= max(nx + nb, kb_lo); kb--) ER[(kb - nx - nb) * 32 + lane] = *at(kb);
-    for (int kb = min(nx + nb - 1, kb_hi); kb >= max(nx, kb_lo); kb--) { float *q = at(kb); *q = *q + ER[(nx - 1 - (kb - nb)) * 32 + lane]; }
+    if (kb_hi == L - 1) {
+        // first stage of the pass: it holds the whole right end (2nb <= 32 steps), so every mirror pair
+        // B_{nx+nb-1-r} + B_{nx+nb+r} is formed directly; all loads are independent
+#pragma unroll 4
+        for (int r = 0; r < nb; r++) {
+            float *q = O + ((nb + r) >> 2) * GP + ((nb + r) & 3);
+            const float *m = O + ((nb - 1 - r) >> 2) * GP + ((nb - 1 - r) & 3);
+            *q = *q + *m;
+        }
+    } else {
+        for (int kb = min(L - 1, kb_hi); kb >= max(nx + nb, kb_lo); kb--) ER[(kb - nx - nb) * 32 + lane] = *at(kb);
+        for (int kb = min(nx + nb - 1, kb_hi); kb >= max(nx, kb_lo); kb--) { float *q = at(kb); *q = *q + ER[(nx - 1 - (kb - nb)) * 32 + lane]; }
+    }
+#pragma unroll 4
     for (int kb = min(2 * nb - 1, kb_hi); kb >= max(nb, kb_lo); kb--) EH[(kb - nb) * 32 + lane] = *at(kb);
+#pragma unroll 4
     for (int kb = min(nb - 1, kb_hi); kb >= max(0, kb_lo); kb--) { float *q = at(kb); *q = EH[(nb - 1 - kb) * 32 + lane] + *q; }
 }
 

@@ -67,7 +67,12 @@ def test_allpass_bit_exact(ctx, port, order, xline, der):
 
 @pytest.mark.parametrize("shape,rect", [((40, 12, 9), (5, 5, 5)), ((33, 7, 5), (3, 4, 2)),
                                         ((64, 20, 1), (10, 10, 1)), ((30, 12, 6), (2, 15, 9)),
-                                        ((300, 9, 4), (40, 3, 1)), ((17, 5, 3), (1, 1, 1))])
+                                        ((300, 9, 4), (40, 3, 1)), ((17, 5, 3), (1, 1, 1)),
+                                        # streaming kernel (n1 % 4 == 0, radius <= 16): many tiles per CTA,
+                                        # partial 32-line tiles, line ends inside / across pipeline stages
+                                        ((256, 200, 150), (5, 5, 5)), ((100, 70, 37), (16, 2, 7)),
+                                        ((1000, 40, 33), (8, 3, 10)), ((36, 1030, 9), (4, 6, 2)),
+                                        ((12, 6, 1030), (3, 2, 13)), ((64, 64, 64), (9, 11, 12))])
 def test_smooth3_bit_exact(ctx, port, shape, rect):
     import pyseistr_b200 as ps
     x = synth.cube(*shape, seed=33)
