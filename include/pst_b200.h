@@ -136,6 +136,18 @@ int pst_soint3d_dev(pst_ctx *ctx, const float *d_din, const float *d_mask, const
                     const float *d_dipx, int n1, int n2, int n3, int nw, int nj1, int nj2, int niter,
                     int drift, int seed, int hasmask, float var, int verb, float *d_out);
 
+/* ---- 3-D interpolation by shaping-regularised CG with the plane-wave smoother as shaping operator.
+ * Replaces soint3dcfun.csint3d (pyseistr/src/soint3d_cfuns.c:2510-2640, "OOOOiiiiiiiiif": din, dipi,
+ * dipx, mask, n1, n2, n3, niter, ns1, ns2, order1, order2, verb, eps); called by sint3dc
+ * (pyseistr/sint.py:97-131).  Known samples are mask != 0; eps is the regularisation of the
+ * plane-wave predictions (squared internally, like the reference). */
+int pst_sint3d(pst_ctx *ctx, const float *din, const float *dipi, const float *dipx, const float *mask,
+               int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, int verb,
+               float eps, float *out);
+int pst_sint3d_dev(pst_ctx *ctx, const float *d_din, const float *d_dipi, const float *d_dipx,
+                   const float *d_mask, int n1, int n2, int n3, int niter, int ns1, int ns2,
+                   int order1, int order2, int verb, float eps, float *d_out);
+
 /* ---- building blocks exposed for parity tests and for the smoothing wrapper (SURVEY §8f
  * rank 1: dipcfun.smoothcf, dip_cfuns.c:2006-2123 with adj=0).  Device pointers. */
 int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1, int n2, int n3,

@@ -176,6 +176,22 @@ def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=[1, 1], drift=0, see
     return out.reshape(n1, n2, n3, order="F")
 
 
+def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, order2=1, verb=1, ctx=None):
+    """3-D structure-oriented interpolation by shaping-regularised CG, the plane-wave smoother
+    (inline then xline, radii ns1/ns2, PWD orders order1/order2) being the shaping operator
+    (reference pyseistr/sint.py:97-131 -> csint3d, soint3d_cfuns.c:2510-2640)."""
+    din = np.asarray(din)
+    n1, n2, n3 = _shape3(din)
+    c = _ctx(ctx)
+    d, a, b, m = _F(din), _F(dipi), _F(dipx), _F(mask)
+    if a.size != d.size or b.size != d.size or m.size != d.size:
+        raise ValueError("data, mask and slope volumes must have the same size")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_sint3d(c.handle, _p(d), _p(a), _p(b), _p(m), n1, n2, n3, int(niter), int(ns1), int(ns2),
+                                int(order1), int(order2), int(verb), float(eps), _p(out)))
+    return out.reshape(n1, n2, n3, order="F")
+
+
 def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=0, ctx=None):
     """N-D triangle smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf,
     dip_cfuns.c:2006-2123).  GPU path: the ps_smooth2 kernel dip3d uses, i.e. adj=0, no

@@ -469,3 +469,22 @@ extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, i
     t.stop();
     return PST_OK;
 }
+
+extern "C" int pst_sint3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx, const float *mask,
+                          int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, int verb,
+                          float eps, float *out)
+{
+    PST_ENTRY(c);
+    if (!din || !dipi || !dipx || !mask || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("sint3d: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * n3;
+    CallTimer t(c);
+    DevBuf d, m, a, b, o;
+    PST_TRY(up(c, d, din, n));
+    PST_TRY(up(c, m, mask, n));
+    PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_sint3d_dev(c, d.f(), a.f(), b.f(), m.f(), n1, n2, n3, niter, ns1, ns2, order1, order2, verb, eps, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}

@@ -703,3 +703,534 @@ int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, i
     if (option != 1) { pst_set_error("somf2d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
     return spray_filter_dev(c, 3, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, nmf, order, eps * eps, d_out);
 }
+
+// =======================================================================================
+// csint3d: interpolation by shaping-regularised CG with the plane-wave smoother as shaping
+// operator (reference soint3d_cfuns.c:2510-2640; ps_conjgrad with hasp0 = true :  p0 = data,
+// L = known-data mask :1350-1372, S = pwsmooth3_lop :2231-2300 = inline 2-D pwsmooth, transpose,
+// xline 2-D pwsmooth).  The forward smoother is the 2-D chain spray + normalised triangle
+// weights already used by somean2d; its ADJOINT needs the adjoint spray (pwspray_lop(adj)
+// :1963-2003) whose step is predict_step(adj = true) :1777-1804: solve the banded system FIRST,
+// then apply (W'W)' and the end terms.
+//
+// Volumes live in two trace-minor layouts: A = [i3][i1][i2] (panels = xline planes, traces along
+// i2) for the inline smoother and B = [i2][i1][i3] for the xline smoother; swap_ab_kernel moves
+// between them (a strided 2-D transpose per i1).  The CG vectors stay in layout A.
+// =======================================================================================
+
+// in: [P][n1][Q] (Q fastest)  ->  out: [Q][n1][P] (P fastest)
+__global__ void swap_ab_kernel(const float *__restrict__ in, float *__restrict__ out, int P, int n1, int Q, int zero_plus)
+{
+    __shared__ float tile[32][33];
+    const int i1 = blockIdx.z;
+    const int q0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, q = q0 + threadIdx.x;
+        if (p < P && q < Q) tile[r][threadIdx.x] = in[((long)p * n1 + i1) * Q + q];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int q = q0 + r, p = p0 + threadIdx.x;
+        if (p < P && q < Q) {
+            float v = tile[threadIdx.x][r];
+            if (zero_plus) v = 0.f + v;                      // "smooth[] += xtmp" onto a zeroed volume (:2296)
+            out[((long)q * n1 + i1) * P + p] = v;
+        }
+    }
+}
+
+static int swap_ab(pst_ctx *c, const float *in, float *out, int P, int n1, int Q, bool zero_plus = false)
+{
+    const int zmax = 32768;
+    if (n1 > zmax) { pst_set_error("sint3d: n1 > %d unsupported", zmax); return PST_EUNSUP; }
+    dim3 grid((Q + 31) / 32, (P + 31) / 32, n1), block(32, 8);
+    PST_LAUNCHB(c, PST_K_OTHER, 8.0 * (double)P * n1 * Q, (swap_ab_kernel<<<grid, block, 0, c->stream>>>(in, out, P, n1, Q, zero_plus ? 1 : 0)));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+struct AdjArgs {
+    float *tr;                 // [panel][k][i2]: running adjoint trace of every model trace i (in/out)
+    const float *data;         // data-side volume ("out" of pwsmooth_lop), same layout
+    const float *tnorm;        // normalisation t; ws = (t != 0 ? 1/t : 0)
+    const float *sg;           // slopes, same layout
+    float *scr;                // factor scratch [panel in launch][k][NB+2][i2]
+    float wslot;               // triangle weight of the slot feeding this level
+    int shift;                 // data trace ip = i + shift
+    int sg_shift;              // slope trace = i + sg_shift
+    int forw;
+    int n1, n2;
+    int p0;                    // first panel of this launch
+    RegC reg;
+    BTabS tb;
+};
+
+// One thread = one model trace i of one panel:  tr <- predict_step(adj)( tr + u_slot[ip] ),
+// u_slot[ip] = (data[ip] * wslot) * ws[ip]  (pwsmooth_lop(adj) :2096-2104, pwspray_lop(adj) :1971-1999).
+template <int NW>
+__global__ void __launch_bounds__(128)
+predict_adj_kernel(const AdjArgs A)
+{
+    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 2;
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= A.n2) return;
+    const int ip = i2 + A.shift;
+    if (ip < 0 || ip >= A.n2) return;                        // "continue": the running trace is left alone
+    const int n1 = A.n1, n2 = A.n2;
+    const long pbase = (long)(A.p0 + blockIdx.y) * n1 * n2;
+    float *tr = A.tr + pbase + i2;
+    const float *dat = A.data + pbase + ip;
+    const float *tn = A.tnorm + pbase + ip;
+    const float *g1 = A.sg + pbase + (i2 + A.sg_shift);
+    float *scr = A.scr + ((long)blockIdx.y * n1 * NC) * n2 + i2;
+    const bool f1 = A.forw != 0;
+    const RegC rg = A.reg;
+
+    // ---- pass 1 (ascending): taps -> W'W bands + regularisation -> LDL' column -> forward substitution
+    float W1[NA][NA];
+    float O[NB][NB], D[NB], Bh[NB];
+#pragma unroll
+    for (int cc = 0; cc < NA; cc++)
+#pragma unroll
+        for (int j = 0; j < NA; j++) W1[cc][j] = 0.f;
+#pragma unroll
+    for (int h = 0; h < NB; h++) {
+        D[h] = 0.f; Bh[h] = 0.f;
+#pragma unroll
+        for (int m = 0; m < NB; m++) O[h][m] = 0.f;
+    }
+    for (int i = -NW; i < n1; i++) {
+        const int kk = i + NW;
+        {
+            float a1[NA];
+            if (kk < n1) spray_taps<NW>(A.tb, g1[(long)kk * n2], f1, a1);
+            else {
+#pragma unroll
+                for (int j = 0; j < NA; j++) a1[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < NA; j++) W1[NA - 1][j] = a1[j];
+        }
+        if (i >= 0) {
+            float dg = rg.d_in;
+            if (i == 0 || i == n1 - 1) dg = rg.d_e0;
+            if (i == 1 || i == n1 - 2) dg = rg.d_e1;
+            float of[NB];
+            of[0] = (i == 0 || i == n1 - 2) ? rg.o0_e : rg.o0_in;
+            of[1] = rg.o1;
+#pragma unroll
+            for (int m = 2; m < NB; m++) of[m] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NA; j++) {
+                const int k = i + j - NW;
+                if (k >= NW && k < n1 - NW) { const float aj = W1[j][j]; dg += aj * aj; }
+            }
+#pragma unroll
+            for (int m = 0; m < NB; m++) {
+#pragma unroll
+                for (int j = m + 1; j < NA; j++) {
+                    const int k = i + j - NW;
+                    if (k >= NW && k < n1 - NW) of[m] += W1[j][j - m - 1] * W1[j][j];
+                }
+            }
+            // right-hand side: the running trace plus the slot contribution
+            const float tv = tn[(long)i * n2];
+            const float ws = (0.0f != tv) ? (float)(1.0 / (double)tv) : 0.0f;
+            const float u = dat[(long)i * n2] * A.wslot * ws;
+            const float rhs = tr[(long)i * n2] + u;
+            float t = dg;
+#pragma unroll
+            for (int m = 0; m < NB; m++)
+                if (m < i) t -= (O[m][m] * O[m][m]) * D[m];
+            const float dk = t;
+            float ok[NB];
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                float v = of[q];
+#pragma unroll
+                for (int m = 0; m < NB - q - 1; m++)
+                    if (m < i) v -= (O[m][m] * O[m][q + m + 1]) * D[m];
+                ok[q] = (q < n1 - i - 1) ? v / dk : 0.f;
+            }
+            float bk = rhs;
+#pragma unroll
+            for (int m = 0; m < NB; m++)
+                if (m < i) bk -= O[m][m] * Bh[m];
+            float *sc = scr + (long)i * NC * n2;
+            sc[0] = dk;
+#pragma unroll
+            for (int q = 0; q < NB; q++) sc[(long)(1 + q) * n2] = ok[q];
+            sc[(long)(NB + 1) * n2] = bk;
+#pragma unroll
+            for (int h = NB - 1; h > 0; h--) {
+                D[h] = D[h - 1]; Bh[h] = Bh[h - 1];
+#pragma unroll
+                for (int m = 0; m < NB; m++) O[h][m] = O[h - 1][m];
+            }
+            D[0] = dk; Bh[0] = bk;
+#pragma unroll
+            for (int m = 0; m < NB; m++) O[0][m] = ok[m];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NA - 1; cc++)
+#pragma unroll
+            for (int j = 0; j < NA; j++) W1[cc][j] = W1[cc + 1][j];
+    }
+    // ---- pass 2 (descending): back substitution, y stored in place
+    float Y[NB];
+#pragma unroll
+    for (int m = 0; m < NB; m++) Y[m] = 0.f;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int k = n1 - 1; k >= 0; k--) {
+        const float *sc = scr + (long)k * NC * n2;
+        const float dk = sc[0];
+        float t = sc[(long)(NB + 1) * n2] / dk;
+#pragma unroll
+        for (int m = 0; m < NB; m++)
+            if (m < n1 - k - 1) t -= sc[(long)(1 + m) * n2] * Y[m];
+        tr[(long)k * n2] = t;
+        if (k == 0) t0 = t;
+        if (k == 1) t1 = t;
+        if (k == n1 - 2) t2 = t;
+        if (k == n1 - 1) t3 = t;
+#pragma unroll
+        for (int m = NB - 1; m > 0; m--) Y[m] = Y[m - 1];
+        Y[0] = t;
+    }
+    // ---- pass 3 (ascending): pwd_set(adj = true): tmp = W y (rows [nw, n-nw), scatter order), out = W' tmp
+    // windows at leading row e: YW[c] = y[e - NW + c]; W1[c][.] / TM[c] <-> row e - 2NW + c
+    float YW[NA], TM[NA];
+#pragma unroll
+    for (int cc = 0; cc < NA; cc++) {
+        const int idx = cc - NW;
+        YW[cc] = (idx >= 0 && idx < n1) ? tr[(long)idx * n2] : 0.f;
+        TM[cc] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NA; j++) W1[cc][j] = 0.f;
+    }
+    for (int e = 0; e < n1 + NW; e++) {
+        float a1[NA];
+        float tm = 0.f;
+        if (e >= NW && e < n1 - NW) {
+            spray_taps<NW>(A.tb, g1[(long)e * n2], f1, a1);
+#pragma unroll
+            for (int j = NA - 1; j >= 0; j--) tm += a1[j] * YW[NA - 1 - j];      // io index ascending
+        } else {
+#pragma unroll
+            for (int j = 0; j < NA; j++) a1[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NA; j++) W1[NA - 1][j] = a1[j];
+        TM[NA - 1] = tm;
+        const int m = e - NW;
+        if (m >= 0) {
+            float o = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < NA; cc++) {
+                const int i = m - NW + cc;
+                if (i >= NW && i < n1 - NW) o += W1[cc][NA - 1 - cc] * TM[cc];
+            }
+            if (m == 0) o += rg.eps2 * t0;
+            if (m == 1) o += rg.eps2 * t1;
+            if (m == n1 - 2) o += rg.eps2 * t2;
+            if (m == n1 - 1) o += rg.eps2 * t3;
+            tr[(long)m * n2] = o;
+        }
+#pragma unroll
+        for (int cc = 0; cc < NA - 1; cc++) {
+            YW[cc] = YW[cc + 1]; TM[cc] = TM[cc + 1];
+#pragma unroll
+            for (int j = 0; j < NA; j++) W1[cc][j] = W1[cc + 1][j];
+        }
+        {
+            const int idx = e + 1 + NW;
+            YW[NA - 1] = (idx < n1) ? tr[(long)idx * n2] : 0.f;
+        }
+    }
+}
+
+// in = ((in + trP) + trM) + (data * w_centre) * ws      (pwspray_lop(adj) :1985-2001)
+__global__ void __launch_bounds__(256)
+adj_combine_kernel(float *__restrict__ in, const float *__restrict__ trP, const float *__restrict__ trM,
+                   const float *__restrict__ data, const float *__restrict__ tnorm, float wc, int add, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float tv = tnorm[i];
+        const float ws = (0.0f != tv) ? (float)(1.0 / (double)tv) : 0.0f;
+        float v = add ? in[i] : 0.f;
+        v += trP[i];
+        v += trM[i];
+        v += data[i] * wc * ws;
+        in[i] = v;
+    }
+}
+
+// 2-D plane-wave smoother over the traces of every panel of a trace-minor volume
+struct Smoother2 {
+    int n1, nt, npanel, ns, nw;        // nt traces per panel
+    float eps_reg;
+    const float *dip;                  // slopes (trace-minor)
+    float *tnorm;                      // spray of ones through the weights (pwsmooth_set)
+    SprayPlan P;
+};
+
+static void smoother_plan(Smoother2 &S)
+{
+    SprayPlan &P = S.P;
+    P = SprayPlan{};
+    P.n1 = S.n1; P.n2 = S.nt; P.n3 = S.npanel; P.ns2 = S.ns; P.ns3 = 0; P.nw = S.nw;
+    P.np2 = 2 * S.ns + 1; P.np3 = 1; P.np = P.np2;
+    P.eps_reg = S.eps_reg;
+    P.zs0 = 0; P.zs1 = S.npanel; P.zt0 = 0; P.zt1 = S.npanel;
+    for (int s = 0; s < P.np; s++) P.live[s] = true;
+}
+
+static int smoother_fwd(pst_ctx *c, const Smoother2 &S, const float *in, float *out, bool norm)
+{
+    const size_t mark = c->arena_used;
+    ReduceOut R{out, 0, norm ? S.tnorm : nullptr, norm ? 1 : 0};
+    PST_TRY(spray_run(c, S.P, in, S.dip, nullptr, reduce_wsum, &R));
+    c->arena_used = mark;
+    return PST_OK;
+}
+
+static int smoother_set(pst_ctx *c, Smoother2 &S, float *ones_scratch)
+{
+    const size_t n = (size_t)S.n1 * S.nt * S.npanel;
+    PST_LAUNCH(c, PST_K_OTHER, (fill_kernel_s<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(ones_scratch, 1.0f, n)));
+    return smoother_fwd(c, S, ones_scratch, S.tnorm, false);
+}
+
+// in (+)= S' data ; trP / trM: two work volumes
+static int smoother_adj(pst_ctx *c, const Smoother2 &S, float *in, const float *data, bool add, float *trP, float *trM)
+{
+    const size_t plane = (size_t)S.n1 * S.nt, n = plane * S.npanel;
+    const int NC = 2 * S.nw + 2;
+    PST_CUDA(cudaMemsetAsync(trP, 0, n * sizeof(float), c->stream));
+    PST_CUDA(cudaMemsetAsync(trM, 0, n * sizeof(float), c->stream));
+    const size_t mark = c->arena_used;
+    int cz = (int)std::max<double>(1.0, std::min<double>((double)S.npanel, 3.0e9 / ((double)plane * 4.0 * NC)));
+    float *scr;
+    PST_TRY(pst_arena_get(c, plane * (size_t)cz * NC, &scr));
+    AdjArgs A{};
+    A.data = data; A.tnorm = S.tnorm; A.sg = S.dip; A.scr = scr; A.n1 = S.n1; A.n2 = S.nt;
+    A.reg = make_reg(S.eps_reg); A.tb = make_btab_s(S.nw);
+    const int threads = S.nt >= 128 ? 128 : (S.nt >= 64 ? 64 : 32);
+    for (int side = 0; side < 2; side++) {
+        A.tr = side == 0 ? trP : trM;
+        A.forw = side == 0 ? 1 : 0;
+        for (int is = S.ns - 1; is >= 0; is--) {
+            A.shift = side == 0 ? (is + 1) : -(is + 1);
+            A.sg_shift = side == 0 ? is : -(is + 1);                     // dip[ip-1] (forw) / dip[ip]
+            const int slot = side == 0 ? S.ns + is + 1 : S.ns - is - 1;
+            A.wslot = (float)(S.ns + 1 - abs(slot - S.ns));
+            for (int p0 = 0; p0 < S.npanel; p0 += cz) {
+                A.p0 = p0;
+                dim3 grid((S.nt + threads - 1) / threads, std::min(cz, S.npanel - p0));
+                PST_LAUNCHB(c, PST_K_PREDICT, 20.0 * (double)plane * grid.y,
+                    if (S.nw == 1) predict_adj_kernel<1><<<grid, threads, 0, c->stream>>>(A);
+                    else           predict_adj_kernel<2><<<grid, threads, 0, c->stream>>>(A));
+                c->stats.predictions += (long long)grid.y * S.nt;
+            }
+        }
+    }
+    PST_LAUNCH(c, PST_K_SLOTRED, (adj_combine_kernel<<<pst_grid_for(c, n, 256), 256, 0, c->stream>>>(
+        in, trP, trM, data, S.tnorm, (float)(S.ns + 1), add ? 1 : 0, n)));
+    PST_CUDA(cudaGetLastError());
+    c->arena_used = mark;
+    return PST_OK;
+}
+
+// ---- vector kernels of ps_conjgrad as csint3d runs it (dip_cfuns.c-style shaping CG, soint3d_cfuns.c copy)
+__global__ void __launch_bounds__(256)
+sint_init_kernel(const float *__restrict__ d, float *__restrict__ p, float *__restrict__ r, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = d[i];
+        p[i] = v; r[i] = -v;
+    }
+}
+// r += L x (known samples) ; partial r.r
+__global__ void __launch_bounds__(256)
+sint_resid_kernel(float *__restrict__ r, const float *__restrict__ x, const unsigned char *__restrict__ known, size_t n,
+                  double *__restrict__ partial)
+{
+    double acc[1] = {0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = r[i];
+        if (known[i]) v += x[i];
+        r[i] = v;
+        acc[0] += (double)v * v;
+    }
+    pst_block_reduce<1>(acc, partial);
+}
+// gp = eps p ; gx = -eps x (+ r where known)
+__global__ void __launch_bounds__(256)
+sint_grad_kernel(const float *__restrict__ p, const float *__restrict__ x, const float *__restrict__ r,
+                 const unsigned char *__restrict__ known, float eps, float *__restrict__ gp, float *__restrict__ gx, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        gp[i] = eps * p[i];
+        float g = -eps * x[i];
+        if (known[i]) g += r[i];
+        gx[i] = g;
+    }
+}
+// gr = L gx ; s = g (+ alpha s) with the reference's swap ; partials: gn is formed before (separate kernel)
+template <bool FIRST>
+__global__ void __launch_bounds__(256)
+sint_dir_kernel(float *__restrict__ gp, float *__restrict__ gx, const unsigned char *__restrict__ known,
+                float *__restrict__ sp, float *__restrict__ sx, float *__restrict__ sr, float alpha, size_t n,
+                double *__restrict__ partial)
+{
+    double acc[3] = {0., 0., 0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gpi = gp[i], gxi = gx[i];
+        float gri = 0.f;
+        if (known[i]) gri += gxi;
+        float a, b, cc;
+        if (FIRST) { a = gpi; b = gxi; cc = gri; }
+        else {
+            a = gpi + alpha * sp[i];
+            b = gxi + alpha * sx[i];
+            cc = gri + alpha * sr[i];
+        }
+        sp[i] = a; sx[i] = b; sr[i] = cc;
+        acc[0] += (double)cc * cc;
+        acc[1] += (double)a * a;
+        acc[2] += (double)b * b;
+    }
+    pst_block_reduce<3>(acc, partial);
+}
+__global__ void __launch_bounds__(256)
+sint_update_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r, const float *__restrict__ sp,
+                   const float *__restrict__ sx, const float *__restrict__ sr, float alpha, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        p[i] += alpha * sp[i];
+        x[i] += alpha * sx[i];
+        r[i] += alpha * sr[i];
+    }
+}
+__global__ void __launch_bounds__(256)
+sint_sumsq_kernel(const float *__restrict__ v, size_t n, double *__restrict__ partial)
+{
+    double acc[1] = {0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc[0] += (double)v[i] * v[i];
+    pst_block_reduce<1>(acc, partial);
+}
+// known = (mask != 0), partial count
+__global__ void __launch_bounds__(256)
+sint_known_kernel(const float *__restrict__ mask, unsigned char *__restrict__ known, size_t n, double *__restrict__ partial)
+{
+    double acc[1] = {0.};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned char k = mask[i] != 0.f;
+        known[i] = k;
+        acc[0] += k;
+    }
+    pst_block_reduce<1>(acc, partial);
+}
+
+extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dipi, const float *d_dipx,
+                              const float *d_mask, int n1, int n2, int n3, int niter, int ns1, int ns2,
+                              int order1, int order2, int verb, float eps, float *d_out)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    if (!d_din || !d_dipi || !d_dipx || !d_mask || !d_out) { pst_set_error("sint3d: null pointer"); return PST_EINVAL; }
+    PST_TRY(check_spray_args(n1, n2, n3, ns1, 0, order1));
+    PST_TRY(check_spray_args(n1, n3, n2, ns2, 0, order2));
+    if (niter < 0) { pst_set_error("sint3d: niter < 0"); return PST_EINVAL; }
+    if (c->comm && c->nranks > 1) { pst_set_error("sint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
+    PST_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)n1 * n2 * n3;
+    const int NCmax = 2 * std::max(order1, order2) + 2, nsmax = std::max(ns1, ns2);
+    // 9 CG vectors + 2 dips + 2 norms + 4 work volumes + mask + spray slots/scratch (bounded chunks)
+    const double chunk = std::min<double>(6.0e9 + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * nsmax + 1 + NCmax));
+    PST_TRY(pst_arena_reserve(c, (size_t)(19 * n * sizeof(float) + n + chunk + 3.0e9 + 64 * 4096)));
+    pst_arena_reset(c);
+    float *dipA, *dipB, *tnA, *tnB, *p, *x, *r, *sp, *sx, *sr, *gp, *gx, *wA1, *wA2, *wB1, *wB2, *dA;
+    unsigned char *known;
+    float **all[] = {&dipA, &dipB, &tnA, &tnB, &p, &x, &r, &sp, &sx, &sr, &gp, &gx, &wA1, &wA2, &wB1, &wB2, &dA};
+    for (float **q : all) PST_TRY(pst_arena_get(c, n, q));
+    PST_TRY(pst_arena_get(c, n, &known));
+    const int threads = 256, grid = pst_grid_for(c, n, threads);
+    double h[PST_RED_SLOTS];
+
+    // reference layout [i3][i2][i1] -> A = [i3][i1][i2];  B = [i2][i1][i3] = swap(A)
+    PST_TRY(transpose_planes(c, d_dipi, dipA, n2, n1, n3));
+    PST_TRY(transpose_planes(c, d_dipx, wA1, n2, n1, n3));
+    PST_TRY(swap_ab(c, wA1, dipB, n3, n1, n2));
+    PST_TRY(transpose_planes(c, d_din, dA, n2, n1, n3));
+    PST_TRY(transpose_planes(c, d_mask, wA1, n2, n1, n3));
+    PST_LAUNCH(c, PST_K_OTHER, (sint_known_kernel<<<grid, threads, 0, c->stream>>>(wA1, known, n, c->d_partial)));
+    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_TRY(pst_fetch_record(c, 8, 1, h));
+    // "lam += 1." on a float saturates at 2^24 (soint3d_cfuns.c:2583-2592)
+    float lam = (float)std::min(h[0], 16777216.0);
+    lam = sqrtf(lam / (float)n);
+    const float ceps = lam * lam;
+    const double tol = 10 * 1.19209290e-07F;
+
+    Smoother2 SA{n1, n2, n3, ns1, order1, eps * eps, dipA, tnA, {}}, SB{n1, n3, n2, ns2, order2, eps * eps, dipB, tnB, {}};
+    smoother_plan(SA);
+    smoother_plan(SB);
+    PST_TRY(smoother_set(c, SA, wA1));
+    PST_TRY(smoother_set(c, SB, wB1));
+    // S (forward): out = swap(SB(swap(SA(in))))
+    auto S_fwd = [&](const float *in, float *out) -> int {
+        PST_TRY(smoother_fwd(c, SA, in, wA1, true));
+        PST_TRY(swap_ab(c, wA1, wB1, n3, n1, n2));
+        PST_TRY(smoother_fwd(c, SB, wB1, wB2, true));
+        PST_TRY(swap_ab(c, wB2, out, n2, n1, n3, true));
+        return PST_OK;
+    };
+    // S' (adjoint, accumulating): io += SA'(swap(SB'(swap(data))))
+    auto S_adj_add = [&](float *io, const float *data) -> int {
+        PST_TRY(swap_ab(c, data, wB1, n3, n1, n2));
+        // work volumes for the xline side: wB2 (result), wA1/wA2 reinterpreted as B-layout scratch (same size)
+        PST_TRY(smoother_adj(c, SB, wB2, wB1, false, wA1, wA2));
+        PST_TRY(swap_ab(c, wB2, wA1, n2, n1, n3));
+        PST_TRY(smoother_adj(c, SA, io, wA1, true, wA2, wB1));
+        return PST_OK;
+    };
+
+    PST_LAUNCH(c, PST_K_OTHER, (sint_init_kernel<<<grid, threads, 0, c->stream>>>(dA, p, r, n)));
+    PST_TRY(S_fwd(p, x));
+    PST_LAUNCH(c, PST_K_OTHER, (sint_resid_kernel<<<grid, threads, 0, c->stream>>>(r, x, known, n, c->d_partial)));
+    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_TRY(pst_fetch_record(c, 8, 1, h));
+    if (h[0] != 0.) {
+        double gn, gnp = 0., alpha, beta, g0 = 0., dg;
+        for (int iter = 0; iter < niter; iter++) {
+            PST_LAUNCH(c, PST_K_CGHEAD, (sint_grad_kernel<<<grid, threads, 0, c->stream>>>(p, x, r, known, ceps, gp, gx, n)));
+            PST_TRY(S_adj_add(gp, gx));
+            PST_TRY(S_fwd(gp, gx));
+            PST_LAUNCH(c, PST_K_OTHER, (sint_sumsq_kernel<<<grid, threads, 0, c->stream>>>(gp, n, c->d_partial)));
+            PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+            PST_TRY(pst_fetch_record(c, 8, 1, h));
+            gn = h[0];
+            if (iter == 0) {
+                g0 = gn;
+                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<true><<<grid, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, 0.f, n, c->d_partial)));
+            } else {
+                alpha = gn / gnp;
+                dg = gn / g0;
+                if (alpha < tol || dg < tol) break;
+                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<false><<<grid, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, (float)alpha, n, c->d_partial)));
+            }
+            PST_TRY(pst_finish_reduce(c, grid, 3, 9));
+            PST_TRY(pst_fetch_record(c, 9, 3, h));
+            beta = h[0] + (double)ceps * (h[1] - h[2]);
+            alpha = -gn / beta;
+            if (verb) printf("[pst] sint3d iteration %d gn %g\n", iter + 1, gn);
+            PST_LAUNCH(c, PST_K_CGHEAD, (sint_update_kernel<<<grid, threads, 0, c->stream>>>(p, x, r, sp, sx, sr, (float)alpha, n)));
+            gnp = gn;
+            c->stats.cg_iterations++;
+        }
+    }
+    PST_TRY(transpose_planes(c, x, d_out, n1, n2, n3));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
