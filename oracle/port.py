@@ -138,7 +138,8 @@ def somean2dc(dn, dip, ns, order, eps, adj=0, verb=0):
     n1, n2, n3 = _shape3(dn)
     d, a = _F(dn), _F(dip)
     out = np.zeros_like(d)
-    lib().pso_somean2d(_p(d), _p(a), n1, n2, n3, ns, order, ctypes.c_float(eps), _p(out))
+    fn = lib().pso_somean2d_adj if adj else lib().pso_somean2d
+    fn(_p(d), _p(a), n1, n2, n3, ns, order, ctypes.c_float(eps), _p(out))
     return np.squeeze(out.reshape(n1, n2, n3, order="F"))
 
 

@@ -917,6 +917,20 @@ static void smoother2_adj(smoother2 *s, const float *dip, int add, float *in, co
     spray2_adj(s->P, s->u, dip, s->n1, s->n2, s->ns, in);
 }
 
+/* csomean2d with adj=1 (sof_cfuns.c:1503-1508): per slice pwsmooth_set, then smooth = S' input */
+int pso_somean2d_adj(const float *din, const float *dip, int n1, int n2, int n3, int ns, int order,
+                     float eps, float *out)
+{
+    size_t n12 = (size_t)n1 * n2;
+    smoother2 s = { predictor_new(n1, order, eps * eps), n1, n2, ns, falloc(n12 * (2 * ns + 1)), falloc(n12), falloc(n12) };
+    for (int i3 = 0; i3 < n3; i3++) {
+        smoother2_set(&s, dip + i3 * n12);
+        smoother2_adj(&s, dip + i3 * n12, 0, out + i3 * n12, din + i3 * n12);
+    }
+    predictor_free(s.P); free(s.u); free(s.w1); free(s.t);
+    return 0;
+}
+
 typedef struct {
     int n1, n2, n3, ns1, ns2, o1, o2; float eps;
     const float *idip; float *xdipT;              /* xline slopes as [n2][n3][n1] */

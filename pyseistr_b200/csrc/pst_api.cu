@@ -396,6 +396,8 @@ extern "C" int pst_somf3d(pst_ctx *c, const float *din, const float *dipi, const
 
 int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
                      int order, float eps, float *d_out);
+int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                         int order, float eps, float *d_out);
 int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
                    int nmf, int option, int order, float eps, float *d_out);
 
@@ -405,13 +407,14 @@ extern "C" int pst_somean2d(pst_ctx *c, const float *din, const float *dip, int 
     (void)verb;
     PST_ENTRY(c);
     if (!din || !dip || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean2d: null pointer or bad shape"); return PST_EINVAL; }
-    if (adj) { pst_set_error("somean2d: adj=1 (adjoint smoothing) not implemented on the GPU path"); return PST_EUNSUP; }
+
     const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
     CallTimer t(c);
     DevBuf d, a, o;
     PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dip, n));
     PST_TRY(o.alloc(n * sizeof(float)));
-    PST_TRY(pst_somean2d_dev(c, d.f(), a.f(), n1, n2, n3, ns, order, eps, o.f()));
+    if (adj) PST_TRY(pst_somean2d_adj_dev(c, d.f(), a.f(), n1, n2, n3, ns, order, eps, o.f()));
+    else PST_TRY(pst_somean2d_dev(c, d.f(), a.f(), n1, n2, n3, ns, order, eps, o.f()));
     PST_TRY(down(c, out, o, n));
     t.stop();
     return PST_OK;

@@ -1234,3 +1234,29 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
+
+// csomean2d with adj = 1 (sof_cfuns.c:1503-1508): out = S' din per slice
+int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
+                         int order, float eps, float *d_out)
+{
+    PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
+    if (c->comm && c->nranks > 1) { pst_set_error("somean2d(adj): distributed contexts not supported"); return PST_EUNSUP; }
+    PST_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)n1 * n2 * n3;
+    const int NC = 2 * order + 2;
+    const double chunk = std::min<double>(6.0e9 + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * ns + 1 + NC));
+    PST_TRY(pst_arena_reserve(c, (size_t)(7 * n * sizeof(float) + chunk + 3.0e9 + 64 * 4096)));
+    pst_arena_reset(c);
+    float *dipA, *tn, *dA, *oA, *w1, *w2;
+    float **all[] = {&dipA, &tn, &dA, &oA, &w1, &w2};
+    for (float **q : all) PST_TRY(pst_arena_get(c, n, q));
+    PST_TRY(transpose_planes(c, d_dip, dipA, n2, n1, n3));
+    PST_TRY(transpose_planes(c, d_din, dA, n2, n1, n3));
+    Smoother2 S{n1, n2, n3, ns, order, eps * eps, dipA, tn, {}};
+    smoother_plan(S);
+    PST_TRY(smoother_set(c, S, w1));
+    PST_TRY(smoother_adj(c, S, oA, dA, false, w1, w2));
+    PST_TRY(transpose_planes(c, oA, d_out, n1, n2, n3));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}

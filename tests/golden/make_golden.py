@@ -70,6 +70,8 @@ def main():
                                    out=ref.somf2dc(d2e, p2, ns, order, eps))
         g["somean2d_" + name] = dict(dn=d2e, dip=p2, ns=ns, order=order, eps=eps,
                                      out=ref.somean2dc(d2e, p2, ns, order, eps))
+    g["somean2dadj_ns3o2"] = dict(dn=d2e, dip=p2, ns=3, order=2, eps=0.01, out=ref.somean2dc(d2e, p2, 3, 2, 0.01, adj=1))
+    g["somean2dadj_ns2o1"] = dict(dn=d2e, dip=p2, ns=2, order=1, eps=0.05, out=ref.somean2dc(d2e, p2, 2, 1, 0.05, adj=1))
     # ---- smoothing (ps_smooth2 through smoothcf adj=0), incl. a radius larger than an axis
     xs = synth.cube(30, 12, 6, seed=13)
     g["smooth_534"] = dict(x=xs, rect=[5, 3, 4], out=ref.smoothc(xs, [5, 3, 4]))

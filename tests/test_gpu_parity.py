@@ -207,6 +207,30 @@ def test_somf3d_option2_is_refused_not_faked(ctx):
     assert e.value.code == -5
 
 
+@pytest.mark.parametrize("name", golden_names("somean2dadj_"))
+def test_somean2d_adjoint_golden_bit_exact(ctx, name):
+    """somean2dc(adj=1): adjoint chain spray, level by level, in the reference's accumulation order."""
+    import pyseistr_b200 as ps
+    g = golden(name)
+    out = ps.somean2dc(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]), adj=1, verb=0, ctx=ctx)
+    assert np.array_equal(out, g["out"])
+
+
+def test_somean2d_adjoint_dot_product(ctx):
+    """<S x, y> = <x, S' y> (pwsmooth_lop is a linear operator for fixed slopes)."""
+    import pyseistr_b200 as ps
+    n1, n2 = 96, 70
+    p, _ = synth.smooth_dips(n1, n2, 1, seed=66, amp=0.7)
+    p = np.asarray(p).reshape(n1, n2)
+    rng = np.random.default_rng(67)
+    x = rng.standard_normal((n1, n2)).astype(np.float32)
+    y = rng.standard_normal((n1, n2)).astype(np.float32)
+    sx = ps.somean2dc(x, p, 4, 2, 0.01, adj=0, verb=0, ctx=ctx).astype(np.float64)
+    sty = ps.somean2dc(y, p, 4, 2, 0.01, adj=1, verb=0, ctx=ctx).astype(np.float64)
+    a, b = float((sx * y).sum()), float((x * sty).sum())
+    assert abs(a - b) <= 2e-4 * max(abs(a), abs(b)), (a, b)
+
+
 # ------------------------------------------------------------------ interpolation
 @pytest.mark.parametrize("name", golden_names("soint3d_"))
 def test_soint3d_golden(ctx, name):

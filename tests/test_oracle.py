@@ -41,6 +41,13 @@ def test_port_spray2d_matches_golden(port, name):
     assert np.array_equal(out, g["out"])
 
 
+@pytest.mark.parametrize("name", golden_names("somean2dadj_"))
+def test_port_somean2d_adjoint_matches_golden(port, name):
+    g = golden(name)
+    out = port.somean2dc(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]), adj=1)
+    assert np.array_equal(out, g["out"])
+
+
 @pytest.mark.parametrize("name", golden_names("soint3d_"))
 def test_port_soint3d_matches_golden(port, name):
     g = golden(name)
