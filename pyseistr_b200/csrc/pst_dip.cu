@@ -1020,6 +1020,95 @@ cg_dir_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
     pst_block_reduce<3>(acc, partial);
 }
 
+
+// ---- 16-byte variants of the three CG streaming kernels (n % 4 == 0, 16-byte aligned vectors): one
+// thread moves 4 consecutive samples per array per step, i.e. 4x the bytes in flight per thread.
+// Elementwise arithmetic is unchanged; the double sums run over a different (still fixed) partition.
+__device__ __forceinline__ float4 ld4(const float *p, size_t i) { return *reinterpret_cast<const float4 *>(p + i); }
+__device__ __forceinline__ void st4(float *p, size_t i, float4 v) { *reinterpret_cast<float4 *>(p + i) = v; }
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(256)
+cg_head4_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r,
+                const float *__restrict__ sp, const float *__restrict__ sx,
+                const float *__restrict__ sr, const float *__restrict__ w, float a, float eps,
+                float *__restrict__ tmp, size_t n)
+{
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+        float4 xv = ld4(x, i), rv = ld4(r, i);
+        const float4 wv = ld4(w, i);
+        if (UPDATE) {
+            float4 pv = ld4(p, i);
+            const float4 spv = ld4(sp, i), sxv = ld4(sx, i), srv = ld4(sr, i);
+            pv.x += a * spv.x; pv.y += a * spv.y; pv.z += a * spv.z; pv.w += a * spv.w;
+            xv.x += a * sxv.x; xv.y += a * sxv.y; xv.z += a * sxv.z; xv.w += a * sxv.w;
+            rv.x += a * srv.x; rv.y += a * srv.y; rv.z += a * srv.z; rv.w += a * srv.w;
+            st4(p, i, pv); st4(x, i, xv); st4(r, i, rv);
+        }
+        float4 g;
+        g.x = -eps * xv.x; g.x += rv.x * wv.x;
+        g.y = -eps * xv.y; g.y += rv.y * wv.y;
+        g.z = -eps * xv.z; g.z += rv.z * wv.z;
+        g.w = -eps * xv.w; g.w += rv.w * wv.w;
+        st4(tmp, i, g);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cg_gp4_kernel(const float *__restrict__ p, const float *__restrict__ tmp, float *__restrict__ gp,
+              float eps, size_t n, double *__restrict__ partial)
+{
+    double acc[1] = {0.0};
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+        const float4 pv = ld4(p, i), tv = ld4(tmp, i);
+        float4 g;
+        g.x = eps * pv.x; g.x += tv.x;
+        g.y = eps * pv.y; g.y += tv.y;
+        g.z = eps * pv.z; g.z += tv.z;
+        g.w = eps * pv.w; g.w += tv.w;
+        st4(gp, i, g);
+        acc[0] += (double)g.x * (double)g.x;
+        acc[0] += (double)g.y * (double)g.y;
+        acc[0] += (double)g.z * (double)g.z;
+        acc[0] += (double)g.w * (double)g.w;
+    }
+    pst_block_reduce<1>(acc, partial);
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void cg_dir_one(float gpi, float t, float wi, float spi, float sxi, float sri, float alpha,
+                                           float &a, float &b, float &c, double (&acc)[3])
+{
+    const float gxi = 0.f + t;
+    const float gri = 0.f + gxi * wi;
+    if (FIRST) { a = gpi; b = gxi; c = gri; }
+    else { a = gpi + alpha * spi; b = gxi + alpha * sxi; c = gri + alpha * sri; }
+    acc[0] += (double)c * (double)c;
+    acc[1] += (double)a * (double)a;
+    acc[2] += (double)b * (double)b;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256)
+cg_dir4_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
+               const float *__restrict__ w, float *__restrict__ sp, float *__restrict__ sx,
+               float *__restrict__ sr, float alpha, size_t n, double *__restrict__ partial)
+{
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+        const float4 g = ld4(gp, i), t = ld4(tmp, i), wv = ld4(w, i);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1;
+        if (!FIRST) { s1 = ld4(sp, i); s2 = ld4(sx, i); s3 = ld4(sr, i); }
+        float4 a, b, c;
+        cg_dir_one<FIRST>(g.x, t.x, wv.x, s1.x, s2.x, s3.x, alpha, a.x, b.x, c.x, acc);
+        cg_dir_one<FIRST>(g.y, t.y, wv.y, s1.y, s2.y, s3.y, alpha, a.y, b.y, c.y, acc);
+        cg_dir_one<FIRST>(g.z, t.z, wv.z, s1.z, s2.z, s3.z, alpha, a.z, b.z, c.z, acc);
+        cg_dir_one<FIRST>(g.w, t.w, wv.w, s1.w, s2.w, s3.w, alpha, a.w, b.w, c.w, acc);
+        st4(sp, i, a); st4(sx, i, b); st4(sr, i, c);
+    }
+    pst_block_reduce<3>(acc, partial);
+}
+
 __global__ void fill_kernel(float *__restrict__ x, float v, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
@@ -1226,6 +1315,7 @@ struct EpiSpec {
     float *gp = nullptr, *sp = nullptr, *sx = nullptr, *sr = nullptr;
     float eps = 0.f, alpha = 0.f;
     int rec = -1;                 // reduction record receiving the fused sums
+    bool stream_only = false;     // fuse only if the streaming kernel takes it (else: plain pass, *fused = false)
 };
 // called right before the last axis is launched: lets the caller fetch scalars the epilogue
 // needs (alpha) and veto the launch (CG early exit).  Return <0 error, 0 go on, 1 skip.
@@ -1356,7 +1446,21 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     c->stats.smooth_passes++;
     // main path: the streaming (persistent, TMA-staged, ping-pong chain) kernel, pst_tri_stream.cu
     static const bool stream_on = []() { const char *e = getenv("PST_TRI_STREAM"); return !(e && e[0] == '0'); }();
-    if (stream_on && !has_epi && pst_tri_stream_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
+    const bool stream_ok = stream_on && pst_tri_stream_ok(axis, g.n1, g.n2, g.n3, nb, src, dst);
+    if (stream_ok && has_epi && epi->kind == EPI_GP && al16(epi->gp) && al16(epi->p)) {
+        // gp = eps*p + S(src) and sum gp^2 in the store side of the streaming kernel
+        pst_tri_stream_epi e{epi->p, epi->eps, c->d_partial, PST_RED_SLOTS};
+        int rc = 0, grid = 0;
+        PST_LAUNCHB(c, cls, 12.0 * (double)g.n,
+                    rc = pst_tri_stream_launch(c->stream, c->sm_count, axis, src, epi->gp, g.n1, g.n2, g.n3, nb, nullptr, &e, &grid));
+        if (rc != 0) { pst_set_error("pst_tri_stream_launch failed (%d)", rc); return PST_ECUDA; }
+        PST_TRY(pst_finish_reduce(c, grid, 1, epi->rec));
+        if (fused) *fused = true;
+        return PST_OK;
+    }
+    if (has_epi && epi->stream_only) { epi = nullptr; }
+    const bool has_epi2 = epi && epi->kind != EPI_NONE;
+    if (stream_ok && !has_epi2) {
         int rc = 0;
         PST_LAUNCHB(c, cls, 8.0 * (double)g.n,
                     rc = pst_tri_stream_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb, nullptr));
@@ -1520,13 +1624,24 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     // epilogue of the last smoothing pass costs more than it saves (4.83 s unfused vs 5.15 s fused per
     // step): the streaming kernels run at ~5.5 TB/s, the tile kernel's phase 3 does not.  Default: off.
     static const bool fuse = []() { const char *e = getenv("PST_FUSE_EPILOGUE"); return e && e[0] == '1'; }();
+    static const bool fuse_gp = fuse || []() { const char *e = getenv("PST_FUSE_GP"); return e && e[0] == '1'; }();   // measured: 4.5 ms fused pass vs 2.5 + 2.7 ms separate -> off
+    // 16-byte kernels when every vector is 16-byte aligned and n % 4 == 0
+    auto a16 = [](const void *q) { return (((uintptr_t)q) & 15) == 0; };
+    static const bool vec_on = []() { const char *e = getenv("PST_CG_VEC4"); return !(e && e[0] == '0'); }();
+    const bool vec4 = vec_on && (n % 4 == 0) && a16(w.p) && a16(rat) && a16(w.r) && a16(w.sp) && a16(w.sx) && a16(w.sr) &&
+                      a16(den) && a16(w.tmp) && a16(w.gp);
+    const int grid4 = pst_grid_for(c, n / 4 + 1, threads, 2);
     CgLate L{c, 0., 0., 0., tol, 0, false, 0.f};
     float a_pending = 0.f;
     bool pending = false;
     int iter;
     for (iter = 0; iter < liter; iter++) {
         PST_LAUNCHB(c, PST_K_CGHEAD, (pending ? 44.0 : 16.0) * (double)n,
-            if (pending)
+            if (vec4 && pending)
+                cg_head4_kernel<true><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, a_pending, eps, w.tmp, n);
+            else if (vec4)
+                cg_head4_kernel<false><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, 0.f, eps, w.tmp, n);
+            else if (pending)
                 cg_head_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, a_pending, eps, w.tmp, n);
             else
                 cg_head_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, 0.f, eps, w.tmp, n));
@@ -1534,11 +1649,14 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         // gp = eps*p + S(gx), sum gp^2 -> record 1
         EpiSpec e1;
         e1.kind = EPI_GP; e1.p = w.p; e1.gp = w.gp; e1.eps = eps; e1.rec = 1;
+        e1.stream_only = !fuse;      // default: fuse gp only where the streaming kernel does it (chain-bound pass, free bytes)
         bool fused = false;
-        PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, fuse ? &e1 : nullptr, nullptr, nullptr, &fused));
+        PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, fuse_gp ? &e1 : nullptr, nullptr, nullptr, &fused));
         if (!fused) {
-            PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n, (cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial)));
-            PST_TRY(pst_finish_reduce(c, grid, 1, 1));
+            PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n,
+                if (vec4) cg_gp4_kernel<<<grid4, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial);
+                else cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial));
+            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 1, 1));
         }
         // gx = S(gp); direction update fused into the last axis once alpha is known
         EpiSpec e2;
@@ -1550,10 +1668,14 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         if (L.stop) break;
         if (!fused) {
             if (iter == 0)
-                PST_LAUNCHB(c, PST_K_CGDIR, 24.0 * (double)n, (cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial)));
+                PST_LAUNCHB(c, PST_K_CGDIR, 24.0 * (double)n,
+                    if (vec4) cg_dir4_kernel<true><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial);
+                    else cg_dir_kernel<true><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, 0.f, n, c->d_partial));
             else
-                PST_LAUNCHB(c, PST_K_CGDIR, 36.0 * (double)n, (cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, L.alpha, n, c->d_partial)));
-            PST_TRY(pst_finish_reduce(c, grid, 3, 2));
+                PST_LAUNCHB(c, PST_K_CGDIR, 36.0 * (double)n,
+                    if (vec4) cg_dir4_kernel<false><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, L.alpha, n, c->d_partial);
+                    else cg_dir_kernel<false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, L.alpha, n, c->d_partial));
+            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 3, 2));
         }
         PST_TRY(pst_fetch_record(c, 2, 3, h));
         const double beta = h[0] + (double)eps * (h[1] - h[2]);

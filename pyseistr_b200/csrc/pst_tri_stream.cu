@@ -86,6 +86,12 @@ struct Args {
     int XW, pad;           // contiguous: row pitch of an x stage, left pad of the box
     float wm, w2;
     unsigned *err;
+    // optional fused CG epilogue of the storers (ps_conjgrad dip_cfuns.c:303,318,320):
+    //   gp = eps*p + S(gx) written to dst, partial sum of gp^2 (double) per CTA
+    const float *epi_p;
+    float epi_eps;
+    double *partial;
+    int partial_stride;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -102,10 +108,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned byte
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_probe(uint64_t *b, unsigned parity)
+__device__ __forceinline__ bool mbar_probe(uint64_t *b, unsigned parity)      // never suspends (test_wait, not try_wait)
 {
     unsigned ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     return ok != 0;
 }
@@ -135,6 +141,8 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, int
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float tri_t3(float xa, float xb, float xc, float wm, float w2)
 {
@@ -309,6 +317,7 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
     if (m <= 0) return;
     const int NS = A.NS, nb = NB > 0 ? NB : A.nb, nx = A.nx, L = A.L, Lp = A.Lp;
     const long nstage = m * NS;
+    double acc = 0.0;                                        // storers: fused sum of gp^2
 
     if (warp == 0) {
         // ================================ chain warp ================================
@@ -327,21 +336,50 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
 #undef TS_PASS
     } else if (warp == 1) {
         // ================================ loader ================================
-        if (lane == 0) {
-            Cursor cx;
-            cx.init(0, A.nxs);
-            const unsigned xbytes = (unsigned)A.xsf * 4u;
-            for (long p = 0; p < m; p++) {
-                const long tile = (long)blockIdx.x + p * (long)gridDim.x;
-                int c0 = 0, ib = 0;
-                if (!CONTIG) { const long b = tile / A.tilesA; ib = (int)b; c0 = (int)(tile - b * A.tilesA) * 32; }
-                for (int q = 0; q < NS; q++) {
+        // lane 0 streams the x tiles (TMA).  With a fused epilogue the whole warp also pulls the epilogue
+        // operand of the tile whose BACKWARD sum runs in the same pass into L2 (one 128-byte row or line
+        // segment per lane): the loader runs a ring ahead of the chain, which hides the DRAM latency the
+        // storers would otherwise wait for.
+        Cursor cx;
+        cx.init(0, A.nxs);
+        const unsigned xbytes = (unsigned)A.xsf * 4u;
+        for (long p = 0; p <= m; p++) {
+            const long tile = (long)blockIdx.x + p * (long)gridDim.x;
+            int c0 = 0, ib = 0;
+            if (!CONTIG) { const long b = tile / A.tilesA; ib = (int)b; c0 = (int)(tile - b * A.tilesA) * 32; }
+            // epilogue operand rows of tile p-1
+            const float *pf = nullptr;
+            if (A.epi_p && p > 0) {
+                const long tprev = tile - (long)gridDim.x;
+                if (CONTIG) {
+                    const long line = tprev * 32 + lane;
+                    if (line < A.na) pf = A.epi_p + line * nx;
+                } else {
+                    const long b = tprev / A.tilesA;
+                    pf = A.epi_p + b * A.sb + (long)(tprev - b * A.tilesA) * 32;
+                }
+            }
+            if (p == m && !A.epi_p) break;
+            for (int q = 0; q < NS; q++) {
+                if (p < m && lane == 0) {
                     mbar_wait(empty_x + cx.slot, cx.par ^ 1u, A.err);
                     mbar_arrive_expect_tx(full_x + cx.slot, xbytes);
                     float *dstx = Xr + (size_t)cx.slot * A.xsf;
                     if (CONTIG) tma_load_2d(dstx, &tmap, q * KB - (Lp - L) - 2 * nb - A.pad, (int)(tile * 32), full_x + cx.slot);
                     else tma_load_3d(dstx, &tmap, c0, q * KB - (Lp - L) - 2 * nb, ib, full_x + cx.slot);
-                    cx.advance(1);
+                }
+                if (p < m) cx.advance(1);
+                __syncwarp();
+                if (pf) {
+                    const int kb0 = L - 1 - q * KB;                 // stage q of the backward pass covers samples (kb0-31 .. kb0) - nb
+                    if (CONTIG) {
+                        const int i0 = min(max(kb0 - (KB - 1) - nb, 0), nx - 1), i1 = min(max(kb0 - nb, 0), nx - 1);
+                        prefetch_l2(pf + i0);
+                        prefetch_l2(pf + i1);
+                    } else {
+                        const int i = kb0 - lane - nb;
+                        if (i >= 0 && i < nx) prefetch_l2(pf + (long)i * A.d);
+                    }
                 }
             }
         }
@@ -409,12 +447,29 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                 if (kb >= nx + nb || kb < 0) { i = 0; valid = false; }
                 else if (kb >= nb) { i = kb - nb; valid = i >= nb; }
                 else { i = nb - 1 - kb; valid = true; }
+                float pv[32];
+                if (A.epi_p && valid) {                          // operands of the epilogue: in flight before the stage is ready
+                    const float *pl = A.epi_p + line0 * nx + i;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) pv[c] = (c < nl) ? pl[(long)c * nx] : 0.f;
+                }
                 mbar_wait(full_o + co.slot, co.par, A.err);
                 const float *ol = Or + co.slot * TSTAGE + (lane >> 2) * GP + (lane & 3);
                 float *dl = A.dst + line0 * nx + i;
                 if (valid) {
+                    if (A.epi_p) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            if (c >= nl) break;
+                            float gq = A.epi_eps * pv[c];
+                            gq += ol[4 * c];
+                            dl[(long)c * nx] = gq;
+                            acc += (double)gq * (double)gq;
+                        }
+                    } else {
 #pragma unroll 8
-                    for (int c = 0; c < nl; c++) dl[(long)c * nx] = ol[4 * c];
+                        for (int c = 0; c < nl; c++) dl[(long)c * nx] = ol[4 * c];
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_o + co.slot);
@@ -424,6 +479,14 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                 const int c0 = (int)(tile - ib * A.tilesA) * 32;
                 const bool live = (c0 + lane) < A.na;
                 float *dtile = A.dst + ib * A.sb + c0 + lane;
+                const int kb0 = L - 1 - q * KB;                        // backward position of step 0 of the stage
+                const bool interior = kb0 < nx + nb && kb0 - (KB - 1) >= 2 * nb;   // every step is a plain sample
+                float pv[32];
+                if (A.epi_p && live && interior) {                     // epilogue operands: in flight before the stage is ready
+                    const float *pp = A.epi_p + (dtile - A.dst) + (long)(kb0 - nb) * A.d;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) pv[j] = pp[-(long)j * A.d];
+                }
                 mbar_wait(full_o + co.slot, co.par, A.err);
                 const float *ol = Or + co.slot * TSTAGE + 4 * lane;
                 float4 o[8];
@@ -431,11 +494,22 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                 for (int g = 0; g < 8; g++) o[g] = *reinterpret_cast<const float4 *>(ol + g * GP);
                 __syncwarp();
                 if (TS_EARLY && lane == 0) mbar_arrive(empty_o + co.slot);        // slot is in registers: release it before storing
-                const int kb0 = L - 1 - q * KB;                        // backward position of step 0 of the stage
-                if (kb0 < nx + nb && kb0 - (KB - 1) >= 2 * nb) {        // interior stage: every step is a plain sample
+                if (interior) {
                     float *op = dtile + (long)(kb0 - nb) * A.d;
                     const long d = A.d;
-                    if (live) {
+                    if (live && A.epi_p) {
+#pragma unroll
+                        for (int g = 0; g < 8; g++) {
+                            const float ov[4] = {o[g].x, o[g].y, o[g].z, o[g].w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                float gq = A.epi_eps * pv[4 * g + e];
+                                gq += ov[e];
+                                op[-(long)(4 * g + e) * d] = gq;
+                                acc += (double)gq * (double)gq;
+                            }
+                        }
+                    } else if (live) {
 #pragma unroll
                         for (int g = 0; g < 8; g++) {
                             op[0] = o[g].x; op[-d] = o[g].y; op[-2 * d] = o[g].z; op[-3 * d] = o[g].w;
@@ -454,13 +528,34 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
                             if (kb >= nx + nb || kb < 0) { i = 0; valid = false; }
                             else if (kb >= nb) { i = kb - nb; valid = i >= nb; }
                             else { i = nb - 1 - kb; valid = true; }
-                            if (valid && live) dtile[(long)i * A.d] = oa[e];
+                            if (valid && live) {
+                                float gq = oa[e];
+                                if (A.epi_p) {
+                                    gq = A.epi_eps * A.epi_p[(dtile - A.dst) + (long)i * A.d];
+                                    gq += oa[e];
+                                    acc += (double)gq * (double)gq;
+                                }
+                                dtile[(long)i * A.d] = gq;
+                            }
                         }
                     }
                 }
             }
             if (!CONTIG && !TS_EARLY) { __syncwarp(); if (lane == 0) mbar_arrive(empty_o + co.slot); }
             co.advance(NSW);
+        }
+    }
+    if (A.partial) {
+        // deterministic CTA sum: fixed lane tree, then warps in index order
+        __shared__ double red[NWARPS];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NWARPS; w++) t += red[w];
+            A.partial[(size_t)blockIdx.x * A.partial_stride] = t;
         }
     }
 }
@@ -496,10 +591,10 @@ int launch_nb(bool contig, unsigned grid, size_t smem, cudaStream_t stream, cons
 {
     static bool attr0 = false, attr1 = false;
     if (contig) {
-        if (!attr0) { if (cudaFuncSetAttribute(tri_stream_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -4; attr0 = true; }
+        if (!attr0) { if (cudaFuncSetAttribute(tri_stream_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr0 = true; }
         tri_stream_kernel<true, NB><<<grid, NWARPS * 32, smem, stream>>>(tm, A);
     } else {
-        if (!attr1) { if (cudaFuncSetAttribute(tri_stream_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -4; attr1 = true; }
+        if (!attr1) { if (cudaFuncSetAttribute(tri_stream_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr1 = true; }
         tri_stream_kernel<false, NB><<<grid, NWARPS * 32, smem, stream>>>(tm, A);
     }
     return 0;
@@ -524,13 +619,14 @@ bool pst_tri_stream_ok(int axis, int n1, int n2, int n3, int nb, const void *src
 }
 
 int pst_tri_stream_launch(cudaStream_t stream, int sm_count, int axis, const float *src, float *dst,
-                          int n1, int n2, int n3, int nb, unsigned *d_err)
+                          int n1, int n2, int n3, int nb, unsigned *d_err, const pst_tri_stream_epi *epi, int *grid_out)
 {
     const int nn[3] = {n1, n2, n3};
     const int nx = nn[axis];
     const bool contig = axis == 0;
     Args A{};
     A.dst = dst; A.nx = nx; A.nb = nb; A.err = d_err;
+    if (epi) { A.epi_p = epi->p; A.epi_eps = epi->eps; A.partial = epi->partial; A.partial_stride = epi->partial_stride; }
     A.L = nx + 2 * nb;
     A.Lp = (A.L + KB - 1) / KB * KB;
     A.NS = A.Lp / KB;
@@ -576,6 +672,7 @@ int pst_tri_stream_launch(cudaStream_t stream, int sm_count, int axis, const flo
     const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
     long grid = (long)sm_count * ctas_per_sm;
     if (grid > A.ntiles) grid = A.ntiles;
+    if (grid_out) *grid_out = (int)grid;
     int rc = 0;
     switch (nb) {
 #define TS_CASE(N) case N: rc = launch_nb<N>(contig, (unsigned)grid, smem, stream, tm, A); break;

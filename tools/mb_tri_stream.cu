@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../pyseistr_b200/csrc/pst_tri_stream.cuh"
@@ -68,6 +69,34 @@ static int check(int n1, int n2, int n3, int axis, int nb, bool inplace)
     printf("  %dx%dx%d axis %d nb %d %s: %s", n1, n2, n3, axis, nb, inplace ? "in-place" : "out-of-place", bad ? "MISMATCH" : "bit-exact");
     if (bad) printf(" (%zu of %zu, first at %zu: got %g want %g)", bad, n, first, out[first], ref[first]);
     printf("\n");
+    // fused epilogue: dst = eps*p + S(src), partial sums of dst^2
+    if (!bad && !inplace) {
+        std::vector<float> hp(n);
+        for (size_t i = 0; i < n; i++) { s = s * 1664525u + 1013904223u; hp[i] = ((int)(s >> 8) % 2001 - 1000) * 1e-3f; }
+        float *d_p; double *d_part;
+        CK(cudaMalloc(&d_p, n * 4)); CK(cudaMalloc(&d_part, 4096 * 8 * sizeof(double)));
+        CK(cudaMemcpy(d_p, hp.data(), n * 4, cudaMemcpyHostToDevice));
+        pst_tri_stream_epi e{d_p, 0.75f, d_part, 8};
+        int grid = 0;
+        rc = pst_tri_stream_launch(0, sm, axis, d_in, d_out, n1, n2, n3, nb, d_err, &e, &grid);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        if (rc != 0 || e2 != cudaSuccess) { printf("    epilogue launch rc %d, %s\n", rc, cudaGetErrorString(e2)); return 1; }
+        CK(cudaMemcpy(out.data(), d_out, n * 4, cudaMemcpyDeviceToHost));
+        std::vector<double> part((size_t)grid * 8);
+        CK(cudaMemcpy(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost));
+        double want = 0., got = 0.;
+        size_t bad2 = 0;
+        for (size_t i = 0; i < n; i++) {
+            float gq = 0.75f * hp[i];
+            gq += ref[i];
+            want += (double)gq * gq;
+            if (memcmp(&out[i], &gq, 4) != 0) bad2++;
+        }
+        for (int b = 0; b < grid; b++) got += part[(size_t)b * 8];
+        const bool oksum = fabs(got - want) <= 1e-9 * fabs(want) + 1e-30;
+        if (bad2 || !oksum) { printf("    epilogue MISMATCH: %zu values, sum %.17g vs %.17g\n", bad2, got, want); bad = 1; }
+        cudaFree(d_p); cudaFree(d_part);
+    }
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_err);
     return bad ? 1 : 0;
 }
@@ -117,6 +146,24 @@ int main(int argc, char **argv)
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         ms /= reps;
         printf("bench %dx%dx%d axis %d nb %d: %.3f ms/pass  %.1f GB/s algorithmic (8 B/voxel)\n", n1, n2, n3, axis, nb, ms, 8.0 * n / ms * 1e-6);
+    }
+    {   // fused epilogue (dst = eps*p + S(src), sum dst^2): 12 B/voxel
+        float *pbuf; double *d_part;
+        CK(cudaMalloc(&pbuf, n * 4)); CK(cudaMalloc(&d_part, 4096 * 8 * sizeof(double)));
+        CK(cudaMemset(pbuf, 0, n * 4));
+        pst_tri_stream_epi e{pbuf, 1.0f, d_part, 8};
+        for (int axis = 0; axis < 3; axis++) {
+            pst_tri_stream_launch(0, sm, axis, a, b, n1, n2, n3, nb, d_err, &e);
+            CK(cudaDeviceSynchronize());
+            const int reps = 5;
+            cudaEventRecord(e0);
+            for (int r = 0; r < reps; r++) pst_tri_stream_launch(0, sm, axis, a, b, n1, n2, n3, nb, d_err, &e);
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            ms /= reps;
+            printf("bench+gp %dx%dx%d axis %d nb %d: %.3f ms/pass  %.1f GB/s algorithmic (12 B/voxel)\n", n1, n2, n3, axis, nb, ms, 12.0 * n / ms * 1e-6);
+        }
     }
     return 0;
 }
