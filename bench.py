@@ -329,6 +329,9 @@ def _main(real_stdout):
     st = ctx.stats()
     ctx.set_profile(False)
     clocks = sampler.stop()
+    if os.environ.get("PST_BENCH_ALLRANKS"):          # debugging aid: every rank's per-class device time
+        print(f"[rank {rank}] ms {ms:.1f} " + " ".join(f"{k}={v / args.steps:.1f}" for k, v in
+              zip(_lib.KERNEL_CLASSES, st["class_ms"]) if v > 0), file=sys.stderr, flush=True)
     if dist is not None:
         import torch
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")

@@ -191,15 +191,22 @@ extern "C" int pst_ctx_slab(pst_ctx *c, int n3, int *z0, int *z1)
 }
 
 // ---- carry mailboxes ---------------------------------------------------------------------
-static size_t mbox_layout(size_t L, size_t *off_cb, size_t *off_ff, size_t *off_fb, size_t *off_err)
+static size_t mbox_layout(size_t L, size_t *off_cb, size_t *off_ff, size_t *off_fb, size_t *off_err,
+                          size_t *off_pf = nullptr, size_t *off_pb = nullptr)
 {
-    const size_t nblk = (L + 127) / 128;
+    const size_t nblk = (L + 31) / 32;          // one flag per CTA; the narrowest tile is 32 lines
     size_t o = 0;
     o += L * sizeof(float);                 *off_cb = o;
     o += L * sizeof(float);                 *off_ff = o;
     o += nblk * sizeof(unsigned);           *off_fb = o;
     o += nblk * sizeof(unsigned);           *off_err = o;
     o += 64;
+    o = (o + 255) & ~(size_t)255;
+    // self-validating carries of the tile kernels: one 8-byte {carry, epoch} pair per line and direction
+    if (off_pf) *off_pf = o;
+    o += L * 8;
+    if (off_pb) *off_pb = o;
+    o += L * 8;
     return (o + 255) & ~(size_t)255;
 }
 
@@ -235,7 +242,12 @@ int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v)
         if (c->rank < c->nranks - 1)
             PST_CUDA(cudaIpcOpenMemHandle((void **)&m->mbox_next, all[(size_t)c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
     }
-    mbox_layout(m->mbox_L, &ocb, &off, &ofb, &oerr);
+    size_t opf, opb;
+    mbox_layout(m->mbox_L, &ocb, &off, &ofb, &oerr, &opf, &opb);
+    v->pf_in = (uint2 *)(m->mbox + opf);
+    v->pb_in = (uint2 *)(m->mbox + opb);
+    v->pf_out = m->mbox_next ? (uint2 *)(m->mbox_next + opf) : nullptr;
+    v->pb_out = m->mbox_prev ? (uint2 *)(m->mbox_prev + opb) : nullptr;
     v->cf_in = (float *)m->mbox;                        // written by rank-1
     v->cb_in = (float *)(m->mbox + ocb);                // written by rank+1
     v->ff_in = (unsigned *)(m->mbox + off);

@@ -42,6 +42,8 @@ struct pst_mailbox_view {
     unsigned *ff_out, *fb_out;
     unsigned *err;                   // set when a wait times out
     unsigned epoch;
+    // tile kernels: self-validating 8-byte {carry bits, epoch} pairs, one per line (no fence, no flag)
+    uint2 *pf_in, *pb_in, *pf_out, *pb_out;
 };
 
 struct pst_ctx {

@@ -1179,6 +1179,7 @@ struct Tri3Args {
     // outgoing carries + flag in the NEIGHBOUR's mailbox (peer memory over NVLink; nullptr = edge)
     const float *cin; const unsigned *fin;
     float *cout; unsigned *fout;
+    const uint2 *pin; uint2 *pout;   // tile kernels: {carry, epoch} pairs (mine, incoming) / (neighbour's, outgoing)
     unsigned *err; unsigned epoch;
     float *dst;            // fold output [nz][L]
     long L, l0, l1;        // lines per plane, chunk [l0, l1)
@@ -1195,17 +1196,21 @@ __device__ __forceinline__ float tri3_x(const Tri3Args &A, int j, long l)
 
 // consumer side of the carry hand-off: one thread spins (acquire, system scope) on this CTA's
 // flag, with a generous timeout so that a failed neighbour cannot hang the GPU
+__device__ int g_tri3_variant = 0;      // experiment switch (PST_TRI3_VARIANT): bit0 fence after the flag store, bit1 relaxed polling, bit2 no sleep
 __device__ __forceinline__ void tri3_wait(const unsigned *flag, unsigned epoch, unsigned *err)
 {
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
+        const int var = g_tri3_variant;
         unsigned v;
         for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (var & 2) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            else asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v == epoch) break;
             if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
-            __nanosleep(200);
+            if (!(var & 4)) __nanosleep(200);
         }
+        if (var & 2) __threadfence_system();
     }
     __syncthreads();
 }
@@ -1214,7 +1219,10 @@ __device__ __forceinline__ void tri3_signal(unsigned *flag, unsigned epoch)
 {
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    if (threadIdx.x == 0) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        if (g_tri3_variant & 1) __threadfence_system();
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -1306,6 +1314,148 @@ tri3_dist_bwd_kernel(const Tri3Args A)
         if (A.cout) A.cout[l] = s;
     }
     if (A.cout) tri3_signal(A.fout + blockIdx.x, A.epoch);
+}
+
+
+// ---- distributed axis 3, tile kernels -------------------------------------------------------
+// What every downstream rank waits for is the LATENCY of one CTA of the upstream rank (7 hops at 8
+// GPUs), so a CTA must be short: it first pulls its whole tile (W lines x all local rows) into
+// shared memory with one burst of 16-byte cp.async (all requests in flight at once, issued BEFORE
+// the carry flag is awaited), then each line's running sum is a pure shared-memory/FADD loop
+// (~10 instructions per sample) instead of a chain of dependent global loads.
+//   forward : rows = x planes [K0-2nb, K1) (zero outside the cube) -> F rows [K0, K1) to scratch
+//   backward: rows = F rows [K0, K1) -> fold2 -> dst; parked reflections live in the consumed rows
+// Carry hand-off of the tile kernels: every line's carry travels as ONE 8-byte store {carry bits, epoch}
+// into the neighbour's mailbox and is polled by the consuming thread itself (the same trick as NCCL's
+// LL protocol: an aligned 8-byte store is delivered atomically, so the epoch validates the payload).
+// No system-scope fence, no separate flag: measured, a fence + flag per CTA doubled the kernel time.
+__device__ __forceinline__ float tri3_pair_recv(const uint2 *p, unsigned epoch, unsigned *err)
+{
+    const long long t0 = clock64();
+    unsigned x, y;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+        if (y == epoch) break;
+        if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
+    }
+    return __uint_as_float(x);
+}
+__device__ __forceinline__ void tri3_pair_send(uint2 *p, float v, unsigned epoch)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+
+template <int W>
+__global__ void __launch_bounds__(128)
+tri3_tile_fwd_kernel(const Tri3Args A)
+{
+    extern __shared__ __align__(16) float t3s[];
+    const int nb = A.nb, R = A.K1 - A.K0 + 2 * nb, tid = threadIdx.x;
+    const long l0 = (long)blockIdx.x * W;
+    const long l = l0 + tid;
+    const bool live = tid < W && l < A.L;
+    // ---- burst load: row r <-> global plane j = K0 - 2nb + r
+    constexpr int CPR = W / 4;                                 // 16-byte chunks per row
+    float s = 0.f;
+    {
+        for (int idx = tid; idx < R * CPR; idx += 128) {
+            const int r = idx / CPR, ch = idx - r * CPR;
+            const int j = A.K0 - 2 * nb + r;
+            const long l = l0 + 4 * ch;
+            float *dsts = t3s + (size_t)r * W + 4 * ch;
+            if (j < 0 || j >= A.n3g || l >= A.L) {
+                *reinterpret_cast<float4 *>(dsts) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float *srcp;
+                if (j >= A.z0 && j < A.z0 + A.nz) srcp = A.x + (long)(j - A.z0) * A.L + l;
+                else if (j < A.z0) srcp = A.hb + (long)(j - (A.z0 - nb)) * A.L + l;
+                else srcp = A.ha + (long)(j - (A.z0 + A.nz)) * A.L + l;
+                cp_async16(dsts, srcp);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (A.pin && live) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);      // polled while the tile is in flight
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (live) {
+        const float wm = -A.wt, w2 = A.w2;
+        const float *xc = t3s + tid;                           // x_{k-2nb} of step k = K0 + i at row i
+        float *Fo = A.F + l;
+        const int n = A.K1 - A.K0;
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {
+            float t = wm * xc[(size_t)(i + 2 * nb) * W];
+            t = t + w2 * xc[(size_t)(i + nb) * W];
+            t = t + wm * xc[(size_t)i * W];
+            s += t;
+            Fo[(long)i * A.L] = s;
+        }
+        if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(128)
+tri3_tile_bwd_kernel(const Tri3Args A)
+{
+    extern __shared__ __align__(16) float t3s[];
+    const int nb = A.nb, n3g = A.n3g, R = A.K1 - A.K0, tid = threadIdx.x;
+    const long l0 = (long)blockIdx.x * W;
+    const long l = l0 + tid;
+    const bool live = tid < W && l < A.L;
+    constexpr int CPR = W / 4;
+    float s = 0.f;
+    {
+        for (int idx = tid; idx < R * CPR; idx += 128) {
+            const int r = idx / CPR, ch = idx - r * CPR;
+            const long lc = l0 + 4 * ch;
+            if (lc < A.L) cp_async16(t3s + (size_t)r * W + 4 * ch, A.F + (long)r * A.L + lc);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (A.pin && live) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (live) {
+        float *Fc = t3s + tid;                                 // row (k - K0); consumed rows are reused as parking slots
+        float *dl = A.dst + l;
+        int k = A.K1 - 1;
+        for (; k >= nb + n3g && k >= A.K0; k--) {               // right pad (last rank): park B_k in its own row
+            s += Fc[(size_t)(k - A.K0) * W];
+            Fc[(size_t)(k - A.K0) * W] = s;
+        }
+        const int kmid = max(nb, A.K0);
+#pragma unroll 4
+        for (; k >= kmid; k--) {                               // samples gi = k - nb
+            s += Fc[(size_t)(k - A.K0) * W];
+            const int gi = k - nb;
+            float v = s;
+            if (gi >= n3g - nb) v = v + Fc[(size_t)(nb + n3g + (n3g - 1 - gi) - A.K0) * W];
+            if (gi < nb) Fc[(size_t)(k - A.K0) * W] = v;        // head: completed by the left pad (rank 0)
+            else dl[(long)(gi - A.z0) * A.L] = v;
+        }
+        for (; k >= A.K0; k--) {                                // left pad (rank 0): y_i = head_i + B_{nb-1-i}
+            s += Fc[(size_t)(k - A.K0) * W];
+            const int gi = nb - 1 - k;
+            dl[(long)(gi - A.z0) * A.L] = Fc[(size_t)(gi + nb - A.K0) * W] + s;
+        }
+        if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
+    }
+}
+
+// widest tile (lines per CTA) whose rows fit in shared memory; 0 = use the line kernels
+static int tri3_tile_width(int rows_max, long L, const void *a, const void *b, const void *c2, const void *d, const void *e)
+{
+    auto a16 = [](const void *q) { return (((uintptr_t)q) & 15) == 0; };
+    if (L % 4 != 0 || !a16(a) || !a16(b) || !a16(c2) || !a16(d) || !a16(e)) return 0;
+    static const bool on = []() { const char *v = getenv("PST_TRI3_TILE"); return !(v && v[0] == '0'); }();
+    if (!on) return 0;
+    // narrower tiles leave too few chain threads per SM: measured at 2 GPUs (527 rows, W = 32) the tile
+    // kernels take 2.6 ms per launch against 1.4 ms for the line kernels, so tall slabs keep the latter
+    const int ws[2] = {128, 64};
+    for (int w : ws) if ((size_t)rows_max * w * 4 <= 75 * 1024) return w;
+    return 0;
 }
 
 // ---- shaping operator driver ------------------------------------------------------------
@@ -1412,15 +1562,55 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.wt = (float)(1.0 / ((double)nb * nb));
     A.w2 = (float)(2. * A.wt);
     A.err = mb.err; A.epoch = mb.epoch;
-    const unsigned blocks = (unsigned)((L + 127) / 128);
+    // tile kernels (burst-loaded shared-memory tiles, short CTA latency) when they fit; the tile width
+    // must be the same on every rank (the carry flags are per CTA): derived from the tallest slab
+    {
+        static int var_set = -1;
+        if (var_set < 0) {
+            const char *e = getenv("PST_TRI3_VARIANT");
+            var_set = e ? atoi(e) : 0;
+            PST_CUDA(cudaMemcpyToSymbol(g_tri3_variant, &var_set, sizeof(int)));
+        }
+    }
+    const int nz_max = (n3g + c->nranks - 1) / c->nranks;
+    const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, g.hb, g.ha);
+    const unsigned blocks = (unsigned)((L + (W ? W : 128) - 1) / (W ? W : 128));
+    const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
     // forward sums: carries flow rank -> rank+1, CTA by CTA, through the neighbour's mailbox
     A.cin = first ? nullptr : mb.cf_in;  A.fin = mb.ff_in;
     A.cout = last ? nullptr : mb.cf_out; A.fout = mb.ff_out;
-    PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+    A.pin = first ? nullptr : mb.pf_in; A.pout = last ? nullptr : mb.pf_out;
+    if (W) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+            attr_done = true;
+        }
+        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
+            if (W == 128) tri3_tile_fwd_kernel<128><<<blocks, 128, smem_f, c->stream>>>(A);
+            else if (W == 64) tri3_tile_fwd_kernel<64><<<blocks, 128, smem_f, c->stream>>>(A);
+            else tri3_tile_fwd_kernel<32><<<blocks, 128, smem_f, c->stream>>>(A));
+    } else {
+        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+    }
     // backward sums (+ fold): carries flow rank -> rank-1
     A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;
     A.cout = first ? nullptr : mb.cb_out; A.fout = mb.fb_out;
-    PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+    A.pin = last ? nullptr : mb.pb_in; A.pout = first ? nullptr : mb.pb_out;
+    static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? 11 : PST_K_TRI3; }();
+    if (W) {
+        PST_LAUNCHB(c, bwd_cls, 8.0 * (double)g.n,
+            if (W == 128) tri3_tile_bwd_kernel<128><<<blocks, 128, smem_b, c->stream>>>(A);
+            else if (W == 64) tri3_tile_bwd_kernel<64><<<blocks, 128, smem_b, c->stream>>>(A);
+            else tri3_tile_bwd_kernel<32><<<blocks, 128, smem_b, c->stream>>>(A));
+    } else {
+        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+    }
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -1437,6 +1627,31 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     if (axis == 2 && g.dist) {
         c->stats.smooth_passes++;
         return smooth_axis3_dist(c, g, src, dst, scr);
+    }
+    // measurement hook: run the DISTRIBUTED axis-3 tile kernels on one GPU (no neighbours, no carries)
+    // to time them without communication: PST_TRI3_TILE_SELFTEST=1 and a slab-shaped volume
+    static const bool selftest = []() { const char *e = getenv("PST_TRI3_TILE_SELFTEST"); return e && e[0] == '1'; }();
+    if (selftest && axis == 2 && 2 * nb <= g.n3 && !(epi && epi->kind != EPI_NONE)) {
+        const long L = (long)g.n1 * g.n2;
+        const int W = tri3_tile_width(g.n3 + 3 * nb, L, src, dst, scr, nullptr, nullptr);
+        if (W == 128) {
+            c->stats.smooth_passes++;
+            Tri3Args A{};
+            A.x = src; A.F = scr; A.dst = dst; A.L = L; A.l0 = 0; A.l1 = L;
+            A.n3g = g.n3; A.z0 = 0; A.nz = g.n3; A.nb = nb; A.K0 = 0; A.K1 = g.n3 + 2 * nb;
+            A.wt = (float)(1.0 / ((double)nb * nb)); A.w2 = (float)(2. * A.wt);
+            const unsigned blocks = (unsigned)((L + 127) / 128);
+            static bool ad = false;
+            if (!ad) {
+                PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                ad = true;
+            }
+            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_fwd_kernel<128><<<blocks, 128, (size_t)(A.K1 + 2 * nb) * 128 * 4, c->stream>>>(A)));
+            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_bwd_kernel<128><<<blocks, 128, (size_t)A.K1 * 128 * 4, c->stream>>>(A)));
+            PST_CUDA(cudaGetLastError());
+            return PST_OK;
+        }
     }
     // 16-byte path: every row/line start must be 16-byte aligned
     auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
