@@ -380,24 +380,37 @@ def _main(real_stdout):
     cls_ms = dict(zip(names, st["class_ms"]))
     cls_n = dict(zip(names, st["class_launches"]))
     cls_b = dict(zip(names, st["class_bytes"]))
-    hbm = [k for k in names if cls_n[k] > 0 and cls_b[k] > 0 and k not in ("predict", "other", "slot_reduce")]
-    dom = max(hbm, key=lambda k: cls_ms[k])
+    # kernels, not classes: the three smoothing classes are ONE kernel (tri_stream_kernel, pst_tri_stream.cu;
+    # the classes only split its launches by axis), every other class is one kernel family
+    groups = {"tri_smooth": ("tri_axis1", "tri_axis2", "tri_axis3")}
+    for k in names:
+        if k not in groups["tri_smooth"] and k not in ("predict", "other", "slot_reduce", "reserved"):
+            groups[k] = (k,)
+    g_ms = {g: sum(cls_ms[k] for k in ks) for g, ks in groups.items()}
+    g_n = {g: sum(cls_n[k] for k in ks) for g, ks in groups.items()}
+    g_b = {g: sum(cls_b[k] for k in ks) for g, ks in groups.items()}
+    hbm = [g for g in groups if g_n[g] > 0 and g_b[g] > 0]
+    dom = max(hbm, key=lambda g: g_ms[g])
     total_cls = sum(cls_ms.values()) or 1.0
-    roof = {"bound": "hbm", "kernel_class": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-            "achieved": cls_b[dom] / (cls_ms[dom] * 1e-3) / 1e9,
+    kernel_names = {"tri_smooth": "tri_stream_kernel<CONTIG,NB> (axes 1-3; distributed axis 3: tri3_tile_fwd/bwd_kernel)",
+                    "cg_head": "cg_head4_kernel", "cg_dir": "cg_dir4_kernel", "cg_gp": "cg_gp4_kernel",
+                    "allpass": "allpass_kernel", "cg_setup": "divne_prescale/scale_init_kernel"}
+    roof = {"bound": "hbm", "kernel_class": dom, "kernel": kernel_names.get(dom, dom), "peak": peak, "unit": "GB/s",
+            "peak_source": peak_src,
+            "achieved": g_b[dom] / (g_ms[dom] * 1e-3) / 1e9,
             "traffic": None,
-            "avg_launch_ms": cls_ms[dom] / cls_n[dom], "launches": cls_n[dom],
-            "algorithmic_bytes_per_launch": cls_b[dom] / cls_n[dom],
-            "share_of_step": cls_ms[dom] / total_cls}
+            "avg_launch_ms": g_ms[dom] / g_n[dom], "launches": g_n[dom],
+            "algorithmic_bytes_per_launch": g_b[dom] / g_n[dom],
+            "share_of_step": g_ms[dom] / total_cls}
     roof["frac"] = roof["achieved"] / peak
     # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
-    # capture of that kernel (profiles/r01_*_ncu_summary.md), as a ratio to its algorithmic bytes
-    ncu_ratio = {"cg_head": (3.670121 + 2.059249) / (44 * 0.131072), "cg_dir": (3.145735 + 1.533136) / (36 * 0.131072),
-                 "tri_axis1": (1.048597 + 0.992547) / 2.097152, "tri_axis2": (1.048627 + 0.994858) / 2.097152,
-                 "tri_axis3": (1.051120 + 0.997099) / 2.097152}
+    # capture of that kernel (profiles/r01b_ncu_summary.md, 500x512x512), as a ratio to its algorithmic bytes
+    ncu_ratio = {"cg_head": (3.670041 + 2.054506) / (44 * 0.131072), "cg_dir": (3.145764 + 1.531844) / (36 * 0.131072),
+                 "cg_gp": (1.048588 + 0.494331) / (12 * 0.131072),
+                 "tri_smooth": (0.524381 + 0.470106) / (8 * 0.131072)}
     if dom in ncu_ratio:
         roof["traffic"] = ncu_ratio[dom] * roof["algorithmic_bytes_per_launch"]
-        roof["traffic_source"] = "ncu --set full capture scaled by voxel count, see profiles/"
+        roof["traffic_source"] = "ncu --set full capture scaled by voxel count, see profiles/r01b_ncu_summary.md"
     roof["classes"] = {k: {"ms_per_step": cls_ms[k] / args.steps, "launches_per_step": cls_n[k] / args.steps,
                            "algorithmic_GBps": (cls_b[k] / (cls_ms[k] * 1e-3) / 1e9) if cls_ms[k] > 0 and cls_b[k] > 0 else None,
                            "share": cls_ms[k] / total_cls}

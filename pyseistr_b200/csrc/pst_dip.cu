@@ -1194,23 +1194,41 @@ __device__ __forceinline__ float tri3_x(const Tri3Args &A, int j, long l)
     return A.ha[(long)(j - (A.z0 + A.nz)) * A.L + l];
 }
 
+// Carry hand-off of the distributed axis-3 kernels: every line's carry travels as ONE 8-byte store {carry bits, epoch}
+// into the neighbour's mailbox and is polled by the consuming thread itself (the same trick as NCCL's
+// LL protocol: an aligned 8-byte store is delivered atomically, so the epoch validates the payload).
+// No system-scope fence, no separate flag: measured, a fence + flag per CTA doubled the kernel time.
+__device__ __forceinline__ float tri3_pair_recv(const uint2 *p, unsigned epoch, unsigned *err)
+{
+    const long long t0 = clock64();
+    unsigned x, y;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+        if (y == epoch) break;
+        if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
+    }
+    return __uint_as_float(x);
+}
+__device__ __forceinline__ void tri3_pair_send(uint2 *p, float v, unsigned epoch)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+
+// line kernels (tall slabs): one flag per CTA (one polling thread); measured at 2 GPUs the per-thread pair
+// polling of the tile kernels costs more here (303K resident pollers per GPU)
 // consumer side of the carry hand-off: one thread spins (acquire, system scope) on this CTA's
 // flag, with a generous timeout so that a failed neighbour cannot hang the GPU
-__device__ int g_tri3_variant = 0;      // experiment switch (PST_TRI3_VARIANT): bit0 fence after the flag store, bit1 relaxed polling, bit2 no sleep
 __device__ __forceinline__ void tri3_wait(const unsigned *flag, unsigned epoch, unsigned *err)
 {
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
-        const int var = g_tri3_variant;
         unsigned v;
         for (;;) {
-            if (var & 2) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            else asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v == epoch) break;
             if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
-            if (!(var & 4)) __nanosleep(200);
+            __nanosleep(200);
         }
-        if (var & 2) __threadfence_system();
     }
     __syncthreads();
 }
@@ -1219,10 +1237,7 @@ __device__ __forceinline__ void tri3_signal(unsigned *flag, unsigned epoch)
 {
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-        if (g_tri3_variant & 1) __threadfence_system();
-    }
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
 }
 
 __global__ void __launch_bounds__(128)
@@ -1325,26 +1340,6 @@ tri3_dist_bwd_kernel(const Tri3Args A)
 // (~10 instructions per sample) instead of a chain of dependent global loads.
 //   forward : rows = x planes [K0-2nb, K1) (zero outside the cube) -> F rows [K0, K1) to scratch
 //   backward: rows = F rows [K0, K1) -> fold2 -> dst; parked reflections live in the consumed rows
-// Carry hand-off of the tile kernels: every line's carry travels as ONE 8-byte store {carry bits, epoch}
-// into the neighbour's mailbox and is polled by the consuming thread itself (the same trick as NCCL's
-// LL protocol: an aligned 8-byte store is delivered atomically, so the epoch validates the payload).
-// No system-scope fence, no separate flag: measured, a fence + flag per CTA doubled the kernel time.
-__device__ __forceinline__ float tri3_pair_recv(const uint2 *p, unsigned epoch, unsigned *err)
-{
-    const long long t0 = clock64();
-    unsigned x, y;
-    for (;;) {
-        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
-        if (y == epoch) break;
-        if (clock64() - t0 > 20000000000LL) { *err = 1u; break; }     // ~10 s
-    }
-    return __uint_as_float(x);
-}
-__device__ __forceinline__ void tri3_pair_send(uint2 *p, float v, unsigned epoch)
-{
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
-}
-
 template <int W>
 __global__ void __launch_bounds__(128)
 tri3_tile_fwd_kernel(const Tri3Args A)
@@ -1564,14 +1559,6 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.err = mb.err; A.epoch = mb.epoch;
     // tile kernels (burst-loaded shared-memory tiles, short CTA latency) when they fit; the tile width
     // must be the same on every rank (the carry flags are per CTA): derived from the tallest slab
-    {
-        static int var_set = -1;
-        if (var_set < 0) {
-            const char *e = getenv("PST_TRI3_VARIANT");
-            var_set = e ? atoi(e) : 0;
-            PST_CUDA(cudaMemcpyToSymbol(g_tri3_variant, &var_set, sizeof(int)));
-        }
-    }
     const int nz_max = (n3g + c->nranks - 1) / c->nranks;
     const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, g.hb, g.ha);
     const unsigned blocks = (unsigned)((L + (W ? W : 128) - 1) / (W ? W : 128));

@@ -31,7 +31,9 @@ def main():
     ctx = pd.context_from_torch(dist, local)
     ok = True
     for (shape, kw) in [((60, 24, 12 * world), dict(niter=3, liter=6, order=2, rect=(5, 5, 5))),
-                        ((40, 17, 10 * world + 3), dict(niter=2, liter=5, order=1, rect=(3, 4, 4)))]:
+                        ((40, 17, 10 * world + 3), dict(niter=2, liter=5, order=1, rect=(3, 4, 4))),
+                        # tall slabs: the axis-3 tile kernels run with 64-line tiles (rows x 128 lines > 75 KB)
+                        ((16, 12, 200 * world + 1), dict(niter=2, liter=4, order=2, rect=(3, 3, 6)))]:
         n1, n2, n3 = shape
         cube = synth.cube(n1, n2, n3, seed=77)
         noisy = synth.erratic(cube, ntraces=9)
