@@ -20,14 +20,20 @@
 //   * everything that is parallel is taken off the chain warp: a loader thread streams x tiles
 //     with TMA (cp.async.bulk.tensor, mbarrier complete_tx; the box overlaps the previous one
 //     by 2nb rows so that no look-back state exists; out-of-range rows/columns are zero-filled
-//     by the TMA unit, which is exactly "tap skipped"), builder warps turn x into t_k and write
-//     it in the chain's k-minor-4 layout, and (contiguous axis only) storer warps transpose the
-//     B values back to coalesced 128-byte stores.  Strided axes store straight from the chain
-//     warp (a warp row is 128 contiguous bytes).
-//   * rings are guarded by mbarrier full/empty pairs; the chain warp is warp 0 and warps 4 and 8
-//     stay idle so that it does not share its scheduler's issue slots with a busy warp.
-// HBM traffic is the compulsory 8 B/voxel.  Reflections (fold2) are applied by the chain warp
-// in the 2 of ~33 stages that touch the line ends.
+//     by the TMA unit, which is exactly "tap skipped"), four builder warps turn x into t_k and
+//     write it in the chain's k-minor-4 layout, and four storer warps move the B values of the
+//     backward chain to global memory (transposing for the contiguous axis, so every global
+//     access is a coalesced 128-byte row).  A padded line's dummy steps LEAD the forward pass
+//     (k = j - D): their t is +0 by zero fill, so the slots they leave behind add nothing to the
+//     backward chain that reads them last.
+//   * rings (x, t, B) are guarded by mbarrier full/empty pairs; a ring's slot count is a multiple
+//     of the number of warps that consume it (see the PROTOCOL RULE at the constants); the chain
+//     warp is warp 0 and warps 4 and 8 stay idle so that it does not share its scheduler's issue
+//     slots with a busy warp; it probes the barriers of stage q+1 while stage q's FADD chains run.
+// HBM traffic is the compulsory 8 B/voxel (ncu: profiles/r01b_ncu_summary.md).  Reflections (fold2)
+// are applied by the chain warp, in place in the B ring slot, in the 2 of ~33 stages that touch a
+// line end.  Optional epilogue in the storers: dst = eps*p + S(src) with the sum of dst^2 (the gp
+// step of ps_conjgrad), operand prefetched into L2 by the otherwise idle lanes of the loader warp.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
