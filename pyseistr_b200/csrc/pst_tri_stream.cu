@@ -66,6 +66,10 @@ constexpr int NBW = 4;                 // builder warps
 constexpr int NSW = 4;                 // storer warps
 constexpr int NWARPS = 12;
 constexpr int NBMAX = 16;
+constexpr int NSMAX = 48;               // stages per line the F hand-off barriers are laid out for (lines up to 48*32 steps)
+#ifndef TS_SPLIT
+#define TS_SPLIT 1                      // 1: forward and backward chains on two warps (0 and 4) of the same scheduler
+#endif
 constexpr int NXS_MAX = TS_NXS;
 static_assert(NTS % NBW == 0 && NXS_MAX % NBW == 0 && NOS % NSW == 0, "ring slots must be a multiple of their consumer warps");
 
@@ -265,6 +269,84 @@ __device__ __forceinline__ void chain_pass(float *Fl, const float *Tr, float *Or
     }
 }
 
+// ---- the two chains on two warps (TS_SPLIT): warp 0 runs the backward chain of tile p-1, warp 4 the forward
+// chain of tile p, one stage behind it.  They share the F buffer slot by slot: f_read[q] (backward warp -> forward
+// warp: "stage q of this pass is in my registers, overwrite it") and f_written[q] (forward warp -> backward warp:
+// "stage q of this pass is stored", consumed one pass later).  Both are indexed by the PHYSICAL stage of the F buffer
+// (the slot order alternates from pass to pass).  Each barrier completes once per pass, so its parity is the pass
+// parity and neither warp can run two phases ahead of the other.
+template <bool REV>
+__device__ __forceinline__ void bwd_pass(float *Fl, float *Or, float *ER, float *EH, int lane, uint64_t *full_o,
+                                         uint64_t *empty_o, uint64_t *f_read, uint64_t *f_written, Cursor &co,
+                                         unsigned wpar, int NS, int nx, int nb, int L, unsigned *err)
+{
+    const int NG = NS * (KB / 4);
+    float B = 0.f;
+    int kb_hi = L - 1;
+    bool ro = false;
+    for (int q = 0; q < NS; q++, kb_hi -= KB) {
+        if (!ro) mbar_wait(empty_o + co.slot, co.par ^ 1u, err);
+        const int ps = REV ? NS - 1 - q : q;                       // PHYSICAL stage of the F buffer (slot order alternates per pass)
+        mbar_wait(f_written + ps, wpar, err);                      // stored by the forward warp in the previous pass
+        float *O = Or + co.slot * TSTAGE + 4 * lane;
+        uint64_t *const sig_o = full_o + co.slot;
+        float4 fv[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int G = q * (KB / 4) + g;
+            fv[g] = *reinterpret_cast<const float4 *>(Fl + (size_t)(REV ? NG - 1 - G : G) * 128);
+        }
+        co.slot = co.slot + 1 == NOS ? 0 : co.slot + 1; co.par ^= (co.slot == 0);
+        ro = (q + 1 < NS) ? mbar_probe(empty_o + co.slot, co.par ^ 1u) : false;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            float4 o;
+            if (!REV) { B += fv[g].x; o.x = B; B += fv[g].y; o.y = B; B += fv[g].z; o.z = B; B += fv[g].w; o.w = B; }
+            else      { B += fv[g].w; o.x = B; B += fv[g].z; o.y = B; B += fv[g].y; o.z = B; B += fv[g].x; o.w = B; }
+            *reinterpret_cast<float4 *>(O + g * GP) = o;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(f_read + ps);                   // all lanes' F values are in registers (consumed above)
+        if (kb_hi >= nx || kb_hi - (KB - 1) < 2 * nb) chain_fold_fix(O, ER, EH, lane, kb_hi, nx, nb, L);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sig_o);
+    }
+}
+template <bool REV>
+__device__ __forceinline__ void fwd_pass(float *Fl, const float *Tr, int lane, uint64_t *full_t, uint64_t *empty_t,
+                                         uint64_t *f_read, uint64_t *f_written, Cursor &ct, bool wait_read,
+                                         unsigned rpar, int NS, unsigned *err)
+{
+    const int NG = NS * (KB / 4);
+    float Fs = 0.f;
+    bool rt = false;
+    for (int q = 0; q < NS; q++) {
+        if (!rt) mbar_wait(full_t + ct.slot, ct.par, err);
+        const float *T = Tr + ct.slot * TSTAGE + 4 * lane;
+        uint64_t *const rel_t = empty_t + ct.slot;
+        float4 tv[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) tv[g] = *reinterpret_cast<const float4 *>(T + g * GP);
+        ct.slot = ct.slot + 1 == NTS ? 0 : ct.slot + 1; ct.par ^= (ct.slot == 0);
+        rt = (q + 1 < NS) ? mbar_probe(full_t + ct.slot, ct.par) : false;
+        float4 fn[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            if (!REV) { Fs += tv[g].x; fn[g].x = Fs; Fs += tv[g].y; fn[g].y = Fs; Fs += tv[g].z; fn[g].z = Fs; Fs += tv[g].w; fn[g].w = Fs; }
+            else      { Fs += tv[g].x; fn[g].w = Fs; Fs += tv[g].y; fn[g].z = Fs; Fs += tv[g].z; fn[g].y = Fs; Fs += tv[g].w; fn[g].x = Fs; }
+        }
+        const int ps = REV ? NS - 1 - q : q;
+        if (wait_read) mbar_wait(f_read + ps, rpar, err);           // the backward warp has taken the old values of this stage
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int G = q * (KB / 4) + g;
+            *reinterpret_cast<float4 *>(Fl + (size_t)(REV ? NG - 1 - G : G) * 128) = fn[g];
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(rel_t); mbar_arrive(f_written + ps); }
+    }
+}
+
 // x stage -> t stage, lane = line, radius known at compile time: every x sample is read from shared
 // memory ONCE into a register window (the generic path reads it three times)
 template <bool CONTIG, int NB>
@@ -308,12 +390,14 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
     uint64_t *const full_x = bars, *const empty_x = full_x + NXS_MAX;
     uint64_t *const full_t = empty_x + NXS_MAX, *const empty_t = full_t + NTS;
     uint64_t *const full_o = empty_t + NTS, *const empty_o = full_o + NOS;
+    uint64_t *const f_read = empty_o + NOS, *const f_written = f_read + NSMAX;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < A.nxs; i++) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, 1); }
         for (int i = 0; i < NTS; i++) { mbar_init(full_t + i, 1); mbar_init(empty_t + i, 1); }
         for (int i = 0; i < NOS; i++) { mbar_init(full_o + i, 1); mbar_init(empty_o + i, 1); }
+        for (int i = 0; i < NSMAX; i++) { mbar_init(f_read + i, 1); mbar_init(f_written + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -325,7 +409,27 @@ tri_stream_kernel(const __grid_constant__ CUtensorMap tmap, const Args A)
     const long nstage = m * NS;
     double acc = 0.0;                                        // storers: fused sum of gp^2
 
-    if (warp == 0) {
+    if (TS_SPLIT && warp == 0) {
+        // ================================ backward chain warp ================================
+        float *const Fl = Fbuf + 4 * lane;
+        Cursor co;
+        co.init(0, NOS);
+        for (long p = 1; p <= m; p++) {
+            // reads what the forward warp stored in pass p-1: phase p-1 of f_written
+            if (p & 1) bwd_pass<true>(Fl, Or, ER, EH, lane, full_o, empty_o, f_read, f_written, co, (unsigned)((p - 1) & 1), NS, nx, nb, L, A.err);
+            else bwd_pass<false>(Fl, Or, ER, EH, lane, full_o, empty_o, f_read, f_written, co, (unsigned)((p - 1) & 1), NS, nx, nb, L, A.err);
+        }
+    } else if (TS_SPLIT && warp == 4) {
+        // ================================ forward chain warp ================================
+        float *const Fl = Fbuf + 4 * lane;
+        Cursor ct;
+        ct.init(0, NTS);
+        for (long p = 0; p < m; p++) {
+            // overwrites what the backward warp reads in the same pass: phase p-1 of f_read (none in pass 0)
+            if (p & 1) fwd_pass<true>(Fl, Tr, lane, full_t, empty_t, f_read, f_written, ct, p > 0, (unsigned)((p - 1) & 1), NS, A.err);
+            else fwd_pass<false>(Fl, Tr, lane, full_t, empty_t, f_read, f_written, ct, p > 0, (unsigned)((p - 1) & 1), NS, A.err);
+        }
+    } else if (!TS_SPLIT && warp == 0) {
         // ================================ chain warp ================================
         float *const Fl = Fbuf + 4 * lane;
         Cursor ct, co;
@@ -589,7 +693,7 @@ size_t smem_bytes(bool contig, int Lp, int nxs, int xsf, int nb)
 {
     (void)contig;
     size_t fl = (size_t)Lp * 32 + (size_t)nxs * xsf + (size_t)NTS * TSTAGE + (size_t)NOS * TSTAGE + (size_t)2 * nb * 32;
-    return fl * 4 + (size_t)(2 * NXS_MAX + 2 * NTS + 2 * NOS) * 8;
+    return fl * 4 + (size_t)(2 * NXS_MAX + 2 * NTS + 2 * NOS + 2 * NSMAX) * 8;
 }
 
 template <int NB>
@@ -621,6 +725,7 @@ bool pst_tri_stream_ok(int axis, int n1, int n2, int n3, int nb, const void *src
     const int L = nx + 2 * nb, Lp = (L + KB - 1) / KB * KB;
     const int XW = xw_of(nb);
     const int xsf = axis == 0 ? 32 * XW : (KB + 2 * nb) * 32;
+    if (Lp / KB > NSMAX) return false;
     return smem_bytes(axis == 0, Lp, NBW, xsf, nb) <= 226 * 1024;
 }
 
