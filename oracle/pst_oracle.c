@@ -763,15 +763,56 @@ static float sumsq_f(size_t n, const float *x)       /* ps_cblas_snrm2 :805-818:
     return s;
 }
 
-int pso_soint3d(const float *din, const float *mask, const float *dipi, const float *dipx,
-                int n1, int n2, int n3, int order, int niter, float *out)
+/* MT19937 (init_genrand / genrand_int32 / genrand_real1, soint3d_cfuns.c:2304-2370) and the Box-Muller pair
+ * generator ps_randn_one_bm (:2372-2402): the second value of each pair is returned first, the first one is kept
+ * for the next call. */
+typedef struct { unsigned long mt[624]; int mti; int have; float kept; } noise_gen;
+static void noise_seed(noise_gen *g, unsigned long s)
+{
+    g->mt[0] = s & 0xffffffffUL;
+    for (int i = 1; i < 624; i++) g->mt[i] = (1812433253UL * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + i) & 0xffffffffUL;
+    g->mti = 624; g->have = 0; g->kept = 0.f;
+}
+static unsigned long noise_u32(noise_gen *g)
+{
+    if (g->mti >= 624) {
+        for (int k = 0; k < 624; k++) {
+            unsigned long y = (g->mt[k] & 0x80000000UL) | (g->mt[(k + 1) % 624] & 0x7fffffffUL);
+            g->mt[k] = g->mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1UL) ? 0x9908b0dfUL : 0UL);
+        }
+        g->mti = 0;
+    }
+    unsigned long y = g->mt[g->mti++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680UL; y ^= (y << 15) & 0xefc60000UL; y ^= (y >> 18);
+    return y & 0xffffffffUL;
+}
+static float noise_normal(noise_gen *g)
+{
+    if (g->have) { g->have = 0; return g->kept; }
+    double x1, x2;
+    do { x1 = noise_u32(g) * (1.0 / 4294967295.0); } while (x1 == 0.0);
+    x2 = noise_u32(g) * (1.0 / 4294967295.0);
+    double z1 = sqrt(-2.0 * log(x1)), z2 = 2.0 * 3.14159265358979323846264338328 * x2;
+    double y1 = z1 * cos(z2), y2 = z1 * sin(z2);
+    g->have = 1; g->kept = (float)y1;
+    return (float)y2;
+}
+
+/* csoint3d :2405-2508; var > 0 puts a*randn (a = sqrtf(var), MT19937 seeded with `seed`) on the right-hand side */
+int pso_soint3d_noise(const float *din, const float *mask, const float *dipi, const float *dipx,
+                      int n1, int n2, int n3, int order, int niter, int seed, float var, float *out)
 {
     size_t n = (size_t)n1 * n2 * n3, ny = 2 * n;
     float *x = out, *g = falloc(n), *rr = falloc(ny), *gg = falloc(ny), *S = falloc(n), *Ss = falloc(ny);
     unsigned char *known = (unsigned char *)malloc(n);
     for (size_t i = 0; i < n; i++) known[i] = mask ? (mask[i] != 0.f) : (din[i] != 0.f);
     /* ps_solver :1018-1040: rr = -dat (dat = 0 when var = 0); x = x0; rr += L x */
-    for (size_t i = 0; i < ny; i++) rr[i] = -0.0f;
+    {
+        noise_gen G;
+        noise_seed(&G, (unsigned long)seed);
+        const float a = sqrtf(var);
+        for (size_t i = 0; i < ny; i++) { float d = a * noise_normal(&G); rr[i] = -d; }
+    }
     memcpy(x, din, n * sizeof(float));
     pwd3_lop(0, 1, n1, n2, n3, order, dipi, dipx, x, rr);
     float dpr0 = sumsq_f(ny, rr), dpg0 = 1.f, dpr, dpg;
@@ -811,6 +852,12 @@ int pso_soint3d(const float *din, const float *mask, const float *dipi, const fl
     }
     free(g); free(rr); free(gg); free(S); free(Ss); free(known);
     return 0;
+}
+
+int pso_soint3d(const float *din, const float *mask, const float *dipi, const float *dipx,
+                int n1, int n2, int n3, int order, int niter, float *out)
+{
+    return pso_soint3d_noise(din, mask, dipi, dipx, n1, n2, n3, order, niter, 202223, 0.f, out);
 }
 
 /* ------------------------------------------------------------------ spray-operator interpolation */

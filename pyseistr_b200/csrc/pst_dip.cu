@@ -2229,9 +2229,64 @@ __global__ void known_kernel(const float *__restrict__ ref, unsigned char *__res
         known[i] = (ref[i] != 0.f);
 }
 
+// Right-hand side noise of csoint3d (var > 0): a * N(0,1) drawn on the HOST exactly like the reference --
+// MT19937 seeded per call (init_genrand / genrand_real1, soint3d_cfuns.c:2304-2370) feeding a Box-Muller pair
+// generator that hands out the SECOND value of a pair first (ps_randn_one_bm :2372-2402) -- so that the same
+// seed gives the same interpolation.  The draws are sequential by construction; they are produced in chunks and
+// copied into rr as -d (ps_solver :1018-1024).
+namespace {
+struct NoiseGen {
+    uint32_t mt[624]; int mti; bool have; float kept;
+    explicit NoiseGen(uint32_t s) : mti(624), have(false), kept(0.f)
+    {
+        mt[0] = s;
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    }
+    uint32_t u32()
+    {
+        if (mti >= 624) {
+            for (int k = 0; k < 624; k++) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    float normal()
+    {
+        if (have) { have = false; return kept; }
+        double x1, x2;
+        do { x1 = u32() * (1.0 / 4294967295.0); } while (x1 == 0.0);
+        x2 = u32() * (1.0 / 4294967295.0);
+        const double z1 = sqrt(-2.0 * log(x1)), z2 = 2.0 * 3.14159265358979323846264338328 * x2;
+        const double y1 = z1 * cos(z2), y2 = z1 * sin(z2);
+        have = true; kept = (float)y1;
+        return (float)y2;
+    }
+};
+}  // namespace
+
+static int soint3d_noise_rhs(pst_ctx *c, float *d_rr, size_t ny, int seed, float var)
+{
+    NoiseGen G((uint32_t)(unsigned long)seed);
+    const float a = sqrtf(var);
+    const size_t chunk = (size_t)1 << 24;
+    std::vector<float> h(std::min(chunk, ny));
+    for (size_t o = 0; o < ny; o += chunk) {
+        const size_t m = std::min(chunk, ny - o);
+        for (size_t i = 0; i < m; i++) { const float d = a * G.normal(); h[i] = -d; }
+        PST_CUDA(cudaMemcpyAsync(d_rr + o, h.data(), m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PST_OK;
+}
+
 template <int NW>
 static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, const float *d_pp, const float *d_qq,
-                       int n1, int n2, int n3, int niter, int verb, float *d_out)
+                       int n1, int n2, int n3, int niter, int seed, float var, int verb, float *d_out)
 {
     static const BTab tb = make_btab(NW);
     constexpr int NA = 2 * NW + 1;
@@ -2255,7 +2310,8 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     PST_LAUNCH(c, PST_K_OTHER, (known_kernel<<<grid, threads, 0, c->stream>>>(d_mask ? d_mask : d_din, known, n)));
     // ps_solver :1018-1040 with dat = 0 (var = 0): rr = -0; x = x0 = data; rr += L x
     PST_CUDA(cudaMemcpyAsync(x, d_din, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
+    if (var != 0.f) PST_TRY(soint3d_noise_rhs(c, rr, 2 * n, seed, var));
+    else PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
     PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
                 (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, c->d_partial)));
     PST_CUDA(cudaMemsetAsync(S, 0, n * sizeof(float), c->stream));
@@ -2313,17 +2369,16 @@ extern "C" int pst_soint3d_dev(pst_ctx *c, const float *d_din, const float *d_ma
                                const float *d_dipx, int n1, int n2, int n3, int nw, int nj1, int nj2, int niter,
                                int drift, int seed, int hasmask, float var, int verb, float *d_out)
 {
-    (void)seed;
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (n1 < 1 || n2 < 1 || n3 < 1 || niter < 0) { pst_set_error("soint3d: bad dimensions"); return PST_EINVAL; }
     if (nw != 1 && nw != 2) { pst_set_error("soint3d: order=%d unsupported (1 or 2)", nw); return PST_EUNSUP; }
     if (n1 < 2 * nw + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
     if (nj1 != 1 || nj2 != 1 || drift != 0) { pst_set_error("soint3d: njs != 1 / drift are not implemented on the GPU path"); return PST_EUNSUP; }
-    if (var != 0.f) { pst_set_error("soint3d: var != 0 (random right-hand side) is not implemented on the GPU path"); return PST_EUNSUP; }
+    if (var < 0.f) { pst_set_error("soint3d: var < 0"); return PST_EINVAL; }
     if (c->comm && c->nranks > 1) { pst_set_error("soint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
     if (hasmask && !d_mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     const float *m = hasmask ? d_mask : nullptr;
-    if (nw == 1) return soint3d_run<1>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, verb, d_out);
-    return soint3d_run<2>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, verb, d_out);
+    if (nw == 1) return soint3d_run<1>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, seed, var, verb, d_out);
+    return soint3d_run<2>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, seed, var, verb, d_out);
 }

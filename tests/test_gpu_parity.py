@@ -290,10 +290,23 @@ def test_sint3d_vs_oracle_and_fills_gaps(ctx, port):
     assert rel_l2(got1, want1) <= 1e-6, rel_l2(got1, want1)
 
 
+def test_soint3d_noise_rhs_matches_oracle(ctx, port):
+    """var > 0: the right-hand side is a*N(0,1) from MT19937(seed) + Box-Muller drawn like the reference
+    (soint3d_cfuns.c:2304-2402); same seed, same interpolation (rel. L2 <= 1e-5)."""
+    import pyseistr_b200 as ps
+    g = golden("soint3d_o2n20")
+    for var, seed in ((0.01, 202223), (0.3, 7)):
+        got = ps.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=2, niter=8, var=var, seed=seed, verb=0, ctx=ctx)
+        want = port.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=2, niter=8, var=var, seed=seed)
+        assert rel_l2(got, want) <= TOL, (var, seed, rel_l2(got, want))
+    other = ps.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=2, niter=8, var=0.3, seed=8, verb=0, ctx=ctx)
+    assert rel_l2(other, want) > 1e-3                                   # a different seed is a different answer
+
+
 def test_soint3d_unsupported_options_refused(ctx):
     import pyseistr_b200 as ps
     d = synth.cube(20, 6, 4, seed=83)
-    for kw in (dict(var=0.1), dict(drift=1), dict(njs=[2, 1])):
+    for kw in (dict(drift=1), dict(njs=[2, 1])):
         with pytest.raises(ps.PstError) as e:
             ps.soint3dc(d, np.ones_like(d), 0 * d, 0 * d, niter=2, verb=0, ctx=ctx, **kw)
         assert e.value.code == -5
