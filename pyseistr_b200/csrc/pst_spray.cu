@@ -21,9 +21,19 @@
 #include "pst_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #define PST_MAXSLOT 81
+
+// Budget of the per-chunk slot + factor-scratch buffers.  One thread runs one target trace, so a chunk must
+// hold enough planes to fill the GPU (148 SMs x 1536+ threads): at 1000x1024x1024 the first session's 6 GB gave
+// 85 planes = 87 K threads (29 % of capacity, ncu: long-scoreboard bound); 24 GB gives 340 planes.
+static double spray_chunk_bytes()
+{
+    static const double v = []() { const char *e = getenv("PST_SPRAY_CHUNK_GB"); const double g = e ? atof(e) : 24.0; return (g > 0.5 ? g : 0.5) * 1.0e9; }();
+    return v;
+}
 
 struct BTabS { double b[PST_MAXTAP]; };
 
@@ -459,7 +469,7 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     const int NC = 2 * nw + 2;
     // chunk height: bound slot + scratch memory to ~6 GB
     const double bytes_per_plane = (double)plane * 4.0 * (nlive + NC);
-    int cz = (int)(6.0e9 / bytes_per_plane) - 2 * ns3;
+    int cz = (int)(spray_chunk_bytes() / bytes_per_plane) - 2 * ns3;
     if (cz < 1) cz = 1;
     if (cz > P.zt1 - P.zt0) cz = P.zt1 - P.zt0;
     const int nzl_max = std::min(P.zs1 - P.zs0, cz + 2 * ns3);
@@ -625,7 +635,7 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     const long plane = (long)n1 * n2;
     const size_t n = (size_t)plane * nz, nex = (size_t)plane * ne;
     const int NC = 2 * order + 2;
-    double chunk_planes = 6.0e9 / ((double)plane * 4.0 * (nlive + NC));
+    double chunk_planes = spray_chunk_bytes() / ((double)plane * 4.0 * (nlive + NC));
     if (chunk_planes > nz) chunk_planes = nz;
     const size_t nzl = (size_t)std::min<double>(ne, std::max(1.0, floor(chunk_planes) - 2 * ns3) + 2 * ns3);
     const size_t need = (4 * nex + 2 * n + (size_t)plane * nzl * (nlive + NC)) * sizeof(float) + 64 * 256 + (size_t)nlive * 256;
@@ -1147,7 +1157,7 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     const size_t n = (size_t)n1 * n2 * n3;
     const int NCmax = 2 * std::max(order1, order2) + 2, nsmax = std::max(ns1, ns2);
     // 9 CG vectors + 2 dips + 2 norms + 4 work volumes + mask + spray slots/scratch (bounded chunks)
-    const double chunk = std::min<double>(6.0e9 + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * nsmax + 1 + NCmax));
+    const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * nsmax + 1 + NCmax));
     PST_TRY(pst_arena_reserve(c, (size_t)(19 * n * sizeof(float) + n + chunk + 3.0e9 + 64 * 4096)));
     pst_arena_reset(c);
     float *dipA, *dipB, *tnA, *tnB, *p, *x, *r, *sp, *sx, *sr, *gp, *gx, *wA1, *wA2, *wB1, *wB2, *dA;
@@ -1244,7 +1254,7 @@ int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int
     PST_CUDA(cudaSetDevice(c->device));
     const size_t n = (size_t)n1 * n2 * n3;
     const int NC = 2 * order + 2;
-    const double chunk = std::min<double>(6.0e9 + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * ns + 1 + NC));
+    const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * ns + 1 + NC));
     PST_TRY(pst_arena_reserve(c, (size_t)(7 * n * sizeof(float) + chunk + 3.0e9 + 64 * 4096)));
     pst_arena_reset(c);
     float *dipA, *tn, *dA, *oA, *w1, *w2;

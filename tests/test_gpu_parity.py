@@ -336,6 +336,27 @@ def test_das_panel_config1(ctx, port):
     assert np.array_equal(f, port.somf2dc(d, po, 8, 2, 0.01))
 
 
+def test_interpolators_at_scale(ctx):
+    """200x128x64, half of the traces missing: soint3dc and sint3dc run through their chunked paths, return finite
+    volumes and fill the gaps (properties instead of the oracle, which needs minutes here)."""
+    import pyseistr_b200 as ps
+    n1, n2, n3 = 200, 128, 64
+    d = synth.cube(n1, n2, n3, seed=91, noise=0.0)
+    di, dx = ps.dip3dc(d, verb=0, ctx=ctx)
+    keep = np.random.default_rng(92).random((n2, n3)) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    d0 = d * mask
+    gap = np.linalg.norm(d0 - d)
+    a = ps.soint3dc(d0, mask, di, dx, order=2, niter=20, verb=0, ctx=ctx)
+    assert np.isfinite(a).all() and np.array_equal(a[:, keep], d0[:, keep])
+    assert np.linalg.norm(a - d) < 0.35 * gap
+    b = ps.sint3dc(d0, mask, di, dx, niter=8, ns1=2, ns2=2, order1=2, order2=2, verb=0, ctx=ctx)
+    assert np.isfinite(b).all() and np.linalg.norm(b - d) < 0.6 * gap
+    b2 = ps.sint3dc(d0, mask, di, dx, niter=8, ns1=2, ns2=2, order1=2, order2=2, verb=0, ctx=ctx)
+    assert np.array_equal(b, b2)                                        # run-to-run reproducible
+
+
 # ------------------------------------------------------------------ properties at scale
 def test_pipeline_properties_at_scale(ctx):
     """200x128x64 (the survey's proxy cube; the oracle needs ~30 s there so properties are used
