@@ -166,15 +166,42 @@ predict_kernel(const PredArgs A)
         for (int c = 0; c < NA; c++) { X1[c] = t1[c]; if (TWO) X2[c] = t2[c]; }
     }
 
-    for (int i = -NW; i < n1; i++) {
+    // Loads run PF steps ahead of their use (register queues, loop unrolled by PF so the queue index is static):
+    // one thread owns one trace, so without this every step waits for its own slope / input sample
+    // (ncu, first version: 10 long-scoreboard stall cycles per issued instruction).
+    constexpr int PF = 4;
+    float gq1[PF], gq2[PF], xq1[PF], xq2[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        const int kk = u;                                   // step i = -NW + u uses slope sample kk = i + NW = u
+        gq1[u] = (kk < n1) ? g1[(long)kk * n2] : 0.f;
+        gq2[u] = (TWO && kk < n1) ? g2[(long)kk * n2] : 0.f;
+        const int idx = kk + 1 + NW;                        // and feeds input sample (kk + 1) + NW to the window
+        xq1[u] = (idx < n1) ? x1[(long)idx * n2] : 0.f;
+        xq2[u] = (TWO && idx < n1) ? x2[(long)idx * n2] : 0.f;
+    }
+    for (int i0 = -NW; i0 < n1; i0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        const int i = i0 + u;
+        if (i >= n1) break;
         // ---- leading sample kk = i + NW enters the windows at c = NA-1
         const int kk = i + NW;
+        const float gv1 = gq1[u], gv2 = gq2[u], xn1 = xq1[u], xn2 = xq2[u];
+        {                                                   // refill the queue slot for step i + PF
+            const int kn = kk + PF;
+            gq1[u] = (kn < n1) ? g1[(long)kn * n2] : 0.f;
+            if (TWO) gq2[u] = (kn < n1) ? g2[(long)kn * n2] : 0.f;
+            const int idn = kn + 1 + NW;
+            xq1[u] = (idn < n1) ? x1[(long)idn * n2] : 0.f;
+            if (TWO) xq2[u] = (idn < n1) ? x2[(long)idn * n2] : 0.f;
+        }
         {
             float a1[NA], a2[NA];
             float tm1 = 0.f, tm2 = 0.f;
             if (kk < n1) {
-                spray_taps<NW>(A.tb, g1[(long)kk * n2], f1, a1);
-                if (TWO) spray_taps<NW>(A.tb, g2[(long)kk * n2], f2, a2);
+                spray_taps<NW>(A.tb, gv1, f1, a1);
+                if (TWO) spray_taps<NW>(A.tb, gv2, f2, a2);
                 if (kk >= NW && kk < n1 - NW) {               // pwd_set :481-486
 #pragma unroll
                     for (int j = 0; j < NA; j++) {
@@ -292,28 +319,46 @@ predict_kernel(const PredArgs A)
 #pragma unroll
             for (int j = 0; j < NA; j++) { W1[c][j] = W1[c + 1][j]; if (TWO) W2[c][j] = W2[c + 1][j]; }
         }
-        {
-            const int idx = kk + 1 + NW;       // X[NA-1] for the next step = inp[(kk+1) + NW]
-            X1[NA - 1] = (idx < n1) ? x1[(long)idx * n2] : 0.f;
-            if (TWO) X2[NA - 1] = (idx < n1) ? x2[(long)idx * n2] : 0.f;
-        }
+        X1[NA - 1] = xn1;                      // X[NA-1] for the next step = inp[(kk+1) + NW] (0 beyond the trace)
+        if (TWO) X2[NA - 1] = xn2;
+      }
     }
 
     // ---- back substitution (sf_banded_solve :257-263)
     float Y[NB];
 #pragma unroll
     for (int m = 0; m < NB; m++) Y[m] = 0.f;
-    for (int k = n1 - 1; k >= 0; k--) {
-        const float *sc = scr + (long)k * NC * n2;
-        const float dk = sc[0];
-        float t = sc[(long)(NB + 1) * n2] / dk;
+    constexpr int PB = 4;                                   // factor columns in flight ahead of the recurrence
+    float cq[PB][NC];
+#pragma unroll
+    for (int u = 0; u < PB; u++) {
+        const int k = n1 - 1 - u;
+#pragma unroll
+        for (int q = 0; q < NC; q++) cq[u][q] = (k >= 0) ? scr[((long)k * NC + q) * n2] : 1.f;
+    }
+    for (int k0 = n1 - 1; k0 >= 0; k0 -= PB) {
+#pragma unroll
+      for (int u = 0; u < PB; u++) {
+        const int k = k0 - u;
+        if (k < 0) break;
+        float col[NC];
+#pragma unroll
+        for (int q = 0; q < NC; q++) col[q] = cq[u][q];
+        {
+            const int kn = k - PB;
+#pragma unroll
+            for (int q = 0; q < NC; q++) cq[u][q] = (kn >= 0) ? scr[((long)kn * NC + q) * n2] : 1.f;
+        }
+        const float dk = col[0];
+        float t = col[NB + 1] / dk;
 #pragma unroll
         for (int m = 0; m < NB; m++)
-            if (m < n1 - k - 1) t -= sc[(long)(1 + m) * n2] * Y[m];
+            if (m < n1 - k - 1) t -= col[1 + m] * Y[m];
         out[(long)k * n2] = t;
 #pragma unroll
         for (int m = NB - 1; m > 0; m--) Y[m] = Y[m - 1];
         Y[0] = t;
+      }
     }
 }
 
