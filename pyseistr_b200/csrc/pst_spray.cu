@@ -854,11 +854,36 @@ predict_adj_kernel(const AdjArgs A)
 #pragma unroll
         for (int m = 0; m < NB; m++) O[h][m] = 0.f;
     }
-    for (int i = -NW; i < n1; i++) {
+    // loads run PF steps ahead of their use (register queues, see predict_kernel)
+    constexpr int PF = 4;
+    float gq[PF], tq[PF], dq[PF], rq[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        const int kk = u, ii = u - NW;                      // step i = -NW + u: slope sample kk, right-hand side sample i
+        gq[u] = (kk < n1) ? g1[(long)kk * n2] : 0.f;
+        const bool in = ii >= 0 && ii < n1;
+        tq[u] = in ? tn[(long)ii * n2] : 0.f;
+        dq[u] = in ? dat[(long)ii * n2] : 0.f;
+        rq[u] = in ? tr[(long)ii * n2] : 0.f;
+    }
+    for (int i0 = -NW; i0 < n1; i0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        const int i = i0 + u;
+        if (i >= n1) break;
         const int kk = i + NW;
+        const float gv = gq[u], tv = tq[u], dv = dq[u], rv = rq[u];
+        {
+            const int kn = kk + PF, in2 = i + PF;
+            gq[u] = (kn < n1) ? g1[(long)kn * n2] : 0.f;
+            const bool in = in2 >= 0 && in2 < n1;
+            tq[u] = in ? tn[(long)in2 * n2] : 0.f;
+            dq[u] = in ? dat[(long)in2 * n2] : 0.f;
+            rq[u] = in ? tr[(long)in2 * n2] : 0.f;
+        }
         {
             float a1[NA];
-            if (kk < n1) spray_taps<NW>(A.tb, g1[(long)kk * n2], f1, a1);
+            if (kk < n1) spray_taps<NW>(A.tb, gv, f1, a1);
             else {
 #pragma unroll
                 for (int j = 0; j < NA; j++) a1[j] = 0.f;
@@ -889,10 +914,9 @@ predict_adj_kernel(const AdjArgs A)
                 }
             }
             // right-hand side: the running trace plus the slot contribution
-            const float tv = tn[(long)i * n2];
             const float ws = (0.0f != tv) ? (float)(1.0 / (double)tv) : 0.0f;
-            const float u = dat[(long)i * n2] * A.wslot * ws;
-            const float rhs = tr[(long)i * n2] + u;
+            const float uu = dv * A.wslot * ws;
+            const float rhs = rv + uu;
             float t = dg;
 #pragma unroll
             for (int m = 0; m < NB; m++)
@@ -930,19 +954,39 @@ predict_adj_kernel(const AdjArgs A)
         for (int cc = 0; cc < NA - 1; cc++)
 #pragma unroll
             for (int j = 0; j < NA; j++) W1[cc][j] = W1[cc + 1][j];
+      }
     }
     // ---- pass 2 (descending): back substitution, y stored in place
     float Y[NB];
 #pragma unroll
     for (int m = 0; m < NB; m++) Y[m] = 0.f;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    for (int k = n1 - 1; k >= 0; k--) {
-        const float *sc = scr + (long)k * NC * n2;
-        const float dk = sc[0];
-        float t = sc[(long)(NB + 1) * n2] / dk;
+    constexpr int PB = 4;
+    float cq[PB][NC];
+#pragma unroll
+    for (int u = 0; u < PB; u++) {
+        const int k = n1 - 1 - u;
+#pragma unroll
+        for (int q = 0; q < NC; q++) cq[u][q] = (k >= 0) ? scr[((long)k * NC + q) * n2] : 1.f;
+    }
+    for (int k0 = n1 - 1; k0 >= 0; k0 -= PB) {
+#pragma unroll
+      for (int u = 0; u < PB; u++) {
+        const int k = k0 - u;
+        if (k < 0) break;
+        float col[NC];
+#pragma unroll
+        for (int q = 0; q < NC; q++) col[q] = cq[u][q];
+        {
+            const int kn = k - PB;
+#pragma unroll
+            for (int q = 0; q < NC; q++) cq[u][q] = (kn >= 0) ? scr[((long)kn * NC + q) * n2] : 1.f;
+        }
+        const float dk = col[0];
+        float t = col[NB + 1] / dk;
 #pragma unroll
         for (int m = 0; m < NB; m++)
-            if (m < n1 - k - 1) t -= sc[(long)(1 + m) * n2] * Y[m];
+            if (m < n1 - k - 1) t -= col[1 + m] * Y[m];
         tr[(long)k * n2] = t;
         if (k == 0) t0 = t;
         if (k == 1) t1 = t;
@@ -951,6 +995,7 @@ predict_adj_kernel(const AdjArgs A)
 #pragma unroll
         for (int m = NB - 1; m > 0; m--) Y[m] = Y[m - 1];
         Y[0] = t;
+      }
     }
     // ---- pass 3 (ascending): pwd_set(adj = true): tmp = W y (rows [nw, n-nw), scatter order), out = W' tmp
     // windows at leading row e: YW[c] = y[e - NW + c]; W1[c][.] / TM[c] <-> row e - 2NW + c
