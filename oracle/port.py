@@ -158,8 +158,8 @@ def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=(1, 1), drift=0, see
     d, a, b = _F(din), _F(dipi), _F(dipx)
     m = _F(mask) if hasmask else None
     out = np.zeros_like(d)
-    lib().pso_soint3d_noise(_p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, n3, int(order), int(niter),
-                            int(seed), ctypes.c_float(var), _p(out))
+    lib().pso_soint3d_full(_p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, n3, int(order),
+                           int(njs[0]), int(njs[1]), int(niter), int(seed), ctypes.c_float(var), _p(out))
     return out.reshape(n1, n2, n3, order="F")
 
 

@@ -722,9 +722,10 @@ int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int n
 
 /* allpass3_lop :625-729 (drift=false, nj=1): y[0:N] = inline PWD of x, y[N:2N] = xline PWD;
  * adjoint scatters in the same loop order. */
-static void pwd3_lop(int adj, int add, int n1, int n2, int n3, int nw, const float *pp, const float *qq,
-                     float *xx, float *yy)
+static void pwd3_lop(int adj, int add, int n1, int n2, int n3, int nw, int nj1, int nj2, const float *pp,
+                     const float *qq, float *xx, float *yy)
 {
+    /* allpass3_lop soint3d_cfuns.c:625-729 (drift = false): shifts (iw - nw) * nj, rows [nw*nj, n1 - nw*nj) */
     size_t n = (size_t)n1 * n2 * n3;
     float flt[MAXTAP];
     if (!add) {
@@ -733,11 +734,11 @@ static void pwd3_lop(int adj, int add, int n1, int n2, int n3, int nw, const flo
     }
     for (int iz = 0; iz < n3; iz++)
         for (int iy = 0; iy < n2 - 1; iy++)
-            for (int ix = nw; ix < n1 - nw; ix++) {
+            for (int ix = nw * nj1; ix < n1 - nw * nj1; ix++) {
                 long i = ix + (long)n1 * (iy + (long)n2 * iz);
                 pso_passfilter(nw, pp[i], flt);
                 for (int iw = 0; iw <= 2 * nw; iw++) {
-                    int is = iw - nw;
+                    int is = (iw - nw) * nj1;
                     if (adj) { xx[i + n1 + is] += yy[i] * flt[iw]; xx[i - is] -= yy[i] * flt[iw]; }
                     else     yy[i] += (xx[i + n1 + is] - xx[i - is]) * flt[iw];
                 }
@@ -745,11 +746,11 @@ static void pwd3_lop(int adj, int add, int n1, int n2, int n3, int nw, const flo
     long pl = (long)n1 * n2;
     for (int iz = 0; iz < n3 - 1; iz++)
         for (int iy = 0; iy < n2; iy++)
-            for (int ix = nw; ix < n1 - nw; ix++) {
+            for (int ix = nw * nj2; ix < n1 - nw * nj2; ix++) {
                 long i = ix + (long)n1 * (iy + (long)n2 * iz);
                 pso_passfilter(nw, qq[i], flt);
                 for (int iw = 0; iw <= 2 * nw; iw++) {
-                    int is = iw - nw;
+                    int is = (iw - nw) * nj2;
                     if (adj) { xx[i + pl + is] += yy[i + n] * flt[iw]; xx[i - is] -= yy[i + n] * flt[iw]; }
                     else     yy[i + n] += (xx[i + pl + is] - xx[i - is]) * flt[iw];
                 }
@@ -802,6 +803,12 @@ static float noise_normal(noise_gen *g)
 int pso_soint3d_noise(const float *din, const float *mask, const float *dipi, const float *dipx,
                       int n1, int n2, int n3, int order, int niter, int seed, float var, float *out)
 {
+    return pso_soint3d_full(din, mask, dipi, dipx, n1, n2, n3, order, 1, 1, niter, seed, var, out);
+}
+
+int pso_soint3d_full(const float *din, const float *mask, const float *dipi, const float *dipx,
+                     int n1, int n2, int n3, int order, int nj1, int nj2, int niter, int seed, float var, float *out)
+{
     size_t n = (size_t)n1 * n2 * n3, ny = 2 * n;
     float *x = out, *g = falloc(n), *rr = falloc(ny), *gg = falloc(ny), *S = falloc(n), *Ss = falloc(ny);
     unsigned char *known = (unsigned char *)malloc(n);
@@ -814,13 +821,13 @@ int pso_soint3d_noise(const float *din, const float *mask, const float *dipi, co
         for (size_t i = 0; i < ny; i++) { float d = a * noise_normal(&G); rr[i] = -d; }
     }
     memcpy(x, din, n * sizeof(float));
-    pwd3_lop(0, 1, n1, n2, n3, order, dipi, dipx, x, rr);
+    pwd3_lop(0, 1, n1, n2, n3, order, nj1, nj2, dipi, dipx, x, rr);
     float dpr0 = sumsq_f(ny, rr), dpg0 = 1.f, dpr, dpg;
     int first = 1;
     for (int iter = 0; iter < niter; iter++) {
-        pwd3_lop(1, 0, n1, n2, n3, order, dipi, dipx, g, rr);
+        pwd3_lop(1, 0, n1, n2, n3, order, nj1, nj2, dipi, dipx, g, rr);
         for (size_t i = 0; i < n; i++) if (known[i]) g[i] = 0.0;
-        pwd3_lop(0, 0, n1, n2, n3, order, dipi, dipx, g, gg);
+        pwd3_lop(0, 0, n1, n2, n3, order, nj1, nj2, dipi, dipx, g, gg);
         if (iter == 0) { dpg0 = sumsq_f(n, g); dpr = 1.; dpg = 1.; }
         else { dpr = sumsq_f(ny, rr) / dpr0; dpg = sumsq_f(n, g) / dpg0; }
         if (dpr < 1.e-12f || dpg < 1.e-12f) break;

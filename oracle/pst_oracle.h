@@ -68,6 +68,10 @@ int pso_soint3d(const float *din, const float *mask, const float *dipi, const fl
 int pso_soint3d_noise(const float *din, const float *mask, const float *dipi, const float *dipx,
                       int n1, int n2, int n3, int order, int niter, int seed, float var, float *out);
 
+/* same with dealiasing strides njs = (nj1, nj2) of the inline / xline stencils (allpass_init :…, shifts (iw-nw)*nj) */
+int pso_soint3d_full(const float *din, const float *mask, const float *dipi, const float *dipx,
+                     int n1, int n2, int n3, int order, int nj1, int nj2, int niter, int seed, float var, float *out);
+
 /* csint3d: soint3d_cfuns.c:2510-2640 (shaping CG, L = known-data mask :1350-1372, S = pwsmooth3_lop
  * :2231-2300 = inline 2-D pwsmooth o transpose o xline 2-D pwsmooth, adjoint spray :1963-2003,
  * predict_step(adj) :1777-1804; ps_conjgrad with hasp0 = true, eps = lam^2, tol = 10*FLT_EPSILON). */

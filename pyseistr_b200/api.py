@@ -159,7 +159,7 @@ def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=[1, 1], drift=0, see
              verb=1, ctx=None):
     """3-D structure-oriented interpolation: CG on the inline + xline PWD residual with the known
     samples held fixed (reference pyseistr/soint3d.py:65-108 -> csoint3d, soint3d_cfuns.c:2405).
-    GPU path: njs=[1,1], drift=0; anything else raises (PST_EUNSUP).  var > 0 adds the reference's
+    GPU path: any njs >= 1, drift=0 (drift != 0 raises PST_EUNSUP).  var > 0 adds the reference's
     MT19937(seed) + Box-Muller noise to the right-hand side (drawn on the host, same stream of numbers)."""
     din = np.asarray(din)
     n1, n2, n3 = _shape3(din)

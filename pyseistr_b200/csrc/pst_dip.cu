@@ -1666,8 +1666,9 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
         int rc = 0;
         PST_LAUNCHB(c, cls, 8.0 * (double)g.n,
                     rc = pst_tri_stream_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb, nullptr));
-        if (rc != 0) { pst_set_error("pst_tri_stream_launch failed (%d)", rc); return PST_ECUDA; }
-        return PST_OK;
+        if (rc == 0) return PST_OK;
+        if (rc == -5) { pst_set_error("pst_tri_stream_launch: kernel launch failed"); return PST_ECUDA; }
+        // set-up refused (tensor map encoding, shared-memory attribute): nothing was launched, use the tile kernels
     }
     const TilePlan tp = tile_plan(axis == 0, vec, nx, nb);
     if (tp.ok) {
@@ -2104,7 +2105,7 @@ template <int NW, bool ADD, bool DOTS>
 __global__ void __launch_bounds__(256)
 pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const float *__restrict__ fx,
                 float *__restrict__ y, const float *__restrict__ Ss, const float *__restrict__ rr,
-                int n1, int n2, int n3, double *__restrict__ partial)
+                int n1, int n2, int n3, int nj1, int nj2, double *__restrict__ partial)
 {
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
@@ -2112,15 +2113,14 @@ pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int i1 = (int)(i % n1), i2 = (int)((i / n1) % n2), i3 = (int)(i / pl);
         float yi = ADD ? y[i] : 0.f, yx = ADD ? y[i + n] : 0.f;
-        if (i1 >= NW && i1 < n1 - NW) {
-            if (i2 < n2 - 1) {
+        // shifts (w - NW) * nj on rows [NW*nj, n1 - NW*nj)  (allpass3_lop soint3d_cfuns.c:640-662,684-706)
+        if (i1 >= NW * nj1 && i1 < n1 - NW * nj1 && i2 < n2 - 1) {
 #pragma unroll
-                for (int w = 0; w <= 2 * NW; w++) { const int s = w - NW; yi += (x[i + n1 + s] - x[i - s]) * fi[(size_t)w * n + i]; }
-            }
-            if (i3 < n3 - 1) {
+            for (int w = 0; w <= 2 * NW; w++) { const int s = (w - NW) * nj1; yi += (x[i + n1 + s] - x[i - s]) * fi[(size_t)w * n + i]; }
+        }
+        if (i1 >= NW * nj2 && i1 < n1 - NW * nj2 && i3 < n3 - 1) {
 #pragma unroll
-                for (int w = 0; w <= 2 * NW; w++) { const int s = w - NW; yx += (x[i + pl + s] - x[i - s]) * fx[(size_t)w * n + i]; }
-            }
+            for (int w = 0; w <= 2 * NW; w++) { const int s = (w - NW) * nj2; yx += (x[i + pl + s] - x[i - s]) * fx[(size_t)w * n + i]; }
         }
         y[i] = yi;
         y[i + n] = yx;
@@ -2141,7 +2141,7 @@ template <int NW>
 __global__ void __launch_bounds__(256)
 pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, const float *__restrict__ fx,
                 const unsigned char *__restrict__ known, float *__restrict__ g, int n1, int n2, int n3,
-                double *__restrict__ partial)
+                int nj1, int nj2, double *__restrict__ partial)
 {
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
@@ -2153,30 +2153,30 @@ pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, cons
         if (j2 >= 1) {
 #pragma unroll
             for (int s = NW; s >= -NW; s--) {
-                const int ix = j1 - s;
-                if (ix >= NW && ix < n1 - NW) { const size_t i = j - n1 - s; v += yy[i] * fi[(size_t)(s + NW) * n + i]; }
+                const int ix = j1 - s * nj1;
+                if (ix >= NW * nj1 && ix < n1 - NW * nj1) { const size_t i = j - n1 - s * nj1; v += yy[i] * fi[(size_t)(s + NW) * n + i]; }
             }
         }
         if (j2 <= n2 - 2) {
 #pragma unroll
             for (int s = -NW; s <= NW; s++) {
-                const int ix = j1 + s;
-                if (ix >= NW && ix < n1 - NW) { const size_t i = j + s; v -= yy[i] * fi[(size_t)(s + NW) * n + i]; }
+                const int ix = j1 + s * nj1;
+                if (ix >= NW * nj1 && ix < n1 - NW * nj1) { const size_t i = j + s * nj1; v -= yy[i] * fi[(size_t)(s + NW) * n + i]; }
             }
         }
         // xline operator
         if (j3 >= 1) {
 #pragma unroll
             for (int s = NW; s >= -NW; s--) {
-                const int ix = j1 - s;
-                if (ix >= NW && ix < n1 - NW) { const size_t i = j - pl - s; v += yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
+                const int ix = j1 - s * nj2;
+                if (ix >= NW * nj2 && ix < n1 - NW * nj2) { const size_t i = j - pl - s * nj2; v += yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
             }
         }
         if (j3 <= n3 - 2) {
 #pragma unroll
             for (int s = -NW; s <= NW; s++) {
-                const int ix = j1 + s;
-                if (ix >= NW && ix < n1 - NW) { const size_t i = j + s; v -= yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
+                const int ix = j1 + s * nj2;
+                if (ix >= NW * nj2 && ix < n1 - NW * nj2) { const size_t i = j + s * nj2; v -= yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
             }
         }
         if (known[j]) v = 0.0f;
@@ -2286,7 +2286,7 @@ static int soint3d_noise_rhs(pst_ctx *c, float *d_rr, size_t ny, int seed, float
 
 template <int NW>
 static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, const float *d_pp, const float *d_qq,
-                       int n1, int n2, int n3, int niter, int seed, float var, int verb, float *d_out)
+                       int n1, int n2, int n3, int nj1, int nj2, int niter, int seed, float var, int verb, float *d_out)
 {
     static const BTab tb = make_btab(NW);
     constexpr int NA = 2 * NW + 1;
@@ -2313,7 +2313,7 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     if (var != 0.f) PST_TRY(soint3d_noise_rhs(c, rr, 2 * n, seed, var));
     else PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
     PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
-                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, c->d_partial)));
+                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, nj1, nj2, c->d_partial)));
     PST_CUDA(cudaMemsetAsync(S, 0, n * sizeof(float), c->stream));
     PST_CUDA(cudaMemsetAsync(Ss, 0, 2 * n * sizeof(float), c->stream));
     // dpr0 = rr.rr (:1042)
@@ -2325,10 +2325,10 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     bool first = true;
     for (int iter = 0; iter < niter; iter++) {
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 13.0) * (double)n,
-                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, c->d_partial)));
+                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, nj1, nj2, c->d_partial)));
         PST_TRY(pst_finish_reduce(c, grid, 1, 8));
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 28.0) * (double)n,
-                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, c->d_partial)));
+                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, nj1, nj2, c->d_partial)));
         PST_TRY(pst_finish_reduce(c, grid, 5, 9));
         PST_TRY(pst_fetch_record(c, 8, 1, h));
         const double g2 = h[0];
@@ -2372,13 +2372,14 @@ extern "C" int pst_soint3d_dev(pst_ctx *c, const float *d_din, const float *d_ma
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (n1 < 1 || n2 < 1 || n3 < 1 || niter < 0) { pst_set_error("soint3d: bad dimensions"); return PST_EINVAL; }
     if (nw != 1 && nw != 2) { pst_set_error("soint3d: order=%d unsupported (1 or 2)", nw); return PST_EUNSUP; }
-    if (n1 < 2 * nw + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
-    if (nj1 != 1 || nj2 != 1 || drift != 0) { pst_set_error("soint3d: njs != 1 / drift are not implemented on the GPU path"); return PST_EUNSUP; }
+    if (nj1 < 1 || nj2 < 1) { pst_set_error("soint3d: njs must be >= 1"); return PST_EINVAL; }
+    if (n1 < 2 * nw * std::max(nj1, nj2) + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
+    if (drift != 0) { pst_set_error("soint3d: drift is not implemented on the GPU path (data-dependent scatter)"); return PST_EUNSUP; }
     if (var < 0.f) { pst_set_error("soint3d: var < 0"); return PST_EINVAL; }
     if (c->comm && c->nranks > 1) { pst_set_error("soint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
     if (hasmask && !d_mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     const float *m = hasmask ? d_mask : nullptr;
-    if (nw == 1) return soint3d_run<1>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, seed, var, verb, d_out);
-    return soint3d_run<2>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, niter, seed, var, verb, d_out);
+    if (nw == 1) return soint3d_run<1>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, nj1, nj2, niter, seed, var, verb, d_out);
+    return soint3d_run<2>(c, d_din, m, d_dipi, d_dipx, n1, n2, n3, nj1, nj2, niter, seed, var, verb, d_out);
 }

@@ -66,6 +66,15 @@ def test_port_soint3d_noise_matches_compiled_reference(port):
         assert np.array_equal(a, b)
 
 
+def test_port_soint3d_strides_match_compiled_reference(port):
+    ref = _ref_or_skip()
+    g = golden("soint3d_o2n20")
+    for njs, order in (((2, 1), 2), ((1, 3), 1), ((2, 2), 2)):
+        a = port.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=order, niter=6, njs=njs)
+        b = ref.soint3dc(g["din"], g["mask"], g["dipi"], g["dipx"], order=order, niter=6, njs=njs)
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("name", golden_names("sint3d_"))
 def test_port_sint3d_matches_golden(port, name):
     g = golden(name)
