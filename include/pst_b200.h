@@ -129,7 +129,8 @@ int pst_somf2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n2,
  * (pyseistr/src/soint3d_cfuns.c:2405-2508, "OOOOiiiiiiiiiifi"); called by soint3dc
  * (pyseistr/soint3d.py:65-108).  GPU path: any njs >= 1; drift = 0 only (drift != 0: PST_EUNSUP).
  * hasmask=1: known samples are mask != 0, else din != 0.  var > 0 puts sqrt(var)*N(0,1) on the right-hand
- * side, drawn on the host from MT19937(seed) + Box-Muller exactly like the reference (:2304-2402). */
+ * side, drawn on the host from MT19937(seed) + Box-Muller exactly like the reference (:2304-2402).
+ * Distributed contexts (var = 0): global n3, slab pointers; one halo plane per operator application. */
 int pst_soint3d(pst_ctx *ctx, const float *din, const float *mask, const float *dipi, const float *dipx,
                 int n1, int n2, int n3, int nw, int nj1, int nj2, int niter, int drift, int seed,
                 int hasmask, float var, int verb, float *out);

@@ -2105,8 +2105,10 @@ template <int NW, bool ADD, bool DOTS>
 __global__ void __launch_bounds__(256)
 pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const float *__restrict__ fx,
                 float *__restrict__ y, const float *__restrict__ Ss, const float *__restrict__ rr,
-                int n1, int n2, int n3, int nj1, int nj2, double *__restrict__ partial)
+                int n1, int n2, int n3, int nj1, int nj2, int z0, int n3g, const float *__restrict__ xnext,
+                double *__restrict__ partial)
 {
+    // n3 = planes held here (global planes [z0, z0 + n3) of n3g); xnext = plane z0 + n3 of x (next rank's first)
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[5] = {0., 0., 0., 0., 0.};
@@ -2118,9 +2120,10 @@ pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const
 #pragma unroll
             for (int w = 0; w <= 2 * NW; w++) { const int s = (w - NW) * nj1; yi += (x[i + n1 + s] - x[i - s]) * fi[(size_t)w * n + i]; }
         }
-        if (i1 >= NW * nj2 && i1 < n1 - NW * nj2 && i3 < n3 - 1) {
+        if (i1 >= NW * nj2 && i1 < n1 - NW * nj2 && z0 + i3 < n3g - 1) {
+            const float *xu = (i3 < n3 - 1) ? x + i + pl : xnext + (i - (size_t)(n3 - 1) * pl);   // sample (i1, i2) of plane i3 + 1
 #pragma unroll
-            for (int w = 0; w <= 2 * NW; w++) { const int s = (w - NW) * nj2; yx += (x[i + pl + s] - x[i - s]) * fx[(size_t)w * n + i]; }
+            for (int w = 0; w <= 2 * NW; w++) { const int s = (w - NW) * nj2; yx += (xu[s] - x[i - s]) * fx[(size_t)w * n + i]; }
         }
         y[i] = yi;
         y[i + n] = yx;
@@ -2141,8 +2144,10 @@ template <int NW>
 __global__ void __launch_bounds__(256)
 pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, const float *__restrict__ fx,
                 const unsigned char *__restrict__ known, float *__restrict__ g, int n1, int n2, int n3,
-                int nj1, int nj2, double *__restrict__ partial)
+                int nj1, int nj2, int z0, int n3g, const float *__restrict__ yprev, const float *__restrict__ fxprev,
+                double *__restrict__ partial)
 {
+    // yprev / fxprev: xline residual and xline taps ([w][plane]) of global plane z0 - 1 (previous rank's last)
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[1] = {0.};
@@ -2171,8 +2176,14 @@ pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, cons
                 const int ix = j1 - s * nj2;
                 if (ix >= NW * nj2 && ix < n1 - NW * nj2) { const size_t i = j - pl - s * nj2; v += yy[n + i] * fx[(size_t)(s + NW) * n + i]; }
             }
+        } else if (z0 >= 1) {                                  // sources in the previous rank's last plane
+#pragma unroll
+            for (int s = NW; s >= -NW; s--) {
+                const int ix = j1 - s * nj2;
+                if (ix >= NW * nj2 && ix < n1 - NW * nj2) { const size_t i = j - s * nj2; v += yprev[i] * fxprev[(size_t)(s + NW) * pl + i]; }
+            }
         }
-        if (j3 <= n3 - 2) {
+        if (z0 + j3 <= n3g - 2) {
 #pragma unroll
             for (int s = -NW; s <= NW; s++) {
                 const int ix = j1 + s * nj2;
@@ -2290,10 +2301,23 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
 {
     static const BTab tb = make_btab(NW);
     constexpr int NA = 2 * NW + 1;
-    const size_t n = (size_t)n1 * n2 * n3;
-    PST_TRY(pst_arena_reserve(c, (size_t)(2 * NA + 8) * n * sizeof(float) + n + 64 * 256));
+    // distributed contexts: n3 is the GLOBAL plane count, every pointer is this rank's n3-slab.  What crosses
+    // slabs: plane z1 of the operand of L (next rank's first plane), plane z0-1 of the xline residual
+    // for L' (previous rank's last plane; its taps once), and the five dots (all-reduced in pst_finish_reduce).
+    const bool dist = c->comm != nullptr && c->nranks > 1;
+    const int n3g = n3;
+    int z0 = 0;
+    if (dist) {
+        int za = 0, zb = n3g;
+        PST_TRY(pst_ctx_slab(c, n3g, &za, &zb));
+        z0 = za; n3 = zb - za;
+        if (n3 < 1) { pst_set_error("soint3d: empty slab"); return PST_EUNSUP; }
+    }
+    const size_t n = (size_t)n1 * n2 * n3, pln = (size_t)n1 * n2;
+    PST_TRY(pst_arena_reserve(c, (size_t)(2 * NA + 8) * n * sizeof(float) + n + (NA + 4) * pln * sizeof(float) + 64 * 256));
     pst_arena_reset(c);
     float *fi, *fx, *g, *S, *rr, *gg, *Ss;
+    float *xnext = nullptr, *yprev = nullptr, *fxprev = nullptr, *dum_lo = nullptr, *dum_hi = nullptr;
     unsigned char *known;
     PST_TRY(pst_arena_get(c, NA * n, &fi));
     PST_TRY(pst_arena_get(c, NA * n, &fx));
@@ -2303,17 +2327,36 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     PST_TRY(pst_arena_get(c, 2 * n, &gg));
     PST_TRY(pst_arena_get(c, 2 * n, &Ss));
     PST_TRY(pst_arena_get(c, n, &known));
+    if (dist) {
+        PST_TRY(pst_arena_get(c, pln, &xnext));
+        PST_TRY(pst_arena_get(c, pln, &yprev));
+        PST_TRY(pst_arena_get(c, NA * pln, &fxprev));
+        PST_TRY(pst_arena_get(c, pln, &dum_lo));
+        PST_TRY(pst_arena_get(c, pln, &dum_hi));
+    }
+    // halo of the operand of L: my first plane goes to the previous rank, the next rank's first plane comes here
+    auto halo_next = [&](const float *v) -> int {
+        if (!dist) return PST_OK;
+        return pst_comm_halo_exchange(c, v, v + (n - pln), dum_lo, xnext, pln);
+    };
+    // halo of the xline residual for L': my last plane goes to the next rank, the previous rank's last comes here
+    auto halo_prev = [&](const float *v, float *into) -> int {
+        if (!dist) return PST_OK;
+        return pst_comm_halo_exchange(c, v, v + (n - pln), into, dum_hi, pln);
+    };
     float *x = d_out;
     const int threads = 256, grid = pst_grid_for(c, n, threads);
     double h[PST_RED_SLOTS];
     PST_LAUNCHB(c, PST_K_OTHER, 48.0 * (double)n, (pwd3_taps_kernel<NW><<<grid, threads, 0, c->stream>>>(d_pp, d_qq, fi, fx, n, tb)));
+    for (int w = 0; dist && w < NA; w++) PST_TRY(halo_prev(fx + (size_t)w * n, fxprev + (size_t)w * pln));   // once: taps are fixed
     PST_LAUNCH(c, PST_K_OTHER, (known_kernel<<<grid, threads, 0, c->stream>>>(d_mask ? d_mask : d_din, known, n)));
     // ps_solver :1018-1040 with dat = 0 (var = 0): rr = -0; x = x0 = data; rr += L x
     PST_CUDA(cudaMemcpyAsync(x, d_din, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     if (var != 0.f) PST_TRY(soint3d_noise_rhs(c, rr, 2 * n, seed, var));
     else PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
+    PST_TRY(halo_next(x));
     PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
-                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, nj1, nj2, c->d_partial)));
+                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, c->d_partial)));
     PST_CUDA(cudaMemsetAsync(S, 0, n * sizeof(float), c->stream));
     PST_CUDA(cudaMemsetAsync(Ss, 0, 2 * n * sizeof(float), c->stream));
     // dpr0 = rr.rr (:1042)
@@ -2324,11 +2367,13 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     double dpg0 = 1., rr2 = dpr0;
     bool first = true;
     for (int iter = 0; iter < niter; iter++) {
+        PST_TRY(halo_prev(rr + n, yprev));
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 13.0) * (double)n,
-                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, nj1, nj2, c->d_partial)));
+                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, nj1, nj2, z0, n3g, yprev, fxprev, c->d_partial)));
         PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+        PST_TRY(halo_next(g));
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 28.0) * (double)n,
-                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, nj1, nj2, c->d_partial)));
+                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, c->d_partial)));
         PST_TRY(pst_finish_reduce(c, grid, 5, 9));
         PST_TRY(pst_fetch_record(c, 8, 1, h));
         const double g2 = h[0];
@@ -2376,7 +2421,7 @@ extern "C" int pst_soint3d_dev(pst_ctx *c, const float *d_din, const float *d_ma
     if (n1 < 2 * nw * std::max(nj1, nj2) + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
     if (drift != 0) { pst_set_error("soint3d: drift is not implemented on the GPU path (data-dependent scatter)"); return PST_EUNSUP; }
     if (var < 0.f) { pst_set_error("soint3d: var < 0"); return PST_EINVAL; }
-    if (c->comm && c->nranks > 1) { pst_set_error("soint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
+    if (c->comm && c->nranks > 1 && var != 0.f) { pst_set_error("soint3d: var != 0 is single-GPU only (the noise stream is sequential over the whole cube)"); return PST_EUNSUP; }
     if (hasmask && !d_mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     const float *m = hasmask ? d_mask : nullptr;

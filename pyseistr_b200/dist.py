@@ -85,3 +85,16 @@ def somean3dc_slab(ctx, slab, dipi, dipx, n3, r1, r2, order):
     _lib.check(ctx.lib.pst_somean3d(ctx.handle, _p(d), _p(a), _p(b), n1, n2, int(n3), int(r1), int(r2),
                                     int(order), 0.01, 0, _p(out)))
     return out.reshape(n1, n2, nz, order="F")
+
+
+def soint3dc_slab(ctx, slab, mask, dipi, dipx, n3, order=1, niter=100, njs=(1, 1), hasmask=1, verb=0):
+    """soint3dc on this rank's slab: the xline stencil reads one plane of the next rank, its adjoint one plane of
+    the previous rank, the CG dots are all-reduced (var = 0, drift = 0)."""
+    n1, n2, nz = slab.shape
+    d, a, b = _F(slab), _F(dipi), _F(dipx)
+    m = _F(mask) if mask is not None else None
+    out = np.empty_like(d)
+    _lib.check(ctx.lib.pst_soint3d(ctx.handle, _p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, int(n3),
+                                   int(order), int(njs[0]), int(njs[1]), int(niter), 0, 202223, int(hasmask), 0.0,
+                                   int(verb), _p(out)))
+    return out.reshape(n1, n2, nz, order="F")

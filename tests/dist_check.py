@@ -59,6 +59,28 @@ def main():
             print(f"[dist_check] world={world} shape={shape}: dip rel-L2 {e1:.2e}/{e2:.2e} "
                   f"somf bit-exact={bf} somean bit-exact={bm}", flush=True)
             ok = ok and e1 <= 1e-5 and e2 <= 1e-5 and bf and bm
+    # ---- soint3dc across slabs: halo planes for the xline stencil and its adjoint, all-reduced dots
+    n1, n2, n3 = 48, 18, 7 * world + 2
+    clean = synth.cube(n1, n2, n3, seed=78, noise=0.0)
+    z0, z1 = pd.slab_bounds(n3, rank, world)
+    keep = np.random.default_rng(79).random((n2, n3)) > 0.5
+    mask = np.zeros_like(clean)
+    mask[:, keep] = 1
+    gaps = clean * mask
+    from oracle import port as _port                     # dips of the full cube from the checker (inputs, not the test)
+    pi, px = _port.dip3dc(clean, 3, 6, 2, rect=(4, 4, 3))
+    for order, njs, niter in ((2, (1, 1), 12), (1, (2, 1), 8)):
+        mine = pd.soint3dc_slab(ctx, gaps[:, :, z0:z1], mask[:, :, z0:z1], pi[:, :, z0:z1], px[:, :, z0:z1], n3,
+                                order=order, niter=niter, njs=njs)
+        parts = [None] * world
+        dist.all_gather_object(parts, (z0, np.asarray(mine)))
+        if rank == 0:
+            parts.sort(key=lambda t: t[0])
+            full = np.concatenate([p[1] for p in parts], axis=2)
+            want = _port.soint3dc(gaps, mask, pi, px, order=order, niter=niter, njs=njs)
+            e = rel_l2(full, want)
+            print(f"[dist_check] world={world} soint3d order={order} njs={njs}: rel-L2 {e:.2e}", flush=True)
+            ok = ok and e <= 1e-5
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.barrier()
