@@ -1966,7 +1966,7 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     const size_t n = g.n, plane = (size_t)n1 * n2;
     size_t scr = tri_scratch_floats(g);
     if (dist) scr = std::max(scr, (size_t)(nz + 2 * r3) * plane);
-    const size_t extra = dist ? (plane * (size_t)(2 * r3 + 2 + 2) + n + plane) : 0;
+    const size_t extra = dist ? (plane * (size_t)(2 * r3 + 2 + 2) + n + plane + (d_mask ? n + 2 * plane : 0)) : 0;
     const size_t need = (11 * n + scr + extra) * sizeof(float) + 2 * n + 32 * 256;
     PST_TRY(pst_arena_reserve(c, need));
     pst_arena_reset(c);
@@ -2003,7 +2003,16 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
         PST_TRY(pst_arena_get(c, plane, &g.cout));
     }
     if (d_mask) {
-        if (dist) { pst_set_error("dip: mask= is not supported in distributed contexts yet"); return PST_EUNSUP; }
+        if (dist) {
+            // mask32 (dip_cfuns.c:914-997) looks at the xline stencil footprint, i.e. at plane i3+1 of the mask
+            // volume: same one-plane halo as the data
+            float *me, *dummy;
+            PST_TRY(pst_arena_get(c, n + plane, &me));
+            PST_TRY(pst_arena_get(c, plane, &dummy));
+            PST_CUDA(cudaMemcpyAsync(me, d_mask, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            PST_TRY(pst_comm_halo_exchange(c, d_mask, d_mask, dummy, me + n, plane));
+            um = me;
+        }
         PST_TRY(pst_arena_get(c, n, &m_in));
         PST_TRY(pst_arena_get(c, n, &m_x));
         const int grid = (int)min((long)n2 * nz, (long)c->sm_count * 8);

@@ -58,12 +58,13 @@ def _p(a):
     return a.ctypes.data_as(_fp)
 
 
-def dip3dc_slab(ctx, slab, n3, niter=5, liter=10, order=2, rect=(5, 5, 5), verb=0):
-    """dip3dc on this rank's slab (n1, n2, z1-z0) of a cube with n3 planes in total."""
+def dip3dc_slab(ctx, slab, n3, niter=5, liter=10, order=2, rect=(5, 5, 5), verb=0, mask=None):
+    """dip3dc on this rank's slab (n1, n2, z1-z0) of a cube with n3 planes in total (mask: the slab of the mask)."""
     n1, n2, nz = slab.shape
     d = _F(slab)
+    m = _F(mask) if mask is not None else None
     out = np.empty(2 * d.size, np.float32)
-    _lib.check(ctx.lib.pst_dip(ctx.handle, _p(d), None, n1, n2, int(n3), int(niter), int(liter), int(order),
+    _lib.check(ctx.lib.pst_dip(ctx.handle, _p(d), _p(m) if m is not None else None, n1, n2, int(n3), int(niter), int(liter), int(order),
                                0.01, 1.0, 1e-6, int(rect[0]), int(rect[1]), int(rect[2]), int(verb), _p(out)))
     out = out.reshape(n1, n2, nz, 2, order="F")
     return out[:, :, :, 0], out[:, :, :, 1]

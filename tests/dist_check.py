@@ -59,6 +59,25 @@ def main():
             print(f"[dist_check] world={world} shape={shape}: dip rel-L2 {e1:.2e}/{e2:.2e} "
                   f"somf bit-exact={bf} somean bit-exact={bm}", flush=True)
             ok = ok and e1 <= 1e-5 and e2 <= 1e-5 and bf and bm
+    # ---- dip3dc with mask= across slabs (the mask footprint of the xline stencil needs the neighbour's plane too)
+    n1, n2, n3 = 40, 16, 6 * world + 1
+    cube = synth.cube(n1, n2, n3, seed=80)
+    kill = np.random.default_rng(81).random((n2, n3)) < 0.25
+    dm = cube.copy(); dm[:, kill] = 0.0
+    mk = np.ones_like(cube); mk[:, kill] = 0.0
+    z0, z1 = pd.slab_bounds(n3, rank, world)
+    di, dx = pd.dip3dc_slab(ctx, dm[:, :, z0:z1], n3, niter=3, liter=6, order=2, rect=(4, 3, 3), mask=mk[:, :, z0:z1])
+    parts = [None] * world
+    dist.all_gather_object(parts, (z0, np.asarray(di), np.asarray(dx)))
+    if rank == 0:
+        from oracle import port
+        parts.sort(key=lambda t: t[0])
+        DI = np.concatenate([p[1] for p in parts], axis=2)
+        DX = np.concatenate([p[2] for p in parts], axis=2)
+        oi, ox = port.dip3dc(dm, 3, 6, 2, rect=(4, 3, 3), mask=mk)
+        e1, e2 = rel_l2(DI, oi), rel_l2(DX, ox)
+        print(f"[dist_check] world={world} masked dip3d: rel-L2 {e1:.2e}/{e2:.2e}", flush=True)
+        ok = ok and e1 <= 1e-5 and e2 <= 1e-5
     # ---- soint3dc across slabs: halo planes for the xline stencil and its adjoint, all-reduced dots
     n1, n2, n3 = 48, 18, 7 * world + 2
     clean = synth.cube(n1, n2, n3, seed=78, noise=0.0)
