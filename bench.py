@@ -240,7 +240,7 @@ def _main(real_stdout):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default=None, help="n1,n2,n3 (default 1000,1024,1024)")
     ap.add_argument("--ref-shape", default="128,64,32", help="per-process sample cube of the reference arm")
-    ap.add_argument("--cpu-shape", default="100,64,24", help="per-process sample cube of cpu_baseline")
+    ap.add_argument("--cpu-shape", default="160,128,64", help="per-process sample cube of cpu_baseline (~10-25 s per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
