@@ -63,10 +63,10 @@ def allpass(u, sigma, nw, xline, der):
     return y.reshape(n1, n2, n3, order="F")
 
 
-def smooth3(x, rect):
+def smooth3(x, rect, repeat=1):
     n1, n2, n3 = _shape3(x)
     xx = _F(x).copy()
-    lib().pso_smooth3(_p(xx), n1, n2, n3, int(rect[0]), int(rect[1]), int(rect[2]))
+    lib().pso_smooth3_rep(_p(xx), n1, n2, n3, int(rect[0]), int(rect[1]), int(rect[2]), int(repeat))
     return xx.reshape(n1, n2, n3, order="F")
 
 

@@ -168,6 +168,23 @@ void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3)
     free(t);
 }
 
+/* smoothcf (dip_cfuns.c:2006-2123) with adj = 0, no diff / box: every line of an axis is smoothed `repeat` times
+ * in a row (ps_smooth2), axes in turn */
+void pso_smooth3_rep(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
+{
+    int nmax = n1 > n2 ? n1 : n2; if (n3 > nmax) nmax = n3;
+    int rmax = r1 > r2 ? r1 : r2; if (r3 > rmax) rmax = r3;
+    float *t = falloc((size_t)nmax + 2 * (size_t)rmax + 2);
+    if (r1 > 1)
+        for (long l = 0; l < (long)n2 * n3; l++) for (int q = 0; q < repeat; q++) tri_line(x, l * n1, 1, n1, r1, t);
+    if (r2 > 1)
+        for (int i3 = 0; i3 < n3; i3++)
+            for (int i1 = 0; i1 < n1; i1++) for (int q = 0; q < repeat; q++) tri_line(x, i1 + (long)n1 * n2 * i3, n1, n2, r2, t);
+    if (r3 > 1)
+        for (long l = 0; l < (long)n1 * n2; l++) for (int q = 0; q < repeat; q++) tri_line(x, l, (long)n1 * n2, n3, r3, t);
+    free(t);
+}
+
 /* ------------------------------------------------------------------ shaping CG + divne */
 
 /* Sensitivity probe (not reference behaviour): mode 1 sums the same exact double products in

@@ -29,6 +29,8 @@ void pso_allpass(const float *u, const float *sigma, int n1, int n2, int n3, int
 
 /* N-D triangle smoothing in place, axes with rect<=1 skipped: dip_cfuns.c:458-727 (ps_smooth2) */
 void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3);
+/* smoothcf dip_cfuns.c:2006-2123, adj = 0: each axis pass repeated `repeat` times per line */
+void pso_smooth3_rep(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat);
 
 /* Smooth division rat ~ num/den (num, den are overwritten): dip_cfuns.c:796-827 + :257-383.
  * Returns the number of CG iterations executed. */

@@ -2041,10 +2041,10 @@ extern "C" int pst_allpass_dev(pst_ctx *c, const float *d_u, const float *d_sigm
     return PST_OK;
 }
 
-extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3)
+extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
-    if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smooth3: bad arguments"); return PST_EINVAL; }
+    if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1 || repeat < 1) { pst_set_error("smooth3: bad arguments"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
     const size_t scr = tri_scratch_floats(g);
@@ -2052,7 +2052,17 @@ extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, i
     pst_arena_reset(c);
     float *s;
     PST_TRY(pst_arena_get(c, scr, &s));
-    PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, r1, r2, r3));
+    if (repeat == 1) {
+        PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, r1, r2, r3));
+    } else {
+        // smoothcf (dip_cfuns.c:2084-2098): every line of an axis is smoothed `repeat` times in a row, axes in turn
+        const int rr[3] = {r1, r2, r3};
+        for (int a = 0; a < 3; a++) {
+            if (rr[a] <= 1) continue;
+            for (int q = 0; q < repeat; q++)
+                PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, a == 0 ? r1 : 1, a == 1 ? r2 : 1, a == 2 ? r3 : 1));
+        }
+    }
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
 }

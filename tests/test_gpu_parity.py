@@ -81,6 +81,15 @@ def test_smooth3_bit_exact(ctx, port, shape, rect):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("shape,rect,repeat", [((64, 20, 12), (5, 3, 4), 2), ((30, 12, 6), (2, 15, 9), 3), ((40, 9, 1), (4, 3, 1), 4)])
+def test_smooth_repeat_bit_exact(ctx, port, shape, rect, repeat):
+    """smoothc(repeat=k): every line of an axis is smoothed k times in a row (smoothcf dip_cfuns.c:2084-2098)."""
+    import pyseistr_b200 as ps
+    x = synth.cube(*shape, seed=34)
+    got = ps.smoothc(x, rect=list(rect), repeat=repeat, ctx=ctx)
+    assert np.array_equal(got, port.smooth3(x, rect, repeat).reshape(x.shape, order="F"))
+
+
 @pytest.mark.parametrize("name", golden_names("smooth_"))
 def test_smooth_golden(ctx, name):
     import pyseistr_b200 as ps
