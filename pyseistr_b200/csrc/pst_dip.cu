@@ -1568,7 +1568,8 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.cout = last ? nullptr : mb.cf_out; A.fout = mb.ff_out;
     A.pin = first ? nullptr : mb.pf_in; A.pout = last ? nullptr : mb.pf_out;
     if (W) {
-        static bool attr_done = false;
+        static bool attr_dev[64] = {};                       // per-device function attribute
+        bool &attr_done = attr_dev[c->device & 63];
         if (!attr_done) {
             PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
             PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));

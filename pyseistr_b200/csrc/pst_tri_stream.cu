@@ -699,12 +699,15 @@ size_t smem_bytes(bool contig, int Lp, int nxs, int xsf, int nb)
 template <int NB>
 int launch_nb(bool contig, unsigned grid, size_t smem, cudaStream_t stream, const CUtensorMap &tm, const Args &A)
 {
-    static bool attr0 = false, attr1 = false;
+    // the opt-in shared-memory limit is a per-device function attribute: remember it per device
+    static bool attr[2][64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -4;
     if (contig) {
-        if (!attr0) { if (cudaFuncSetAttribute(tri_stream_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr0 = true; }
+        if (!attr[0][dev]) { if (cudaFuncSetAttribute(tri_stream_kernel<true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr[0][dev] = true; }
         tri_stream_kernel<true, NB><<<grid, NWARPS * 32, smem, stream>>>(tm, A);
     } else {
-        if (!attr1) { if (cudaFuncSetAttribute(tri_stream_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr1 = true; }
+        if (!attr[1][dev]) { if (cudaFuncSetAttribute(tri_stream_kernel<false, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -4; attr[1][dev] = true; }
         tri_stream_kernel<false, NB><<<grid, NWARPS * 32, smem, stream>>>(tm, A);
     }
     return 0;
