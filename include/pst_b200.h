@@ -154,11 +154,11 @@ int pst_sint3d_dev(pst_ctx *ctx, const float *d_din, const float *d_dipi, const 
  * rank 1: dipcfun.smoothcf, dip_cfuns.c:2006-2123 with adj=0).  Device pointers. */
 int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1, int n2, int n3,
                     int order, int xline, int der, float *d_y);
-int pst_smooth3_dev(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat);
+int pst_smooth3_dev(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj);
 int pst_divne_dev(pst_ctx *ctx, float *d_num, float *d_den, float *d_rat, int n1, int n2, int n3,
                   int r1, int r2, int r3, int liter, int *iters_run);
 int pst_smooth3(pst_ctx *ctx, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
-                int repeat, float *out);
+                int repeat, int adj, float *out);
 
 /* ---- raw device memory helpers so that a host language without a CUDA binding can keep
  * volumes resident between calls (bench `value` leg, pipelines dip -> somf). */

@@ -63,10 +63,11 @@ def allpass(u, sigma, nw, xline, der):
     return y.reshape(n1, n2, n3, order="F")
 
 
-def smooth3(x, rect, repeat=1):
+def smooth3(x, rect, repeat=1, adj=0):
     n1, n2, n3 = _shape3(x)
     xx = _F(x).copy()
-    lib().pso_smooth3_rep(_p(xx), n1, n2, n3, int(rect[0]), int(rect[1]), int(rect[2]), int(repeat))
+    fn = lib().pso_smooth3_fwd if adj else lib().pso_smooth3_rep
+    fn(_p(xx), n1, n2, n3, int(rect[0]), int(rect[1]), int(rect[2]), int(repeat))
     return xx.reshape(n1, n2, n3, order="F")
 
 

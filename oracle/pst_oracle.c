@@ -168,6 +168,45 @@ void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3)
     free(t);
 }
 
+/* ps_smooth (dip_cfuns.c:591-603; smoothcf with adj = 1): fold (copy + reflections) :439-456, doubint (backward
+ * then forward running sum) :487-505, triple :531-547 -- whose `2.*tmp1 - tmp - tmp2` runs in double */
+static void tri_line_fwd(float *x, long o, long d, int nx, int nb, float *t)
+{
+    int np = nx + 2 * nb;
+    float wt = (float)(1.0 / (nb * nb));
+    for (int i = 0; i < nx; i++) t[i + nb] = x[o + i * d];
+    for (int j = nb + nx; j < np; j += nx) {
+        for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + (nx - 1 - i) * d];
+        j += nx;
+        for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + i * d];
+    }
+    for (int j = nb; j >= 0; j -= nx) {
+        for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + i * d];
+        j -= nx;
+        for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + (nx - 1 - i) * d];
+    }
+    float s = 0.f;
+    for (int i = np - 1; i >= 0; i--) { s += t[i]; t[i] = s; }
+    s = 0.f;
+    for (int i = 0; i < np; i++) { s += t[i]; t[i] = s; }
+    for (int i = 0; i < nx; i++) x[o + i * d] = (float)((2. * t[i + nb] - t[i] - t[i + 2 * nb]) * wt);
+}
+
+void pso_smooth3_fwd(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
+{
+    int nmax = n1 > n2 ? n1 : n2; if (n3 > nmax) nmax = n3;
+    int rmax = r1 > r2 ? r1 : r2; if (r3 > rmax) rmax = r3;
+    float *t = falloc((size_t)nmax + 2 * (size_t)rmax + 2);
+    if (r1 > 1)
+        for (long l = 0; l < (long)n2 * n3; l++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, l * n1, 1, n1, r1, t);
+    if (r2 > 1)
+        for (int i3 = 0; i3 < n3; i3++)
+            for (int i1 = 0; i1 < n1; i1++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, i1 + (long)n1 * n2 * i3, n1, n2, r2, t);
+    if (r3 > 1)
+        for (long l = 0; l < (long)n1 * n2; l++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, l, (long)n1 * n2, n3, r3, t);
+    free(t);
+}
+
 /* smoothcf (dip_cfuns.c:2006-2123) with adj = 0, no diff / box: every line of an axis is smoothed `repeat` times
  * in a row (ps_smooth2), axes in turn */
 void pso_smooth3_rep(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)

@@ -195,15 +195,15 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
 
 def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=0, ctx=None):
     """N-D triangle smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf,
-    dip_cfuns.c:2006-2123).  GPU path: the ps_smooth2 kernel dip3d uses, i.e. adj=0, no
-    derivative, no box, any repeat >= 1; other options raise."""
-    if adj or any(diff) or any(box) or int(repeat) < 1:
-        raise NotImplementedError("smoothc on GPU: adj=0, diff=0, box=0 only")
+    dip_cfuns.c:2006-2123).  GPU path: adj=0 is ps_smooth2 (the kernel dip3d uses), adj=1 is ps_smooth
+    (fold, double integration, triple); any repeat >= 1; derivative and box options raise."""
+    if any(diff) or any(box) or int(repeat) < 1:
+        raise NotImplementedError("smoothc on GPU: diff=0, box=0 only")
     din = np.asarray(din)
     n1, n2, n3 = _shape3(din)
     c = _ctx(ctx)
     d = _F(din)
     out = np.empty_like(d)
     _lib.check(c.lib.pst_smooth3(c.handle, _p(d), n1, n2, n3, int(rect[0]), int(rect[1]),
-                                 int(rect[2]), int(repeat), _p(out)))
+                                 int(rect[2]), int(repeat), int(bool(adj)), _p(out)))
     return out.reshape(din.shape, order="F")

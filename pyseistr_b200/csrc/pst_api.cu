@@ -459,7 +459,7 @@ extern "C" int pst_soint3d(pst_ctx *c, const float *din, const float *mask, cons
 }
 
 extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
-                           int repeat, float *out)
+                           int repeat, int adj, float *out)
 {
     PST_ENTRY(c);
     if (!x || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smooth3: null pointer or bad shape"); return PST_EINVAL; }
@@ -467,7 +467,7 @@ extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, i
     CallTimer t(c);
     DevBuf d;
     PST_TRY(up(c, d, x, n));
-    PST_TRY(pst_smooth3_dev(c, d.f(), n1, n2, n3, r1, r2, r3, repeat));
+    PST_TRY(pst_smooth3_dev(c, d.f(), n1, n2, n3, r1, r2, r3, repeat, adj));
     PST_TRY(down(c, out, d, n));
     t.stop();
     return PST_OK;

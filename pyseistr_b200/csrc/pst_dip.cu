@@ -237,6 +237,39 @@ __global__ void tri_lines_literal_kernel(float *x, float *scr,
     }
 }
 
+// ps_smooth (dip_cfuns.c:591-603; smoothcf with adj = 1): fold (copy + reflections) :439-456, doubint (backward, then
+// forward running sum) :487-505, triple :531-547 whose `2.*tmp1 - tmp - tmp2` is evaluated in double.  One thread per
+// line, the extended line in global scratch (user-facing option only; not on the dip3d path).
+__global__ void tri_lines_fwdop_kernel(float *x, float *scr, long nlines, long na, long sa, long sb, long d, int nx,
+                                       int nb, float wt)
+{
+    const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines) return;
+    const long ia = l % na, ib = l / na;
+    float *xl = x + ia * sa + ib * sb;
+    const int np = nx + 2 * nb;
+    float *sl = scr + ia + na * ((long)np * ib);
+    for (int i = 0; i < nx; i++) sl[(long)(i + nb) * na] = xl[(long)i * d];
+    for (int j = nb + nx; j < np; j += nx) {
+        for (int i = 0; i < nx && i < np - j; i++) sl[(long)(j + i) * na] = xl[(long)(nx - 1 - i) * d];
+        j += nx;
+        for (int i = 0; i < nx && i < np - j; i++) sl[(long)(j + i) * na] = xl[(long)i * d];
+    }
+    for (int j = nb; j >= 0; j -= nx) {
+        for (int i = 0; i < nx && i < j; i++) sl[(long)(j - 1 - i) * na] = xl[(long)i * d];
+        j -= nx;
+        for (int i = 0; i < nx && i < j; i++) sl[(long)(j - 1 - i) * na] = xl[(long)(nx - 1 - i) * d];
+    }
+    float s = 0.f;
+    for (int k = np - 1; k >= 0; k--) { s += sl[(long)k * na]; sl[(long)k * na] = s; }
+    s = 0.f;
+    for (int k = 0; k < np; k++) { s += sl[(long)k * na]; sl[(long)k * na] = s; }
+    for (int i = 0; i < nx; i++) {
+        const double t0 = sl[(long)i * na], t1 = sl[(long)(i + nb) * na], t2 = sl[(long)(i + 2 * nb) * na];
+        xl[(long)i * d] = (float)((2. * t1 - t0 - t2) * (double)wt);
+    }
+}
+
 // Axis 1 (contiguous lines): a CTA stages LPC whole lines in shared memory.  Phase 1: all
 // threads build t_k with coalesced loads.  Phase 2: LPC threads run the two serial running
 // sums in shared memory (row pitch odd => conflict-free).  Phase 3: all threads fold and
@@ -2042,7 +2075,30 @@ extern "C" int pst_allpass_dev(pst_ctx *c, const float *d_u, const float *d_sigm
     return PST_OK;
 }
 
-extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
+static int smooth3_fwdop(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
+{
+    const int rr[3] = {r1, r2, r3}, nn[3] = {n1, n2, n3};
+    for (int a = 0; a < 3; a++) {
+        if (rr[a] <= 1) continue;
+        const int nb = rr[a], nx = nn[a];
+        const float wt = (float)(1.0 / ((double)nb * nb));
+        long nlines, na, sa, sb, d;
+        if (a == 0) { nlines = (long)n2 * n3; na = nlines; sa = n1; sb = 0; d = 1; }
+        else if (a == 1) { nlines = (long)n1 * n3; na = n1; sa = 1; sb = (long)n1 * n2; d = n1; }
+        else { nlines = (long)n1 * n2; na = nlines; sa = 1; sb = 0; d = (long)n1 * n2; }
+        const int threads = 128;
+        const long blocks = (nlines + threads - 1) / threads;
+        for (int q = 0; q < repeat; q++) {
+            PST_LAUNCHB(c, a == 0 ? PST_K_TRI1 : (a == 1 ? PST_K_TRI2 : PST_K_TRI3), 8.0 * (double)nlines * nx,
+                (tri_lines_fwdop_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt)));
+            c->stats.smooth_passes++;
+        }
+    }
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj)
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1 || repeat < 1) { pst_set_error("smooth3: bad arguments"); return PST_EINVAL; }
@@ -2053,7 +2109,9 @@ extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, i
     pst_arena_reset(c);
     float *s;
     PST_TRY(pst_arena_get(c, scr, &s));
-    if (repeat == 1) {
+    if (adj) {
+        PST_TRY(smooth3_fwdop(c, d_x, s, n1, n2, n3, r1, r2, r3, repeat));
+    } else if (repeat == 1) {
         PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, r1, r2, r3));
     } else {
         // smoothcf (dip_cfuns.c:2084-2098): every line of an axis is smoothed `repeat` times in a row, axes in turn

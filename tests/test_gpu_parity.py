@@ -90,6 +90,15 @@ def test_smooth_repeat_bit_exact(ctx, port, shape, rect, repeat):
     assert np.array_equal(got, port.smooth3(x, rect, repeat).reshape(x.shape, order="F"))
 
 
+@pytest.mark.parametrize("shape,rect,repeat", [((64, 20, 12), (5, 3, 4), 1), ((30, 12, 6), (2, 15, 9), 2), ((100, 70, 37), (7, 1, 3), 1)])
+def test_smooth_adj1_bit_exact(ctx, port, shape, rect, repeat):
+    """smoothc(adj=1) = ps_smooth: fold, backward + forward running sums, triple in double (dip_cfuns.c:591-603)."""
+    import pyseistr_b200 as ps
+    x = synth.cube(*shape, seed=35)
+    got = ps.smoothc(x, rect=list(rect), repeat=repeat, adj=1, ctx=ctx)
+    assert np.array_equal(got, port.smooth3(x, rect, repeat, adj=1).reshape(x.shape, order="F"))
+
+
 @pytest.mark.parametrize("name", golden_names("smooth_"))
 def test_smooth_golden(ctx, name):
     import pyseistr_b200 as ps

@@ -96,6 +96,13 @@ def test_port_smooth_repeat_matches_compiled_reference(port):
         assert np.array_equal(port.smooth3(x, rect, rep), ref.smoothc(x, rect, repeat=rep))
 
 
+def test_port_smooth_adj1_matches_compiled_reference(port):
+    ref = _ref_or_skip()
+    x = synth.cube(30, 12, 6, seed=13)
+    for rect, rep in (([5, 3, 4], 1), ([2, 15, 9], 2), ([7, 2, 2], 1)):
+        assert np.array_equal(port.smooth3(x, rect, rep, adj=1), ref.smoothc(x, rect, adj=1, repeat=rep))
+
+
 def test_port_filters_closed_form(port):
     """nw=1 taps have the closed form [(1-p)(2-p)/12, (2+p)(2-p)/6, (1+p)(2+p)/12]."""
     for p in (-0.7, 0.0, 0.3, 1.2):

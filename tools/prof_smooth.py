@@ -24,7 +24,7 @@ ctx.set_profile(True)
 for it in range(reps):
     ctx.reset_stats()
     t = time.perf_counter()
-    _lib.check(ctx.lib.pst_smooth3_dev(ctx.handle, d, n1, n2, n3, *r, 1))
+    _lib.check(ctx.lib.pst_smooth3_dev(ctx.handle, d, n1, n2, n3, *r, 1, 0))
     dt = time.perf_counter() - t
     st = ctx.stats()
     ms = dict(zip(_lib.KERNEL_CLASSES, st["class_ms"]))
