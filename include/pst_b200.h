@@ -160,6 +160,14 @@ int pst_divne_dev(pst_ctx *ctx, float *d_num, float *d_den, float *d_rat, int n1
 int pst_smooth3(pst_ctx *ctx, const float *x, int n1, int n2, int n3, int r1, int r2, int r3,
                 int repeat, int adj, float *out);
 
+/* ---- N-D triangle / box smoothing with every option.  Replaces dipcfun.smoothcf (pyseistr/src/dip_cfuns.c:2006-2123,
+ * "Oiiiiiiiiiiiiii": din, n1, n2, n3, repeat, adj, r1, r2, r3, diff1, diff2, diff3, box1, box2, box3); called by smoothc
+ * (pyseistr/smooth.py:115-183, whose default is adj = 1).  adj = 0: ps_smooth2, adj = 1: ps_smooth. */
+int pst_smoothcf(pst_ctx *ctx, const float *x, int n1, int n2, int n3, int repeat, int adj, int r1, int r2, int r3,
+                 int diff1, int diff2, int diff3, int box1, int box2, int box3, float *out);
+int pst_smoothcf_dev(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int repeat, int adj, int r1, int r2, int r3,
+                     int diff1, int diff2, int diff3, int box1, int box2, int box3);
+
 /* ---- raw device memory helpers so that a host language without a CUDA binding can keep
  * volumes resident between calls (bench `value` leg, pipelines dip -> somf). */
 int pst_dev_alloc(pst_ctx *ctx, size_t bytes, void **d_ptr);

@@ -71,6 +71,16 @@ def smooth3(x, rect, repeat=1, adj=0):
     return xx.reshape(n1, n2, n3, order="F")
 
 
+def smoothc(x, rect, diff=(0, 0, 0), box=(0, 0, 0), repeat=1, adj=1):
+    """smoothcf with every option (reference pyseistr/smooth.py:115-183; note the default adj=1)."""
+    n1, n2, n3 = _shape3(x)
+    xx = _F(x).copy()
+    I3 = ctypes.c_int * 3
+    lib().pso_smoothcf(_p(xx), n1, n2, n3, int(repeat), int(adj), I3(*[int(v) for v in rect]), I3(*[int(v) for v in diff]),
+                       I3(*[int(v) for v in box]))
+    return xx.reshape(n1, n2, n3, order="F")
+
+
 def divne(num, den, rect, liter, eps=1.0):
     n1, n2, n3 = _shape3(num)
     a, b = _F(num).copy(), _F(den).copy()

@@ -168,43 +168,87 @@ void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3)
     free(t);
 }
 
-/* ps_smooth (dip_cfuns.c:591-603; smoothcf with adj = 1): fold (copy + reflections) :439-456, doubint (backward
- * then forward running sum) :487-505, triple :531-547 -- whose `2.*tmp1 - tmp - tmp2` runs in double */
-static void tri_line_fwd(float *x, long o, long d, int nx, int nb, float *t)
+/* One line of smoothcf (dip_cfuns.c:2084-2098) with every option:
+ *   adj = 0: ps_smooth2 :616-625 = triple2 :560-577 (box: +wt at 1, -wt at 2nb), doubint2 :508-529 (forward sum,
+ *            then backward unless box || der), fold2 :458-484
+ *   adj = 1: ps_smooth :591-603 = fold :439-456, doubint :487-505 (backward sum, then forward unless box || der),
+ *            triple :531-547 (box: (tmp[i+1] - tmp[i+2nb]) * wt in float; triangle: 2.*tmp1 - tmp - tmp2 in double)
+ *   wt = 1/(2nb-1) for a box, 1/nb^2 for a triangle (ps_triangle_init :415-424) */
+static void tri_line_any(float *x, long o, long d, int nx, int nb, float *t, int adj, int box, int der)
 {
     int np = nx + 2 * nb;
-    float wt = (float)(1.0 / (nb * nb));
-    for (int i = 0; i < nx; i++) t[i + nb] = x[o + i * d];
-    for (int j = nb + nx; j < np; j += nx) {
-        for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + (nx - 1 - i) * d];
-        j += nx;
-        for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + i * d];
+    float wt = box ? (float)(1.0 / (2 * nb - 1)) : (float)(1.0 / (nb * nb));
+    int single = box || der;
+    if (!adj) {
+        for (int i = 0; i < np; i++) t[i] = 0;
+        if (box) {
+            float wp = +wt, wm = -wt;
+            for (int i = 0; i < nx; i++) t[i + 1] += wp * x[o + i * d];
+            for (int i = 0; i < nx; i++) t[i + 2 * nb] += wm * x[o + i * d];
+        } else {
+            float w2 = (float)(2. * wt), wm = -wt;
+            for (int i = 0; i < nx; i++) t[i] += wm * x[o + i * d];
+            for (int i = 0; i < nx; i++) t[i + nb] += w2 * x[o + i * d];
+            for (int i = 0; i < nx; i++) t[i + 2 * nb] += wm * x[o + i * d];
+        }
+        float s = 0.f;
+        for (int i = 0; i < np; i++) { s += t[i]; t[i] = s; }
+        if (!single) { s = 0.f; for (int i = np - 1; i >= 0; i--) { s += t[i]; t[i] = s; } }
+        for (int i = 0; i < nx; i++) x[o + i * d] = t[i + nb];
+        for (int j = nb + nx; j < np; j += nx) {
+            for (int i = 0; i < nx && i < np - j; i++) x[o + (nx - 1 - i) * d] += t[j + i];
+            j += nx;
+            for (int i = 0; i < nx && i < np - j; i++) x[o + i * d] += t[j + i];
+        }
+        for (int j = nb; j >= 0; j -= nx) {
+            for (int i = 0; i < nx && i < j; i++) x[o + i * d] += t[j - 1 - i];
+            j -= nx;
+            for (int i = 0; i < nx && i < j; i++) x[o + (nx - 1 - i) * d] += t[j - 1 - i];
+        }
+    } else {
+        for (int i = 0; i < nx; i++) t[i + nb] = x[o + i * d];
+        for (int j = nb + nx; j < np; j += nx) {
+            for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + (nx - 1 - i) * d];
+            j += nx;
+            for (int i = 0; i < nx && i < np - j; i++) t[j + i] = x[o + i * d];
+        }
+        for (int j = nb; j >= 0; j -= nx) {
+            for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + i * d];
+            j -= nx;
+            for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + (nx - 1 - i) * d];
+        }
+        float s = 0.f;
+        for (int i = np - 1; i >= 0; i--) { s += t[i]; t[i] = s; }
+        if (!single) { s = 0.f; for (int i = 0; i < np; i++) { s += t[i]; t[i] = s; } }
+        if (box) for (int i = 0; i < nx; i++) x[o + i * d] = (t[i + 1] - t[i + 2 * nb]) * wt;
+        else for (int i = 0; i < nx; i++) x[o + i * d] = (float)((2. * t[i + nb] - t[i] - t[i + 2 * nb]) * wt);
     }
-    for (int j = nb; j >= 0; j -= nx) {
-        for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + i * d];
-        j -= nx;
-        for (int i = 0; i < nx && i < j; i++) t[j - 1 - i] = x[o + (nx - 1 - i) * d];
+}
+
+void pso_smoothcf(float *x, int n1, int n2, int n3, int repeat, int adj, const int *rect, const int *diff, const int *box)
+{
+    int nn[3] = {n1, n2, n3};
+    int nmax = n1 > n2 ? n1 : n2; if (n3 > nmax) nmax = n3;
+    int rmax = rect[0] > rect[1] ? rect[0] : rect[1]; if (rect[2] > rmax) rmax = rect[2];
+    float *t = falloc((size_t)nmax + 2 * (size_t)rmax + 2);
+    for (int a = 0; a < 3; a++) {
+        if (rect[a] <= 1) continue;
+        long nl = (long)n1 * n2 * n3 / nn[a];
+        for (long l = 0; l < nl; l++) {
+            long o, d;
+            if (a == 0) { o = l * n1; d = 1; }
+            else if (a == 1) { o = (l % n1) + (long)n1 * n2 * (l / n1); d = n1; }
+            else { o = l; d = (long)n1 * n2; }
+            for (int q = 0; q < repeat; q++) tri_line_any(x, o, d, nn[a], rect[a], t, adj, box[a], diff[a]);
+        }
     }
-    float s = 0.f;
-    for (int i = np - 1; i >= 0; i--) { s += t[i]; t[i] = s; }
-    s = 0.f;
-    for (int i = 0; i < np; i++) { s += t[i]; t[i] = s; }
-    for (int i = 0; i < nx; i++) x[o + i * d] = (float)((2. * t[i + nb] - t[i] - t[i + 2 * nb]) * wt);
+    free(t);
 }
 
 void pso_smooth3_fwd(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
 {
-    int nmax = n1 > n2 ? n1 : n2; if (n3 > nmax) nmax = n3;
-    int rmax = r1 > r2 ? r1 : r2; if (r3 > rmax) rmax = r3;
-    float *t = falloc((size_t)nmax + 2 * (size_t)rmax + 2);
-    if (r1 > 1)
-        for (long l = 0; l < (long)n2 * n3; l++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, l * n1, 1, n1, r1, t);
-    if (r2 > 1)
-        for (int i3 = 0; i3 < n3; i3++)
-            for (int i1 = 0; i1 < n1; i1++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, i1 + (long)n1 * n2 * i3, n1, n2, r2, t);
-    if (r3 > 1)
-        for (long l = 0; l < (long)n1 * n2; l++) for (int q = 0; q < repeat; q++) tri_line_fwd(x, l, (long)n1 * n2, n3, r3, t);
-    free(t);
+    const int rect[3] = {r1, r2, r3}, z[3] = {0, 0, 0};
+    pso_smoothcf(x, n1, n2, n3, repeat, 1, rect, z, z);
 }
 
 /* smoothcf (dip_cfuns.c:2006-2123) with adj = 0, no diff / box: every line of an axis is smoothed `repeat` times

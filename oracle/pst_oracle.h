@@ -33,6 +33,8 @@ void pso_smooth3(float *x, int n1, int n2, int n3, int r1, int r2, int r3);
 void pso_smooth3_rep(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat);
 /* smoothcf with adj = 1: ps_smooth (fold, doubint, triple) dip_cfuns.c:439-456,487-505,531-547,591-603 */
 void pso_smooth3_fwd(float *x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat);
+/* smoothcf with every option (repeat, adj, rect[3], diff[3], box[3]) dip_cfuns.c:2006-2123 */
+void pso_smoothcf(float *x, int n1, int n2, int n3, int repeat, int adj, const int *rect, const int *diff, const int *box);
 
 /* Smooth division rat ~ num/den (num, den are overwritten): dip_cfuns.c:796-827 + :257-383.
  * Returns the number of CG iterations executed. */

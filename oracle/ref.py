@@ -149,11 +149,11 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return d.reshape(n1, n2, n3, order="F")
 
 
-def smoothc(x, rect, adj=0, repeat=1):
+def smoothc(x, rect, adj=0, repeat=1, diff=(0, 0, 0), box=(0, 0, 0)):
     """reference pyseistr/smooth.py:115-183 via dipcfun.smoothcf (dip_cfuns.c:2006-2123);
-    adj=0 selects ps_smooth2, the kernel dip3d uses."""
+    adj=0 selects ps_smooth2, the kernel dip3d uses (the reference wrapper's own default is adj=1)."""
     n1, n2, n3 = _shape3(x)
     with quiet():
-        y = module("dipcfun").smoothcf(_F(x), n1, n2, n3, int(repeat), adj, rect[0], rect[1], rect[2],
-                                       0, 0, 0, 0, 0, 0)
+        y = module("dipcfun").smoothcf(_F(x), n1, n2, n3, int(repeat), int(adj), rect[0], rect[1], rect[2],
+                                       int(diff[0]), int(diff[1]), int(diff[2]), int(box[0]), int(box[1]), int(box[2]))
     return np.asarray(y, dtype=np.float32).reshape(n1, n2, n3, order="F")

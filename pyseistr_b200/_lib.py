@@ -77,6 +77,8 @@ SIGNATURES = {
     "pst_smooth3_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "pst_divne_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),
     "pst_smooth3": (_i, [_vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp]),
+    "pst_smoothcf": (_i, [_vp, _fp] + [_i] * 14 + [_fp]),
+    "pst_smoothcf_dev": (_i, [_vp, _vp] + [_i] * 14),
     "pst_dev_alloc": (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "pst_dev_free": (_i, [_vp, _vp]),
     "pst_h2d": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),

@@ -193,17 +193,18 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return out.reshape(n1, n2, n3, order="F")
 
 
-def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=0, ctx=None):
-    """N-D triangle smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf,
-    dip_cfuns.c:2006-2123).  GPU path: adj=0 is ps_smooth2 (the kernel dip3d uses), adj=1 is ps_smooth
-    (fold, double integration, triple); any repeat >= 1; derivative and box options raise."""
-    if any(diff) or any(box) or int(repeat) < 1:
-        raise NotImplementedError("smoothc on GPU: diff=0, box=0 only")
+def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=1, ctx=None):
+    """N-D triangle / box smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf, dip_cfuns.c:2006-2123),
+    same defaults as the reference (note adj=1).  adj=0 is ps_smooth2 (the operator inside dip3d's shaping CG, here the
+    streaming kernel), adj=1 is ps_smooth; diff / box select single integration / box weights per axis."""
     din = np.asarray(din)
     n1, n2, n3 = _shape3(din)
+    if int(repeat) < 1:
+        raise ValueError("repeat must be >= 1")
     c = _ctx(ctx)
     d = _F(din)
     out = np.empty_like(d)
-    _lib.check(c.lib.pst_smooth3(c.handle, _p(d), n1, n2, n3, int(rect[0]), int(rect[1]),
-                                 int(rect[2]), int(repeat), int(bool(adj)), _p(out)))
-    return out.reshape(din.shape, order="F")
+    _lib.check(c.lib.pst_smoothcf(c.handle, _p(d), n1, n2, n3, int(repeat), int(bool(adj)), int(rect[0]), int(rect[1]),
+                                  int(rect[2]), int(bool(diff[0])), int(bool(diff[1])), int(bool(diff[2])),
+                                  int(bool(box[0])), int(bool(box[1])), int(bool(box[2])), _p(out)))
+    return np.squeeze(out.reshape(n1, n2, n3, order="F"))

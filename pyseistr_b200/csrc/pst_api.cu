@@ -473,6 +473,21 @@ extern "C" int pst_smooth3(pst_ctx *c, const float *x, int n1, int n2, int n3, i
     return PST_OK;
 }
 
+extern "C" int pst_smoothcf(pst_ctx *c, const float *x, int n1, int n2, int n3, int repeat, int adj, int r1, int r2, int r3,
+                            int diff1, int diff2, int diff3, int box1, int box2, int box3, float *out)
+{
+    PST_ENTRY(c);
+    if (!x || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("smoothcf: null pointer or bad shape"); return PST_EINVAL; }
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
+    CallTimer t(c);
+    DevBuf d;
+    PST_TRY(up(c, d, x, n));
+    PST_TRY(pst_smoothcf_dev(c, d.f(), n1, n2, n3, repeat, adj, r1, r2, r3, diff1, diff2, diff3, box1, box2, box3));
+    PST_TRY(down(c, out, d, n));
+    t.stop();
+    return PST_OK;
+}
+
 extern "C" int pst_sint3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx, const float *mask,
                           int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, int verb,
                           float eps, float *out)

@@ -237,11 +237,14 @@ __global__ void tri_lines_literal_kernel(float *x, float *scr,
     }
 }
 
-// ps_smooth (dip_cfuns.c:591-603; smoothcf with adj = 1): fold (copy + reflections) :439-456, doubint (backward, then
-// forward running sum) :487-505, triple :531-547 whose `2.*tmp1 - tmp - tmp2` is evaluated in double.  One thread per
-// line, the extended line in global scratch (user-facing option only; not on the dip3d path).
-__global__ void tri_lines_fwdop_kernel(float *x, float *scr, long nlines, long na, long sa, long sb, long d, int nx,
-                                       int nb, float wt)
+// One line of smoothcf (dip_cfuns.c:2084-2098) with every option, one thread per line, the extended line in global
+// scratch (user-facing options only; dip3d's shaping operator goes through the streaming kernel):
+//   adj = 0: ps_smooth2 :616-625 = triple2 :560-577 (box: +wt at 1, -wt at 2nb), doubint2 :508-529 (forward sum, then
+//            backward unless box || der), fold2 :458-484
+//   adj = 1: ps_smooth :591-603 = fold :439-456, doubint :487-505 (backward sum, then forward unless box || der),
+//            triple :531-547 (box: (tmp[i+1] - tmp[i+2nb]) * wt in float; triangle: 2.*tmp1 - tmp - tmp2 in double)
+__global__ void tri_lines_any_kernel(float *x, float *scr, long nlines, long na, long sa, long sb, long d, int nx,
+                                     int nb, float wt, int adj, int box, int der)
 {
     const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
@@ -249,25 +252,61 @@ __global__ void tri_lines_fwdop_kernel(float *x, float *scr, long nlines, long n
     float *xl = x + ia * sa + ib * sb;
     const int np = nx + 2 * nb;
     float *sl = scr + ia + na * ((long)np * ib);
-    for (int i = 0; i < nx; i++) sl[(long)(i + nb) * na] = xl[(long)i * d];
-    for (int j = nb + nx; j < np; j += nx) {
-        for (int i = 0; i < nx && i < np - j; i++) sl[(long)(j + i) * na] = xl[(long)(nx - 1 - i) * d];
-        j += nx;
-        for (int i = 0; i < nx && i < np - j; i++) sl[(long)(j + i) * na] = xl[(long)i * d];
+    const bool single = box || der;
+#define T_(k) sl[(long)(k) * na]
+#define X_(i) xl[(long)(i) * d]
+    if (!adj) {
+        for (int k = 0; k < np; k++) T_(k) = 0.f;
+        if (box) {
+            const float wp = +wt, wm = -wt;
+            for (int i = 0; i < nx; i++) T_(i + 1) += wp * X_(i);
+            for (int i = 0; i < nx; i++) T_(i + 2 * nb) += wm * X_(i);
+        } else {
+            const float w2 = (float)(2. * wt), wm = -wt;
+            for (int i = 0; i < nx; i++) T_(i) += wm * X_(i);
+            for (int i = 0; i < nx; i++) T_(i + nb) += w2 * X_(i);
+            for (int i = 0; i < nx; i++) T_(i + 2 * nb) += wm * X_(i);
+        }
+        float s = 0.f;
+        for (int k = 0; k < np; k++) { s += T_(k); T_(k) = s; }
+        if (!single) { s = 0.f; for (int k = np - 1; k >= 0; k--) { s += T_(k); T_(k) = s; } }
+        for (int i = 0; i < nx; i++) X_(i) = T_(i + nb);
+        for (int j = nb + nx; j < np; j += nx) {
+            for (int i = 0; i < nx && i < np - j; i++) X_(nx - 1 - i) += T_(j + i);
+            j += nx;
+            for (int i = 0; i < nx && i < np - j; i++) X_(i) += T_(j + i);
+        }
+        for (int j = nb; j >= 0; j -= nx) {
+            for (int i = 0; i < nx && i < j; i++) X_(i) += T_(j - 1 - i);
+            j -= nx;
+            for (int i = 0; i < nx && i < j; i++) X_(nx - 1 - i) += T_(j - 1 - i);
+        }
+    } else {
+        for (int i = 0; i < nx; i++) T_(i + nb) = X_(i);
+        for (int j = nb + nx; j < np; j += nx) {
+            for (int i = 0; i < nx && i < np - j; i++) T_(j + i) = X_(nx - 1 - i);
+            j += nx;
+            for (int i = 0; i < nx && i < np - j; i++) T_(j + i) = X_(i);
+        }
+        for (int j = nb; j >= 0; j -= nx) {
+            for (int i = 0; i < nx && i < j; i++) T_(j - 1 - i) = X_(i);
+            j -= nx;
+            for (int i = 0; i < nx && i < j; i++) T_(j - 1 - i) = X_(nx - 1 - i);
+        }
+        float s = 0.f;
+        for (int k = np - 1; k >= 0; k--) { s += T_(k); T_(k) = s; }
+        if (!single) { s = 0.f; for (int k = 0; k < np; k++) { s += T_(k); T_(k) = s; } }
+        if (box) {
+            for (int i = 0; i < nx; i++) X_(i) = (T_(i + 1) - T_(i + 2 * nb)) * wt;
+        } else {
+            for (int i = 0; i < nx; i++) {
+                const double t0 = T_(i), t1 = T_(i + nb), t2 = T_(i + 2 * nb);
+                X_(i) = (float)((2. * t1 - t0 - t2) * (double)wt);
+            }
+        }
     }
-    for (int j = nb; j >= 0; j -= nx) {
-        for (int i = 0; i < nx && i < j; i++) sl[(long)(j - 1 - i) * na] = xl[(long)i * d];
-        j -= nx;
-        for (int i = 0; i < nx && i < j; i++) sl[(long)(j - 1 - i) * na] = xl[(long)(nx - 1 - i) * d];
-    }
-    float s = 0.f;
-    for (int k = np - 1; k >= 0; k--) { s += sl[(long)k * na]; sl[(long)k * na] = s; }
-    s = 0.f;
-    for (int k = 0; k < np; k++) { s += sl[(long)k * na]; sl[(long)k * na] = s; }
-    for (int i = 0; i < nx; i++) {
-        const double t0 = sl[(long)i * na], t1 = sl[(long)(i + nb) * na], t2 = sl[(long)(i + 2 * nb) * na];
-        xl[(long)i * d] = (float)((2. * t1 - t0 - t2) * (double)wt);
-    }
+#undef T_
+#undef X_
 }
 
 // Axis 1 (contiguous lines): a CTA stages LPC whole lines in shared memory.  Phase 1: all
@@ -2075,33 +2114,33 @@ extern "C" int pst_allpass_dev(pst_ctx *c, const float *d_u, const float *d_sigm
     return PST_OK;
 }
 
-static int smooth3_fwdop(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3, int r1, int r2, int r3, int repeat)
+static int smooth_axis_any(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3, int a, int nb, int adj, int box, int der)
 {
-    const int rr[3] = {r1, r2, r3}, nn[3] = {n1, n2, n3};
-    for (int a = 0; a < 3; a++) {
-        if (rr[a] <= 1) continue;
-        const int nb = rr[a], nx = nn[a];
-        const float wt = (float)(1.0 / ((double)nb * nb));
-        long nlines, na, sa, sb, d;
-        if (a == 0) { nlines = (long)n2 * n3; na = nlines; sa = n1; sb = 0; d = 1; }
-        else if (a == 1) { nlines = (long)n1 * n3; na = n1; sa = 1; sb = (long)n1 * n2; d = n1; }
-        else { nlines = (long)n1 * n2; na = nlines; sa = 1; sb = 0; d = (long)n1 * n2; }
-        const int threads = 128;
-        const long blocks = (nlines + threads - 1) / threads;
-        for (int q = 0; q < repeat; q++) {
-            PST_LAUNCHB(c, a == 0 ? PST_K_TRI1 : (a == 1 ? PST_K_TRI2 : PST_K_TRI3), 8.0 * (double)nlines * nx,
-                (tri_lines_fwdop_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt)));
-            c->stats.smooth_passes++;
-        }
-    }
+    const int nn[3] = {n1, n2, n3};
+    const int nx = nn[a];
+    const float wt = box ? (float)(1.0 / (double)(2 * nb - 1)) : (float)(1.0 / ((double)nb * nb));   // ps_triangle_init :415-424
+    long nlines, na, sa, sb, d;
+    if (a == 0) { nlines = (long)n2 * n3; na = nlines; sa = n1; sb = 0; d = 1; }
+    else if (a == 1) { nlines = (long)n1 * n3; na = n1; sa = 1; sb = (long)n1 * n2; d = n1; }
+    else { nlines = (long)n1 * n2; na = nlines; sa = 1; sb = 0; d = (long)n1 * n2; }
+    const int threads = 128;
+    const long blocks = (nlines + threads - 1) / threads;
+    PST_LAUNCHB(c, a == 0 ? PST_K_TRI1 : (a == 1 ? PST_K_TRI2 : PST_K_TRI3), 8.0 * (double)nlines * nx,
+        (tri_lines_any_kernel<<<(unsigned)blocks, threads, 0, c->stream>>>(x, scr, nlines, na, sa, sb, d, nx, nb, wt, adj, box, der)));
+    c->stats.smooth_passes++;
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
 
-extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj)
+// smoothcf (dip_cfuns.c:2006-2123): axes in turn, every line of an axis smoothed `repeat` times in a row
+extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int repeat, int adj, int r1, int r2, int r3,
+                                int diff1, int diff2, int diff3, int box1, int box2, int box3)
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
-    if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1 || repeat < 1) { pst_set_error("smooth3: bad arguments"); return PST_EINVAL; }
+    if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1 || repeat < 1) { pst_set_error("smoothcf: bad arguments"); return PST_EINVAL; }
+    if (c->comm && c->nranks > 1 && (adj || diff1 || diff2 || diff3 || box1 || box2 || box3 || repeat != 1)) {
+        pst_set_error("smoothcf: options other than adj=0, repeat=1 are single-GPU only"); return PST_EUNSUP;
+    }
     PST_CUDA(cudaSetDevice(c->device));
     DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
     const size_t scr = tri_scratch_floats(g);
@@ -2109,21 +2148,28 @@ extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, i
     pst_arena_reset(c);
     float *s;
     PST_TRY(pst_arena_get(c, scr, &s));
-    if (adj) {
-        PST_TRY(smooth3_fwdop(c, d_x, s, n1, n2, n3, r1, r2, r3, repeat));
-    } else if (repeat == 1) {
+    const int rr[3] = {r1, r2, r3}, df[3] = {diff1, diff2, diff3}, bx[3] = {box1, box2, box3};
+    const bool plain = !adj && !diff1 && !diff2 && !diff3 && !box1 && !box2 && !box3;
+    if (plain && repeat == 1) {
         PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, r1, r2, r3));
     } else {
-        // smoothcf (dip_cfuns.c:2084-2098): every line of an axis is smoothed `repeat` times in a row, axes in turn
-        const int rr[3] = {r1, r2, r3};
         for (int a = 0; a < 3; a++) {
             if (rr[a] <= 1) continue;
-            for (int q = 0; q < repeat; q++)
-                PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, a == 0 ? r1 : 1, a == 1 ? r2 : 1, a == 2 ? r3 : 1));
+            for (int q = 0; q < repeat; q++) {
+                if (!adj && !df[a] && !bx[a])       // ps_smooth2 without options: the streaming kernel
+                    PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, a == 0 ? r1 : 1, a == 1 ? r2 : 1, a == 2 ? r3 : 1));
+                else
+                    PST_TRY(smooth_axis_any(c, d_x, s, n1, n2, n3, a, rr[a], adj ? 1 : 0, bx[a] ? 1 : 0, df[a] ? 1 : 0));
+            }
         }
     }
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
+}
+
+extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj)
+{
+    return pst_smoothcf_dev(c, d_x, n1, n2, n3, repeat, adj, r1, r2, r3, 0, 0, 0, 0, 0, 0);
 }
 
 extern "C" int pst_divne_dev(pst_ctx *c, float *d_num, float *d_den, float *d_rat, int n1, int n2, int n3,

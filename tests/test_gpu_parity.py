@@ -76,8 +76,8 @@ def test_allpass_bit_exact(ctx, port, order, xline, der):
 def test_smooth3_bit_exact(ctx, port, shape, rect):
     import pyseistr_b200 as ps
     x = synth.cube(*shape, seed=33)
-    got = ps.smoothc(x, rect=list(rect), ctx=ctx)
-    want = port.smooth3(x, rect).reshape(x.shape, order="F")
+    got = ps.smoothc(x, rect=list(rect), adj=0, ctx=ctx)
+    want = np.squeeze(port.smooth3(x, rect).reshape(x.shape, order="F"))
     assert np.array_equal(got, want)
 
 
@@ -86,8 +86,8 @@ def test_smooth_repeat_bit_exact(ctx, port, shape, rect, repeat):
     """smoothc(repeat=k): every line of an axis is smoothed k times in a row (smoothcf dip_cfuns.c:2084-2098)."""
     import pyseistr_b200 as ps
     x = synth.cube(*shape, seed=34)
-    got = ps.smoothc(x, rect=list(rect), repeat=repeat, ctx=ctx)
-    assert np.array_equal(got, port.smooth3(x, rect, repeat).reshape(x.shape, order="F"))
+    got = ps.smoothc(x, rect=list(rect), repeat=repeat, adj=0, ctx=ctx)
+    assert np.array_equal(got, np.squeeze(port.smooth3(x, rect, repeat).reshape(x.shape, order="F")))
 
 
 @pytest.mark.parametrize("shape,rect,repeat", [((64, 20, 12), (5, 3, 4), 1), ((30, 12, 6), (2, 15, 9), 2), ((100, 70, 37), (7, 1, 3), 1)])
@@ -95,15 +95,26 @@ def test_smooth_adj1_bit_exact(ctx, port, shape, rect, repeat):
     """smoothc(adj=1) = ps_smooth: fold, backward + forward running sums, triple in double (dip_cfuns.c:591-603)."""
     import pyseistr_b200 as ps
     x = synth.cube(*shape, seed=35)
-    got = ps.smoothc(x, rect=list(rect), repeat=repeat, adj=1, ctx=ctx)
+    got = ps.smoothc(x, rect=list(rect), repeat=repeat, ctx=ctx)                     # the reference's default IS adj=1
     assert np.array_equal(got, port.smooth3(x, rect, repeat, adj=1).reshape(x.shape, order="F"))
+
+
+@pytest.mark.parametrize("adj", [0, 1])
+@pytest.mark.parametrize("diff,box", [((1, 0, 0), (0, 0, 0)), ((0, 0, 0), (1, 1, 1)), ((0, 1, 1), (1, 0, 1))])
+def test_smoothc_options_bit_exact(ctx, port, adj, diff, box):
+    """smoothcf with derivative / box options on both operators (dip_cfuns.c:2006-2123)."""
+    import pyseistr_b200 as ps
+    x = synth.cube(48, 20, 9, seed=36)
+    for rect, rep in (([5, 3, 4], 1), ([2, 25, 3], 2)):
+        got = ps.smoothc(x, rect=rect, diff=list(diff), box=list(box), repeat=rep, adj=adj, ctx=ctx)
+        assert np.array_equal(got, port.smoothc(x, rect, diff, box, rep, adj)), (rect, rep)
 
 
 @pytest.mark.parametrize("name", golden_names("smooth_"))
 def test_smooth_golden(ctx, name):
     import pyseistr_b200 as ps
     g = golden(name)
-    assert np.array_equal(ps.smoothc(g["x"], rect=[int(v) for v in g["rect"]], ctx=ctx), g["out"])
+    assert np.array_equal(ps.smoothc(g["x"], rect=[int(v) for v in g["rect"]], adj=0, ctx=ctx), g["out"])
 
 
 def test_divne_matches_oracle(ctx, port):

@@ -26,8 +26,8 @@ def test_wrappers_validate_before_touching_the_gpu():
         ps.dip3dc(np.zeros((8, 8), np.float32))
     with pytest.raises(ValueError):
         ps.dip2dc(np.zeros((8, 8, 2), np.float32))
-    with pytest.raises(NotImplementedError):
-        ps.smoothc(np.zeros((8, 8, 2), np.float32), rect=[3, 3, 1], box=[1, 0, 0])
+    with pytest.raises(ValueError):
+        ps.smoothc(np.zeros((8, 8, 2), np.float32), rect=[3, 3, 1], repeat=0)
 
 
 def test_public_names_match_reference_entry_points():

@@ -96,6 +96,19 @@ def test_port_smooth_repeat_matches_compiled_reference(port):
         assert np.array_equal(port.smooth3(x, rect, rep), ref.smoothc(x, rect, repeat=rep))
 
 
+def test_port_smoothcf_options_match_compiled_reference(port):
+    """every option of smoothcf (adj, repeat, diff, box per axis): bit-identical to the compiled reference."""
+    ref = _ref_or_skip()
+    x = synth.cube(30, 12, 6, seed=13)
+    for rect in ([5, 3, 4], [2, 15, 9]):
+        for adj in (0, 1):
+            for diff in ((0, 0, 0), (1, 0, 0), (0, 1, 1)):
+                for box in ((0, 0, 0), (1, 1, 1), (0, 0, 1)):
+                    a = port.smoothc(x, rect, diff, box, 2, adj)
+                    b = ref.smoothc(x, rect, adj=adj, repeat=2, diff=diff, box=box)
+                    assert np.array_equal(a, b), (rect, adj, diff, box)
+
+
 def test_port_smooth_adj1_matches_compiled_reference(port):
     ref = _ref_or_skip()
     x = synth.cube(30, 12, 6, seed=13)
