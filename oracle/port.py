@@ -183,6 +183,14 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return out.reshape(n1, n2, n3, order="F")
 
 
+def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=0):
+    n1, n2 = din.shape
+    d, a, m = _F(din), _F(dip), _F(mask)
+    out = np.zeros_like(d)
+    lib().pso_sint2d(_p(d), _p(a), _p(m), n1, n2, int(niter), int(ns), int(order), ctypes.c_float(eps), _p(out))
+    return out.reshape(n1, n2, order="F")
+
+
 def predict_adj(trace, sig, nw, forw, eps=1e-4):
     t = _F(trace).copy()
     s = _F(sig)

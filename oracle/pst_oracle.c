@@ -1130,34 +1130,30 @@ static void smoother3_apply(smoother3 *S, int adj, int add, float *trace, float 
     predictor_free(sb.P); free(sb.u); free(sb.w1); free(sb.t);
 }
 
-/* csint3d :2510-2640 */
-int pso_sint3d(const float *din, const float *dipi, const float *dipx, const float *mask,
-               int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, float eps,
-               float *out)
+/* ps_conjgrad (hasp0 = true, prec = NULL, L = known-data mask, eps = lam^2, tol = 10*FLT_EPSILON) as csint3d
+ * :2590-2600 and csint2d (soint2d_cfuns.c:2508-2520) run it; S is applied through `apply(S, adj, add, trace, smooth)` */
+typedef void (*shape_fn)(void *S, int adj, int add, float *trace, float *smooth);
+
+static void sint_cg(size_t n, const float *din, const float *mask, int niter, shape_fn apply, void *S, float *out)
 {
-    size_t n = (size_t)n1 * n2 * n3;
     unsigned char *known = (unsigned char *)malloc(n);
     float lam = 0.;
     for (size_t i = 0; i < n; i++) { if (mask[i] != 0.) { known[i] = 1; lam += 1.; } else known[i] = 0; }
     lam = sqrtf(lam / n);
-    smoother3 S = { n1, n2, n3, ns1, ns2, order1, order2, eps, dipi, falloc(n), falloc(n), falloc(n), falloc(n) };
-    for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
-        memcpy(S.xdipT + ((size_t)i2 * n3 + i3) * n1, dipx + ((size_t)i3 * n2 + i2) * n1, n1 * sizeof(float));
-    /* ps_conjgrad(NULL, mask, pwsmooth3, p = copy of data, x = mm, dat = mm, niter), hasp0 = true */
     const float ceps = lam * lam, tol = 10 * 1.19209290e-07F;
     float *p = falloc(n), *x = out, *r = falloc(n), *sp = falloc(n), *sx = falloc(n), *sr = falloc(n);
     float *gp = falloc(n), *gx = falloc(n), *gr = falloc(n);
     memcpy(p, din, n * sizeof(float));
     for (size_t i = 0; i < n; i++) r[i] = -din[i];
-    smoother3_apply(&S, 0, 0, p, x);                                   /* x = S p */
+    apply(S, 0, 0, p, x);                                              /* x = S p */
     for (size_t i = 0; i < n; i++) if (known[i]) r[i] += x[i];         /* r += L x */
     double gn, gnp = 0., alpha, beta, g0 = 0., dg;
     if (ddot(n, r, r) != 0.) {
         for (int iter = 0; iter < niter; iter++) {
             for (size_t i = 0; i < n; i++) { gp[i] = ceps * p[i]; gx[i] = -ceps * x[i]; }
             for (size_t i = 0; i < n; i++) if (known[i]) gx[i] += r[i];       /* L' r, add */
-            smoother3_apply(&S, 1, 1, gp, gx);                                 /* gp += S' gx */
-            smoother3_apply(&S, 0, 0, gp, gx);                                 /* gx  = S gp */
+            apply(S, 1, 1, gp, gx);                                            /* gp += S' gx */
+            apply(S, 0, 0, gp, gx);                                            /* gx  = S gp */
             for (size_t i = 0; i < n; i++) { gr[i] = 0.f; if (known[i]) gr[i] += gx[i]; }
             gn = ddot(n, gp, gp);
             if (iter == 0) {
@@ -1182,6 +1178,49 @@ int pso_sint3d(const float *din, const float *dipi, const float *dipx, const flo
         }
     }
     free(p); free(r); free(sp); free(sx); free(sr); free(gp); free(gx); free(gr); free(known);
+}
+
+static void smoother3_shape(void *S, int adj, int add, float *trace, float *smooth) { smoother3_apply((smoother3 *)S, adj, add, trace, smooth); }
+
+/* csint3d :2510-2640 */
+int pso_sint3d(const float *din, const float *dipi, const float *dipx, const float *mask,
+               int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, float eps,
+               float *out)
+{
+    size_t n = (size_t)n1 * n2 * n3;
+    smoother3 S = { n1, n2, n3, ns1, ns2, order1, order2, eps, dipi, falloc(n), falloc(n), falloc(n), falloc(n) };
+    for (int i3 = 0; i3 < n3; i3++) for (int i2 = 0; i2 < n2; i2++)
+        memcpy(S.xdipT + ((size_t)i2 * n3 + i3) * n1, dipx + ((size_t)i3 * n2 + i2) * n1, n1 * sizeof(float));
+    sint_cg(n, din, mask, niter, smoother3_shape, &S, out);
     free(S.xdipT); free(S.itmp); free(S.itmp2); free(S.xtmp);
+    return 0;
+}
+
+/* csint2d soint2d_cfuns.c:2421-2530 (§8f rank 3, oracle groundwork): the same shaping CG with the single 2-D plane-wave
+ * smoother as S (pwsmooth_set once, pwsmooth_lop forward / adjoint) */
+typedef struct { smoother2 sm; const float *dip; } shape2;
+static void smoother2_shape(void *Sv, int adj, int add, float *trace, float *smooth)
+{
+    shape2 *S = (shape2 *)Sv;
+    if (adj) smoother2_adj(&S->sm, S->dip, add, trace, smooth);
+    else {
+        size_t n12 = (size_t)S->sm.n1 * S->sm.n2;
+        if (add) {
+            float *tmp = falloc(n12);
+            smoother2_fwd(&S->sm, S->dip, trace, tmp);
+            for (size_t i = 0; i < n12; i++) smooth[i] += tmp[i];
+            free(tmp);
+        } else smoother2_fwd(&S->sm, S->dip, trace, smooth);
+    }
+}
+
+int pso_sint2d(const float *din, const float *dip, const float *mask, int n1, int n2, int niter, int ns, int order,
+               float eps, float *out)
+{
+    size_t n12 = (size_t)n1 * n2;
+    shape2 S = { { predictor_new(n1, order, eps * eps), n1, n2, ns, falloc(n12 * (2 * ns + 1)), falloc(n12), falloc(n12) }, dip };
+    smoother2_set(&S.sm, dip);
+    sint_cg(n12, din, mask, niter, smoother2_shape, &S, out);
+    predictor_free(S.sm.P); free(S.sm.u); free(S.sm.w1); free(S.sm.t);
     return 0;
 }

@@ -87,6 +87,9 @@ int pso_sint3d(const float *din, const float *dipi, const float *dipx, const flo
 /* csomean2d with adj = 1: sof_cfuns.c:1503-1508 (pwsmooth_lop(adj) :1064-1100, pwspray_lop(adj) :948-1031) */
 int pso_somean2d_adj(const float *din, const float *dip, int n1, int n2, int n3, int ns, int order,
                      float eps, float *out);
+/* csint2d soint2d_cfuns.c:2421-2530 (oracle groundwork, no GPU counterpart yet) */
+int pso_sint2d(const float *din, const float *dip, const float *mask, int n1, int n2, int niter, int ns, int order,
+               float eps, float *out);
 /* one adjoint prediction step in place (unit-test hook): predict_step(adj=true) :1777-1804 */
 void pso_predict_adj(int n1, int nw, float eps, int forw, float *trace, const float *sig);
 

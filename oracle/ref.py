@@ -149,6 +149,14 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return d.reshape(n1, n2, n3, order="F")
 
 
+def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=0):
+    """reference pyseistr/sint.py:61-94 (csint2d, soint2d_cfuns.c:2437); needs the optional soint2dcfun module."""
+    n1, n2 = din.shape
+    with quiet():
+        d = module("soint2dcfun").csint2d(_F(din), _F(dip), _F(mask), n1, n2, niter, ns, order, verb, eps)
+    return d.reshape(n1, n2, order="F")
+
+
 def smoothc(x, rect, adj=0, repeat=1, diff=(0, 0, 0), box=(0, 0, 0)):
     """reference pyseistr/smooth.py:115-183 via dipcfun.smoothcf (dip_cfuns.c:2006-2123);
     adj=0 selects ps_smooth2, the kernel dip3d uses (the reference wrapper's own default is adj=1)."""

@@ -181,3 +181,21 @@ def test_dot_association_probe_is_inert_on_small_cases(port):
     finally:
         port.set_dot_mode(0)
     assert np.array_equal(di, g["dipi"]) and np.array_equal(dx, g["dipx"])
+
+
+def test_port_sint2d_matches_compiled_reference(port):
+    """csint2d: oracle groundwork for the next round, pinned to the compiled reference."""
+    ref = _ref_or_skip()
+    try:
+        ref.module("soint2dcfun")
+    except ImportError:
+        pytest.skip("oracle/_ref/soint2dcfun not built")
+    d = np.asarray(synth.cube(48, 24, 1, seed=3, noise=0.0)).reshape(48, 24)
+    p2 = port.dip2dc(d, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep = np.random.default_rng(5).random(24) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    for ns, order, niter in ((1, 1, 5), (2, 2, 6)):
+        a = port.sint2dc(d * mask, mask, p2, niter=niter, ns=ns, order=order)
+        b = ref.sint2dc(d * mask, mask, p2, niter=niter, ns=ns, order=order)
+        assert np.array_equal(a, b)
