@@ -183,6 +183,13 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return out.reshape(n1, n2, n3, order="F")
 
 
+def soint2dc(din, mask, dip, order=1, niter=100, njs=(1, 1), hasmask=1):
+    """csoint2d default path = csoint3d on an (n1, n2, 1) volume (allpass21_lop is the inline half of allpass3_lop)."""
+    n1, n2 = din.shape
+    r3 = lambda a: np.float32(a).reshape(n1, n2, 1)
+    return soint3dc(r3(din), r3(mask), r3(dip), r3(dip), order=order, niter=niter, njs=njs, hasmask=hasmask).reshape(n1, n2)
+
+
 def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=0):
     n1, n2 = din.shape
     d, a, m = _F(din), _F(dip), _F(mask)

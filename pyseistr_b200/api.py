@@ -177,6 +177,24 @@ def soint3dc(din, mask, dipi, dipx, order=1, niter=100, njs=[1, 1], drift=0, see
     return out.reshape(n1, n2, n3, order="F")
 
 
+def soint2dc(din, mask, dip, order=1, niter=100, njs=[1, 1], drift=0, hasmask=1, twoplane=0, prec=0, verb=1, ctx=None):
+    """2-D structure-oriented interpolation (reference pyseistr/soint2d.py:92-141 -> csoint2d, soint2d_cfuns.c:2260).
+    The default path of csoint2d (one slope field, no preconditioner: ps_solver on allpass21_lop :296-336) is the
+    inline half of allpass3_lop, and is bit-identical to csoint3d on an (n1, n2, 1) volume -- checked on the compiled
+    reference by the CPU test suite -- so it runs through pst_soint3d.  twoplane / prec / drift raise."""
+    if twoplane or prec or drift:
+        raise NotImplementedError("soint2dc on GPU: twoplane=0, prec=0, drift=0 only")
+    din = np.asarray(din)
+    if din.ndim != 2:
+        raise ValueError("soint2dc expects a 2-D panel")
+    n1, n2 = din.shape
+    slope = np.float32(dip).reshape(n1, n2, 1)
+    m3 = np.float32(mask).reshape(n1, n2, 1) if mask is not None else None
+    out = soint3dc(din.reshape(n1, n2, 1), m3, slope, slope, order=order, niter=niter, njs=njs, drift=0, hasmask=hasmask,
+                   var=0, verb=verb, ctx=ctx)
+    return out.reshape(n1, n2)
+
+
 def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, order2=1, verb=1, ctx=None):
     """3-D structure-oriented interpolation by shaping-regularised CG, the plane-wave smoother
     (inline then xline, radii ns1/ns2, PWD orders order1/order2) being the shaping operator

@@ -421,3 +421,19 @@ def test_pipeline_properties_at_scale(ctx):
     de = synth.erratic(d, ntraces=40)
     f = ps.somf3dc(de, di, dx, 2, 2, 0.01, 2, verb=0, ctx=ctx)
     assert np.linalg.norm(f - d) < 0.7 * np.linalg.norm(de - d)
+
+
+# ------------------------------------------------------------------ added last in round 1 (kept at the end of the file)
+def test_soint2d_default_path(ctx, port):
+    """soint2dc (one slope field, no preconditioner) runs through pst_soint3d on an (n1, n2, 1) volume; the equivalence
+    csoint2d == csoint3d(n3 = 1) is pinned on the compiled reference in tests/test_oracle.py."""
+    import pyseistr_b200 as ps
+    d = np.asarray(synth.cube(96, 40, 1, seed=95, noise=0.0)).reshape(96, 40)
+    p2 = port.dip2dc(d, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep = np.random.default_rng(96).random(40) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    got = ps.soint2dc(d * mask, mask, p2, order=2, niter=15, verb=0, ctx=ctx)
+    want = port.soint2dc(d * mask, mask, p2, order=2, niter=15)
+    assert got.shape == (96, 40)
+    assert rel_l2(got, want) <= TOL, rel_l2(got, want)

@@ -28,6 +28,8 @@ def test_wrappers_validate_before_touching_the_gpu():
         ps.dip2dc(np.zeros((8, 8, 2), np.float32))
     with pytest.raises(ValueError):
         ps.smoothc(np.zeros((8, 8, 2), np.float32), rect=[3, 3, 1], repeat=0)
+    with pytest.raises(NotImplementedError):
+        ps.soint2dc(np.zeros((8, 8), np.float32), np.ones((8, 8)), np.zeros((8, 8)), prec=1)
 
 
 def test_public_names_match_reference_entry_points():
@@ -49,6 +51,7 @@ def test_signatures_match_reference_wrappers():
         "somf2dc": "(dn, dip, ns, order, eps, option=1, verb=1, ctx=None)",
         "somean2dc": "(dn, dip, ns, order, eps, adj=0, verb=1, ctx=None)",
         "soint3dc": "(din, mask, dipi, dipx, order=1, niter=100, njs=[1, 1], drift=0, seed=202223, hasmask=1, var=0, verb=1, ctx=None)",
+        "soint2dc": "(din, mask, dip, order=1, niter=100, njs=[1, 1], drift=0, hasmask=1, twoplane=0, prec=0, verb=1, ctx=None)",
         "sint3dc": "(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, order2=1, verb=1, ctx=None)",
         "smoothc": "(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=1, ctx=None)",
     }

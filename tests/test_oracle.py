@@ -199,3 +199,21 @@ def test_port_sint2d_matches_compiled_reference(port):
         a = port.sint2dc(d * mask, mask, p2, niter=niter, ns=ns, order=order)
         b = ref.sint2dc(d * mask, mask, p2, niter=niter, ns=ns, order=order)
         assert np.array_equal(a, b)
+
+
+def test_port_soint2d_default_path_is_soint3d_with_one_plane(port):
+    """csoint2d (twoplane=0, prec=0) == csoint3d on (n1, n2, 1), bit for bit, on the compiled reference."""
+    ref = _ref_or_skip()
+    try:
+        ref.module("soint2dcfun")
+    except ImportError:
+        pytest.skip("oracle/_ref/soint2dcfun not built")
+    d = np.asarray(synth.cube(48, 24, 1, seed=3, noise=0.0)).reshape(48, 24)
+    p2 = port.dip2dc(d, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep = np.random.default_rng(5).random(24) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    for order, niter, njs, hasmask in ((1, 10, (1, 1), 1), (2, 8, (2, 1), 1), (1, 9, (1, 1), 0)):
+        a = ref.soint2dc(d * mask, mask, p2, order=order, niter=niter, njs=njs, hasmask=hasmask)
+        b = port.soint2dc(d * mask, mask, p2, order=order, niter=niter, njs=njs, hasmask=hasmask)
+        assert np.array_equal(a, b)
