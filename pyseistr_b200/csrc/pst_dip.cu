@@ -11,6 +11,7 @@
 // reductions here, sequential sums there) may differ in the last bits of a double.
 #include "pst_common.cuh"
 #include "pst_tri_stream.cuh"
+#include "pst_tri_rc.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1735,6 +1736,16 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     }
     if (has_epi && epi->stream_only) { epi = nullptr; }
     const bool has_epi2 = epi && epi->kind != EPI_NONE;
+    // experiment (off by default): the checkpoint + recompute smoother, pst_tri_rc.cu.  PST_TRI_RC=1: strided axes,
+    // =2: every axis; PST_TRI_RC_BLOCK=16|32: block length
+    static const int rc_mode = []() { const char *e = getenv("PST_TRI_RC"); return e ? atoi(e) : 0; }();
+    static const int rc_block = []() { const char *e = getenv("PST_TRI_RC_BLOCK"); return e ? atoi(e) : 32; }();
+    if (rc_mode > 0 && !has_epi2 && (axis != 0 || rc_mode >= 2) && pst_tri_rc_ok(axis, g.n1, g.n2, g.n3, nb, rc_block)) {
+        int rc = 0;
+        PST_LAUNCHB(c, cls, 8.0 * (double)g.n, rc = pst_tri_rc_launch(c->stream, axis, src, dst, g.n1, g.n2, g.n3, nb, rc_block));
+        if (rc == 0) return PST_OK;
+        if (rc != -1) { pst_set_error("pst_tri_rc_launch failed (%d)", rc); return PST_ECUDA; }
+    }
     if (stream_ok && !has_epi2) {
         int rc = 0;
         PST_LAUNCHB(c, cls, 8.0 * (double)g.n,

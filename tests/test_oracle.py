@@ -217,3 +217,24 @@ def test_port_soint2d_default_path_is_soint3d_with_one_plane(port):
         a = ref.soint2dc(d * mask, mask, p2, order=order, niter=niter, njs=njs, hasmask=hasmask)
         b = port.soint2dc(d * mask, mask, p2, order=order, niter=niter, njs=njs, hasmask=hasmask)
         assert np.array_equal(a, b)
+
+
+def test_ref_sint2d_is_sint3d_with_one_plane():
+    """Groundwork for a GPU sint2dc: csint2d == csint3d on (n1, n2, 1) with ns2 = 0 or 1, bit for bit (compiled reference)."""
+    ref = _ref_or_skip()
+    try:
+        ref.module("soint2dcfun")
+    except ImportError:
+        pytest.skip("oracle/_ref/soint2dcfun not built")
+    d = np.asarray(synth.cube(48, 24, 1, seed=3, noise=0.0)).reshape(48, 24)
+    p2 = ref.dip2dc(d, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep = np.random.default_rng(5).random(24) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    r3 = lambda a: np.float32(a).reshape(48, 24, 1)
+    for niter, ns, order in ((5, 1, 1), (4, 2, 2)):
+        a = ref.sint2dc(d * mask, mask, p2, niter=niter, eps=0.01, ns=ns, order=order)
+        for ns2 in (0, 1):
+            b = ref.sint3dc(r3(d * mask), r3(mask), r3(p2), r3(np.zeros_like(p2)), niter=niter, eps=0.01, ns1=ns, ns2=ns2,
+                            order1=order, order2=order).reshape(48, 24)
+            assert np.array_equal(a, b)

@@ -1,0 +1,77 @@
+"""CPU suite: the checkpoint + recompute smoother core (pyseistr_b200/csrc/pst_tri_rc_core.h) is the per-line code of
+the CUDA kernels in pst_tri_rc.cu.  It is compiled for the host here (tests/native/tri_rc_host.cpp, no FMA
+contraction, like the library) and must reproduce the oracle's ps_smooth2 bit for bit on every axis, radius, block
+length, ragged length and in place."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("tri_rc") / "tri_rc_host.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "pyseistr_b200", "csrc"),
+                    "-o", so, os.path.join(ROOT, "tests", "native", "tri_rc_host.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.tri_rc_host.restype = ctypes.c_int
+    lib.tri_rc_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
+    return lib
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port as p
+    p.build()
+    return p
+
+
+def _run(lib, x, axis, nb, rc, inplace):
+    n1, n2, n3 = x.shape
+    src = np.asfortranarray(x, dtype=np.float32).copy(order="F")
+    dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
+    rcode = lib.tri_rc_host(src.ctypes.data, dst.ctypes.data, n1, n2, n3, axis, nb, rc)
+    assert rcode == 0, rcode
+    return dst
+
+
+@pytest.mark.parametrize("shape", [(70, 37, 9), (33, 64, 40), (12, 5, 131), (32, 32, 32), (100, 11, 64)])
+def test_core_matches_oracle_every_axis(host, port, shape):
+    rng = np.random.default_rng(sum(shape))
+    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
+    for axis in range(3):
+        nx = shape[axis]
+        for nb in (2, 3, 4, 5, 6, 7, 8, 10, 16):
+            if nb > nx:
+                continue
+            rect = [1, 1, 1]
+            rect[axis] = nb
+            want = port.smooth3(x, rect)
+            for rc in (16, 32):
+                if rc == 16 and nb > 8:
+                    continue
+                for inplace in (False, True):
+                    got = _run(host, x, axis, nb, rc, inplace)
+                    assert np.array_equal(got.view(np.uint32), np.asfortranarray(want).view(np.uint32)), (shape, axis, nb, rc, inplace)
+
+
+def test_core_edge_lengths(host, port):
+    """nx == nb, nx just above / below a block multiple, lines of signed zeros."""
+    rng = np.random.default_rng(3)
+    for nx in (5, 6, 9, 10, 11, 22, 27, 31, 32, 33, 54, 59, 63, 64, 65, 96):
+        x = np.asfortranarray(rng.standard_normal((nx, 3, 2)).astype(np.float32))
+        x[:, 1, 0] = -0.0
+        x[::2, 2, 1] = 0.0
+        for nb in (2, 5, 8, 10, 16):
+            if nb > nx:
+                continue
+            want = np.asfortranarray(port.smooth3(x, [nb, 1, 1]))
+            for rc in (16, 32):
+                if rc == 16 and nb > 8:
+                    continue
+                got = _run(host, x, 0, nb, rc, True)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (nx, nb, rc)
