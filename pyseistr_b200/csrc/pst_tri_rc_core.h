@@ -28,6 +28,13 @@
 #define PST_RC_HD inline
 #endif
 
+// full unrolling matters on the device only (register arrays); host compilers do not know the pragma
+#ifdef __CUDA_ARCH__
+#define PST_RC_UNROLL _Pragma("unroll")
+#else
+#define PST_RC_UNROLL
+#endif
+
 namespace tri_rc {
 
 // RC steps of t_k and the forward sum.  xhi = x block b (x_k for the block's k), xlo = x block b-1;
@@ -36,7 +43,7 @@ template <int NB, int RC, bool KEEP>
 PST_RC_HD void fwd_block(const float *xlo, const float *xhi, float wm, float w2, float &F, float *Fb)
 {
     static_assert(2 * NB <= RC, "block shorter than the stencil");
-#pragma unroll
+PST_RC_UNROLL
     for (int j = 0; j < RC; j++) {
         const float xa = xhi[j];
         const float xb = (j >= NB) ? xhi[j - NB] : xlo[RC + j - NB];
@@ -56,7 +63,7 @@ PST_RC_HD void process_line(IO &io, int nx, float wm, float w2, float *ck, int c
     const int nblk = (np + RC - 1) / RC;
     float xlo[RC], xhi[RC];
     // ---- pass A: forward sum, keep F before every block
-#pragma unroll
+PST_RC_UNROLL
     for (int j = 0; j < RC; j++) xlo[j] = 0.f;
     io.prefetch(0);
     io.take(xhi);
@@ -65,18 +72,18 @@ PST_RC_HD void process_line(IO &io, int nx, float wm, float w2, float *ck, int c
         io.prefetch(b + 1);
         ck[(long)b * cks] = F;
         fwd_block<NB, RC, false>(xlo, xhi, wm, w2, F, nullptr);
-#pragma unroll
+PST_RC_UNROLL
         for (int j = 0; j < RC; j++) xlo[j] = xhi[j];
         io.take(xhi);
     }
     // ---- pass B: blocks downwards.  xlo holds x block nblk-1 now.
-#pragma unroll
+PST_RC_UNROLL
     for (int j = 0; j < RC; j++) xhi[j] = xlo[j];
     io.prefetch(nblk - 2);
     io.take(xlo);
     float Bs = 0.f;
     float top[NB], mid[NB];
-#pragma unroll
+PST_RC_UNROLL
     for (int j = 0; j < NB; j++) { top[j] = 0.f; mid[j] = 0.f; }
     for (int b = nblk - 1; b >= 0; b--) {
         // x block b-2 is requested before this block's outputs are stored and x block b-1 is already here:
@@ -87,10 +94,10 @@ PST_RC_HD void process_line(IO &io, int nx, float wm, float w2, float *ck, int c
         fwd_block<NB, RC, true>(xlo, xhi, wm, w2, Fs, Fb);
         const int k0 = b * RC;
         if (k0 + RC <= np) {
-#pragma unroll
+PST_RC_UNROLL
             for (int j = RC - 1; j >= 0; j--) { Bs = Bs + Fb[j]; Fb[j] = Bs; }
         } else {
-#pragma unroll
+PST_RC_UNROLL
             for (int j = RC - 1; j >= 0; j--) { if (k0 + j < np) Bs = Bs + Fb[j]; Fb[j] = Bs; }
         }
         if (k0 >= 2 * NB && k0 + RC <= nx) {
@@ -98,7 +105,7 @@ PST_RC_HD void process_line(IO &io, int nx, float wm, float w2, float *ck, int c
         } else {
             // fold2 (:458-484): B of the top nb samples is added to the last nb outputs (right reflection, first),
             // B of the bottom nb samples to the first nb outputs (left reflection, second)
-#pragma unroll
+PST_RC_UNROLL
             for (int j = RC - 1; j >= 0; j--) {
                 const int k = k0 + j;
                 if (k < np) {
@@ -114,11 +121,11 @@ PST_RC_HD void process_line(IO &io, int nx, float wm, float w2, float *ck, int c
             const int jhi = nx + NB - k0 < RC ? nx + NB - k0 : RC;
             if (jhi > jlo) io.store_block(Fb, k0 - NB, jlo, jhi);
             if (k0 == 0) {
-#pragma unroll
+PST_RC_UNROLL
                 for (int j = NB - 1; j >= 0; j--) io.store_one(NB - 1 - j, mid[NB - 1 - j] + Fb[j]);
             }
         }
-#pragma unroll
+PST_RC_UNROLL
         for (int j = 0; j < RC; j++) xhi[j] = xlo[j];
         io.take(xlo);
     }
@@ -133,10 +140,10 @@ struct StridedIO {
     {
         if (m >= 0 && (m + 1) * RC <= nx) {                     // whole block inside the line: a running pointer
             const float *p = s + (long)m * RC * st;
-#pragma unroll
+PST_RC_UNROLL
             for (int j = 0; j < RC; j++) { pre[j] = *p; p += st; }
         } else {
-#pragma unroll
+PST_RC_UNROLL
             for (int j = 0; j < RC; j++) {
                 const int i = m * RC + j;
                 pre[j] = (m >= 0 && i < nx) ? s[(long)i * st] : 0.f;
@@ -145,17 +152,17 @@ struct StridedIO {
     }
     PST_RC_HD void take(float *x)
     {
-#pragma unroll
+PST_RC_UNROLL
         for (int j = 0; j < RC; j++) x[j] = pre[j];
     }
     PST_RC_HD void store_block(const float *v, int i0, int jlo, int jhi)
     {
         if (jlo == 0 && jhi == RC) {
             float *p = d + (long)i0 * st;
-#pragma unroll
+PST_RC_UNROLL
             for (int j = 0; j < RC; j++) { *p = v[j]; p += st; }
         } else {
-#pragma unroll
+PST_RC_UNROLL
             for (int j = 0; j < RC; j++)
                 if (j >= jlo && j < jhi) d[(long)(i0 + j) * st] = v[j];
         }

@@ -24,6 +24,19 @@ def host(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    """The CUDA kernels' own source run on the host: one thread per CUDA thread, a barrier per warp."""
+    so = str(tmp_path_factory.mktemp("tri_rc_emul") / "tri_rc_emul.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I",
+                    os.path.join(ROOT, "pyseistr_b200", "csrc"), "-o", so,
+                    os.path.join(ROOT, "tests", "native", "tri_rc_emul.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.tri_rc_emul.restype = ctypes.c_int
+    lib.tri_rc_emul.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
+    return lib
+
+
+@pytest.fixture(scope="module")
 def port():
     from oracle import port as p
     p.build()
@@ -75,3 +88,24 @@ def test_core_edge_lengths(host, port):
                     continue
                 got = _run(host, x, 0, nb, rc, True)
                 assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (nx, nb, rc)
+
+
+@pytest.mark.parametrize("shape", [(70, 37, 9), (12, 5, 131), (33, 64, 5)])
+def test_kernels_emulated_on_host_match_oracle(emul, port, shape):
+    """Strided and contiguous kernels with the launcher's own geometry (partial warps, ragged blocks, in place)."""
+    rng = np.random.default_rng(sum(shape) + 1)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
+    n1, n2, n3 = shape
+    for axis in range(3):
+        for nb in (2, 5, 10, 16):
+            if nb > shape[axis]:
+                continue
+            rect = [1, 1, 1]
+            rect[axis] = nb
+            want = np.asfortranarray(port.smooth3(x, rect))
+            for rc in (16, 32):
+                inplace = (nb + rc // 16 + axis) % 2 == 0
+                src = x.copy(order="F")
+                dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
+                assert emul.tri_rc_emul(src.ctypes.data, dst.ctypes.data, n1, n2, n3, axis, nb, rc) == 0
+                assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), (shape, axis, nb, rc, inplace)
