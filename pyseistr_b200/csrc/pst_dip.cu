@@ -12,6 +12,7 @@
 #include "pst_common.cuh"
 #include "pst_tri_stream.cuh"
 #include "pst_tri_rc.cuh"
+#include "pst_tri_sys.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1736,6 +1737,14 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     }
     if (has_epi && epi->stream_only) { epi = nullptr; }
     const bool has_epi2 = epi && epi->kind != EPI_NONE;
+    // experiment (off by default): the systolic register-resident smoother of the strided axes, pst_tri_sys.cu
+    static const bool sys_on = []() { const char *e = getenv("PST_TRI_SYS"); return e && e[0] == '1'; }();
+    if (sys_on && axis != 0 && !has_epi2 && pst_tri_sys_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
+        int rc = 0;
+        PST_LAUNCHB(c, cls, 8.0 * (double)g.n, rc = pst_tri_sys_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb, nullptr));
+        if (rc == 0) return PST_OK;
+        if (rc == -5) { pst_set_error("pst_tri_sys_launch: kernel launch failed"); return PST_ECUDA; }
+    }
     // experiment (off by default): the checkpoint + recompute smoother, pst_tri_rc.cu.  PST_TRI_RC=1: strided axes,
     // =2: every axis; PST_TRI_RC_BLOCK=16|32: block length
     static const int rc_mode = []() { const char *e = getenv("PST_TRI_RC"); return e ? atoi(e) : 0; }();

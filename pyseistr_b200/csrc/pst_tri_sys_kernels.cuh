@@ -1,0 +1,240 @@
+// Device code of the SYSTOLIC triangle smoother (experimental, see pst_tri_sys.cu): ps_smooth2 (reference
+// dip_cfuns.c:458-484,508-529,564-580,616-625) of the lines of a strided axis, bit for bit:
+//   t_k = ((-wt x_k) + 2wt x_{k-nb}) + (-wt x_{k-2nb})          k in [0, L),  L = nx + 2nb
+//   F_k = F_{k-1} + t_k        forward running sum  (float, sequential)
+//   B_k = B_{k+1} + F_k        backward running sum (float, sequential)
+//   y_i = (B_{i+nb} + B_{nb+nx+(nx-1-i)}[i >= nx-nb]) + B_{nb-1-i}[i < nb]
+// A tile is 32 whole lines (lane = line, a warp row = 128 contiguous bytes).  The padded line (D dummy steps lead
+// it, so that its last step is the line's last) is cut into nseg <= 8 SEGMENTS of SEG steps; each segment of a tile
+// belongs to one chain warp, which keeps the segment's t -> F -> B values IN REGISTERS (R[SEG], statically indexed:
+// every loop over the segment is fully unrolled).  The forward sum sweeps the segments upwards, the backward sum
+// downwards; a warp receives the running sum of the neighbouring segment through a 32-float mailbox in shared memory
+// (mbarrier, one phase per tile), runs SEG dependent FADDs, and passes it on.  The ORIENTATION alternates from tile
+// to tile (even tiles: warp w owns segment w; odd tiles: segment nseg-1-w), so the forward sweep of tile p+1 follows
+// the backward sweep of tile p warp by warp: two sweeps are always in flight on different warps, and everything that
+// is not the dependent chain (building t from x, the fold, the stores) is done by warps that would otherwise wait.
+// One loader thread streams x with TMA, one box per segment (SEG + 2nb rows: every segment re-reads its 2nb halo
+// rows, from L2), zero fill outside the volume = "tap skipped".  HBM traffic is the compulsory 8 B per sample, F never
+// touches shared memory, and no warp is special: against pst_tri_stream.cu (one forward and one backward chain warp
+// per SM, F through shared memory) the dependent chain gets 8 warps instead of 2.
+//
+// This header holds only device code over a handful of primitives (mbarrier, TMA, warp / CTA barriers) so that
+// tests/native/tri_sys_emul.cpp can run the kernel on the host, thread for thread, and check protocol and indexing
+// without a GPU.
+#pragma once
+
+namespace tri_sys_k {
+
+constexpr int NCW = 8;                      // chain warps = maximum number of segments
+constexpr int NTHREADS = (NCW + 1) * 32;    // + the loader warp
+
+struct Args {
+    float *dst;
+    long d, sb;            // element stride along the line, batch (slab) stride
+    int na;                // extent of the lane index
+    int nx;
+    int tilesA;            // tiles along na
+    long ntiles;
+    int nseg, L, D;        // segments in use, nx + 2nb, leading dummy steps (nseg * SEG - L)
+    float wm, w2;
+    unsigned *err;
+};
+
+// shared-memory layout (floats, then barriers)
+template <int NB, int SEG>
+struct Layout {
+    static constexpr int XROWS = SEG + 2 * NB;                  // rows of a segment's x box
+    static constexpr size_t xs = 0;                             // [NCW][XROWS][32]
+    static constexpr size_t scratch = xs + (size_t)NCW * XROWS * 32;   // [SEG][32]  bottom zone of segment 0
+    static constexpr size_t mf = scratch + (size_t)SEG * 32;    // [NCW][32] forward carries INTO segment s
+    static constexpr size_t mb = mf + NCW * 32;                 // [NCW][32] backward carries INTO segment s
+    static constexpr size_t floats = mb + NCW * 32;
+    static constexpr size_t bytes = floats * 4 + 5 * NCW * sizeof(mbar_t);
+};
+
+PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
+{
+    float v = wm * xa;          // 0 + wm*x_k: the sign of a zero cannot reach a non-zero sum (F starts at +0)
+    v = v + w2 * xb;
+    v = v + wm * xc;
+    return v;
+}
+
+template <int NB, int SEG>
+PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_TMAP_PARAM tmap, const Args A)
+{
+    static_assert(2 * NB <= SEG && SEG % 4 == 0, "segment shorter than the fold zones");
+    typedef Layout<NB, SEG> LY;
+    PST_SYS_SMEM(smem_f);
+    float *const Xs = smem_f + LY::xs;
+    float *const Sc = smem_f + LY::scratch;
+    float *const Mf = smem_f + LY::mf;
+    float *const Mb = smem_f + LY::mb;
+    mbar_t *const bars = reinterpret_cast<mbar_t *>(smem_f + LY::floats);
+    // full_x / empty_x / cf complete one phase per tile and every phase of tile p is complete before any warp starts
+    // tile p+1 (a warp leaves tile p only after its backward carry, i.e. after the whole forward sweep).  The backward
+    // carries are different: the warp that finishes tile p first waits for its backward carry of tile p+1 while the
+    // backward sweep of tile p is still running, so a single barrier per segment would be waited on two phases ahead
+    // (a parity wait then falls through: found by the host emulation).  cb is therefore doubled by tile parity, which
+    // makes the waiter of each barrier always the same warp (same orientation), hence sequential.
+    mbar_t *const full_x = bars, *const empty_x = bars + NCW, *const cf = bars + 2 * NCW, *const cb2 = bars + 3 * NCW;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 5 * NCW; i++) mbar_init(bars + i, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long m = (A.ntiles - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x;   // tiles of this CTA
+    const int nseg = A.nseg, D = A.D;
+    if (m <= 0) return;
+
+    if (warp == NCW) {
+        // ================================ loader ================================
+        if (lane != 0) return;
+        const unsigned xbytes = (unsigned)(LY::XROWS * 32 * 4);
+        for (long p = 0; p < m; p++) {
+            const long tile = (long)blockIdx.x + p * (long)gridDim.x;
+            const long b = tile / A.tilesA;
+            const int c0 = (int)(tile - b * A.tilesA) * 32;
+            for (int s = 0; s < nseg; s++) {
+                mbar_wait(empty_x + s, (unsigned)((p & 1) ^ 1), A.err);
+                mbar_arrive_expect_tx(full_x + s, xbytes);
+                // box row r of segment s  <->  x sample s*SEG - D - 2nb + r
+                tma_load_3d(Xs + (size_t)s * LY::XROWS * 32, &tmap, c0, s * SEG - D - 2 * NB, (int)b, full_x + s);
+            }
+        }
+        return;
+    }
+    if (warp >= nseg) return;
+
+    // ================================ chain warps ================================
+    float R[SEG];
+    for (long p = 0; p < m; p++) {
+        const unsigned par = (unsigned)(p & 1);
+        const int s = par ? nseg - 1 - warp : warp;              // orientation alternates
+        mbar_t *const cb = cb2 + par * NCW;
+        const unsigned par2 = (unsigned)((p >> 1) & 1);
+        const long tile = (long)blockIdx.x + p * (long)gridDim.x;
+        const long b = tile / A.tilesA;
+        const int c0 = (int)(tile - b * A.tilesA) * 32;
+        const bool live = c0 + lane < A.na;
+        // ---- t of the segment from its x box (every x row is read once: the window lives in registers)
+        mbar_wait(full_x + s, par, A.err);
+        {
+            const float *X = Xs + (size_t)s * LY::XROWS * 32 + lane;
+            float xr[LY::XROWS];
+            PST_SYS_UNROLL
+            for (int r = 0; r < LY::XROWS; r++) xr[r] = X[r * 32];
+            PST_SYS_UNROLL
+            for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_x + s);
+        // ---- forward sum over the segment
+        float F = 0.f;
+        if (s > 0) { mbar_wait(cf + s, par, A.err); F = Mf[s * 32 + lane]; }
+        PST_SYS_UNROLL
+        for (int j = 0; j < SEG; j++) { F = F + R[j]; R[j] = F; }
+        if (s < nseg - 1) {
+            Mf[(s + 1) * 32 + lane] = F;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cf + s + 1);
+        }
+        // ---- backward sum over the segment
+        float B = 0.f;
+        if (s < nseg - 1) { mbar_wait(cb + s, par2, A.err); B = Mb[s * 32 + lane]; }
+        PST_SYS_UNROLL
+        for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; R[j] = B; }
+        if (s > 0) {
+            Mb[(s - 1) * 32 + lane] = B;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cb + s - 1);
+        }
+        // ---- fold2 and the stores.  Step j of segment s is k = s*SEG + j - D; y_i = B_{i+nb} goes to row i = k - nb.
+        float *const dcol = A.dst + b * A.sb + c0 + lane;
+        const long d = A.d;
+        if (s == nseg - 1) {
+            // last segment (k up to L-1): the top nb steps are the right reflections of the nb before them;
+            // both sit at fixed positions of this segment
+            PST_SYS_UNROLL
+            for (int r = 0; r < NB; r++) R[SEG - NB - 1 - r] = R[SEG - NB - 1 - r] + R[SEG - NB + r];
+            if (live) {
+                float *q = dcol + (long)(s * SEG - D - NB) * d;
+                PST_SYS_UNROLL
+                for (int j = 0; j < SEG - NB; j++) { *q = R[j]; q += d; }
+            }
+        } else if (s > 0) {
+            if (live) {
+                float *q = dcol + (long)(s * SEG - D - NB) * d;
+                PST_SYS_UNROLL
+                for (int j = 0; j < SEG; j++) { *q = R[j]; q += d; }
+            }
+        } else {
+            // first segment: D dummy steps, then k in [0, nb) (left reflections), k in [nb, 2nb) (the outputs they
+            // complete), then plain outputs.  D is a run-time value: the two zones go through shared memory.
+            const int zone = D + 2 * NB;                         // <= SEG (checked by the plan)
+            float *const sc = Sc + lane;
+            PST_SYS_UNROLL
+            for (int j = 0; j < SEG; j++)
+                if (j < zone) sc[j * 32] = R[j];
+            if (live) {
+                PST_SYS_UNROLL
+                for (int j = 2 * NB; j < SEG; j++)
+                    if (j >= zone) dcol[(long)(j - D - NB) * d] = R[j];
+                PST_SYS_UNROLL
+                for (int i = 0; i < NB; i++) dcol[(long)i * d] = sc[(D + NB + i) * 32] + sc[(D + NB - 1 - i) * 32];
+            }
+        }
+    }
+}
+
+// launch geometry, shared by pst_tri_sys_launch and the host emulation
+struct Plan {
+    bool ok;
+    int SEG, nseg, L, D, nx, nb;
+    long na, d, sb, nslab, ntiles;
+    int tilesA;
+    float wm, w2;
+};
+
+inline bool nb_built(int nb) { return (nb >= 2 && nb <= 8) || nb == 10; }
+
+inline Plan make_plan(int axis, int n1, int n2, int n3, int nb)
+{
+    Plan P{};
+    if (axis != 1 && axis != 2) return P;
+    P.nx = axis == 1 ? n2 : n3;
+    P.nb = nb;
+    if (!nb_built(nb) || P.nx < 2 * nb) return P;
+    if (n1 % 4 != 0) return P;                                   // TMA: global strides are multiples of 16 bytes
+    P.L = P.nx + 2 * nb;
+    P.SEG = P.L <= NCW * 68 ? 68 : 132;
+    if (P.L > NCW * P.SEG) return P;
+    P.nseg = (P.L + P.SEG - 1) / P.SEG;
+    P.D = P.nseg * P.SEG - P.L;
+    if (P.nseg < 2 || P.D + 2 * nb > P.SEG) return P;
+    P.na = axis == 1 ? n1 : (long)n1 * n2;
+    P.d = P.na;
+    P.sb = axis == 1 ? (long)n1 * n2 : 0;
+    P.nslab = axis == 1 ? n3 : 1;
+    if (P.na >= (1L << 31)) return P;
+    P.tilesA = (int)((P.na + 31) / 32);
+    P.ntiles = (long)P.tilesA * P.nslab;
+    const float wt = (float)(1.0 / ((double)nb * nb));          // ps_triangle_init dip_cfuns.c:421
+    P.wm = -wt;
+    P.w2 = (float)(2. * wt);
+    P.ok = true;
+    return P;
+}
+
+inline Args make_args(const Plan &P, float *dst, unsigned *err)
+{
+    Args A{};
+    A.dst = dst; A.d = P.d; A.sb = P.sb; A.na = (int)P.na; A.nx = P.nx; A.tilesA = P.tilesA; A.ntiles = P.ntiles;
+    A.nseg = P.nseg; A.L = P.L; A.D = P.D; A.wm = P.wm; A.w2 = P.w2; A.err = err;
+    return A;
+}
+
+}  // namespace tri_sys_k

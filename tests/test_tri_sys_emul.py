@@ -1,0 +1,81 @@
+"""CPU suite: the systolic smoother kernel (pyseistr_b200/csrc/pst_tri_sys_kernels.cuh) run on the host, thread for
+thread (tests/native/tri_sys_emul.cpp: mbarriers with the hardware's phase-parity semantics, TMA boxes with zero fill,
+one std::thread per CUDA thread), against the oracle.  Several tiles per CTA so that both orientations, the mailbox
+hand-offs and the loader's ring are exercised; one case runs with schedule fuzzing."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("tri_sys_emul") / "tri_sys_emul.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-I",
+                    os.path.join(ROOT, "pyseistr_b200", "csrc"), "-o", so,
+                    os.path.join(ROOT, "tests", "native", "tri_sys_emul.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.tri_sys_emul.restype = ctypes.c_int
+    lib.tri_sys_emul.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
+    lib.tri_sys_plan.restype = ctypes.c_int
+    lib.tri_sys_plan.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port as p
+    p.build()
+    return p
+
+
+CASES = [  # shape, axis, radius, emulated SM count
+    ((8, 150, 3), 1, 5, 2),
+    ((36, 3, 530), 2, 10, 1),        # 132-step segments, 110 leading dummy steps, 4 tiles on one CTA
+    ((100, 140, 7), 1, 8, 3),        # 28 tiles on 6 CTAs, partial tiles (100 = 3 * 32 + 4 lanes)
+    ((12, 9, 260), 2, 2, 1),
+    ((64, 1034, 2), 1, 5, 1),        # 8 segments of 132 (the 1024-sample case of the bench)
+    ((40, 300, 2), 1, 3, 1),
+]
+
+
+@pytest.mark.parametrize("shape,axis,nb,sm", CASES)
+def test_systolic_kernel_emulated_on_host_matches_oracle(emul, port, shape, axis, nb, sm):
+    plan = (ctypes.c_int * 4)()
+    assert emul.tri_sys_plan(*shape, axis, nb, plan) == 1
+    rng = np.random.default_rng(sum(shape) + nb)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
+    rect = [1, 1, 1]
+    rect[axis] = nb
+    want = np.asfortranarray(port.smooth3(x, rect))
+    for inplace in (False, True):
+        src = x.copy(order="F")
+        dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
+        assert emul.tri_sys_emul(src.ctypes.data, dst.ctypes.data, *shape, axis, nb, sm) == 0
+        assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), (shape, axis, nb, inplace, list(plan))
+
+
+def test_systolic_kernel_under_schedule_fuzzing(emul, port, monkeypatch):
+    monkeypatch.setenv("PST_EMUL_JITTER", "300")
+    shape, axis, nb = (100, 140, 5), 1, 5
+    rng = np.random.default_rng(77)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
+    want = np.asfortranarray(port.smooth3(x, [1, nb, 1]))
+    for rep in range(2):
+        dst = np.full_like(x, np.float32(7.0), order="F")
+        assert emul.tri_sys_emul(x.ctypes.data, dst.ctypes.data, *shape, axis, nb, 1) == 0
+        assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), rep
+
+
+def test_plan_refuses_what_the_kernel_cannot_do(emul):
+    plan = (ctypes.c_int * 4)()
+    assert emul.tri_sys_plan(64, 64, 64, 0, 5, plan) == 0          # contiguous axis: not this kernel
+    assert emul.tri_sys_plan(64, 40, 8, 1, 5, plan) == 0           # one segment only
+    assert emul.tri_sys_plan(62, 300, 8, 1, 5, plan) == 0          # n1 % 4 != 0 (TMA stride)
+    assert emul.tri_sys_plan(64, 2000, 8, 1, 5, plan) == 0         # line longer than 8 segments
+    assert emul.tri_sys_plan(1000, 1024, 1024, 1, 5, plan) == 1 and list(plan)[:3] == [132, 8, 22]
+    assert emul.tri_sys_plan(1000, 1024, 1024, 2, 5, plan) == 1
