@@ -1737,9 +1737,10 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     }
     if (has_epi && epi->stream_only) { epi = nullptr; }
     const bool has_epi2 = epi && epi->kind != EPI_NONE;
-    // experiment (off by default): the systolic register-resident smoother of the strided axes, pst_tri_sys.cu
-    static const bool sys_on = []() { const char *e = getenv("PST_TRI_SYS"); return e && e[0] == '1'; }();
-    if (sys_on && axis != 0 && !has_epi2 && pst_tri_sys_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
+    // experiment (off by default): the systolic register-resident smoother, pst_tri_sys.cu.  PST_TRI_SYS=1: every axis,
+    // =2: strided axes only
+    static const int sys_mode = []() { const char *e = getenv("PST_TRI_SYS"); return e ? atoi(e) : 0; }();
+    if (sys_mode > 0 && (axis != 0 || sys_mode == 1) && !has_epi2 && pst_tri_sys_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
         int rc = 0;
         PST_LAUNCHB(c, cls, 8.0 * (double)g.n, rc = pst_tri_sys_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb, nullptr));
         if (rc == 0) return PST_OK;

@@ -52,6 +52,11 @@ __device__ __forceinline__ void mbar_wait(mbar_t *b, unsigned parity, unsigned *
         if (clock64() - t0 > 4000000000LL) { if (err) *err = 1u; __trap(); }
     }
 }
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, int c0, int c1, mbar_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, int c0, int c1, int c2, mbar_t *bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -85,26 +90,30 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <int NB, int SEG>
+template <bool CONTIG, int NB, int SEG>
 int launch(cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
     static bool attr[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -4;
-    const size_t smem = Layout<NB, SEG>::bytes;
+    const size_t smem = Layout<CONTIG, NB, SEG>::bytes;
     if (!attr[dev]) {
-        if (cudaFuncSetAttribute(tri_sys_kernel<NB, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+        if (cudaFuncSetAttribute(tri_sys_kernel<CONTIG, NB, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
         attr[dev] = true;
     }
-    tri_sys_kernel<NB, SEG><<<grid, NTHREADS, smem, stream>>>(tm, A);
+    tri_sys_kernel<CONTIG, NB, SEG><<<grid, NTHREADS, smem, stream>>>(tm, A);
     return 0;
 }
 
 template <int NB>
-int launch_seg(int SEG, cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
+int launch_seg(bool contig, int SEG, cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
-    return SEG == 68 ? launch<NB, 68>(stream, grid, tm, A) : launch<NB, 132>(stream, grid, tm, A);
+    if (contig) return SEG == 68 ? launch<true, NB, 68>(stream, grid, tm, A) : launch<true, NB, 132>(stream, grid, tm, A);
+    return SEG == 68 ? launch<false, NB, 68>(stream, grid, tm, A) : launch<false, NB, 132>(stream, grid, tm, A);
 }
+
+template <int NB>
+int box_width(int SEG) { return SEG == 68 ? Layout<true, NB, 68>::XW : Layout<true, NB, 132>::XW; }
 
 }  // namespace
 
@@ -126,21 +135,36 @@ int pst_tri_sys_launch(cudaStream_t stream, int sm_count, int axis, const float 
     CUtensorMap tm;
     cuuint64_t gdim[3], gstr[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
-    if (axis == 1) { gdim[0] = (cuuint64_t)n1; gdim[1] = (cuuint64_t)n2; gdim[2] = (cuuint64_t)n3; }
-    else { gdim[0] = (cuuint64_t)n1 * n2; gdim[1] = (cuuint64_t)n3; gdim[2] = 1; }
-    gstr[0] = (cuuint64_t)P.d * 4;
-    gstr[1] = (cuuint64_t)(axis == 1 ? P.sb : P.d * (long)n3) * 4;
-    box[0] = 32; box[1] = (cuuint32_t)(P.SEG + 2 * nb); box[2] = 1;
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, gdim, gstr, box, estr,
+    int rank = 3;
+    if (axis == 0) {
+        rank = 2;
+        int xw = 0;
+        switch (nb) {
+#define SYS_CASE(N) case N: xw = box_width<N>(P.SEG); break;
+            SYS_CASE(2) SYS_CASE(3) SYS_CASE(4) SYS_CASE(5) SYS_CASE(6) SYS_CASE(7) SYS_CASE(8) SYS_CASE(10)
+#undef SYS_CASE
+            default: return -1;
+        }
+        gdim[0] = (cuuint64_t)n1; gdim[1] = (cuuint64_t)P.na;
+        gstr[0] = (cuuint64_t)n1 * 4;
+        box[0] = (cuuint32_t)xw; box[1] = 32;
+    } else {
+        if (axis == 1) { gdim[0] = (cuuint64_t)n1; gdim[1] = (cuuint64_t)n2; gdim[2] = (cuuint64_t)n3; }
+        else { gdim[0] = (cuuint64_t)n1 * n2; gdim[1] = (cuuint64_t)n3; gdim[2] = 1; }
+        gstr[0] = (cuuint64_t)P.d * 4;
+        gstr[1] = (cuuint64_t)(axis == 1 ? P.sb : P.d * (long)n3) * 4;
+        box[0] = 32; box[1] = (cuuint32_t)(P.SEG + 2 * nb); box[2] = 1;
+    }
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)src, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -3;
-    const int per_sm = P.SEG == 68 ? 2 : 1;
+    const int per_sm = (P.SEG == 68 && axis != 0) ? 2 : 1;
     long grid = (long)sm_count * per_sm;
     if (grid > P.ntiles) grid = P.ntiles;
     int rc = 0;
     switch (nb) {
-#define SYS_CASE(N) case N: rc = launch_seg<N>(P.SEG, stream, (unsigned)grid, tm, A); break;
+#define SYS_CASE(N) case N: rc = launch_seg<N>(axis == 0, P.SEG, stream, (unsigned)grid, tm, A); break;
         SYS_CASE(2) SYS_CASE(3) SYS_CASE(4) SYS_CASE(5) SYS_CASE(6) SYS_CASE(7) SYS_CASE(8) SYS_CASE(10)
 #undef SYS_CASE
         default: return -1;

@@ -41,15 +41,22 @@ struct Args {
 };
 
 // shared-memory layout (floats, then barriers)
-template <int NB, int SEG>
+template <bool CONTIG, int NB, int SEG>
 struct Layout {
-    static constexpr int XROWS = SEG + 2 * NB;                  // rows of a segment's x box
-    static constexpr size_t xs = 0;                             // [NCW][XROWS][32]
-    static constexpr size_t scratch = xs + (size_t)NCW * XROWS * 32;   // [SEG][32]  bottom zone of segment 0
+    static constexpr int XROWS = SEG + 2 * NB;                  // samples of a segment's x box along the line
+    // contiguous axis: the box is [32 lines][XW samples]; XW is a multiple of 4 (TMA) with XW/4 odd, so that
+    // "lane = line" 128-bit reads are conflict-free
+    static constexpr int XW4 = (XROWS + 3) / 4 * 4;
+    static constexpr int XW = (XW4 / 4) % 2 == 0 ? XW4 + 4 : XW4;
+    static constexpr int XBOX = CONTIG ? 32 * XW : XROWS * 32;  // floats per box
+    static constexpr size_t xs = 0;                             // [NCW][XBOX]
+    static constexpr size_t scratch = xs + (size_t)NCW * XBOX;  // [SEG][32]  bottom zone of segment 0
     static constexpr size_t mf = scratch + (size_t)SEG * 32;    // [NCW][32] forward carries INTO segment s
     static constexpr size_t mb = mf + NCW * 32;                 // [NCW][32] backward carries INTO segment s
-    static constexpr size_t floats = mb + NCW * 32;
-    static constexpr size_t bytes = floats * 4 + 5 * NCW * sizeof(mbar_t);
+    static constexpr size_t tiles = mb + NCW * 32;              // contiguous axis: [NCW][32][33] store transposition
+    static constexpr size_t floats = tiles + (CONTIG ? (size_t)NCW * 32 * 33 : 0);
+    static constexpr size_t fl_al = (floats + 3) / 4 * 4;       // barriers start 16-byte aligned
+    static constexpr size_t bytes = fl_al * 4 + 5 * NCW * sizeof(mbar_t);
 };
 
 PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
@@ -60,17 +67,17 @@ PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
     return v;
 }
 
-template <int NB, int SEG>
+template <bool CONTIG, int NB, int SEG>
 PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_TMAP_PARAM tmap, const Args A)
 {
     static_assert(2 * NB <= SEG && SEG % 4 == 0, "segment shorter than the fold zones");
-    typedef Layout<NB, SEG> LY;
+    typedef Layout<CONTIG, NB, SEG> LY;
     PST_SYS_SMEM(smem_f);
     float *const Xs = smem_f + LY::xs;
     float *const Sc = smem_f + LY::scratch;
     float *const Mf = smem_f + LY::mf;
     float *const Mb = smem_f + LY::mb;
-    mbar_t *const bars = reinterpret_cast<mbar_t *>(smem_f + LY::floats);
+    mbar_t *const bars = reinterpret_cast<mbar_t *>(smem_f + LY::fl_al);
     // full_x / empty_x / cf complete one phase per tile and every phase of tile p is complete before any warp starts
     // tile p+1 (a warp leaves tile p only after its backward carry, i.e. after the whole forward sweep).  The backward
     // carries are different: the warp that finishes tile p first waits for its backward carry of tile p+1 while the
@@ -93,16 +100,18 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
     if (warp == NCW) {
         // ================================ loader ================================
         if (lane != 0) return;
-        const unsigned xbytes = (unsigned)(LY::XROWS * 32 * 4);
+        const unsigned xbytes = (unsigned)(LY::XBOX * 4);
         for (long p = 0; p < m; p++) {
             const long tile = (long)blockIdx.x + p * (long)gridDim.x;
-            const long b = tile / A.tilesA;
-            const int c0 = (int)(tile - b * A.tilesA) * 32;
+            const long b = CONTIG ? 0 : tile / A.tilesA;
+            const int c0 = CONTIG ? 0 : (int)(tile - b * A.tilesA) * 32;
             for (int s = 0; s < nseg; s++) {
                 mbar_wait(empty_x + s, (unsigned)((p & 1) ^ 1), A.err);
                 mbar_arrive_expect_tx(full_x + s, xbytes);
-                // box row r of segment s  <->  x sample s*SEG - D - 2nb + r
-                tma_load_3d(Xs + (size_t)s * LY::XROWS * 32, &tmap, c0, s * SEG - D - 2 * NB, (int)b, full_x + s);
+                // box sample r of segment s  <->  x sample s*SEG - D - 2nb + r  (a multiple of 4 on the contiguous
+                // axis, where TMA needs a 16-byte aligned start: SEG % 4 == 0 and D + 2nb = nseg*SEG - nx, nx % 4 == 0)
+                if (CONTIG) tma_load_2d(Xs + (size_t)s * LY::XBOX, &tmap, s * SEG - D - 2 * NB, (int)(tile * 32), full_x + s);
+                else tma_load_3d(Xs + (size_t)s * LY::XBOX, &tmap, c0, s * SEG - D - 2 * NB, (int)b, full_x + s);
             }
         }
         return;
@@ -117,13 +126,22 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
         mbar_t *const cb = cb2 + par * NCW;
         const unsigned par2 = (unsigned)((p >> 1) & 1);
         const long tile = (long)blockIdx.x + p * (long)gridDim.x;
-        const long b = tile / A.tilesA;
-        const int c0 = (int)(tile - b * A.tilesA) * 32;
-        const bool live = c0 + lane < A.na;
-        // ---- t of the segment from its x box (every x row is read once: the window lives in registers)
+        const long b = CONTIG ? 0 : tile / A.tilesA;
+        const int c0 = CONTIG ? 0 : (int)(tile - b * A.tilesA) * 32;
+        // contiguous axis: lane = line tile*32 + lane of A.na lines; strided: lane = fast index c0 + lane of A.na
+        const int rows = CONTIG ? (int)((long)A.na - tile * 32 < 32 ? (long)A.na - tile * 32 : 32) : 32;
+        const bool live = CONTIG ? lane < rows : c0 + lane < A.na;
+        // ---- t of the segment from its x box (every x sample is read once: the window lives in registers)
         mbar_wait(full_x + s, par, A.err);
-        {
-            const float *X = Xs + (size_t)s * LY::XROWS * 32 + lane;
+        if (CONTIG) {
+            const float4 *row = reinterpret_cast<const float4 *>(Xs + (size_t)s * LY::XBOX + lane * LY::XW);
+            float xr[LY::XW];
+            PST_SYS_UNROLL
+            for (int q = 0; q < LY::XW / 4; q++) { const float4 v = row[q]; xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w; }
+            PST_SYS_UNROLL
+            for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+        } else {
+            const float *X = Xs + (size_t)s * LY::XBOX + lane;
             float xr[LY::XROWS];
             PST_SYS_UNROLL
             for (int r = 0; r < LY::XROWS; r++) xr[r] = X[r * 32];
@@ -152,37 +170,69 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
             __syncwarp();
             if (lane == 0) mbar_arrive(cb + s - 1);
         }
-        // ---- fold2 and the stores.  Step j of segment s is k = s*SEG + j - D; y_i = B_{i+nb} goes to row i = k - nb.
-        float *const dcol = A.dst + b * A.sb + c0 + lane;
-        const long d = A.d;
+        // ---- fold2 and the stores.  Step j of segment s is k = s*SEG + j - D; y_i = B_{i+nb} goes to sample i = k - nb.
+        const int i0 = s * SEG - D - NB;                         // output sample of step 0
+        int jlo = 0, jhi = SEG;                                  // steps with a plain output
         if (s == nseg - 1) {
             // last segment (k up to L-1): the top nb steps are the right reflections of the nb before them;
             // both sit at fixed positions of this segment
             PST_SYS_UNROLL
             for (int r = 0; r < NB; r++) R[SEG - NB - 1 - r] = R[SEG - NB - 1 - r] + R[SEG - NB + r];
-            if (live) {
-                float *q = dcol + (long)(s * SEG - D - NB) * d;
-                PST_SYS_UNROLL
-                for (int j = 0; j < SEG - NB; j++) { *q = R[j]; q += d; }
-            }
-        } else if (s > 0) {
-            if (live) {
-                float *q = dcol + (long)(s * SEG - D - NB) * d;
-                PST_SYS_UNROLL
-                for (int j = 0; j < SEG; j++) { *q = R[j]; q += d; }
-            }
-        } else {
+            jhi = SEG - NB;
+        } else if (s == 0) {
             // first segment: D dummy steps, then k in [0, nb) (left reflections), k in [nb, 2nb) (the outputs they
             // complete), then plain outputs.  D is a run-time value: the two zones go through shared memory.
-            const int zone = D + 2 * NB;                         // <= SEG (checked by the plan)
+            jlo = D + 2 * NB;                                    // <= SEG (checked by the plan)
             float *const sc = Sc + lane;
             PST_SYS_UNROLL
             for (int j = 0; j < SEG; j++)
-                if (j < zone) sc[j * 32] = R[j];
-            if (live) {
+                if (j < jlo) sc[j * 32] = R[j];
+        }
+        if (CONTIG) {
+            // 32 lines x 32 steps at a time through the warp's padded tile: every global store is a row of a line
+            float *const Tt = smem_f + LY::tiles + (size_t)warp * (32 * 33);
+            float *const dline = A.dst + tile * 32 * (long)A.nx;
+            PST_SYS_UNROLL
+            for (int c = 0; c < (SEG + 31) / 32; c++) {
+                PST_SYS_UNROLL
+                for (int jj = 0; jj < 32; jj++)
+                    if (32 * c + jj < SEG) Tt[lane * 33 + jj] = R[32 * c + jj < SEG ? 32 * c + jj : 0];
+                __syncwarp();
+                const int j = 32 * c + lane;
+                if (j >= jlo && j < jhi) {
+                    float *q = dline + i0 + j;
+                    PST_SYS_UNROLL
+                    for (int r = 0; r < 32; r++)
+                        if (r < rows) q[(long)r * A.nx] = Tt[r * 33 + lane];
+                }
+                __syncwarp();
+            }
+            if (s == 0 && live) {
+                const float *const sc = Sc + lane;
+                float *q = dline + (long)lane * A.nx;
+                PST_SYS_UNROLL
+                for (int i = 0; i < NB; i++) q[i] = sc[(D + NB + i) * 32] + sc[(D + NB - 1 - i) * 32];
+            }
+        } else {
+            float *const dcol = A.dst + b * A.sb + c0 + lane;
+            const long d = A.d;
+            if (s == nseg - 1) {
+                if (live) {
+                    float *q = dcol + (long)i0 * d;
+                    PST_SYS_UNROLL
+                    for (int j = 0; j < SEG - NB; j++) { *q = R[j]; q += d; }
+                }
+            } else if (s > 0) {
+                if (live) {
+                    float *q = dcol + (long)i0 * d;
+                    PST_SYS_UNROLL
+                    for (int j = 0; j < SEG; j++) { *q = R[j]; q += d; }
+                }
+            } else if (live) {
+                const float *const sc = Sc + lane;
                 PST_SYS_UNROLL
                 for (int j = 2 * NB; j < SEG; j++)
-                    if (j >= zone) dcol[(long)(j - D - NB) * d] = R[j];
+                    if (j >= jlo) dcol[(long)(i0 + j) * d] = R[j];
                 PST_SYS_UNROLL
                 for (int i = 0; i < NB; i++) dcol[(long)i * d] = sc[(D + NB + i) * 32] + sc[(D + NB - 1 - i) * 32];
             }
@@ -204,8 +254,8 @@ inline bool nb_built(int nb) { return (nb >= 2 && nb <= 8) || nb == 10; }
 inline Plan make_plan(int axis, int n1, int n2, int n3, int nb)
 {
     Plan P{};
-    if (axis != 1 && axis != 2) return P;
-    P.nx = axis == 1 ? n2 : n3;
+    if (axis < 0 || axis > 2) return P;
+    P.nx = axis == 0 ? n1 : (axis == 1 ? n2 : n3);
     P.nb = nb;
     if (!nb_built(nb) || P.nx < 2 * nb) return P;
     if (n1 % 4 != 0) return P;                                   // TMA: global strides are multiples of 16 bytes
@@ -215,10 +265,15 @@ inline Plan make_plan(int axis, int n1, int n2, int n3, int nb)
     P.nseg = (P.L + P.SEG - 1) / P.SEG;
     P.D = P.nseg * P.SEG - P.L;
     if (P.nseg < 2 || P.D + 2 * nb > P.SEG) return P;
-    P.na = axis == 1 ? n1 : (long)n1 * n2;
-    P.d = P.na;
-    P.sb = axis == 1 ? (long)n1 * n2 : 0;
-    P.nslab = axis == 1 ? n3 : 1;
+    if (axis == 0) {
+        P.na = (long)n2 * n3;                                    // lines
+        P.d = 1; P.sb = 0; P.nslab = 1;
+    } else {
+        P.na = axis == 1 ? n1 : (long)n1 * n2;
+        P.d = P.na;
+        P.sb = axis == 1 ? (long)n1 * n2 : 0;
+        P.nslab = axis == 1 ? n3 : 1;
+    }
     if (P.na >= (1L << 31)) return P;
     P.tilesA = (int)((P.na + 31) / 32);
     P.ntiles = (long)P.tilesA * P.nslab;

@@ -103,6 +103,9 @@ static inline void tma_load_3d(void *dst, const TMapE *m, int c0, int c1, int c2
     mbar_complete_tx(bar, (unsigned)((size_t)m->box[0] * m->box[1] * m->box[2] * 4));
 }
 
+static inline void tma_load_2d(void *dst, const TMapE *m, int c0, int c1, mbar_t *bar) { tma_load_3d(dst, m, c0, c1, 0, bar); }
+struct float4 { float x, y, z, w; };
+
 alignas(1024) static unsigned char g_smem[256 * 1024];
 
 #define PST_SYS_DEV static inline
@@ -115,21 +118,27 @@ alignas(1024) static unsigned char g_smem[256 * 1024];
 
 using namespace tri_sys_k;
 
-template <int NB, int SEG>
+template <bool CONTIG, int NB, int SEG>
 static void run(const Plan &P, const float *src, float *dst, int axis, int n1, int n2, int n3, int sm_count)
 {
     TMapE tm{};
     tm.base = src;
-    if (axis == 1) { tm.dim[0] = n1; tm.dim[1] = n2; tm.dim[2] = n3; }
-    else { tm.dim[0] = (long)n1 * n2; tm.dim[1] = n3; tm.dim[2] = 1; }
-    tm.stride[0] = 1; tm.stride[1] = P.d; tm.stride[2] = axis == 1 ? P.sb : P.d * (long)n3;
-    tm.box[0] = 32; tm.box[1] = SEG + 2 * NB; tm.box[2] = 1;
+    if (CONTIG) {
+        tm.dim[0] = n1; tm.dim[1] = P.na; tm.dim[2] = 1;
+        tm.stride[0] = 1; tm.stride[1] = n1; tm.stride[2] = 0;
+        tm.box[0] = Layout<true, NB, SEG>::XW; tm.box[1] = 32; tm.box[2] = 1;
+    } else {
+        if (axis == 1) { tm.dim[0] = n1; tm.dim[1] = n2; tm.dim[2] = n3; }
+        else { tm.dim[0] = (long)n1 * n2; tm.dim[1] = n3; tm.dim[2] = 1; }
+        tm.stride[0] = 1; tm.stride[1] = P.d; tm.stride[2] = axis == 1 ? P.sb : P.d * (long)n3;
+        tm.box[0] = 32; tm.box[1] = SEG + 2 * NB; tm.box[2] = 1;
+    }
     const Args A = make_args(P, dst, nullptr);
-    const int per_sm = SEG == 68 ? 2 : 1;
+    const int per_sm = (SEG == 68 && !CONTIG) ? 2 : 1;
     long grid = (long)sm_count * per_sm;
     if (grid > P.ntiles) grid = P.ntiles;
     gridDim = {(unsigned)grid, 1, 1};
-    if (Layout<NB, SEG>::bytes > sizeof(g_smem)) abort();
+    if (Layout<CONTIG, NB, SEG>::bytes > sizeof(g_smem)) abort();
     for (unsigned bx = 0; bx < (unsigned)grid; bx++) {
         memset(g_smem, 0xff, sizeof(g_smem));                   // NaN pattern: a read of unwritten shared memory shows
         pthread_barrier_init(&cta_barrier, nullptr, NTHREADS);
@@ -141,7 +150,7 @@ static void run(const Plan &P, const float *src, float *dst, int axis, int n1, i
                 threadIdx = {t, 0, 0};
                 blockIdx = {bx, 0, 0};
                 warp_barrier = &bars[t / 32];
-                tri_sys_kernel<NB, SEG>(tm, A);
+                tri_sys_kernel<CONTIG, NB, SEG>(tm, A);
             });
         for (auto &t : th) t.join();
         for (auto &b : bars) pthread_barrier_destroy(&b);
@@ -156,7 +165,11 @@ extern "C" int tri_sys_emul(const float *src, float *dst, int n1, int n2, int n3
     const char *ej = getenv("PST_EMUL_JITTER");
     g_jitter = ej ? atoi(ej) : 0;
     switch (nb) {
-#define CASE(N) case N: if (P.SEG == 68) run<N, 68>(P, src, dst, axis, n1, n2, n3, sm_count); else run<N, 132>(P, src, dst, axis, n1, n2, n3, sm_count); return 0;
+#define CASE(N) \
+    case N: \
+        if (axis == 0) { if (P.SEG == 68) run<true, N, 68>(P, src, dst, axis, n1, n2, n3, sm_count); else run<true, N, 132>(P, src, dst, axis, n1, n2, n3, sm_count); } \
+        else { if (P.SEG == 68) run<false, N, 68>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132>(P, src, dst, axis, n1, n2, n3, sm_count); } \
+        return 0;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(10)
 #undef CASE
     }

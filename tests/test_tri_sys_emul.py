@@ -40,6 +40,11 @@ CASES = [  # shape, axis, radius, emulated SM count
     ((12, 9, 260), 2, 2, 1),
     ((64, 1034, 2), 1, 5, 1),        # 8 segments of 132 (the 1024-sample case of the bench)
     ((40, 300, 2), 1, 3, 1),
+    # contiguous axis: x box = 32 lines x samples, stores transposed through the warp's tile
+    ((152, 9, 5), 0, 5, 1),          # 45 lines: a full and a 13-line tile
+    ((1032, 5, 9), 0, 5, 1),         # 8 segments of 132
+    ((528, 40, 3), 0, 10, 2),
+    ((260, 70, 1), 0, 2, 1),
 ]
 
 
@@ -73,7 +78,8 @@ def test_systolic_kernel_under_schedule_fuzzing(emul, port, monkeypatch):
 
 def test_plan_refuses_what_the_kernel_cannot_do(emul):
     plan = (ctypes.c_int * 4)()
-    assert emul.tri_sys_plan(64, 64, 64, 0, 5, plan) == 0          # contiguous axis: not this kernel
+    assert emul.tri_sys_plan(62, 64, 64, 0, 5, plan) == 0          # n1 % 4 != 0 (TMA box start / stride)
+    assert emul.tri_sys_plan(1000, 1024, 1024, 0, 5, plan) == 1 and list(plan)[:3] == [132, 8, 46]
     assert emul.tri_sys_plan(64, 40, 8, 1, 5, plan) == 0           # one segment only
     assert emul.tri_sys_plan(62, 300, 8, 1, 5, plan) == 0          # n1 % 4 != 0 (TMA stride)
     assert emul.tri_sys_plan(64, 2000, 8, 1, 5, plan) == 0         # line longer than 8 segments

@@ -2,7 +2,7 @@
 // (pyseistr_b200/csrc/pst_tri_sys.cu) against a plain CPU restatement of ps_smooth2.
 //   nvcc -O3 -std=c++17 -fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo \
 //        tools/mb_tri_rc.cu pyseistr_b200/csrc/pst_tri_sys.cu -o tools/mb_tri_rc.bin
-//   tools/mb_tri_rc.bin                        correctness: small volumes, strided axes, radii, in place
+//   tools/mb_tri_rc.bin                        correctness: small volumes, all axes, radii, in place
 //   tools/mb_tri_rc.bin bench [n1 n2 n3 [nb]]  + timing (default 1000x1024x1024, nb 5)
 #include <cstdio>
 #include <cstdlib>
@@ -76,10 +76,10 @@ int main(int argc, char **argv)
     int fails = 0;
     cudaDeviceGetAttribute(&g_sm, cudaDevAttrMultiProcessorCount, 0);
     // many more tiles than CTAs on the small volumes: every CTA pipelines several tiles of both orientations
-    const int shapes[][3] = {{64, 140, 36}, {100, 300, 37}, {36, 33, 265}, {1000, 530, 8}, {8, 1024, 5}, {12, 6, 1030}, {256, 160, 12}, {32, 150, 300}, {4000, 512, 4}};
+    const int shapes[][3] = {{64, 140, 36}, {100, 300, 37}, {36, 33, 265}, {1000, 530, 8}, {8, 1024, 5}, {12, 6, 1030}, {256, 160, 12}, {32, 150, 300}, {4000, 512, 4}, {1032, 300, 7}, {512, 45, 77}};
     const int radii[] = {5, 2, 3, 8, 10};
     for (auto &sh : shapes)
-        for (int axis = 1; axis < 3; axis++)
+        for (int axis = 0; axis < 3; axis++)
             for (int nb : radii) {
                 for (int rep = 0; rep < 2; rep++) fails += check(sh[0], sh[1], sh[2], axis, nb, ((nb + rep) & 1) != 0);
             }
@@ -104,7 +104,7 @@ int main(int argc, char **argv)
     CK(cudaMemset(d_err, 0, 4));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int axis = 1; axis < 3; axis++)
+    for (int axis = 0; axis < 3; axis++)
         for (int inplace = 0; inplace < 2; inplace++) {
             for (int w = 0; w < 2; w++) pst_tri_sys_launch(0, g_sm, axis, a, inplace ? a : b, n1, n2, n3, nb, d_err);
             CK(cudaDeviceSynchronize());
