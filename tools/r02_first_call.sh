@@ -1,0 +1,36 @@
+#!/bin/bash
+# First GPU call of the next round: measure the two smoothers that were written (and verified on the host only)
+# after round 1's GPU minutes were spent.  Run from the repo root on a B200:
+#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+# Everything lands in gpurun_out/r02a_*.  Each step has its own timeout: a protocol bug must not eat the call.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== systolic smoother: bit-exactness + micro-benchmark" | tee $O/r02a_summary.txt
+timeout 300 tools/mb_tri_sys.bin bench > $O/r02a_mb_tri_sys.log 2>&1; echo "mb_tri_sys rc $?" | tee -a $O/r02a_summary.txt
+grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys.log | tail -12 | tee -a $O/r02a_summary.txt
+echo "== checkpoint + recompute smoother" | tee -a $O/r02a_summary.txt
+timeout 300 tools/mb_tri_rc.bin bench > $O/r02a_mb_tri_rc.log 2>&1; echo "mb_tri_rc rc $?" | tee -a $O/r02a_summary.txt
+grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_rc.log | tail -14 | tee -a $O/r02a_summary.txt
+echo "== streaming smoother (the default) for reference" | tee -a $O/r02a_summary.txt
+timeout 300 tools/mb_tri_stream.bin benchonly > $O/r02a_mb_tri_stream.log 2>&1
+grep -E "^bench " $O/r02a_mb_tri_stream.log | tee -a $O/r02a_summary.txt
+echo "== bench.py: default, PST_TRI_SYS=1, PST_TRI_SYS=2, PST_TRI_RC=1" | tee -a $O/r02a_summary.txt
+for v in "" "PST_TRI_SYS=1" "PST_TRI_SYS=2" "PST_TRI_RC=1"; do
+    tag=$(echo "${v:-default}" | tr '=' '_')
+    env $v timeout 420 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r02a_bench_$tag.json 2> $O/r02a_bench_$tag.err
+    echo "$tag rc $?: $(python - <<PY
+import json
+try:
+    d = json.loads(open("$O/r02a_bench_$tag.json").read().strip().splitlines()[-1])
+    print(d["value"], d["unit"], "ms/step", d["ms_per_step"], "tri frac", d.get("roofline", {}).get("frac"))
+except Exception as e:
+    print("no JSON line:", e)
+PY
+)" | tee -a $O/r02a_summary.txt
+done
+echo "== parity of the dip path with the systolic smoother switched on (GPU tests that smooth)" | tee -a $O/r02a_summary.txt
+PST_TRI_SYS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "smooth or dip" > $O/r02a_pytest_sys.log 2>&1; echo "pytest (PST_TRI_SYS=1) rc $?" | tee -a $O/r02a_summary.txt
+tail -3 $O/r02a_pytest_sys.log | tee -a $O/r02a_summary.txt
+echo "== one ncu capture of the systolic kernel" | tee -a $O/r02a_summary.txt
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:tri_sys_kernel -s 4 -c 3 -o $O/r02a_tri_sys tools/mb_tri_sys.bin benchonly 1000 1024 256 > $O/r02a_ncu.log 2>&1; echo "ncu rc $?" | tee -a $O/r02a_summary.txt
