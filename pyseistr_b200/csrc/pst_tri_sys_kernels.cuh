@@ -260,11 +260,18 @@ inline Plan make_plan(int axis, int n1, int n2, int n3, int nb)
     if (!nb_built(nb) || P.nx < 2 * nb) return P;
     if (n1 % 4 != 0) return P;                                   // TMA: global strides are multiples of 16 bytes
     P.L = P.nx + 2 * nb;
-    P.SEG = P.L <= NCW * 68 ? 68 : 132;
-    if (P.L > NCW * P.SEG) return P;
-    P.nseg = (P.L + P.SEG - 1) / P.SEG;
-    P.D = P.nseg * P.SEG - P.L;
-    if (P.nseg < 2 || P.D + 2 * nb > P.SEG) return P;
+    // shortest built segment length that cuts the line into 2..NCW segments with both fold zones inside the end
+    // segments (the bottom zone sits behind the D leading dummy steps of segment 0)
+    const int segs[2] = {68, 132};
+    bool found = false;
+    for (int c = 0; c < 2 && !found; c++) {
+        P.SEG = segs[c];
+        if (P.L > NCW * P.SEG || 2 * nb > P.SEG) continue;
+        P.nseg = (P.L + P.SEG - 1) / P.SEG;
+        P.D = P.nseg * P.SEG - P.L;
+        found = P.nseg >= 2 && P.D + 2 * nb <= P.SEG;
+    }
+    if (!found) return P;
     if (axis == 0) {
         P.na = (long)n2 * n3;                                    // lines
         P.d = 1; P.sb = 0; P.nslab = 1;
