@@ -150,7 +150,7 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
 
 
 def soint2dc(din, mask, dip, order=1, niter=100, njs=(1, 1), drift=0, hasmask=1, twoplane=0, prec=0, verb=0):
-    """reference pyseistr/soint2d.py:92-141 (csoint2d, soint2d_cfuns.c:2278), one slope field."""
+    """reference pyseistr/soint2d.py:92-141 (csoint2d, soint2d_cfuns.c:2260), one slope field."""
     n1, n2 = din.shape
     with quiet():
         d = module("soint2dcfun").csoint2d(_F(din), _F(mask), _F(dip), _F(dip), n1, n2, order, njs[0], njs[1], niter,
@@ -159,7 +159,7 @@ def soint2dc(din, mask, dip, order=1, niter=100, njs=(1, 1), drift=0, hasmask=1,
 
 
 def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=0):
-    """reference pyseistr/sint.py:61-94 (csint2d, soint2d_cfuns.c:2437); needs the optional soint2dcfun module."""
+    """reference pyseistr/sint.py:61-94 (csint2d, soint2d_cfuns.c:2421); needs the optional soint2dcfun module."""
     n1, n2 = din.shape
     with quiet():
         d = module("soint2dcfun").csint2d(_F(din), _F(dip), _F(mask), n1, n2, niter, ns, order, verb, eps)
