@@ -72,6 +72,15 @@ def main():
                                      out=ref.somean2dc(d2e, p2, ns, order, eps))
     g["somean2dadj_ns3o2"] = dict(dn=d2e, dip=p2, ns=3, order=2, eps=0.01, out=ref.somean2dc(d2e, p2, 3, 2, 0.01, adj=1))
     g["somean2dadj_ns2o1"] = dict(dn=d2e, dip=p2, ns=2, order=1, eps=0.05, out=ref.somean2dc(d2e, p2, 2, 1, 0.05, adj=1))
+    # ---- soint2d default path (one slope field, no preconditioner): csoint2d of the reference
+    d2c = synth.cube(64, 24, 1, seed=12, noise=0.0)
+    p2c = ref.dip2dc(d2c, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep2 = np.random.default_rng(19).random(24) > 0.5
+    mk2 = np.zeros_like(d2c)
+    mk2[:, keep2] = 1
+    for name, (order, niter, njs, hasmask) in {"o1n12": (1, 12, (1, 1), 1), "o2n10": (2, 10, (1, 1), 1), "o1n8nj2": (1, 8, (2, 1), 1)}.items():
+        g["soint2d_" + name] = dict(din=d2c * mk2, mask=mk2, dip=p2c, order=order, niter=niter, njs=list(njs), hasmask=hasmask,
+                                    out=ref.soint2dc(d2c * mk2, mk2, p2c, order=order, niter=niter, njs=njs, hasmask=hasmask))
     # ---- smoothing (ps_smooth2 through smoothcf adj=0), incl. a radius larger than an axis
     xs = synth.cube(30, 12, 6, seed=13)
     g["smooth_534"] = dict(x=xs, rect=[5, 3, 4], out=ref.smoothc(xs, [5, 3, 4]))

@@ -437,3 +437,8 @@ def test_soint2d_default_path(ctx, port):
     want = port.soint2dc(d * mask, mask, p2, order=2, niter=15)
     assert got.shape == (96, 40)
     assert rel_l2(got, want) <= TOL, rel_l2(got, want)
+    for name in golden_names("soint2d_"):                      # csoint2d outputs of the compiled reference
+        g = golden(name)
+        got = ps.soint2dc(g["din"], g["mask"], g["dip"], order=int(g["order"]), niter=int(g["niter"]),
+                          njs=[int(v) for v in g["njs"]], hasmask=int(g["hasmask"]), verb=0, ctx=ctx)
+        assert rel_l2(got, g["out"]) <= TOL, (name, rel_l2(got, g["out"]))

@@ -56,6 +56,15 @@ def test_port_soint3d_matches_golden(port, name):
     assert np.array_equal(out, g["out"])
 
 
+@pytest.mark.parametrize("name", golden_names("soint2d_"))
+def test_port_soint2d_matches_golden(port, name):
+    """csoint2d of the reference (default path) against the one-plane soint3d restatement."""
+    g = golden(name)
+    out = port.soint2dc(g["din"], g["mask"], g["dip"], order=int(g["order"]), niter=int(g["niter"]),
+                        njs=[int(v) for v in g["njs"]], hasmask=int(g["hasmask"]))
+    assert np.array_equal(out, g["out"])
+
+
 def test_port_soint3d_noise_matches_compiled_reference(port):
     """var > 0 (MT19937 + Box-Muller right-hand side): bit-identical to the compiled reference."""
     ref = _ref_or_skip()
