@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pst_tri_sys.cuh"
 
@@ -90,7 +91,7 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <bool CONTIG, int NB, int SEG>
+template <bool CONTIG, int NB, int SEG, bool ILS>
 int launch(cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
     static bool attr[64] = {};
@@ -98,18 +99,21 @@ int launch(cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -4;
     const size_t smem = Layout<CONTIG, NB, SEG>::bytes;
     if (!attr[dev]) {
-        if (cudaFuncSetAttribute(tri_sys_kernel<CONTIG, NB, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+        if (cudaFuncSetAttribute(tri_sys_kernel<CONTIG, NB, SEG, ILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
         attr[dev] = true;
     }
-    tri_sys_kernel<CONTIG, NB, SEG><<<grid, NTHREADS, smem, stream>>>(tm, A);
+    tri_sys_kernel<CONTIG, NB, SEG, ILS><<<grid, NTHREADS, smem, stream>>>(tm, A);
     return 0;
 }
 
 template <int NB>
 int launch_seg(bool contig, int SEG, cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
-    if (contig) return SEG == 68 ? launch<true, NB, 68>(stream, grid, tm, A) : launch<true, NB, 132>(stream, grid, tm, A);
-    return SEG == 68 ? launch<false, NB, 68>(stream, grid, tm, A) : launch<false, NB, 132>(stream, grid, tm, A);
+    // PST_TRI_SYS_ILS=1: outputs stored from inside the backward chain loop (strided axes)
+    static const bool ils = []() { const char *e = getenv("PST_TRI_SYS_ILS"); return e && e[0] == '1'; }();
+    if (contig) return SEG == 68 ? launch<true, NB, 68, false>(stream, grid, tm, A) : launch<true, NB, 132, false>(stream, grid, tm, A);
+    if (ils) return SEG == 68 ? launch<false, NB, 68, true>(stream, grid, tm, A) : launch<false, NB, 132, true>(stream, grid, tm, A);
+    return SEG == 68 ? launch<false, NB, 68, false>(stream, grid, tm, A) : launch<false, NB, 132, false>(stream, grid, tm, A);
 }
 
 template <int NB>

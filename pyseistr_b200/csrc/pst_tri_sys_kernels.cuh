@@ -67,7 +67,9 @@ PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
     return v;
 }
 
-template <bool CONTIG, int NB, int SEG>
+// ILS (strided axes only): the last and the interior segments store their outputs from INSIDE the backward chain loop
+// (the chain issues one FADD per 4 cycles: the stores ride in its shadow) instead of in a pass of their own.
+template <bool CONTIG, int NB, int SEG, bool ILS>
 PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_TMAP_PARAM tmap, const Args A)
 {
     static_assert(2 * NB <= SEG && SEG % 4 == 0, "segment shorter than the fold zones");
@@ -163,15 +165,39 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
         // ---- backward sum over the segment
         float B = 0.f;
         if (s < nseg - 1) { mbar_wait(cb + s, par2, A.err); B = Mb[s * 32 + lane]; }
-        PST_SYS_UNROLL
-        for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; R[j] = B; }
+        const int i0 = s * SEG - D - NB;                         // output sample of step 0 (y_i = B_{i+nb}, k = s*SEG + j - D)
+        const bool inloop = ILS && !CONTIG && s > 0;
+        if (inloop) {
+            float *q = A.dst + b * A.sb + c0 + lane + (long)(i0 + SEG - 1) * A.d;
+            const long d = A.d;
+            if (s == nseg - 1) {
+                // top nb steps first (kept: they are the right reflections of the nb outputs that follow)
+                PST_SYS_UNROLL
+                for (int j = SEG - 1; j >= 0; j--) {
+                    B = B + R[j];
+                    if (j >= SEG - NB) R[j] = B;
+                    else {
+                        float v = B;
+                        if (j >= SEG - 2 * NB) v = v + R[2 * (SEG - NB) - 1 - j];
+                        if (live) *q = v;
+                    }
+                    q -= d;
+                }
+            } else {
+                PST_SYS_UNROLL
+                for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; if (live) *q = B; q -= d; }
+            }
+        } else {
+            PST_SYS_UNROLL
+            for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; R[j] = B; }
+        }
         if (s > 0) {
             Mb[(s - 1) * 32 + lane] = B;
             __syncwarp();
             if (lane == 0) mbar_arrive(cb + s - 1);
         }
+        if (inloop) continue;
         // ---- fold2 and the stores.  Step j of segment s is k = s*SEG + j - D; y_i = B_{i+nb} goes to sample i = k - nb.
-        const int i0 = s * SEG - D - NB;                         // output sample of step 0
         int jlo = 0, jhi = SEG;                                  // steps with a plain output
         if (s == nseg - 1) {
             // last segment (k up to L-1): the top nb steps are the right reflections of the nb before them;

@@ -118,7 +118,7 @@ alignas(1024) static unsigned char g_smem[256 * 1024];
 
 using namespace tri_sys_k;
 
-template <bool CONTIG, int NB, int SEG>
+template <bool CONTIG, int NB, int SEG, bool ILS>
 static void run(const Plan &P, const float *src, float *dst, int axis, int n1, int n2, int n3, int sm_count)
 {
     TMapE tm{};
@@ -150,7 +150,7 @@ static void run(const Plan &P, const float *src, float *dst, int axis, int n1, i
                 threadIdx = {t, 0, 0};
                 blockIdx = {bx, 0, 0};
                 warp_barrier = &bars[t / 32];
-                tri_sys_kernel<CONTIG, NB, SEG>(tm, A);
+                tri_sys_kernel<CONTIG, NB, SEG, ILS>(tm, A);
             });
         for (auto &t : th) t.join();
         for (auto &b : bars) pthread_barrier_destroy(&b);
@@ -164,11 +164,14 @@ extern "C" int tri_sys_emul(const float *src, float *dst, int n1, int n2, int n3
     if (!P.ok) return -1;
     const char *ej = getenv("PST_EMUL_JITTER");
     g_jitter = ej ? atoi(ej) : 0;
+    const char *ei = getenv("PST_TRI_SYS_ILS");
+    const bool ils = ei && ei[0] == '1';
     switch (nb) {
 #define CASE(N) \
     case N: \
-        if (axis == 0) { if (P.SEG == 68) run<true, N, 68>(P, src, dst, axis, n1, n2, n3, sm_count); else run<true, N, 132>(P, src, dst, axis, n1, n2, n3, sm_count); } \
-        else { if (P.SEG == 68) run<false, N, 68>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132>(P, src, dst, axis, n1, n2, n3, sm_count); } \
+        if (axis == 0) { if (P.SEG == 68) run<true, N, 68, false>(P, src, dst, axis, n1, n2, n3, sm_count); else run<true, N, 132, false>(P, src, dst, axis, n1, n2, n3, sm_count); } \
+        else if (ils) { if (P.SEG == 68) run<false, N, 68, true>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132, true>(P, src, dst, axis, n1, n2, n3, sm_count); } \
+        else { if (P.SEG == 68) run<false, N, 68, false>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132, false>(P, src, dst, axis, n1, n2, n3, sm_count); } \
         return 0;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(10)
 #undef CASE

@@ -76,6 +76,22 @@ def test_systolic_kernel_under_schedule_fuzzing(emul, port, monkeypatch):
         assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), rep
 
 
+def test_systolic_kernel_stores_inside_the_chain_variant(emul, port, monkeypatch):
+    """PST_TRI_SYS_ILS=1: last and interior segments store from inside the backward chain loop (strided axes)."""
+    monkeypatch.setenv("PST_TRI_SYS_ILS", "1")
+    for shape, axis, nb, sm in (((100, 140, 7), 1, 8, 3), ((36, 3, 530), 2, 10, 1), ((64, 1034, 2), 1, 5, 1)):
+        rng = np.random.default_rng(sum(shape))
+        x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
+        rect = [1, 1, 1]
+        rect[axis] = nb
+        want = np.asfortranarray(port.smooth3(x, rect))
+        for inplace in (False, True):
+            src = x.copy(order="F")
+            dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
+            assert emul.tri_sys_emul(src.ctypes.data, dst.ctypes.data, *shape, axis, nb, sm) == 0
+            assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), (shape, axis, nb, inplace)
+
+
 def test_plan_refuses_what_the_kernel_cannot_do(emul):
     plan = (ctypes.c_int * 4)()
     assert emul.tri_sys_plan(62, 64, 64, 0, 5, plan) == 0          # n1 % 4 != 0 (TMA box start / stride)

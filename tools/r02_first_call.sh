@@ -9,6 +9,9 @@ O=gpurun_out
 echo "== systolic smoother: bit-exactness + micro-benchmark" | tee $O/r02a_summary.txt
 timeout 300 tools/mb_tri_sys.bin bench > $O/r02a_mb_tri_sys.log 2>&1; echo "mb_tri_sys rc $?" | tee -a $O/r02a_summary.txt
 grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys.log | tail -12 | tee -a $O/r02a_summary.txt
+echo "== systolic smoother, outputs stored from inside the backward chain (PST_TRI_SYS_ILS=1)" | tee -a $O/r02a_summary.txt
+PST_TRI_SYS_ILS=1 timeout 300 tools/mb_tri_sys.bin bench > $O/r02a_mb_tri_sys_ils.log 2>&1; echo "mb_tri_sys ILS rc $?" | tee -a $O/r02a_summary.txt
+grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys_ils.log | tail -8 | tee -a $O/r02a_summary.txt
 echo "== checkpoint + recompute smoother" | tee -a $O/r02a_summary.txt
 timeout 300 tools/mb_tri_rc.bin bench > $O/r02a_mb_tri_rc.log 2>&1; echo "mb_tri_rc rc $?" | tee -a $O/r02a_summary.txt
 grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_rc.log | tail -14 | tee -a $O/r02a_summary.txt
