@@ -168,8 +168,9 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
         const int i0 = s * SEG - D - NB;                         // output sample of step 0 (y_i = B_{i+nb}, k = s*SEG + j - D)
         const bool inloop = ILS && !CONTIG && s > 0;
         if (inloop) {
-            float *q = A.dst + b * A.sb + c0 + lane + (long)(i0 + SEG - 1) * A.d;
-            const long d = A.d;
+            // byte pointer stepped by a byte stride: two integer instructions per store
+            char *q = reinterpret_cast<char *>(A.dst + b * A.sb + c0 + lane + (long)(i0 + SEG - 1) * A.d);
+            const long d = A.d * 4;
             if (s == nseg - 1) {
                 // top nb steps first (kept: they are the right reflections of the nb outputs that follow)
                 PST_SYS_UNROLL
@@ -179,13 +180,13 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
                     else {
                         float v = B;
                         if (j >= SEG - 2 * NB) v = v + R[2 * (SEG - NB) - 1 - j];
-                        if (live) *q = v;
+                        if (live) *reinterpret_cast<float *>(q) = v;
                     }
                     q -= d;
                 }
             } else {
                 PST_SYS_UNROLL
-                for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; if (live) *q = B; q -= d; }
+                for (int j = SEG - 1; j >= 0; j--) { B = B + R[j]; if (live) *reinterpret_cast<float *>(q) = B; q -= d; }
             }
         } else {
             PST_SYS_UNROLL
@@ -242,17 +243,18 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
         } else {
             float *const dcol = A.dst + b * A.sb + c0 + lane;
             const long d = A.d;
+            const long db = d * 4;                               // byte stride: two integer instructions per store
             if (s == nseg - 1) {
                 if (live) {
-                    float *q = dcol + (long)i0 * d;
+                    char *q = reinterpret_cast<char *>(dcol + (long)i0 * d);
                     PST_SYS_UNROLL
-                    for (int j = 0; j < SEG - NB; j++) { *q = R[j]; q += d; }
+                    for (int j = 0; j < SEG - NB; j++) { *reinterpret_cast<float *>(q) = R[j]; q += db; }
                 }
             } else if (s > 0) {
                 if (live) {
-                    float *q = dcol + (long)i0 * d;
+                    char *q = reinterpret_cast<char *>(dcol + (long)i0 * d);
                     PST_SYS_UNROLL
-                    for (int j = 0; j < SEG; j++) { *q = R[j]; q += d; }
+                    for (int j = 0; j < SEG; j++) { *reinterpret_cast<float *>(q) = R[j]; q += db; }
                 }
             } else if (live) {
                 const float *const sc = Sc + lane;
