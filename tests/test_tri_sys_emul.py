@@ -3,8 +3,10 @@ thread (tests/native/tri_sys_emul.cpp: mbarriers with the hardware's phase-parit
 one std::thread per CUDA thread), against the oracle.  Several tiles per CTA so that both orientations, the mailbox
 hand-offs and the loader's ring are exercised; one case runs with schedule fuzzing."""
 import ctypes
+import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -19,18 +21,19 @@ def emul(tmp_path_factory):
                     os.path.join(ROOT, "pyseistr_b200", "csrc"), "-o", so,
                     os.path.join(ROOT, "tests", "native", "tri_sys_emul.cpp")], check=True)
     lib = ctypes.CDLL(so)
-    lib.tri_sys_emul.restype = ctypes.c_int
-    lib.tri_sys_emul.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
     lib.tri_sys_plan.restype = ctypes.c_int
     lib.tri_sys_plan.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    lib.path = so
     return lib
 
 
-@pytest.fixture(scope="module")
-def port():
-    from oracle import port as p
-    p.build()
-    return p
+def run_cases(emul, cases, env=None):
+    """The emulated kernels run in a child process: a protocol deadlock aborts the child, not pytest."""
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "run_emul.py"), emul.path, "tri_sys_emul",
+                        json.dumps(cases)], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 CASES = [  # shape, axis, radius, emulated SM count
@@ -48,48 +51,25 @@ CASES = [  # shape, axis, radius, emulated SM count
 ]
 
 
-@pytest.mark.parametrize("shape,axis,nb,sm", CASES)
-def test_systolic_kernel_emulated_on_host_matches_oracle(emul, port, shape, axis, nb, sm):
+def test_systolic_kernel_emulated_on_host_matches_oracle(emul):
     plan = (ctypes.c_int * 4)()
-    assert emul.tri_sys_plan(*shape, axis, nb, plan) == 1
-    rng = np.random.default_rng(sum(shape) + nb)
-    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
-    rect = [1, 1, 1]
-    rect[axis] = nb
-    want = np.asfortranarray(port.smooth3(x, rect))
-    for inplace in (False, True):
-        src = x.copy(order="F")
-        dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
-        assert emul.tri_sys_emul(src.ctypes.data, dst.ctypes.data, *shape, axis, nb, sm) == 0
-        assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), (shape, axis, nb, inplace, list(plan))
+    cases = []
+    for shape, axis, nb, sm in CASES:
+        assert emul.tri_sys_plan(*shape, axis, nb, plan) == 1, (shape, axis, nb)
+        cases += [[list(shape), axis, nb, sm, 0], [list(shape), axis, nb, sm, 1]]
+    run_cases(emul, cases)
 
 
-def test_systolic_kernel_under_schedule_fuzzing(emul, port, monkeypatch):
-    monkeypatch.setenv("PST_EMUL_JITTER", "300")
-    shape, axis, nb = (100, 140, 5), 1, 5
-    rng = np.random.default_rng(77)
-    x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
-    want = np.asfortranarray(port.smooth3(x, [1, nb, 1]))
-    for rep in range(2):
-        dst = np.full_like(x, np.float32(7.0), order="F")
-        assert emul.tri_sys_emul(x.ctypes.data, dst.ctypes.data, *shape, axis, nb, 1) == 0
-        assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), rep
+def test_systolic_kernel_under_schedule_fuzzing(emul):
+    run_cases(emul, [[[100, 140, 5], 1, 5, 1, 0], [[100, 140, 5], 1, 5, 1, 1], [[152, 9, 5], 0, 5, 1, 0]], {"PST_EMUL_JITTER": "300"})
 
 
-def test_systolic_kernel_stores_inside_the_chain_variant(emul, port, monkeypatch):
+def test_systolic_kernel_stores_inside_the_chain_variant(emul):
     """PST_TRI_SYS_ILS=1: last and interior segments store from inside the backward chain loop (strided axes)."""
-    monkeypatch.setenv("PST_TRI_SYS_ILS", "1")
+    cases = []
     for shape, axis, nb, sm in (((100, 140, 7), 1, 8, 3), ((36, 3, 530), 2, 10, 1), ((64, 1034, 2), 1, 5, 1)):
-        rng = np.random.default_rng(sum(shape))
-        x = np.asfortranarray(rng.standard_normal(shape).astype(np.float32))
-        rect = [1, 1, 1]
-        rect[axis] = nb
-        want = np.asfortranarray(port.smooth3(x, rect))
-        for inplace in (False, True):
-            src = x.copy(order="F")
-            dst = src if inplace else np.full_like(src, np.float32(7.0), order="F")
-            assert emul.tri_sys_emul(src.ctypes.data, dst.ctypes.data, *shape, axis, nb, sm) == 0
-            assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), (shape, axis, nb, inplace)
+        cases += [[list(shape), axis, nb, sm, 0], [list(shape), axis, nb, sm, 1]]
+    run_cases(emul, cases, {"PST_TRI_SYS_ILS": "1"})
 
 
 def test_plan_refuses_what_the_kernel_cannot_do(emul):
