@@ -29,6 +29,7 @@ __device__ __forceinline__ void mbar_fence_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_fence_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(mbar_t *b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
@@ -91,7 +92,7 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <bool CONTIG, int NB, int SEG, bool ILS>
+template <bool CONTIG, int NB, int SEG, bool ILS, bool PRE>
 int launch(cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
     static bool attr[64] = {};
@@ -99,10 +100,10 @@ int launch(cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -4;
     const size_t smem = Layout<CONTIG, NB, SEG>::bytes;
     if (!attr[dev]) {
-        if (cudaFuncSetAttribute(tri_sys_kernel<CONTIG, NB, SEG, ILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+        if (cudaFuncSetAttribute(tri_sys_kernel<CONTIG, NB, SEG, ILS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
         attr[dev] = true;
     }
-    tri_sys_kernel<CONTIG, NB, SEG, ILS><<<grid, NTHREADS, smem, stream>>>(tm, A);
+    tri_sys_kernel<CONTIG, NB, SEG, ILS, PRE><<<grid, NTHREADS, smem, stream>>>(tm, A);
     return 0;
 }
 
@@ -110,10 +111,14 @@ template <int NB>
 int launch_seg(bool contig, int SEG, cudaStream_t stream, unsigned grid, const CUtensorMap &tm, const Args &A)
 {
     // PST_TRI_SYS_ILS=1: outputs stored from inside the backward chain loop (strided axes)
+    // PST_TRI_SYS_PRE=1: t of the next tile built in place in the x box while waiting for a carry
     static const bool ils = []() { const char *e = getenv("PST_TRI_SYS_ILS"); return e && e[0] == '1'; }();
-    if (contig) return SEG == 68 ? launch<true, NB, 68, false>(stream, grid, tm, A) : launch<true, NB, 132, false>(stream, grid, tm, A);
-    if (ils) return SEG == 68 ? launch<false, NB, 68, true>(stream, grid, tm, A) : launch<false, NB, 132, true>(stream, grid, tm, A);
-    return SEG == 68 ? launch<false, NB, 68, false>(stream, grid, tm, A) : launch<false, NB, 132, false>(stream, grid, tm, A);
+    static const bool pre = []() { const char *e = getenv("PST_TRI_SYS_PRE"); return e && e[0] == '1'; }();
+#define SYS_GO(C, I, P) (SEG == 68 ? launch<C, NB, 68, I, P>(stream, grid, tm, A) : launch<C, NB, 132, I, P>(stream, grid, tm, A))
+    if (contig) return pre ? SYS_GO(true, false, true) : SYS_GO(true, false, false);
+    if (ils) return pre ? SYS_GO(false, true, true) : SYS_GO(false, true, false);
+    return pre ? SYS_GO(false, false, true) : SYS_GO(false, false, false);
+#undef SYS_GO
 }
 
 template <int NB>

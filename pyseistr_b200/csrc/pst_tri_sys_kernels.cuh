@@ -56,7 +56,7 @@ struct Layout {
     static constexpr size_t tiles = mb + NCW * 32;              // contiguous axis: [NCW][32][33] store transposition
     static constexpr size_t floats = tiles + (CONTIG ? (size_t)NCW * 32 * 33 : 0);
     static constexpr size_t fl_al = (floats + 3) / 4 * 4;       // barriers start 16-byte aligned
-    static constexpr size_t bytes = fl_al * 4 + 5 * NCW * sizeof(mbar_t);
+    static constexpr size_t bytes = fl_al * 4 + 6 * NCW * sizeof(mbar_t);
 };
 
 PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
@@ -69,7 +69,62 @@ PST_SYS_DEV float tri_t3(float xa, float xb, float xc, float wm, float w2)
 
 // ILS (strided axes only): the last and the interior segments store their outputs from INSIDE the backward chain loop
 // (the chain issues one FADD per 4 cycles: the stores ride in its shadow) instead of in a pass of their own.
-template <bool CONTIG, int NB, int SEG, bool ILS>
+// PRE: t of a warp's segment of the NEXT tile is built IN PLACE in that segment's x box (row j <- t_j) while the warp
+// waits for a carry of the current tile, and only moved to registers (SEG shared-memory loads) when the next tile
+// starts: the lag between the backward sweep of a tile and the forward sweep of the next drops from store + build to
+// store + load.
+template <bool CONTIG, int NB, int SEG>
+PST_SYS_DEV void sys_prebuild(float *box, int lane, float wm, float w2)
+{
+    typedef Layout<CONTIG, NB, SEG> LY;
+    if (CONTIG) {
+        float4 *const X4 = reinterpret_cast<float4 *>(box + lane * LY::XW);
+        constexpr int HW = (2 * NB + 3) / 4 + 1;                 // 16-byte words held ahead of the chunk being built
+        float xw[LY::XW];
+        PST_SYS_UNROLL
+        for (int q = 0; q < HW; q++) { const float4 v = X4[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
+        PST_SYS_UNROLL
+        for (int c = 0; c < SEG / 4; c++) {
+            if (c + HW < LY::XW / 4) {
+                const int q = c + HW < LY::XW / 4 ? c + HW : 0;
+                const float4 v = X4[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+            }
+            float4 t;
+            t.x = tri_t3(xw[4 * c + 2 * NB], xw[4 * c + NB], xw[4 * c], wm, w2);
+            t.y = tri_t3(xw[4 * c + 1 + 2 * NB], xw[4 * c + 1 + NB], xw[4 * c + 1], wm, w2);
+            t.z = tri_t3(xw[4 * c + 2 + 2 * NB], xw[4 * c + 2 + NB], xw[4 * c + 2], wm, w2);
+            t.w = tri_t3(xw[4 * c + 3 + 2 * NB], xw[4 * c + 3 + NB], xw[4 * c + 3], wm, w2);
+            X4[c] = t;
+        }
+    } else {
+        float *const X = box + lane;
+        constexpr int PF = 4;                                    // rows loaded ahead of the step being built
+        float xr[LY::XROWS];
+        PST_SYS_UNROLL
+        for (int r = 0; r < 2 * NB + PF; r++) xr[r] = X[r * 32];
+        PST_SYS_UNROLL
+        for (int j = 0; j < SEG; j++) {
+            if (j + 2 * NB + PF < LY::XROWS) xr[j + 2 * NB + PF < LY::XROWS ? j + 2 * NB + PF : 0] = X[(j + 2 * NB + PF) * 32];
+            X[j * 32] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], wm, w2);
+        }
+    }
+}
+
+template <bool CONTIG, int NB, int SEG>
+PST_SYS_DEV void sys_rload(const float *box, int lane, float *R)
+{
+    typedef Layout<CONTIG, NB, SEG> LY;
+    if (CONTIG) {
+        const float4 *const X4 = reinterpret_cast<const float4 *>(box + lane * LY::XW);
+        PST_SYS_UNROLL
+        for (int c = 0; c < SEG / 4; c++) { const float4 v = X4[c]; R[4 * c] = v.x; R[4 * c + 1] = v.y; R[4 * c + 2] = v.z; R[4 * c + 3] = v.w; }
+    } else {
+        PST_SYS_UNROLL
+        for (int j = 0; j < SEG; j++) R[j] = box[j * 32 + lane];
+    }
+}
+
+template <bool CONTIG, int NB, int SEG, bool ILS, bool PRE>
 PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_TMAP_PARAM tmap, const Args A)
 {
     static_assert(2 * NB <= SEG && SEG % 4 == 0, "segment shorter than the fold zones");
@@ -86,11 +141,13 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
     // backward sweep of tile p is still running, so a single barrier per segment would be waited on two phases ahead
     // (a parity wait then falls through: found by the host emulation).  cb is therefore doubled by tile parity, which
     // makes the waiter of each barrier always the same warp (same orientation), hence sequential.
-    mbar_t *const full_x = bars, *const empty_x = bars + NCW, *const cf = bars + 2 * NCW, *const cb2 = bars + 3 * NCW;
+    // full_x is doubled by tile parity as well: with PRE a warp waits for the NEXT tile's box while it works on the
+    // current one, and nothing orders that wait after the landing of the current tile's box of the same segment.
+    mbar_t *const full_x2 = bars, *const empty_x = bars + 2 * NCW, *const cf = bars + 3 * NCW, *const cb2 = bars + 4 * NCW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 5 * NCW; i++) mbar_init(bars + i, 1);
+        for (int i = 0; i < 6 * NCW; i++) mbar_init(bars + i, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -108,12 +165,13 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
             const long b = CONTIG ? 0 : tile / A.tilesA;
             const int c0 = CONTIG ? 0 : (int)(tile - b * A.tilesA) * 32;
             for (int s = 0; s < nseg; s++) {
+                mbar_t *const fx = full_x2 + (p & 1) * NCW + s;
                 mbar_wait(empty_x + s, (unsigned)((p & 1) ^ 1), A.err);
-                mbar_arrive_expect_tx(full_x + s, xbytes);
+                mbar_arrive_expect_tx(fx, xbytes);
                 // box sample r of segment s  <->  x sample s*SEG - D - 2nb + r  (a multiple of 4 on the contiguous
                 // axis, where TMA needs a 16-byte aligned start: SEG % 4 == 0 and D + 2nb = nseg*SEG - nx, nx % 4 == 0)
-                if (CONTIG) tma_load_2d(Xs + (size_t)s * LY::XBOX, &tmap, s * SEG - D - 2 * NB, (int)(tile * 32), full_x + s);
-                else tma_load_3d(Xs + (size_t)s * LY::XBOX, &tmap, c0, s * SEG - D - 2 * NB, (int)b, full_x + s);
+                if (CONTIG) tma_load_2d(Xs + (size_t)s * LY::XBOX, &tmap, s * SEG - D - 2 * NB, (int)(tile * 32), fx);
+                else tma_load_3d(Xs + (size_t)s * LY::XBOX, &tmap, c0, s * SEG - D - 2 * NB, (int)b, fx);
             }
         }
         return;
@@ -134,24 +192,41 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
         const int rows = CONTIG ? (int)((long)A.na - tile * 32 < 32 ? (long)A.na - tile * 32 : 32) : 32;
         const bool live = CONTIG ? lane < rows : c0 + lane < A.na;
         // ---- t of the segment from its x box (every x sample is read once: the window lives in registers)
-        mbar_wait(full_x + s, par, A.err);
-        if (CONTIG) {
-            const float4 *row = reinterpret_cast<const float4 *>(Xs + (size_t)s * LY::XBOX + lane * LY::XW);
-            float xr[LY::XW];
-            PST_SYS_UNROLL
-            for (int q = 0; q < LY::XW / 4; q++) { const float4 v = row[q]; xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w; }
-            PST_SYS_UNROLL
-            for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+        float *const box = Xs + (size_t)s * LY::XBOX;
+        if (!PRE) {
+            mbar_wait(full_x2 + par * NCW + s, par2, A.err);
+            if (CONTIG) {
+                const float4 *row = reinterpret_cast<const float4 *>(box + lane * LY::XW);
+                float xr[LY::XW];
+                PST_SYS_UNROLL
+                for (int q = 0; q < LY::XW / 4; q++) { const float4 v = row[q]; xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w; }
+                PST_SYS_UNROLL
+                for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+            } else {
+                const float *X = box + lane;
+                float xr[LY::XROWS];
+                PST_SYS_UNROLL
+                for (int r = 0; r < LY::XROWS; r++) xr[r] = X[r * 32];
+                PST_SYS_UNROLL
+                for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+            }
         } else {
-            const float *X = Xs + (size_t)s * LY::XBOX + lane;
-            float xr[LY::XROWS];
-            PST_SYS_UNROLL
-            for (int r = 0; r < LY::XROWS; r++) xr[r] = X[r * 32];
-            PST_SYS_UNROLL
-            for (int j = 0; j < SEG; j++) R[j] = tri_t3(xr[j + 2 * NB], xr[j + NB], xr[j], A.wm, A.w2);
+            // t of this segment was built in place during the previous tile (this warp owned nothing else of that box)
+            if (p == 0) { mbar_wait(full_x2 + par * NCW + s, par2, A.err); sys_prebuild<CONTIG, NB, SEG>(box, lane, A.wm, A.w2); }
+            sys_rload<CONTIG, NB, SEG>(box, lane, R);
+            mbar_fence_proxy();                                  // my in-place writes before the TMA unit refills the box
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_x + s);
+        // with PRE: build t of my segment of the next tile while I wait for a carry -- before the forward sum for the
+        // segments the forward sweep reaches late, after it for the others
+        const bool pre_more = PRE && p + 1 < m;
+        const int sn = nseg - 1 - s;
+        const bool pre_before = 2 * s >= nseg;
+        if (pre_more && pre_before) {
+            mbar_wait(full_x2 + (par ^ 1u) * NCW + sn, (unsigned)(((p + 1) >> 1) & 1), A.err);
+            sys_prebuild<CONTIG, NB, SEG>(Xs + (size_t)sn * LY::XBOX, lane, A.wm, A.w2);
+        }
         // ---- forward sum over the segment
         float F = 0.f;
         if (s > 0) { mbar_wait(cf + s, par, A.err); F = Mf[s * 32 + lane]; }
@@ -161,6 +236,10 @@ PST_SYS_GLOBAL(NTHREADS, (SEG <= 68 ? 2 : 1)) void tri_sys_kernel(const PST_SYS_
             Mf[(s + 1) * 32 + lane] = F;
             __syncwarp();
             if (lane == 0) mbar_arrive(cf + s + 1);
+        }
+        if (pre_more && !pre_before) {
+            mbar_wait(full_x2 + (par ^ 1u) * NCW + sn, (unsigned)(((p + 1) >> 1) & 1), A.err);
+            sys_prebuild<CONTIG, NB, SEG>(Xs + (size_t)sn * LY::XBOX, lane, A.wm, A.w2);
         }
         // ---- backward sum over the segment
         float B = 0.f;

@@ -50,6 +50,7 @@ static inline void mbar_init(mbar_t *b, unsigned count)
     b->phase = 0; b->pending = (int)count; b->count = (int)count; b->tx = 0;
 }
 static inline void mbar_fence_init() {}
+static inline void mbar_fence_proxy() {}
 static inline void mbar_arrive(mbar_t *b)
 {
     jitter();
@@ -118,7 +119,7 @@ alignas(1024) static unsigned char g_smem[256 * 1024];
 
 using namespace tri_sys_k;
 
-template <bool CONTIG, int NB, int SEG, bool ILS>
+template <bool CONTIG, int NB, int SEG, bool ILS, bool PRE>
 static void run(const Plan &P, const float *src, float *dst, int axis, int n1, int n2, int n3, int sm_count)
 {
     TMapE tm{};
@@ -150,12 +151,22 @@ static void run(const Plan &P, const float *src, float *dst, int axis, int n1, i
                 threadIdx = {t, 0, 0};
                 blockIdx = {bx, 0, 0};
                 warp_barrier = &bars[t / 32];
-                tri_sys_kernel<CONTIG, NB, SEG, ILS>(tm, A);
+                tri_sys_kernel<CONTIG, NB, SEG, ILS, PRE>(tm, A);
             });
         for (auto &t : th) t.join();
         for (auto &b : bars) pthread_barrier_destroy(&b);
         pthread_barrier_destroy(&cta_barrier);
     }
+}
+
+template <int NB>
+static void dispatch(const Plan &P, const float *src, float *dst, int axis, int n1, int n2, int n3, int sm_count, bool ils, bool pre)
+{
+#define GO(C, I, Q) do { if (P.SEG == 68) run<C, NB, 68, I, Q>(P, src, dst, axis, n1, n2, n3, sm_count); else run<C, NB, 132, I, Q>(P, src, dst, axis, n1, n2, n3, sm_count); } while (0)
+    if (axis == 0) { if (pre) GO(true, false, true); else GO(true, false, false); }
+    else if (ils) { if (pre) GO(false, true, true); else GO(false, true, false); }
+    else { if (pre) GO(false, false, true); else GO(false, false, false); }
+#undef GO
 }
 
 extern "C" int tri_sys_emul(const float *src, float *dst, int n1, int n2, int n3, int axis, int nb, int sm_count)
@@ -164,15 +175,10 @@ extern "C" int tri_sys_emul(const float *src, float *dst, int n1, int n2, int n3
     if (!P.ok) return -1;
     const char *ej = getenv("PST_EMUL_JITTER");
     g_jitter = ej ? atoi(ej) : 0;
-    const char *ei = getenv("PST_TRI_SYS_ILS");
-    const bool ils = ei && ei[0] == '1';
+    const char *ei = getenv("PST_TRI_SYS_ILS"), *ep = getenv("PST_TRI_SYS_PRE");
+    const bool ils = ei && ei[0] == '1', pre = ep && ep[0] == '1';
     switch (nb) {
-#define CASE(N) \
-    case N: \
-        if (axis == 0) { if (P.SEG == 68) run<true, N, 68, false>(P, src, dst, axis, n1, n2, n3, sm_count); else run<true, N, 132, false>(P, src, dst, axis, n1, n2, n3, sm_count); } \
-        else if (ils) { if (P.SEG == 68) run<false, N, 68, true>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132, true>(P, src, dst, axis, n1, n2, n3, sm_count); } \
-        else { if (P.SEG == 68) run<false, N, 68, false>(P, src, dst, axis, n1, n2, n3, sm_count); else run<false, N, 132, false>(P, src, dst, axis, n1, n2, n3, sm_count); } \
-        return 0;
+#define CASE(N) case N: dispatch<N>(P, src, dst, axis, n1, n2, n3, sm_count, ils, pre); return 0;
         CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(10)
 #undef CASE
     }

@@ -72,6 +72,18 @@ def test_systolic_kernel_stores_inside_the_chain_variant(emul):
     run_cases(emul, cases, {"PST_TRI_SYS_ILS": "1"})
 
 
+def test_systolic_kernel_prebuild_variant(emul):
+    """PST_TRI_SYS_PRE=1: t of the next tile built in place in the x box while waiting for a carry; several tiles per
+    CTA so that the hand-over between tiles is exercised, once with schedule fuzzing, once combined with ILS."""
+    cases = []
+    for shape, axis, nb, sm in (((100, 140, 7), 1, 8, 2), ((36, 3, 530), 2, 10, 1), ((64, 1034, 2), 1, 5, 1),
+                                ((152, 9, 25), 0, 5, 1), ((528, 40, 3), 0, 10, 1)):
+        cases += [[list(shape), axis, nb, sm, 0], [list(shape), axis, nb, sm, 1]]
+    run_cases(emul, cases, {"PST_TRI_SYS_PRE": "1"})
+    run_cases(emul, cases[:4], {"PST_TRI_SYS_PRE": "1", "PST_EMUL_JITTER": "200"})
+    run_cases(emul, cases[:6], {"PST_TRI_SYS_PRE": "1", "PST_TRI_SYS_ILS": "1"})
+
+
 def test_plan_refuses_what_the_kernel_cannot_do(emul):
     plan = (ctypes.c_int * 4)()
     assert emul.tri_sys_plan(62, 64, 64, 0, 5, plan) == 0          # n1 % 4 != 0 (TMA box start / stride)

@@ -12,6 +12,9 @@ grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys.log | tail -12 | te
 echo "== systolic smoother, outputs stored from inside the backward chain (PST_TRI_SYS_ILS=1)" | tee -a $O/r02a_summary.txt
 PST_TRI_SYS_ILS=1 timeout 300 tools/mb_tri_sys.bin bench > $O/r02a_mb_tri_sys_ils.log 2>&1; echo "mb_tri_sys ILS rc $?" | tee -a $O/r02a_summary.txt
 grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys_ils.log | tail -8 | tee -a $O/r02a_summary.txt
+echo "== systolic smoother, next tile's t pre-built in place (PST_TRI_SYS_PRE=1)" | tee -a $O/r02a_summary.txt
+PST_TRI_SYS_PRE=1 timeout 300 tools/mb_tri_sys.bin bench > $O/r02a_mb_tri_sys_pre.log 2>&1; echo "mb_tri_sys PRE rc $?" | tee -a $O/r02a_summary.txt
+grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_sys_pre.log | tail -8 | tee -a $O/r02a_summary.txt
 echo "== checkpoint + recompute smoother" | tee -a $O/r02a_summary.txt
 timeout 300 tools/mb_tri_rc.bin bench > $O/r02a_mb_tri_rc.log 2>&1; echo "mb_tri_rc rc $?" | tee -a $O/r02a_summary.txt
 grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_rc.log | tail -14 | tee -a $O/r02a_summary.txt
