@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: measure the two smoothers that were written (and verified on the host only)
 # after round 1's GPU minutes were spent.  Run from the repo root on a B200:
-#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+#   gpurun --timeout 2400 -- 'bash tools/r02_first_call.sh'
 # Everything lands in gpurun_out/r02a_*.  Each step has its own timeout: a protocol bug must not eat the call.
 set -u
 mkdir -p gpurun_out
@@ -21,9 +21,9 @@ grep -E "correctness|bench|MISMATCH|CUDA" $O/r02a_mb_tri_rc.log | tail -14 | tee
 echo "== streaming smoother (the default) for reference" | tee -a $O/r02a_summary.txt
 timeout 300 tools/mb_tri_stream.bin benchonly > $O/r02a_mb_tri_stream.log 2>&1
 grep -E "^bench " $O/r02a_mb_tri_stream.log | tee -a $O/r02a_summary.txt
-echo "== bench.py: default, PST_TRI_SYS=1, PST_TRI_SYS=2, PST_TRI_RC=1" | tee -a $O/r02a_summary.txt
-for v in "" "PST_TRI_SYS=1" "PST_TRI_SYS=2" "PST_TRI_RC=1"; do
-    tag=$(echo "${v:-default}" | tr '=' '_')
+echo "== bench.py: default, PST_TRI_SYS=1 (+PRE), PST_TRI_SYS=2, PST_TRI_RC=1" | tee -a $O/r02a_summary.txt
+for v in "" "PST_TRI_SYS=1" "PST_TRI_SYS=1 PST_TRI_SYS_PRE=1" "PST_TRI_SYS=2" "PST_TRI_RC=1"; do
+    tag=$(echo "${v:-default}" | tr ' =' '__')
     env $v timeout 420 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r02a_bench_$tag.json 2> $O/r02a_bench_$tag.err
     echo "$tag rc $?: $(python - <<PY
 import json
