@@ -127,13 +127,15 @@ static int ctx_init(pst_ctx *c, int device)
 
 void pst_comm_destroy(pst_ctx *c);   // pst_comm.cu
 
+extern "C" void pst_ctx_destroy(pst_ctx *c);
+
 extern "C" int pst_ctx_create(int device, pst_ctx **out)
 {
     if (!out) { pst_set_error("null out pointer"); return PST_EINVAL; }
     *out = nullptr;
     pst_ctx *c = new pst_ctx();
     int rc = ctx_init(c, device);
-    if (rc != PST_OK) { delete c; return rc; }
+    if (rc != PST_OK) { pst_ctx_destroy(c); return rc; }      // releases whatever ctx_init got as far as creating
     *out = c;
     return PST_OK;
 }

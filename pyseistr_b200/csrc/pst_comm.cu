@@ -232,6 +232,9 @@ int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v)
         char *d_h = nullptr;
         PST_CUDA(cudaMalloc((void **)&d_h, sizeof(mine) * (size_t)(c->nranks + 1)));
         PST_CUDA(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        // the memset and the handle upload ran on the legacy default stream, c->stream is non-blocking: order them
+        // before the all-gather (whose completion then also proves every peer's mailbox is zeroed)
+        PST_CUDA(cudaDeviceSynchronize());
         PST_NCCL(g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0 /* ncclInt8 */, m->comm, c->stream));
         PST_CUDA(cudaStreamSynchronize(c->stream));
         std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);

@@ -1220,6 +1220,46 @@ static size_t tri_scratch_floats(const DipGeom &g)
     return m > a3 ? m : a3;
 }
 
+// Geometry of this rank's part of a cube with n3 GLOBAL planes: the whole cube on a single-GPU context, the
+// rank's n3-slab (pst_ctx_slab rule) in a distributed one.  *scr = floats of smoothing scratch the geometry needs.
+static int slab_geom(pst_ctx *c, const char *who, int n1, int n2, int n3, int r1, int r2, int r3, DipGeom *g, size_t *scr)
+{
+    const bool dist = c->comm != nullptr && c->nranks > 1;
+    int z0 = 0, z1 = n3;
+    if (dist) {
+        z0 = (int)(((long)n3 * c->rank) / c->nranks);
+        z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+        const int need_planes = std::max(2 * (r3 > 1 ? r3 : 0), 1);
+        if ((n3 / c->nranks) < need_planes) {
+            pst_set_error("%s: %d planes over %d ranks leaves slabs thinner than 2*r3 = %d", who, n3, c->nranks, 2 * r3);
+            return PST_EUNSUP;
+        }
+    }
+    *g = make_geom(n1, n2, z1 - z0, r1, r2, r3);
+    g->n3g = n3; g->z0 = z0; g->nglob = (double)n1 * n2 * n3; g->dist = dist;
+    *scr = tri_scratch_floats(*g);
+    if (dist) *scr = std::max(*scr, (size_t)(z1 - z0 + 2 * r3) * (size_t)n1 * n2);
+    return PST_OK;
+}
+
+// floats slab_halos() takes from the arena
+static size_t slab_halo_floats(const DipGeom &g)
+{
+    return g.dist ? (size_t)g.n1 * g.n2 * (size_t)(2 * std::max(g.r3, 1) + 2) + 4 * 64 : 0;
+}
+
+// work planes of the distributed axis-3 pass (smooth_axis3_dist): r3-plane halos either side + carry planes
+static int slab_halos(pst_ctx *c, DipGeom *g)
+{
+    if (!g->dist) return PST_OK;
+    const size_t plane = (size_t)g->n1 * g->n2;
+    PST_TRY(pst_arena_get(c, plane * (size_t)std::max(g->r3, 1), &g->hb));
+    PST_TRY(pst_arena_get(c, plane * (size_t)std::max(g->r3, 1), &g->ha));
+    PST_TRY(pst_arena_get(c, plane, &g->cin));
+    PST_TRY(pst_arena_get(c, plane, &g->cout));
+    return PST_OK;
+}
+
 static int tri_lines_launch(pst_ctx *c, int cls, float *x, float *scr, long nlines, long na, long sa, long sb,
                             long d, int nx, int nb)
 {
@@ -1588,11 +1628,13 @@ static int tile_launch_k(pst_ctx *c, int cls, K kern, bool *attr_done, const Tri
 template <int EPI>
 static int tile_launch_epi(pst_ctx *c, int cls, bool contig, bool vec, const TriArgs &A, size_t smem, int grid)
 {
-    static bool d0 = false, d1 = false, d2 = false, d3 = false;
-    if (vec) return contig ? tile_launch_k(c, cls, tri_tile_contig_v4_kernel<EPI>, &d0, A, smem, grid)
-                           : tile_launch_k(c, cls, tri_tile_strided_v4_kernel<EPI>, &d1, A, smem, grid);
-    return contig ? tile_launch_k(c, cls, tri_tile_kernel<true, EPI>, &d2, A, smem, grid)
-                  : tile_launch_k(c, cls, tri_tile_kernel<false, EPI>, &d3, A, smem, grid);
+    // cudaFuncSetAttribute is per device: one flag per (kernel, device)
+    static bool done[4][64] = {};
+    bool *d = &done[0][c->device & 63];
+    if (vec) return contig ? tile_launch_k(c, cls, tri_tile_contig_v4_kernel<EPI>, d, A, smem, grid)
+                           : tile_launch_k(c, cls, tri_tile_strided_v4_kernel<EPI>, d + 64, A, smem, grid);
+    return contig ? tile_launch_k(c, cls, tri_tile_kernel<true, EPI>, d + 128, A, smem, grid)
+                  : tile_launch_k(c, cls, tri_tile_kernel<false, EPI>, d + 192, A, smem, grid);
 }
 
 static int tile_launch(pst_ctx *c, int cls, int epi, bool contig, bool vec, const TriArgs &A, size_t smem, int grid)
@@ -1703,7 +1745,8 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
             A.n3g = g.n3; A.z0 = 0; A.nz = g.n3; A.nb = nb; A.K0 = 0; A.K1 = g.n3 + 2 * nb;
             A.wt = (float)(1.0 / ((double)nb * nb)); A.w2 = (float)(2. * A.wt);
             const unsigned blocks = (unsigned)((L + 127) / 128);
-            static bool ad = false;
+            static bool ad_dev[64] = {};
+            bool &ad = ad_dev[c->device & 63];
             if (!ad) {
                 PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
                 PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
@@ -2043,23 +2086,12 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_dip_args(n1, n2, n3, niter, liter, order, r1, r2, r3));
     PST_CUDA(cudaSetDevice(c->device));
-    const bool dist = c->comm != nullptr && c->nranks > 1;
-    int z0 = 0, z1 = n3;
-    if (dist) {
-        z0 = (int)(((long)n3 * c->rank) / c->nranks);
-        z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
-        const int need_planes = std::max(2 * (r3 > 1 ? r3 : 0), 1);
-        if ((n3 / c->nranks) < need_planes) {
-            pst_set_error("dip: %d planes over %d ranks leaves slabs thinner than 2*r3 = %d", n3, c->nranks, 2 * r3);
-            return PST_EUNSUP;
-        }
-    }
-    const int nz = z1 - z0;
-    DipGeom g = make_geom(n1, n2, nz, r1, r2, r3);
-    g.n3g = n3; g.z0 = z0; g.nglob = (double)n1 * n2 * n3; g.dist = dist;
+    DipGeom g;
+    size_t scr = 0;
+    PST_TRY(slab_geom(c, "dip", n1, n2, n3, r1, r2, r3, &g, &scr));
+    const bool dist = g.dist;
+    const int nz = g.n3;
     const size_t n = g.n, plane = (size_t)n1 * n2;
-    size_t scr = tri_scratch_floats(g);
-    if (dist) scr = std::max(scr, (size_t)(nz + 2 * r3) * plane);
     const size_t extra = dist ? (plane * (size_t)(2 * r3 + 2 + 2) + n + plane + (d_mask ? n + 2 * plane : 0)) : 0;
     const size_t need = (11 * n + scr + extra) * sizeof(float) + 2 * n + 32 * 256;
     PST_TRY(pst_arena_reserve(c, need));
@@ -2091,10 +2123,7 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
         PST_TRY(pst_comm_halo_exchange(c, d_din, d_din, dummy, ue + n, plane));
         u = ue;
         n3_live = (c->rank == c->nranks - 1) ? nz - 1 : nz;
-        PST_TRY(pst_arena_get(c, plane * (size_t)std::max(r3, 1), &g.hb));
-        PST_TRY(pst_arena_get(c, plane * (size_t)std::max(r3, 1), &g.ha));
-        PST_TRY(pst_arena_get(c, plane, &g.cin));
-        PST_TRY(pst_arena_get(c, plane, &g.cout));
+        PST_TRY(slab_halos(c, &g));
     }
     if (d_mask) {
         if (dist) {
@@ -2130,6 +2159,7 @@ extern "C" int pst_allpass_dev(pst_ctx *c, const float *d_u, const float *d_sigm
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     if (n1 < 2 * order + 1) { pst_set_error("allpass: n1 too short"); return PST_EINVAL; }
+    if (c->comm && c->nranks > 1) { pst_set_error("allpass: single-GPU contexts only (test hook; pst_dip runs the stencil on slabs)"); return PST_EUNSUP; }
     PST_TRY(pst_allpass_launch(c, d_u, d_sigma, nullptr, 0.f, nullptr, d_y, n1, n2, n3, order, xline, der != 0, false, 5));
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
@@ -2163,16 +2193,19 @@ extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, 
         pst_set_error("smoothcf: options other than adj=0, repeat=1 are single-GPU only"); return PST_EUNSUP;
     }
     PST_CUDA(cudaSetDevice(c->device));
-    DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
-    const size_t scr = tri_scratch_floats(g);
-    PST_TRY(pst_arena_reserve(c, scr * sizeof(float) + 4096));
+    // distributed contexts: n3 is the GLOBAL plane count and d_x this rank's slab (the plain triangle smoother only)
+    DipGeom g;
+    size_t scr = 0;
+    PST_TRY(slab_geom(c, "smoothcf", n1, n2, n3, r1, r2, r3, &g, &scr));
+    PST_TRY(pst_arena_reserve(c, (scr + slab_halo_floats(g)) * sizeof(float) + 4096));
     pst_arena_reset(c);
     float *s;
     PST_TRY(pst_arena_get(c, scr, &s));
+    PST_TRY(slab_halos(c, &g));
     const int rr[3] = {r1, r2, r3}, df[3] = {diff1, diff2, diff3}, bx[3] = {box1, box2, box3};
     const bool plain = !adj && !diff1 && !diff2 && !diff3 && !box1 && !box2 && !box3;
     if (plain && repeat == 1) {
-        PST_TRY(pst_smooth3_inplace(c, d_x, s, n1, n2, n3, r1, r2, r3));
+        PST_TRY(pst_shape_apply(c, g, d_x, d_x, s, nullptr, nullptr, nullptr, nullptr));
     } else {
         for (int a = 0; a < 3; a++) {
             if (rr[a] <= 1) continue;
@@ -2184,6 +2217,7 @@ extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, 
             }
         }
     }
+    if (g.dist) PST_TRY(pst_comm_check(c));
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
 }
@@ -2199,10 +2233,14 @@ extern "C" int pst_divne_dev(pst_ctx *c, float *d_num, float *d_den, float *d_ra
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     if (r1 < 1 || r2 < 1 || r3 < 1 || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("divne: bad arguments"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
-    DipGeom g = make_geom(n1, n2, n3, r1, r2, r3);
-    const size_t n = g.n, scr = tri_scratch_floats(g);
-    PST_TRY(pst_arena_reserve(c, (7 * n + scr) * sizeof(float) + 16 * 256));
+    // distributed contexts: n3 is the GLOBAL plane count, the pointers are this rank's slab, the sums are all-reduced
+    DipGeom g;
+    size_t scr = 0;
+    PST_TRY(slab_geom(c, "divne", n1, n2, n3, r1, r2, r3, &g, &scr));
+    const size_t n = g.n;
+    PST_TRY(pst_arena_reserve(c, (7 * n + scr + slab_halo_floats(g)) * sizeof(float) + 16 * 256));
     pst_arena_reset(c);
+    PST_TRY(slab_halos(c, &g));
     CgWork w{};
     PST_TRY(pst_arena_get(c, n, &w.p));
     PST_TRY(pst_arena_get(c, n, &w.r));
@@ -2213,6 +2251,7 @@ extern "C" int pst_divne_dev(pst_ctx *c, float *d_num, float *d_den, float *d_ra
     PST_TRY(pst_arena_get(c, n, &w.tmp));
     PST_TRY(pst_arena_get(c, scr, &w.scr));
     PST_TRY(pst_divne_run(c, g, d_num, d_den, d_rat, nullptr, w, liter, 1.0f, iters_run));
+    if (g.dist) PST_TRY(pst_comm_check(c));
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
 }

@@ -489,6 +489,20 @@ static void plan_close_parents(SprayPlan &P)
         }
 }
 
+// Chunk height along n3 (target planes per chunk, *cz) and the planes a chunk's slot / scratch volumes hold
+// (*nzl = chunk + ns3 planes of halo sources either side), from the PST_SPRAY_CHUNK_GB budget.  The ONE place that
+// decides it: the arena reservation and spray_run must agree.
+static void spray_chunk_planes(const SprayPlan &P, int nlive, int *cz, int *nzl)
+{
+    const int NC = 2 * P.nw + 2;
+    const double bytes_per_plane = (double)P.n1 * P.n2 * 4.0 * (nlive + NC);
+    int z = (int)(spray_chunk_bytes() / bytes_per_plane) - 2 * P.ns3;
+    if (z < 1) z = 1;
+    if (z > P.zt1 - P.zt0) z = P.zt1 - P.zt0;
+    *cz = z;
+    *nzl = std::min(P.zs1 - P.zs0, z + 2 * P.ns3);
+}
+
 template <int NW>
 static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 {
@@ -513,11 +527,8 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
     const int NC = 2 * nw + 2;
     // chunk height: bound slot + scratch memory to ~6 GB
-    const double bytes_per_plane = (double)plane * 4.0 * (nlive + NC);
-    int cz = (int)(spray_chunk_bytes() / bytes_per_plane) - 2 * ns3;
-    if (cz < 1) cz = 1;
-    if (cz > P.zt1 - P.zt0) cz = P.zt1 - P.zt0;
-    const int nzl_max = std::min(P.zs1 - P.zs0, cz + 2 * ns3);
+    int cz, nzl_max;
+    spray_chunk_planes(P, nlive, &cz, &nzl_max);
     float *slotbuf[PST_MAXSLOT];
     const int centre = ns3 * P.np2 + P.ns2;
     for (int s = 0; s < P.np; s++) {
@@ -680,9 +691,9 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     const long plane = (long)n1 * n2;
     const size_t n = (size_t)plane * nz, nex = (size_t)plane * ne;
     const int NC = 2 * order + 2;
-    double chunk_planes = spray_chunk_bytes() / ((double)plane * 4.0 * (nlive + NC));
-    if (chunk_planes > nz) chunk_planes = nz;
-    const size_t nzl = (size_t)std::min<double>(ne, std::max(1.0, floor(chunk_planes) - 2 * ns3) + 2 * ns3);
+    int cz_, nzl_;
+    spray_chunk_planes(P, nlive, &cz_, &nzl_);
+    const size_t nzl = (size_t)nzl_;
     const size_t need = (4 * nex + 2 * n + (size_t)plane * nzl * (nlive + NC)) * sizeof(float) + 64 * 256 + (size_t)nlive * 256;
     PST_TRY(pst_arena_reserve(c, need));
     pst_arena_reset(c);
