@@ -45,6 +45,7 @@ typedef struct pst_stats {
     double    class_ms[12];
     long long class_launches[12];
     double    class_bytes[12];   /* ALGORITHMIC bytes (compulsory reads + writes) of those launches */
+    double    class_flops[12];   /* ALGORITHMIC flops of those launches (ALU-bound classes: PST_K_PREDICT) */
 } pst_stats;
 
 #define PST_K_ALLPASS   0   /* PWD stencil (+ fused line-search update, sum of squares) */
@@ -124,6 +125,11 @@ int pst_somean2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n
                  int ns, int order, int adj, float eps, int verb, float *out);
 int pst_somf2d(pst_ctx *ctx, const float *din, const float *dip, int n1, int n2, int n3,
                int ns, int nmf, int option, int order, float eps, int verb, float *out);
+/* device-pointer variants (forward operator; adj = 1 of csomean2d is host-pointer only) */
+int pst_somean2d_dev(pst_ctx *ctx, const float *d_din, const float *d_dip, int n1, int n2, int n3,
+                     int ns, int order, float eps, float *d_out);
+int pst_somf2d_dev(pst_ctx *ctx, const float *d_din, const float *d_dip, int n1, int n2, int n3,
+                   int ns, int nmf, int option, int order, float eps, float *d_out);
 
 /* ---- 3-D structure-oriented interpolation (PWD-residual CG).  Replaces soint3dcfun.csoint3d
  * (pyseistr/src/soint3d_cfuns.c:2405-2508, "OOOOiiiiiiiiiifi"); called by soint3dc

@@ -104,6 +104,13 @@ def dip3dc(din, niter=5, liter=10, order=2, eps_dv=0.01, eps_cg=1, tol_cg=0.0000
     return out[:, :, :, 0], out[:, :, :, 1]
 
 
+def dip_counts():
+    """{CG iterations, line-search evaluations, GN iterations} executed by the last dip3dc / dip2dc call."""
+    c = (ctypes.c_longlong * 3)()
+    lib().pso_get_counts(c)
+    return {"cg_iterations": int(c[0]), "linesearch_evals": int(c[1]), "gn_iterations": int(c[2])}
+
+
 def dip2dc(din, niter=5, liter=20, order=2, eps_dv=0.01, eps_cg=1, tol_cg=0.000001,
            rect=(10, 10, 1), verb=0, mask=None):
     n1, n2 = din.shape

@@ -381,6 +381,11 @@ int pso_divne(float *num, float *den, float *rat, int n1, int n2, int n3,
 /* dip3 :1619-1691 for one direction.  eps handed to divne is 1.0: the file-scope `eps`
  * shared by the CG and dip3 sections is overwritten by ps_conjgrad_init.
  * pmin/pmax are -/+FLT_MAX in dipc (:1779-1782) so the clip never acts on finite values. */
+/* executed-iteration counters of the last pso_dip call (test aid: the data-dependent branches -- CG early exit,
+ * line-search halvings -- must go the same way on the GPU): {CG iterations, line-search evaluations, GN iterations} */
+static long long g_counts[3];
+void pso_get_counts(long long *out3) { out3[0] = g_counts[0]; out3[1] = g_counts[1]; out3[2] = g_counts[2]; }
+
 static void gauss_newton(const float *u, float *p, const unsigned char *mask, int xline,
                          int n1, int n2, int n3, int niter, int liter, int nw,
                          int r1, int r2, int r3)
@@ -395,9 +400,11 @@ static void gauss_newton(const float *u, float *p, const unsigned char *mask, in
         for (size_t i = 0; i < n; i++) { p0[i] = p[i]; usum += u2[i] * u2[i]; }
         if (mask)
             for (size_t i = 0; i < n; i++) if (mask[i]) { u1[i] = 0.f; u2[i] = 0.f; }
-        pso_divne(u2, u1, dp, n1, n2, n3, r1, r2, r3, liter, 1.0f);
+        g_counts[0] += pso_divne(u2, u1, dp, n1, n2, n3, r1, r2, r3, liter, 1.0f);
+        g_counts[2]++;
         float lam = 1.f;
         for (int k = 0; k < 8; k++) {
+            g_counts[1]++;
             for (size_t i = 0; i < n; i++) {
                 float pi = p0[i] + lam * dp[i];
                 if (pi < pmin) pi = pmin;
@@ -425,6 +432,7 @@ int pso_dip(const float *din, const float *mask, int n1, int n2, int n3, int nit
         footprint_mask(mask, n1, n2, n3, order, m_in, m_x);
     }
     memset(dip_out, 0, (n3 == 1 ? n : 2 * n) * sizeof(float));
+    g_counts[0] = g_counts[1] = g_counts[2] = 0;
     gauss_newton(din, dip_out, m_in, 0, n1, n2, n3, niter, liter, order, r1, r2, r3);
     if (n3 != 1)
         gauss_newton(din, dip_out + n, m_x, 1, n1, n2, n3, niter, liter, order, r1, r2, r3);

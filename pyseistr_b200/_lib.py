@@ -32,7 +32,8 @@ class Stats(ctypes.Structure):
                 ("smooth_passes", ctypes.c_longlong), ("predictions", ctypes.c_longlong),
                 ("device_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
                 ("d2h_bytes", ctypes.c_double), ("class_ms", ctypes.c_double * 12),
-                ("class_launches", ctypes.c_longlong * 12), ("class_bytes", ctypes.c_double * 12)]
+                ("class_launches", ctypes.c_longlong * 12), ("class_bytes", ctypes.c_double * 12),
+                ("class_flops", ctypes.c_double * 12)]
 
     def as_dict(self):
         d = {}
@@ -69,6 +70,8 @@ SIGNATURES = {
     "pst_somf3d_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pst_somean2d": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _i, _fp]),
     "pst_somf2d": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _fp]),
+    "pst_somean2d_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "pst_somf2d_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pst_soint3d": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _fp]),
     "pst_soint3d_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "pst_sint3d": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _fp]),

@@ -188,6 +188,7 @@ void pst_prof_resolve(pst_ctx *c)
             c->stats.class_ms[k] += ms;
             c->stats.class_launches[k]++;
             c->stats.class_bytes[k] += c->prof_bytes[s / 2];
+            c->stats.class_flops[k] += c->prof_flops[s / 2];
         }
     }
     c->prof_used = 0;
@@ -202,6 +203,7 @@ extern "C" int pst_ctx_set_profile(pst_ctx *c, int on)
         c->prof_ev.resize(2 * pairs);
         c->prof_cls.resize(pairs);
         c->prof_bytes.resize(pairs);
+        c->prof_flops.resize(pairs);
         for (auto &e : c->prof_ev) PST_CUDA(cudaEventCreate(&e));
     }
     if (!on) pst_prof_resolve(c);

@@ -64,7 +64,7 @@ struct pst_ctx {
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;    // 2 events per timed launch
     std::vector<int> prof_cls;
-    std::vector<double> prof_bytes;
+    std::vector<double> prof_bytes, prof_flops;
     size_t prof_used = 0;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     pst_comm *comm = nullptr;        // null for single-GPU contexts
@@ -75,7 +75,7 @@ struct pst_ctx {
 void pst_prof_resolve(pst_ctx *c);                       // sync + accumulate pending pairs
 struct KTimer {                                          // RAII around one kernel launch
     pst_ctx *c; size_t slot; bool on;
-    KTimer(pst_ctx *ctx, int cls, double bytes = 0.0) : c(ctx), slot(0), on(ctx->prof)
+    KTimer(pst_ctx *ctx, int cls, double bytes = 0.0, double flops = 0.0) : c(ctx), slot(0), on(ctx->prof)
     {
         c->stats.kernel_launches++;
         if (!on) return;
@@ -84,6 +84,7 @@ struct KTimer {                                          // RAII around one kern
         c->prof_used += 2;
         c->prof_cls[slot / 2] = cls;
         c->prof_bytes[slot / 2] = bytes;
+        c->prof_flops[slot / 2] = flops;
         cudaEventRecord(c->prof_ev[slot], c->stream);
     }
     ~KTimer() { if (on) cudaEventRecord(c->prof_ev[slot + 1], c->stream); }
@@ -93,6 +94,8 @@ struct KTimer {                                          // RAII around one kern
 #define PST_LAUNCH(c, cls, ...) do { KTimer kt__((c), (cls)); __VA_ARGS__; } while (0)
 // same, with the algorithmic bytes the launch moves (for the live roofline)
 #define PST_LAUNCHB(c, cls, bytes, ...) do { KTimer kt__((c), (cls), (double)(bytes)); __VA_ARGS__; } while (0)
+// same, plus the algorithmic flops (ALU-bound kernels)
+#define PST_LAUNCHBF(c, cls, bytes, flops, ...) do { KTimer kt__((c), (cls), (double)(bytes), (double)(flops)); __VA_ARGS__; } while (0)
 
 // ---- arena ---------------------------------------------------------------------------
 int pst_arena_reserve(pst_ctx *c, size_t bytes);            // (re)allocate if too small

@@ -508,7 +508,9 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 {
     const int threads = A.n2 >= 128 ? 128 : (A.n2 >= 64 ? 64 : 32);
     dim3 grid((A.n2 + threads - 1) / threads, A.zlb - A.zla);
-    PST_LAUNCHB(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * A.n2 * (A.zlb - A.zla),
+    // algorithmic flops per predicted sample: predict1 47 (nw=1) / 116 (nw=2), predict2 78 / 187
+    const double fl = NW == 1 ? (two ? 78.0 : 47.0) : (two ? 187.0 : 116.0);
+    PST_LAUNCHBF(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * A.n2 * (A.zlb - A.zla), fl * (double)A.n1 * A.n2 * (A.zlb - A.zla),
         if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
         else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A));
 }
@@ -758,6 +760,7 @@ extern "C" int pst_somf3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
 int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
                      int order, float eps, float *d_out)
 {
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
     return spray_filter_dev(c, 2, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, 0, order, eps * eps, d_out);
 }
@@ -765,6 +768,7 @@ int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1,
 int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
                    int nmf, int option, int order, float eps, float *d_out)
 {
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
     if (option != 1) { pst_set_error("somf2d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
     return spray_filter_dev(c, 3, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, nmf, order, eps * eps, d_out);
@@ -1138,7 +1142,7 @@ static int smoother_adj(pst_ctx *c, const Smoother2 &S, float *in, const float *
             for (int p0 = 0; p0 < S.npanel; p0 += cz) {
                 A.p0 = p0;
                 dim3 grid((S.nt + threads - 1) / threads, std::min(cz, S.npanel - p0));
-                PST_LAUNCHB(c, PST_K_PREDICT, 20.0 * (double)plane * grid.y,
+                PST_LAUNCHBF(c, PST_K_PREDICT, 20.0 * (double)plane * grid.y, (S.nw == 1 ? 47.0 : 116.0) * (double)plane * grid.y,
                     if (S.nw == 1) predict_adj_kernel<1><<<grid, threads, 0, c->stream>>>(A);
                     else           predict_adj_kernel<2><<<grid, threads, 0, c->stream>>>(A));
                 c->stats.predictions += (long long)grid.y * S.nt;

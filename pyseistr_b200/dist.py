@@ -99,3 +99,14 @@ def soint3dc_slab(ctx, slab, mask, dipi, dipx, n3, order=1, niter=100, njs=(1, 1
                                    int(order), int(njs[0]), int(njs[1]), int(niter), 0, 202223, int(hasmask), 0.0,
                                    int(verb), _p(out)))
     return out.reshape(n1, n2, nz, order="F")
+
+
+def smoothc_slab(ctx, slab, n3, rect):
+    """Plain N-D triangle smoothing (smoothcf with adj = 0, repeat = 1, no diff / box) of this rank's slab: the
+    axis-3 running sums run across the ranks in the reference's order, so the result is the single-GPU one."""
+    n1, n2, nz = slab.shape
+    d = _F(slab)
+    out = np.empty_like(d)
+    _lib.check(ctx.lib.pst_smoothcf(ctx.handle, _p(d), n1, n2, int(n3), 1, 0, int(rect[0]), int(rect[1]), int(rect[2]),
+                                    0, 0, 0, 0, 0, 0, _p(out)))
+    return out.reshape(n1, n2, nz, order="F")

@@ -33,7 +33,9 @@ def main():
     for (shape, kw) in [((60, 24, 12 * world), dict(niter=3, liter=6, order=2, rect=(5, 5, 5))),
                         ((40, 17, 10 * world + 3), dict(niter=2, liter=5, order=1, rect=(3, 4, 4))),
                         # tall slabs: the axis-3 tile kernels run with 64-line tiles (rows x 128 lines > 75 KB)
-                        ((16, 12, 200 * world + 1), dict(niter=2, liter=4, order=2, rect=(3, 3, 6)))]:
+                        ((16, 12, 200 * world + 1), dict(niter=2, liter=4, order=2, rect=(3, 3, 6))),
+                        # 128-plane slabs, default radii: the geometry of the headline cube on 8 GPUs (128-line tiles)
+                        ((16, 12, 128 * world), dict(niter=2, liter=4, order=2, rect=(5, 5, 5)))]:
         n1, n2, n3 = shape
         cube = synth.cube(n1, n2, n3, seed=77)
         noisy = synth.erratic(cube, ntraces=9)
@@ -100,6 +102,21 @@ def main():
             e = rel_l2(full, want)
             print(f"[dist_check] world={world} soint3d order={order} njs={njs}: rel-L2 {e:.2e}", flush=True)
             ok = ok and e <= 1e-5
+    # ---- plain triangle smoothing of a slab-distributed volume (smoothcf, adj = 0): bit-exact vs the oracle
+    for shape, rect in (((24, 12, 9 * world + 1), (3, 4, 4)), ((16, 12, 128 * world), (5, 5, 5))):
+        n1, n2, n3 = shape
+        x = np.asfortranarray(np.random.default_rng(90).standard_normal(shape).astype(np.float32))
+        z0, z1 = pd.slab_bounds(n3, rank, world)
+        mine = pd.smoothc_slab(ctx, x[:, :, z0:z1], n3, rect)
+        parts = [None] * world
+        dist.all_gather_object(parts, (z0, np.asarray(mine)))
+        if rank == 0:
+            parts.sort(key=lambda t: t[0])
+            full = np.concatenate([p[1] for p in parts], axis=2)
+            want = _port.smoothc(x, rect, adj=0)
+            b = bool(np.array_equal(full, want))
+            print(f"[dist_check] world={world} smoothc {shape} rect={rect}: bit-exact={b}", flush=True)
+            ok = ok and b
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.barrier()
