@@ -498,7 +498,7 @@ extern "C" int pst_sint3d(pst_ctx *c, const float *din, const float *dipi, const
 {
     PST_ENTRY(c);
     if (!din || !dipi || !dipx || !mask || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("sint3d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * n3;
+    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);      /* this rank's slab in a distributed context */
     CallTimer t(c);
     DevBuf d, m, a, b, o;
     PST_TRY(up(c, d, din, n));

@@ -2464,17 +2464,26 @@ struct NoiseGen {
 };
 }  // namespace
 
-static int soint3d_noise_rhs(pst_ctx *c, float *d_rr, size_t ny, int seed, float var)
+// The stream is sequential over the WHOLE cube (2 * nglob draws: inline residual, then xline residual).  A rank of a
+// distributed context draws all of it and keeps the two runs that fall on its slab [off, off + n) -- every rank sees
+// the reference's sequence, at the price of drawing it nranks times.
+static int soint3d_noise_rhs(pst_ctx *c, float *d_rr, size_t nglob, size_t off, size_t n, int seed, float var)
 {
     NoiseGen G((uint32_t)(unsigned long)seed);
     const float a = sqrtf(var);
     const size_t chunk = (size_t)1 << 24;
-    std::vector<float> h(std::min(chunk, ny));
-    for (size_t o = 0; o < ny; o += chunk) {
-        const size_t m = std::min(chunk, ny - o);
-        for (size_t i = 0; i < m; i++) { const float d = a * G.normal(); h[i] = -d; }
-        PST_CUDA(cudaMemcpyAsync(d_rr + o, h.data(), m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        PST_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<float> h(std::min(chunk, n));
+    size_t pos = 0;                                               // draws consumed so far
+    for (int half = 0; half < 2; half++) {
+        const size_t start = (size_t)half * nglob + off;
+        for (; pos < start; pos++) (void)G.normal();
+        for (size_t o = 0; o < n; o += chunk) {
+            const size_t m = std::min(chunk, n - o);
+            for (size_t i = 0; i < m; i++) { const float d = a * G.normal(); h[i] = -d; }
+            pos += m;
+            PST_CUDA(cudaMemcpyAsync(d_rr + (size_t)half * n + o, h.data(), m * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            PST_CUDA(cudaStreamSynchronize(c->stream));
+        }
     }
     return PST_OK;
 }
@@ -2536,7 +2545,7 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     PST_LAUNCH(c, PST_K_OTHER, (known_kernel<<<grid, threads, 0, c->stream>>>(d_mask ? d_mask : d_din, known, n)));
     // ps_solver :1018-1040 with dat = 0 (var = 0): rr = -0; x = x0 = data; rr += L x
     PST_CUDA(cudaMemcpyAsync(x, d_din, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    if (var != 0.f) PST_TRY(soint3d_noise_rhs(c, rr, 2 * n, seed, var));
+    if (var != 0.f) PST_TRY(soint3d_noise_rhs(c, rr, pln * (size_t)n3g, pln * (size_t)z0, n, seed, var));
     else PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
     PST_TRY(halo_next(x));
     PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
@@ -2605,7 +2614,6 @@ extern "C" int pst_soint3d_dev(pst_ctx *c, const float *d_din, const float *d_ma
     if (n1 < 2 * nw * std::max(nj1, nj2) + 1) { pst_set_error("soint3d: n1 too short"); return PST_EINVAL; }
     if (drift != 0) { pst_set_error("soint3d: drift is not implemented on the GPU path (data-dependent scatter)"); return PST_EUNSUP; }
     if (var < 0.f) { pst_set_error("soint3d: var < 0"); return PST_EINVAL; }
-    if (c->comm && c->nranks > 1 && var != 0.f) { pst_set_error("soint3d: var != 0 is single-GPU only (the noise stream is sequential over the whole cube)"); return PST_EUNSUP; }
     if (hasmask && !d_mask) { pst_set_error("soint3d: hasmask=1 needs a mask"); return PST_EINVAL; }
     PST_CUDA(cudaSetDevice(c->device));
     const float *m = hasmask ? d_mask : nullptr;

@@ -102,6 +102,8 @@ struct PredArgs {
     int ze0;                    // global index of chunk-local plane 0
     int zla, zlb;               // chunk-local plane range to produce
     int a, b;                   // slot offsets: source = target - (a,b)
+    int t_off, ntg;             // traces of a panel cut over ranks (distributed xline smoother of sint3d): global index
+                                // of local trace 0 and global trace count; whole panels: 0, n2
     RegC reg;
     BTabS tb;
 };
@@ -121,8 +123,9 @@ predict_kernel(const PredArgs A)
     const long base = (long)zl * n1 * n2 + i2;
     float *out = A.out + base;
     // slot stays zero when its source lies outside the cube (csomf3d :1656)
-    const int s2 = i2 - A.a, s3 = (A.ze0 + zl) - A.b;
-    if (s2 < 0 || s2 >= n2 || s3 < 0 || s3 >= A.n3) {
+    // (a source outside the LOCAL trace range of a cut panel feeds only halo targets nobody reads: zero as well)
+    const int s2 = i2 - A.a, s3 = (A.ze0 + zl) - A.b, s2g = s2 + A.t_off;
+    if (s2 < 0 || s2 >= n2 || s2g < 0 || s2g >= A.ntg || s3 < 0 || s3 >= A.n3) {
         for (int k = 0; k < n1; k++) out[(long)k * n2] = 0.f;
         return;
     }
@@ -475,6 +478,7 @@ struct SprayPlan {
     // input volumes hold planes [zs0, zs1); outputs are produced for planes [zt0, zt1).
     // Single GPU: zs = zt = [0, n3).  Distributed: zt = this rank's slab, zs = slab + ns3 halos.
     int zs0, zs1, zt0, zt1;
+    int t_off = 0, ntg = 0;        // cut panels (see PredArgs); ntg = 0 means whole panels (ntg = n2)
 };
 
 static void plan_close_parents(SprayPlan &P)
@@ -559,6 +563,7 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
                 PredArgs A{};
                 A.n1 = n1; A.n2 = n2; A.n3 = n3; A.ze0 = ze0; A.zla = lo - ze0; A.zlb = hi - ze0;
                 A.a = a; A.b = b; A.reg = reg; A.tb = tb; A.out = slot[s]; A.scr = scr;
+                A.t_off = P.t_off; A.ntg = P.ntg > 0 ? P.ntg : n2;
                 int nin = 0;
                 const float *inp[2]; const float *sg[2]; long ioff[2], soff[2]; int fw[2];
                 if (a != 0) {                       // inline parent (get_update bit 1, :1661-1673)
@@ -788,12 +793,13 @@ int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, i
 // between them (a strided 2-D transpose per i1).  The CG vectors stay in layout A.
 // =======================================================================================
 
-// in: [P][n1][Q] (Q fastest)  ->  out: [Q][n1][P] (P fastest)
-__global__ void swap_ab_kernel(const float *__restrict__ in, float *__restrict__ out, int P, int n1, int Q, int zero_plus)
+// in: [P][n1][Q] (Q fastest)  ->  out: [Q][n1][P] (P fastest); only q in [q_lo, q_lo + nq) is written, at q - q_lo
+__global__ void swap_ab_kernel(const float *__restrict__ in, float *__restrict__ out, int P, int n1, int Q, int zero_plus,
+                               int q_lo, int nq)
 {
     __shared__ float tile[32][33];
     const int i1 = blockIdx.z;
-    const int q0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    const int q0 = q_lo + blockIdx.x * 32, p0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int p = p0 + r, q = q0 + threadIdx.x;
         if (p < P && q < Q) tile[r][threadIdx.x] = in[((long)p * n1 + i1) * Q + q];
@@ -801,20 +807,21 @@ __global__ void swap_ab_kernel(const float *__restrict__ in, float *__restrict__
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int q = q0 + r, p = p0 + threadIdx.x;
-        if (p < P && q < Q) {
+        if (p < P && q < q_lo + nq) {
             float v = tile[threadIdx.x][r];
             if (zero_plus) v = 0.f + v;                      // "smooth[] += xtmp" onto a zeroed volume (:2296)
-            out[((long)q * n1 + i1) * P + p] = v;
+            out[((long)(q - q_lo) * n1 + i1) * P + p] = v;
         }
     }
 }
 
-static int swap_ab(pst_ctx *c, const float *in, float *out, int P, int n1, int Q, bool zero_plus = false)
+static int swap_ab(pst_ctx *c, const float *in, float *out, int P, int n1, int Q, bool zero_plus = false, int q_lo = 0, int nq = -1)
 {
     const int zmax = 32768;
     if (n1 > zmax) { pst_set_error("sint3d: n1 > %d unsupported", zmax); return PST_EUNSUP; }
-    dim3 grid((Q + 31) / 32, (P + 31) / 32, n1), block(32, 8);
-    PST_LAUNCHB(c, PST_K_OTHER, 8.0 * (double)P * n1 * Q, (swap_ab_kernel<<<grid, block, 0, c->stream>>>(in, out, P, n1, Q, zero_plus ? 1 : 0)));
+    if (nq < 0) nq = Q - q_lo;
+    dim3 grid((nq + 31) / 32, (P + 31) / 32, n1), block(32, 8);
+    PST_LAUNCHB(c, PST_K_OTHER, 8.0 * (double)P * n1 * nq, (swap_ab_kernel<<<grid, block, 0, c->stream>>>(in, out, P, n1, Q, zero_plus ? 1 : 0, q_lo, nq)));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -831,6 +838,7 @@ struct AdjArgs {
     int forw;
     int n1, n2;
     int p0;                    // first panel of this launch
+    int t_off, ntg;            // cut panels: global index of local trace 0, global trace count
     RegC reg;
     BTabS tb;
 };
@@ -844,8 +852,11 @@ predict_adj_kernel(const AdjArgs A)
     constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 2;
     const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
     if (i2 >= A.n2) return;
-    const int ip = i2 + A.shift;
-    if (ip < 0 || ip >= A.n2) return;                        // "continue": the running trace is left alone
+    const int ip = i2 + A.shift, ipg = ip + A.t_off;
+    // "continue": the running trace is left alone (data trace outside the panel; outside the local range of a cut panel
+    // the model trace is a halo trace nobody reads)
+    if (ip < 0 || ip >= A.n2 || ipg < 0 || ipg >= A.ntg) return;
+    { const int ig = i2 + A.sg_shift; if (ig < 0 || ig >= A.n2) return; }
     const int n1 = A.n1, n2 = A.n2;
     const long pbase = (long)(A.p0 + blockIdx.y) * n1 * n2;
     float *tr = A.tr + pbase + i2;
@@ -1087,6 +1098,7 @@ struct Smoother2 {
     const float *dip;                  // slopes (trace-minor)
     float *tnorm;                      // spray of ones through the weights (pwsmooth_set)
     SprayPlan P;
+    int t_off = 0, ntg = 0;            // cut panels (distributed xline smoother): see PredArgs
 };
 
 static void smoother_plan(Smoother2 &S)
@@ -1097,6 +1109,7 @@ static void smoother_plan(Smoother2 &S)
     P.np2 = 2 * S.ns + 1; P.np3 = 1; P.np = P.np2;
     P.eps_reg = S.eps_reg;
     P.zs0 = 0; P.zs1 = S.npanel; P.zt0 = 0; P.zt1 = S.npanel;
+    P.t_off = S.t_off; P.ntg = S.ntg;
     for (int s = 0; s < P.np; s++) P.live[s] = true;
 }
 
@@ -1129,6 +1142,7 @@ static int smoother_adj(pst_ctx *c, const Smoother2 &S, float *in, const float *
     PST_TRY(pst_arena_get(c, plane * (size_t)cz * NC, &scr));
     AdjArgs A{};
     A.data = data; A.tnorm = S.tnorm; A.sg = S.dip; A.scr = scr; A.n1 = S.n1; A.n2 = S.nt;
+    A.t_off = S.t_off; A.ntg = S.ntg > 0 ? S.ntg : S.nt;
     A.reg = make_reg(S.eps_reg); A.tb = make_btab_s(S.nw);
     const int threads = S.nt >= 128 ? 128 : (S.nt >= 64 ? 64 : 32);
     for (int side = 0; side < 2; side++) {
@@ -1248,6 +1262,13 @@ sint_known_kernel(const float *__restrict__ mask, unsigned char *__restrict__ kn
     pst_block_reduce<1>(acc, partial);
 }
 
+// Distributed contexts (n3-slabs): n3 is the GLOBAL plane count, the pointers are this rank's slab.  The inline
+// smoother works inside (n1 x n2) panels, i.e. inside the slab.  The xline smoother's panels are (n1 x n3): their
+// traces are cut over the ranks, so each application first exchanges an ns2-plane halo of ITS INPUT with both
+// neighbours (forward: the inline-smoothed model; adjoint: the data -- the adjoint is evaluated per model trace as a
+// gather over the data traces within ns2, so it needs the same halo, not a halo-add) and then runs on the extended
+// local trace range with global edge tests; halo traces are computed redundantly and dropped.  The normalisation of
+// the halo traces comes from their owner (exchanged once).  The CG dots are all-reduced.  Same bits as one GPU.
 extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dipi, const float *d_dipx,
                               const float *d_mask, int n1, int n2, int n3, int niter, int ns1, int ns2,
                               int order1, int order2, int verb, float eps, float *d_out)
@@ -1257,56 +1278,91 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     PST_TRY(check_spray_args(n1, n2, n3, ns1, 0, order1));
     PST_TRY(check_spray_args(n1, n3, n2, ns2, 0, order2));
     if (niter < 0) { pst_set_error("sint3d: niter < 0"); return PST_EINVAL; }
-    if (c->comm && c->nranks > 1) { pst_set_error("sint3d: distributed contexts not supported yet"); return PST_EUNSUP; }
     PST_CUDA(cudaSetDevice(c->device));
-    const size_t n = (size_t)n1 * n2 * n3;
+    const bool dist = c->comm != nullptr && c->nranks > 1;
+    int z0 = 0, z1 = n3;
+    if (dist) {
+        z0 = (int)(((long)n3 * c->rank) / c->nranks);
+        z1 = (int)(((long)n3 * (c->rank + 1)) / c->nranks);
+        if (n3 / c->nranks < std::max(ns2, 1)) { pst_set_error("sint3d: slabs thinner than the xline smoothing radius"); return PST_EUNSUP; }
+    }
+    const int nz = z1 - z0;
+    const int ze0 = std::max(0, z0 - ns2), ze1 = std::min(n3, z1 + ns2), nzl = ze1 - ze0, offs = z0 - ze0;
+    const size_t plane = (size_t)n1 * n2;
+    const size_t n = plane * nz, nex = plane * nzl;               // slab / slab + halos
+    const double nglob = (double)plane * n3;
     const int NCmax = 2 * std::max(order1, order2) + 2, nsmax = std::max(ns1, ns2);
-    // 9 CG vectors + 2 dips + 2 norms + 4 work volumes + mask + spray slots/scratch (bounded chunks)
-    const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * nsmax + 1 + NCmax));
-    PST_TRY(pst_arena_reserve(c, (size_t)(19 * n * sizeof(float) + n + chunk + 3.0e9 + 64 * 4096)));
+    // 9 CG vectors + 2 dips + 2 norms + 5 work volumes + mask + spray slots/scratch (bounded chunks)
+    const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * nex, (double)nex * 4.0 * (2 * nsmax + 1 + NCmax));
+    PST_TRY(pst_arena_reserve(c, (size_t)((11 * n + 9 * nex) * sizeof(float) + n + chunk + 3.0e9 + 64 * 4096)));
     pst_arena_reset(c);
-    float *dipA, *dipB, *tnA, *tnB, *p, *x, *r, *sp, *sx, *sr, *gp, *gx, *wA1, *wA2, *wB1, *wB2, *dA;
+    float *dipA, *dipB, *tnA, *tnB, *p, *x, *r, *sp, *sx, *sr, *gp, *gx, *wA1, *wA2, *wB1, *wB2, *dA, *eA;
     unsigned char *known;
-    float **all[] = {&dipA, &dipB, &tnA, &tnB, &p, &x, &r, &sp, &sx, &sr, &gp, &gx, &wA1, &wA2, &wB1, &wB2, &dA};
-    for (float **q : all) PST_TRY(pst_arena_get(c, n, q));
+    float **slabv[] = {&dipA, &tnA, &p, &x, &r, &sp, &sx, &sr, &gp, &gx, &dA};
+    float **extv[] = {&dipB, &tnB, &wA1, &wA2, &wB1, &wB2, &eA};
+    for (float **q : slabv) PST_TRY(pst_arena_get(c, n, q));
+    for (float **q : extv) PST_TRY(pst_arena_get(c, nex, q));
     PST_TRY(pst_arena_get(c, n, &known));
     const int threads = 256, grid = pst_grid_for(c, n, threads);
     double h[PST_RED_SLOTS];
+    float *const eS = eA + (size_t)offs * plane;                 // the slab inside the extended A volume
 
-    // reference layout [i3][i2][i1] -> A = [i3][i1][i2];  B = [i2][i1][i3] = swap(A)
-    PST_TRY(transpose_planes(c, d_dipi, dipA, n2, n1, n3));
-    PST_TRY(transpose_planes(c, d_dipx, wA1, n2, n1, n3));
-    PST_TRY(swap_ab(c, wA1, dipB, n3, n1, n2));
-    PST_TRY(transpose_planes(c, d_din, dA, n2, n1, n3));
-    PST_TRY(transpose_planes(c, d_mask, wA1, n2, n1, n3));
+    // ns2 planes of the slab held in eA -> the neighbours' halos, theirs -> mine
+    auto halo = [&]() -> int {
+        if (!dist || ns2 == 0) return PST_OK;
+        const size_t cnt = plane * (size_t)ns2;
+        return pst_comm_halo_exchange(c, eS, eS + n - cnt, eA, eS + n, cnt);
+    };
+
+    // reference layout [i3][i2][i1] -> A = [i3][i1][i2];  B = [i2][i1][i3] = swap(A), i3 over slab + halos
+    PST_TRY(transpose_planes(c, d_dipi, dipA, n2, n1, nz));
+    PST_TRY(transpose_planes(c, d_dipx, eS, n2, n1, nz));
+    PST_TRY(halo());
+    PST_TRY(swap_ab(c, eA, dipB, nzl, n1, n2));
+    PST_TRY(transpose_planes(c, d_din, dA, n2, n1, nz));
+    PST_TRY(transpose_planes(c, d_mask, wA1, n2, n1, nz));
     PST_LAUNCH(c, PST_K_OTHER, (sint_known_kernel<<<grid, threads, 0, c->stream>>>(wA1, known, n, c->d_partial)));
     PST_TRY(pst_finish_reduce(c, grid, 1, 8));
     PST_TRY(pst_fetch_record(c, 8, 1, h));
     // "lam += 1." on a float saturates at 2^24 (soint3d_cfuns.c:2583-2592)
     float lam = (float)std::min(h[0], 16777216.0);
-    lam = sqrtf(lam / (float)n);
+    lam = sqrtf(lam / (float)nglob);
     const float ceps = lam * lam;
     const double tol = 10 * 1.19209290e-07F;
 
-    Smoother2 SA{n1, n2, n3, ns1, order1, eps * eps, dipA, tnA, {}}, SB{n1, n3, n2, ns2, order2, eps * eps, dipB, tnB, {}};
+    Smoother2 SA{n1, n2, nz, ns1, order1, eps * eps, dipA, tnA, {}}, SB{n1, nzl, n2, ns2, order2, eps * eps, dipB, tnB, {}};
+    SB.t_off = ze0; SB.ntg = n3;
     smoother_plan(SA);
     smoother_plan(SB);
     PST_TRY(smoother_set(c, SA, wA1));
     PST_TRY(smoother_set(c, SB, wB1));
+    if (dist && ns2 > 0) {
+        // the normalisation of my halo traces lacks the sources beyond them: take it from the owning rank
+        PST_TRY(swap_ab(c, tnB, eA, n2, n1, nzl));
+        PST_TRY(halo());
+        PST_TRY(swap_ab(c, eA, tnB, nzl, n1, n2));
+    }
     // S (forward): out = swap(SB(swap(SA(in))))
     auto S_fwd = [&](const float *in, float *out) -> int {
-        PST_TRY(smoother_fwd(c, SA, in, wA1, true));
-        PST_TRY(swap_ab(c, wA1, wB1, n3, n1, n2));
+        PST_TRY(smoother_fwd(c, SA, in, eS, true));
+        PST_TRY(halo());
+        PST_TRY(swap_ab(c, eA, wB1, nzl, n1, n2));
         PST_TRY(smoother_fwd(c, SB, wB1, wB2, true));
-        PST_TRY(swap_ab(c, wB2, out, n2, n1, n3, true));
+        PST_TRY(swap_ab(c, wB2, out, n2, n1, nzl, true, offs, nz));
         return PST_OK;
     };
     // S' (adjoint, accumulating): io += SA'(swap(SB'(swap(data))))
     auto S_adj_add = [&](float *io, const float *data) -> int {
-        PST_TRY(swap_ab(c, data, wB1, n3, n1, n2));
+        if (dist) {
+            PST_CUDA(cudaMemcpyAsync(eS, data, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            PST_TRY(halo());
+            PST_TRY(swap_ab(c, eA, wB1, nzl, n1, n2));
+        } else {
+            PST_TRY(swap_ab(c, data, wB1, n3, n1, n2));
+        }
         // work volumes for the xline side: wB2 (result), wA1/wA2 reinterpreted as B-layout scratch (same size)
         PST_TRY(smoother_adj(c, SB, wB2, wB1, false, wA1, wA2));
-        PST_TRY(swap_ab(c, wB2, wA1, n2, n1, n3));
+        PST_TRY(swap_ab(c, wB2, wA1, n2, n1, nzl, false, offs, nz));
         PST_TRY(smoother_adj(c, SA, io, wA1, true, wA2, wB1));
         return PST_OK;
     };
@@ -1345,7 +1401,7 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
             c->stats.cg_iterations++;
         }
     }
-    PST_TRY(transpose_planes(c, x, d_out, n1, n2, n3));
+    PST_TRY(transpose_planes(c, x, d_out, n1, n2, nz));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
@@ -1355,8 +1411,9 @@ int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int
                          int order, float eps, float *d_out)
 {
     PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
-    if (c->comm && c->nranks > 1) { pst_set_error("somean2d(adj): distributed contexts not supported"); return PST_EUNSUP; }
     PST_CUDA(cudaSetDevice(c->device));
+    // distributed contexts: n3 is the global plane count; the (n1 x n2) panels are independent, each rank smooths its own
+    if (c->comm && c->nranks > 1) n3 = (int)(((long)n3 * (c->rank + 1)) / c->nranks) - (int)(((long)n3 * c->rank) / c->nranks);
     const size_t n = (size_t)n1 * n2 * n3;
     const int NC = 2 * order + 2;
     const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * ns + 1 + NC));

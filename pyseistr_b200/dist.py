@@ -88,15 +88,15 @@ def somean3dc_slab(ctx, slab, dipi, dipx, n3, r1, r2, order):
     return out.reshape(n1, n2, nz, order="F")
 
 
-def soint3dc_slab(ctx, slab, mask, dipi, dipx, n3, order=1, niter=100, njs=(1, 1), hasmask=1, verb=0):
+def soint3dc_slab(ctx, slab, mask, dipi, dipx, n3, order=1, niter=100, njs=(1, 1), hasmask=1, verb=0, var=0.0, seed=202223):
     """soint3dc on this rank's slab: the xline stencil reads one plane of the next rank, its adjoint one plane of
-    the previous rank, the CG dots are all-reduced (var = 0, drift = 0)."""
+    the previous rank, the CG dots are all-reduced (drift = 0; var > 0: every rank draws the whole noise stream)."""
     n1, n2, nz = slab.shape
     d, a, b = _F(slab), _F(dipi), _F(dipx)
     m = _F(mask) if mask is not None else None
     out = np.empty_like(d)
     _lib.check(ctx.lib.pst_soint3d(ctx.handle, _p(d), _p(m) if m is not None else None, _p(a), _p(b), n1, n2, int(n3),
-                                   int(order), int(njs[0]), int(njs[1]), int(niter), 0, 202223, int(hasmask), 0.0,
+                                   int(order), int(njs[0]), int(njs[1]), int(niter), 0, int(seed), int(hasmask), float(var),
                                    int(verb), _p(out)))
     return out.reshape(n1, n2, nz, order="F")
 
@@ -109,4 +109,24 @@ def smoothc_slab(ctx, slab, n3, rect):
     out = np.empty_like(d)
     _lib.check(ctx.lib.pst_smoothcf(ctx.handle, _p(d), n1, n2, int(n3), 1, 0, int(rect[0]), int(rect[1]), int(rect[2]),
                                     0, 0, 0, 0, 0, 0, _p(out)))
+    return out.reshape(n1, n2, nz, order="F")
+
+
+def sint3dc_slab(ctx, slab, mask, dipi, dipx, n3, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, order2=1, verb=0):
+    """sint3dc on this rank's slab: the inline plane-wave smoother is local, the xline smoother exchanges an ns2-plane
+    halo of its input with both neighbours per application (forward and adjoint), the CG dots are all-reduced."""
+    n1, n2, nz = slab.shape
+    d, m, a, b = _F(slab), _F(mask), _F(dipi), _F(dipx)
+    out = np.empty_like(d)
+    _lib.check(ctx.lib.pst_sint3d(ctx.handle, _p(d), _p(a), _p(b), _p(m), n1, n2, int(n3), int(niter), int(ns1), int(ns2),
+                                  int(order1), int(order2), int(verb), float(eps), _p(out)))
+    return out.reshape(n1, n2, nz, order="F")
+
+
+def somean2dc_slab(ctx, slab, dip, n3, ns, order, eps, adj=0):
+    """somean2dc on a stack of (n1 x n2) panels cut into n3-slabs: the panels are independent."""
+    n1, n2, nz = slab.shape
+    d, a = _F(slab), _F(dip)
+    out = np.empty_like(d)
+    _lib.check(ctx.lib.pst_somean2d(ctx.handle, _p(d), _p(a), n1, n2, int(n3), int(ns), int(order), int(adj), float(eps), 0, _p(out)))
     return out.reshape(n1, n2, nz, order="F")

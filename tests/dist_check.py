@@ -102,6 +102,43 @@ def main():
             e = rel_l2(full, want)
             print(f"[dist_check] world={world} soint3d order={order} njs={njs}: rel-L2 {e:.2e}", flush=True)
             ok = ok and e <= 1e-5
+    # ---- soint3dc with a noisy right-hand side (var > 0): every rank draws the reference's whole MT19937 stream
+    mine = pd.soint3dc_slab(ctx, gaps[:, :, z0:z1], mask[:, :, z0:z1], pi[:, :, z0:z1], px[:, :, z0:z1], n3,
+                            order=1, niter=6, var=0.01, seed=7)
+    parts = [None] * world
+    dist.all_gather_object(parts, (z0, np.asarray(mine)))
+    if rank == 0:
+        parts.sort(key=lambda t: t[0])
+        full = np.concatenate([p[1] for p in parts], axis=2)
+        want = _port.soint3dc(gaps, mask, pi, px, order=1, niter=6, var=0.01, seed=7)
+        e = rel_l2(full, want)
+        print(f"[dist_check] world={world} soint3d var=0.01: rel-L2 {e:.2e}", flush=True)
+        ok = ok and e <= 1e-5
+    # ---- sint3dc across slabs (spray-operator shaping CG): xline smoother with ns2-plane halos, forward and adjoint
+    for (ns1, ns2, o1, o2, niter) in ((2, 2, 1, 1, 6), (1, 3, 2, 2, 4)):
+        mine = pd.sint3dc_slab(ctx, gaps[:, :, z0:z1], mask[:, :, z0:z1], pi[:, :, z0:z1], px[:, :, z0:z1], n3,
+                               niter=niter, eps=0.01, ns1=ns1, ns2=ns2, order1=o1, order2=o2)
+        parts = [None] * world
+        dist.all_gather_object(parts, (z0, np.asarray(mine)))
+        if rank == 0:
+            parts.sort(key=lambda t: t[0])
+            full = np.concatenate([p[1] for p in parts], axis=2)
+            want = _port.sint3dc(gaps, mask, pi, px, niter=niter, eps=0.01, ns1=ns1, ns2=ns2, order1=o1, order2=o2)
+            e = rel_l2(full, want)
+            print(f"[dist_check] world={world} sint3dc_slab ns=({ns1},{ns2}) order=({o1},{o2}): rel-L2 {e:.2e}", flush=True)
+            ok = ok and e <= 1e-5
+    # ---- somean2dc (forward and adjoint) on a stack of panels cut into slabs: bit-exact
+    for adj in (0, 1):
+        mine = pd.somean2dc_slab(ctx, clean[:, :, z0:z1], pi[:, :, z0:z1], n3, 2, 2, 0.01, adj=adj)
+        parts = [None] * world
+        dist.all_gather_object(parts, (z0, np.asarray(mine)))
+        if rank == 0:
+            parts.sort(key=lambda t: t[0])
+            full = np.concatenate([p[1] for p in parts], axis=2)
+            want = _port.somean2dc(clean, pi, 2, 2, 0.01, adj=adj)
+            b = bool(np.array_equal(full, want))
+            print(f"[dist_check] world={world} somean2dc adj={adj} on slabs: bit-exact={b}", flush=True)
+            ok = ok and b
     # ---- plain triangle smoothing of a slab-distributed volume (smoothcf, adj = 0): bit-exact vs the oracle
     for shape, rect in (((24, 12, 9 * world + 1), (3, 4, 4)), ((16, 12, 128 * world), (5, 5, 5))):
         n1, n2, n3 = shape
