@@ -155,6 +155,9 @@ extern "C" void pst_ctx_destroy(pst_ctx *c)
     if (c->tm0) cudaEventDestroy(c->tm0);
     if (c->tm1) cudaEventDestroy(c->tm1);
     for (auto &e : c->prof_ev) cudaEventDestroy(e);
+    for (auto &e : c->ev_pool) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -317,6 +320,88 @@ struct CallTimer {
     }
 };
 
+// ---- transfer pipeline of the host-pointer entry points ------------------------------------------------------
+// Uploads run on s_in in plane chunks (an event per chunk), downloads on s_out; the compute stream waits only for
+// the planes a kernel is about to read (pst_pipe_wait_planes) and hands finished output planes to s_out
+// (pst_pipe_emit), so PCIe runs under the kernels in both directions.
+static int pipe_streams(pst_ctx *c)
+{
+    if (!c->s_in) PST_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_out) PST_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    return PST_OK;
+}
+static int pipe_event(pst_ctx *c, cudaEvent_t *e)
+{
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t ne;
+        PST_CUDA(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
+        c->ev_pool.push_back(ne);
+    }
+    *e = c->ev_pool[c->ev_used++];
+    return PST_OK;
+}
+// upload nvol volumes of nz planes each, interleaved in chunks of `cz` planes; events land in c->pipe
+static int pipe_upload(pst_ctx *c, int nvol, float *const *dst, const float *const *src, size_t plane, int nz, int cz)
+{
+    PST_TRY(pipe_streams(c));
+    c->ev_used = 0;
+    c->pipe = pst_ctx::Pipe();
+    c->pipe.plane = plane;
+    // the staging buffers were just allocated: nothing of an earlier call may still be reading them
+    for (int z = 0; z < nz; z += cz) {
+        const int ze = std::min(nz, z + cz);
+        for (int v = 0; v < nvol; v++)
+            PST_CUDA(cudaMemcpyAsync(dst[v] + (size_t)z * plane, src[v] + (size_t)z * plane, (size_t)(ze - z) * plane * sizeof(float),
+                                     cudaMemcpyHostToDevice, c->s_in));
+        cudaEvent_t e;
+        PST_TRY(pipe_event(c, &e));
+        PST_CUDA(cudaEventRecord(e, c->s_in));
+        c->pipe.up_planes.push_back(ze);
+        c->pipe.up_events.push_back(e);
+        c->stats.h2d_bytes += (double)nvol * (ze - z) * plane * sizeof(float);
+    }
+    c->pipe.on = true;
+    return PST_OK;
+}
+int pst_pipe_wait_planes(pst_ctx *c, int zhi)
+{
+    pst_ctx::Pipe &P = c->pipe;
+    if (!P.on || zhi <= P.waited) return PST_OK;
+    for (size_t k = 0; k < P.up_planes.size(); k++) {
+        if (P.up_planes[k] <= P.waited) continue;
+        PST_CUDA(cudaStreamWaitEvent(c->stream, P.up_events[k], 0));
+        P.waited = P.up_planes[k];
+        if (P.waited >= zhi) break;
+    }
+    return PST_OK;
+}
+int pst_pipe_emit(pst_ctx *c, const float *d_src_plane0, int z0, int z1)
+{
+    pst_ctx::Pipe &P = c->pipe;
+    if (!P.on || !P.h_out || z1 <= z0) return PST_OK;
+    cudaEvent_t e;
+    PST_TRY(pipe_event(c, &e));
+    PST_CUDA(cudaEventRecord(e, c->stream));
+    PST_CUDA(cudaStreamWaitEvent(c->s_out, e, 0));
+    PST_CUDA(cudaMemcpyAsync(P.h_out + (size_t)z0 * P.plane, d_src_plane0 + (size_t)z0 * P.plane, (size_t)(z1 - z0) * P.plane * sizeof(float),
+                             cudaMemcpyDeviceToHost, c->s_out));
+    c->stats.d2h_bytes += (double)(z1 - z0) * P.plane * sizeof(float);
+    return PST_OK;
+}
+// end of a pipelined call: everything emitted has landed; the pipe is switched off
+static int pipe_finish(pst_ctx *c)
+{
+    c->pipe.on = false;
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->s_in) PST_CUDA(cudaStreamSynchronize(c->s_in));
+    if (c->s_out) PST_CUDA(cudaStreamSynchronize(c->s_out));
+    return PST_OK;
+}
+struct PipeGuard {           // an error return must not leave a stale pipe behind
+    pst_ctx *c;
+    ~PipeGuard() { if (c->pipe.on) { c->pipe.on = false; cudaStreamSynchronize(c->stream); if (c->s_in) cudaStreamSynchronize(c->s_in); if (c->s_out) cudaStreamSynchronize(c->s_out); } }
+};
+
 static int up(pst_ctx *c, DevBuf &b, const float *h, size_t n)
 {
     PST_TRY(b.alloc(n * sizeof(float)));
@@ -350,14 +435,50 @@ extern "C" int pst_dip(pst_ctx *c, const float *din, const float *mask, int n1, 
     (void)eps_dv; (void)eps_cg; (void)tol_cg;      // ignored by the reference's C
     PST_ENTRY(c);
     if (!din || !dip_out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("dip: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
+    const int nz = slab_planes(c, n3);
+    const size_t plane = (size_t)n1 * n2, n = plane * nz;      /* n = this rank's slab */
     CallTimer t(c);
     DevBuf d, m, o;
-    PST_TRY(up(c, d, din, n));
-    if (mask) PST_TRY(up(c, m, mask, n));
-    PST_TRY(o.alloc((n3 == 1 ? n : 2 * n) * sizeof(float)));   /* n = this rank's slab */
+    PST_TRY(d.alloc(n * sizeof(float)));
+    if (mask) PST_TRY(m.alloc(n * sizeof(float)));
+    PST_TRY(o.alloc((n3 == 1 ? n : 2 * n) * sizeof(float)));
+    // transfers on the copy streams: the inputs go up while the workspace is set up; the inline dip goes down while the
+    // xline dip is being estimated (pst_dip_dev hands it over through the pipe), the xline dip after the call
+    PipeGuard guard{c};
+    float *dst[2] = {d.f(), m.f()};
+    const float *src[2] = {din, mask};
+    PST_TRY(pipe_upload(c, mask ? 2 : 1, dst, src, plane, nz, nz));
+    c->pipe.h_out = dip_out;
     PST_TRY(pst_dip_dev(c, d.f(), mask ? m.f() : nullptr, n1, n2, n3, niter, liter, order, r1, r2, r3, verb, o.f()));
-    PST_TRY(down(c, dip_out, o, n3 == 1 ? n : 2 * n));
+    if (n3 == 1) PST_TRY(pst_pipe_emit(c, o.f(), 0, nz));
+    else         PST_TRY(pst_pipe_emit(c, o.f(), nz, 2 * nz));
+    PST_TRY(pipe_finish(c));
+    t.stop();
+    return PST_OK;
+}
+
+// csomean3d / csomf3d on host buffers: the three inputs go up in plane chunks on the copy stream while the spray works
+// on the chunks that have arrived, finished output planes go down on a second copy stream under the next chunk
+static int spray3d_host(pst_ctx *c, int median, const float *din, const float *dipi, const float *dipx, int n1, int n2, int n3,
+                        int ns2, int ns3, int nmf, int option, int order, float *out)
+{
+    const int nz = slab_planes(c, n3);
+    const size_t plane = (size_t)n1 * n2, n = plane * nz;
+    CallTimer t(c);
+    DevBuf d, a, b, o;
+    PST_TRY(d.alloc(n * sizeof(float))); PST_TRY(a.alloc(n * sizeof(float))); PST_TRY(b.alloc(n * sizeof(float)));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PipeGuard guard{c};
+    float *dst[3] = {d.f(), a.f(), b.f()};
+    const float *src[3] = {din, dipi, dipx};
+    // ~0.4 GB per volume and chunk: fine enough to start early, coarse enough for full PCIe speed
+    const int cz = (int)std::max<size_t>(1, std::min<size_t>((size_t)nz, (size_t)100e6 / plane + 1));
+    PST_TRY(pipe_upload(c, 3, dst, src, plane, nz, cz));
+    c->pipe.h_out = out;
+    int rc = median ? pst_somf3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, nmf, option, order, o.f())
+                    : pst_somean3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, order, o.f());
+    if (rc != PST_OK) return rc;
+    PST_TRY(pipe_finish(c));
     t.stop();
     return PST_OK;
 }
@@ -369,15 +490,7 @@ extern "C" int pst_somean3d(pst_ctx *c, const float *din, const float *dipi, con
     (void)eps; (void)verb;                          // eps overridden with 0.01 by the reference (Q2)
     PST_ENTRY(c);
     if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somean3d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
-    CallTimer t(c);
-    DevBuf d, a, b, o;
-    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
-    PST_TRY(o.alloc(n * sizeof(float)));
-    PST_TRY(pst_somean3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, order, o.f()));
-    PST_TRY(down(c, out, o, n));
-    t.stop();
-    return PST_OK;
+    return spray3d_host(c, 0, din, dipi, dipx, n1, n2, n3, ns2, ns3, 0, 1, order, out);
 }
 
 extern "C" int pst_somf3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx,
@@ -387,15 +500,7 @@ extern "C" int pst_somf3d(pst_ctx *c, const float *din, const float *dipi, const
     (void)eps; (void)verb;
     PST_ENTRY(c);
     if (!din || !dipi || !dipx || !out || n1 < 1 || n2 < 1 || n3 < 1) { pst_set_error("somf3d: null pointer or bad shape"); return PST_EINVAL; }
-    const size_t n = (size_t)n1 * n2 * slab_planes(c, n3);
-    CallTimer t(c);
-    DevBuf d, a, b, o;
-    PST_TRY(up(c, d, din, n)); PST_TRY(up(c, a, dipi, n)); PST_TRY(up(c, b, dipx, n));
-    PST_TRY(o.alloc(n * sizeof(float)));
-    PST_TRY(pst_somf3d_dev(c, d.f(), a.f(), b.f(), n1, n2, n3, ns2, ns3, nmf, option, order, o.f()));
-    PST_TRY(down(c, out, o, n));
-    t.stop();
-    return PST_OK;
+    return spray3d_host(c, 1, din, dipi, dipx, n1, n2, n3, ns2, ns3, nmf, option, order, out);
 }
 
 int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,

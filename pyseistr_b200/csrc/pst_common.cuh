@@ -69,7 +69,23 @@ struct pst_ctx {
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     pst_comm *comm = nullptr;        // null for single-GPU contexts
     int rank = 0, nranks = 1;
+    // host-pointer entry points: copy streams + plane-granular pipelining of the transfers under the kernels
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Pipe {
+        bool on = false;
+        std::vector<int> up_planes;            // planes [0, up_planes[k]) of every input volume are uploaded once ...
+        std::vector<cudaEvent_t> up_events;    // ... up_events[k] has fired (recorded on s_in)
+        float *h_out = nullptr;                // where finished output planes go (host), null = no emit
+        size_t plane = 0;                      // floats per plane
+        int waited = 0;                        // planes the compute stream already waits for
+    } pipe;
 };
+
+// plane-granular transfer pipeline (pst_api.cu); all no-ops when c->pipe.on is false
+int pst_pipe_wait_planes(pst_ctx *c, int zhi);                              // c->stream waits until planes < zhi are on the device
+int pst_pipe_emit(pst_ctx *c, const float *d_src_plane0, int z0, int z1);  // planes [z0, z1) of the output are final: D2H them
 
 // ---- per-launch profiling -----------------------------------------------------------------
 void pst_prof_resolve(pst_ctx *c);                       // sync + accumulate pending pairs

@@ -2113,6 +2113,7 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     PST_TRY(pst_arena_get(c, scr, &w.scr));
     const float *u = d_din, *um = d_mask;
     int n3_live = nz - 1;
+    PST_TRY(pst_pipe_wait_planes(c, nz));                 // host-pointer entry: the uploads run on the copy stream
     if (dist) {
         // the xline stencil reads plane i3+1: keep a copy of the slab with the neighbour's first
         // plane appended (static data: exchanged once per call)
@@ -2146,6 +2147,7 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     const int ndip = (n3 == 1) ? 1 : 2;
     PST_CUDA(cudaMemsetAsync(d_dip_out, 0, ndip * n * sizeof(float), c->stream));
     PST_TRY(gauss_newton(c, g, u, d_dip_out, m_in, 0, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
+    if (ndip == 2) PST_TRY(pst_pipe_emit(c, d_dip_out, 0, nz));   // the inline dip leaves while the xline dip is estimated
     if (ndip == 2)
         PST_TRY(gauss_newton(c, g, u, d_dip_out + n, m_x, 1, niter, liter, order, u1, u2, dp, ptrial, w, verb, n3_live));
     if (dist) PST_TRY(pst_comm_check(c));

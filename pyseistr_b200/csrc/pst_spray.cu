@@ -522,10 +522,44 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 typedef int (*chunk_reduce_fn)(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0,
                                int z0, int z1);
 
+// Chunk-wise staging between the caller's reference-order volumes and the trace-minor working volumes, so that the
+// host-pointer entry points can run their transfers under the kernels (pst_pipe_*, pst_api.cu): the inputs of a chunk
+// are transposed right before the chunk (after waiting for exactly those planes), its output planes are transposed
+// back and handed to the download stream right after its reduction.
+struct SprayIO {
+    const float *src[3] = {nullptr, nullptr, nullptr};   // din, dipi, dipx of the slab, reference order [i3][i2][i1]
+    float *dstT[3] = {nullptr, nullptr, nullptr};        // trace-minor, first SLAB plane (halo planes lie before it)
+    int done = 0;                                        // slab planes [0, done) are staged
+    const float *outT = nullptr;                         // trace-minor result, slab planes
+    float *d_out = nullptr;                              // reference-order result
+};
+
+static int transpose_planes(pst_ctx *c, const float *in, float *out, int rows, int cols, int planes);
+
+static int spray_stage_in(pst_ctx *c, const SprayPlan &P, SprayIO *io, int z_upto)
+{
+    const int nz = P.zt1 - P.zt0;
+    const int hi = std::min(nz, z_upto - P.zt0);
+    if (hi <= io->done) return PST_OK;
+    PST_TRY(pst_pipe_wait_planes(c, hi));
+    const size_t off = (size_t)P.n1 * P.n2 * io->done;
+    for (int v = 0; v < 3; v++)
+        if (io->src[v]) PST_TRY(transpose_planes(c, io->src[v] + off, io->dstT[v] + off, P.n2, P.n1, hi - io->done));
+    io->done = hi;
+    return PST_OK;
+}
+
+static int spray_stage_out(pst_ctx *c, const SprayPlan &P, SprayIO *io, int z0, int z1)
+{
+    const size_t off = (size_t)P.n1 * P.n2 * (z0 - P.zt0);
+    PST_TRY(transpose_planes(c, io->outT + off, io->d_out + off, P.n1, P.n2, z1 - z0));
+    return pst_pipe_emit(c, io->d_out, z0 - P.zt0, z1 - P.zt0);
+}
+
 // Spray every live slot for all planes, chunk by chunk along n3, and hand the slot volumes
 // of each chunk to `reduce`.  dT/piT/pxT are full trace-minor volumes.
 static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const float *piT, const float *pxT,
-                     chunk_reduce_fn reduce, void *user)
+                     chunk_reduce_fn reduce, void *user, SprayIO *io = nullptr)
 {
     const int n1 = P.n1, n2 = P.n2, n3 = P.n3, ns3 = P.ns3, nw = P.nw;   // n3: global extent
     const long plane = (long)n1 * n2;
@@ -549,6 +583,7 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     for (int z0 = P.zt0; z0 < P.zt1; z0 += cz) {
         const int z1 = std::min(P.zt1, z0 + cz);
         const int ze0 = std::max(P.zs0, z0 - ns3), ze1 = std::min(P.zs1, z1 + ns3);
+        if (io) PST_TRY(spray_stage_in(c, P, io, ze1));
         float *slot[PST_MAXSLOT];
         for (int s = 0; s < P.np; s++) slot[s] = slotbuf[s];
         slot[centre] = const_cast<float *>(dT) + (long)(ze0 - P.zs0) * plane;
@@ -589,6 +624,7 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
         }
         PST_CUDA(cudaGetLastError());
         PST_TRY(reduce(c, user, P, slot, ze0, z0, z1));
+        if (io && io->d_out) PST_TRY(spray_stage_out(c, P, io, z0, z1));
     }
     return PST_OK;
 }
@@ -710,9 +746,14 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     if (d_dipx) PST_TRY(pst_arena_get(c, nex, &pxT));
     PST_TRY(pst_arena_get(c, n, &outT));
     const size_t off = (size_t)plane * (z0 - P.zs0);    // slab position inside the stored range
-    PST_TRY(transpose_planes(c, d_din, dT + off, n2, n1, nz));
-    PST_TRY(transpose_planes(c, d_dipi, piT + off, n2, n1, nz));
-    if (d_dipx) PST_TRY(transpose_planes(c, d_dipx, pxT + off, n2, n1, nz));
+    SprayIO io;
+    io.src[0] = d_din; io.src[1] = d_dipi; io.src[2] = d_dipx;
+    io.dstT[0] = dT + off; io.dstT[1] = piT + off; io.dstT[2] = pxT ? pxT + off : nullptr;
+    io.outT = outT; io.d_out = d_out;
+    // single GPU, one spray pass: inputs staged chunk by chunk inside spray_run.  Otherwise (halo exchange / the
+    // normalisation pass of the 2-D smoother read everything first): staged here, outputs still leave chunk by chunk.
+    const bool lazy_in = !dist && kind != 2;
+    if (!lazy_in) PST_TRY(spray_stage_in(c, P, &io, z1));
     if (dist && ns3 > 0) {
         const size_t cnt = (size_t)plane * ns3;
         float *vols[3] = {dT, piT, pxT};
@@ -722,8 +763,8 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
         }
     }
     ReduceOut R{outT, nmf, nullptr, 0};
-    if (kind == 0) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_mean, &R));
-    else if (kind == 1 || kind == 3) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_median, &R));
+    if (kind == 0) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_mean, &R, &io));
+    else if (kind == 1 || kind == 3) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_median, &R, &io));
     else {
         // pwsmooth_set (sof_cfuns.c:1113-1132): normalisation = smooth of a volume of ones
         PST_TRY(pst_arena_get(c, n, &tnorm));
@@ -735,9 +776,8 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
         PST_TRY(spray_run(c, P, ones, piT, pxT, reduce_wsum, &R0));
         c->arena_used = mark;          // chunk buffers are reusable
         ReduceOut R1{outT, 0, tnorm, 1};
-        PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_wsum, &R1));
+        PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_wsum, &R1, &io));
     }
-    PST_TRY(transpose_planes(c, outT, d_out, n1, n2, nz));
     PST_CUDA(cudaGetLastError());
     return PST_OK;
 }
