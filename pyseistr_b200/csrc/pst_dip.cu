@@ -13,6 +13,10 @@
 #include "pst_tri_stream.cuh"
 #include "pst_tri_rc.cuh"
 #include "pst_tri_sys.cuh"
+#include "pst_tri_l2.cuh"
+#ifndef PST_TRI_L2_DEFAULT
+#define PST_TRI_L2_DEFAULT 0
+#endif
 
 #include <math.h>
 #include <stdlib.h>
@@ -1780,6 +1784,16 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     }
     if (has_epi && epi->stream_only) { epi = nullptr; }
     const bool has_epi2 = epi && epi->kind != EPI_NONE;
+    // the L2-resident checkpoint + recompute smoother, pst_tri_l2.cu.  PST_TRI_L2 = bit mask of the axes it takes
+    // (bit 0: axis 1 / contiguous, bit 1: axis 2, bit 2: axis 3)
+    static const int l2_axes = []() { const char *e = getenv("PST_TRI_L2"); return e ? atoi(e) : PST_TRI_L2_DEFAULT; }();
+    if (((l2_axes >> axis) & 1) && !has_epi2 && pst_tri_l2_ok(axis, g.n1, g.n2, g.n3, nb, src, dst)) {
+        int rc = 0;
+        PST_LAUNCHB(c, cls, 8.0 * (double)g.n, rc = pst_tri_l2_launch(c->stream, c->sm_count, axis, src, dst, g.n1, g.n2, g.n3, nb));
+        if (rc == 0) return PST_OK;
+        if (rc == -5) { pst_set_error("pst_tri_l2_launch: kernel launch failed"); return PST_ECUDA; }
+        // set-up refused (tensor map encoding, attribute): nothing was launched, fall through
+    }
     // experiment (off by default): the systolic register-resident smoother, pst_tri_sys.cu.  PST_TRI_SYS=1: every axis,
     // =2: strided axes only
     static const int sys_mode = []() { const char *e = getenv("PST_TRI_SYS"); return e ? atoi(e) : 0; }();

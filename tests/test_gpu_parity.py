@@ -446,18 +446,34 @@ def test_soint2d_default_path(ctx, port):
 
 # ------------------------------------------------------------------ round 2: oracle comparisons at realistic sizes
 def test_pipeline_vs_oracle_200x128x64(ctx, port):
-    """The survey's proxy cube (1.6 M voxels, ~40 s of oracle time): dip3dc(defaults) within 1e-5 of the oracle WITH THE
-    SAME data-dependent control flow (CG iterations incl. early exits, line-search evaluations: the GPU compares double
-    tree sums where the reference compares sequential float / double sums), then somf3dc / somean3dc on the oracle's
-    dips bit-exact."""
+    """The survey's proxy cube (1.6 M voxels, ~30 s of oracle time per pass).  At this size the reference's OWN dips
+    move by 1e-5 .. 3e-5 when nothing but the association of its double-precision dot products changes (the oracle's
+    probe pso_set_dot_mode(1): sums in blocks of 4096; beta = sr.sr + eps (sp.sp - sx.sx) cancels, so last-bit changes
+    of the sums flip roundings of the float step lengths), i.e. the 1e-5 tolerance is below the reference's arithmetic
+    noise floor and no parallel reduction can meet it against the SEQUENTIAL sums.  Contract checked here:
+      * dips within 1e-5 of the reference with re-associated dot sums (observed: identical to 14 digits),
+      * within max(1e-5, 3 x the reference's self-noise) of the sequential reference,
+      * the SAME data-dependent control flow (CG iterations incl. early exits, line-search evaluations),
+      * somf3dc / somean3dc on the oracle's dips bit-exact."""
     import pyseistr_b200 as ps
     n1, n2, n3 = 200, 128, 64
     d = synth.erratic(synth.cube(n1, n2, n3, seed=171), ntraces=60)
     oi, ox = port.dip3dc(d)
     want = port.dip_counts()
+    port.set_dot_mode(1)
+    try:
+        bi, bx = port.dip3dc(d)
+    finally:
+        port.set_dot_mode(0)
+    noise = max(rel_l2(bi, oi), rel_l2(bx, ox))
     di, dx = ps.dip3dc(d, verb=0, ctx=ctx)
     st = ctx.stats()
-    assert rel_l2(di, oi) <= TOL and rel_l2(dx, ox) <= TOL, (rel_l2(di, oi), rel_l2(dx, ox))
+    e_seq, e_blk = max(rel_l2(di, oi), rel_l2(dx, ox)), max(rel_l2(di, bi), rel_l2(dx, bx))
+    print(f"[200x128x64] dip rel-L2 vs sequential reference {e_seq:.3e}, vs re-associated reference {e_blk:.3e}; "
+          f"reference self-noise {noise:.3e}; bit-identical to the re-associated reference: "
+          f"{bool(np.array_equal(di, bi) and np.array_equal(dx, bx))}")
+    assert e_blk <= TOL, e_blk
+    assert e_seq <= max(TOL, 3.0 * noise), (e_seq, noise)
     got = {k: int(st[k]) for k in want}
     assert got == want, (got, want)
     f = ps.somf3dc(d, oi, ox, 2, 2, 0.01, 2, verb=0, ctx=ctx)
