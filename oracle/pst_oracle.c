@@ -729,15 +729,59 @@ static void slot_median_row(const float *panel, int n1, int np, int nfw, int kee
     }
 }
 
-/* csomf3d :1707-1736 (option 1) */
+/* svmf(axis=2, ifbound=1) :1110-1136,:1254-1352 on a [np][n1] panel, keeping only the row `keep` (space-varying
+ * median filter, `option=2`): a first median of length nfw+2 over EVERY slot row (window rows i-m2 .. i+m2+2 of the
+ * edge-replicated panel), the panel average of its magnitudes (sequential float sum, row-major), a window length per
+ * sample from |x| against avg/2, avg, 2 avg (nfw+2, nfw, nfw-2, nfw-4), and the median of that length around the sample.
+ * DEFINED-BEHAVIOUR VARIANT: for the last slot row the reference's first pass reads one row past its `extendt` buffer
+ * (:1283: extended row m+i+k-m2 reaches np+2m for i = np-1, k = nfilter-1), i.e. heap contents enter the panel
+ * average; here that row is the edge replica like the rows before it.  Everything else follows the reference. */
+static int svmf_row(const float *panel, int n1, int np, int nfw, int keep, float *row)
+{
+    const int nfilter = nfw + 2, m = (nfilter - 1) / 2, m2 = (nfw - 1) / 2;
+    float win[260];
+    if (nfw - 4 < 1 || nfilter > 258) return -1;          /* the reference calls sf_quantile(-1, -1, ..) below that */
+    float sum = 0.f;
+    for (int i = 0; i < np; i++)
+        for (int j = 0; j < n1; j++) {
+            for (int k = 0; k < nfilter; k++) {
+                int s = (m + i + k - m2) - m;                  /* extended row -> panel row, replicated outside */
+                if (s < 0) s = 0;
+                if (s > np - 1) s = np - 1;
+                win[k] = panel[(size_t)s * n1 + j];
+            }
+            sum = sum + fabsf(kth(m, nfilter, win));
+        }
+    const float avg = sum / (n1 * np);
+    for (int j = 0; j < n1; j++) {
+        const float x = fabsf(panel[(size_t)keep * n1 + j]);
+        int wl;
+        if (x < avg) wl = (x < avg / 2) ? nfw + 2 : nfw + 0;
+        else         wl = (x > avg * 2) ? nfw - 4 : nfw - 2;
+        const int h = (wl - 1) / 2;
+        for (int k = 0; k < wl; k++) {
+            int s = (keep + m + k - h) - m;
+            if (s < 0) s = 0;
+            if (s > np - 1) s = np - 1;
+            win[k] = panel[(size_t)s * n1 + j];
+        }
+        row[j] = kth(h, wl, win);
+    }
+    return 0;
+}
+
+/* csomf3d :1707-1736 (option 1; option 2 in the defined-behaviour variant of svmf_row) */
 int pso_somf3d(const float *din, const float *dipi, const float *dipx, int n1, int n2, int n3,
                int ns2, int ns3, int nmf, int option, int order, float *out)
 {
     int np = (2 * ns2 + 1) * (2 * ns3 + 1), n23 = n2 * n3;
-    if (option != 1 || nmf > 255) return -1;
+    if ((option != 1 && option != 2) || nmf > 255) return -1;
+    if (option == 2 && nmf - 4 < 1) return -1;
     float *u = spray3(din, dipi, dipx, n1, n2, n3, ns2, ns3, order);
-    for (int i = 0; i < n23; i++)
-        slot_median_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2, out + (size_t)i * n1);
+    for (int i = 0; i < n23; i++) {
+        if (option == 1) slot_median_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2, out + (size_t)i * n1);
+        else             svmf_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2, out + (size_t)i * n1);
+    }
     free(u);
     return 0;
 }
@@ -813,14 +857,16 @@ int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int n
 {
     size_t n12 = (size_t)n1 * n2;
     int np = 2 * ns + 1;
-    if (option != 1 || nmf > 255) return -1;
+    if ((option != 1 && option != 2) || nmf > 255) return -1;
+    if (option == 2 && nmf - 4 < 1) return -1;
     predictor *P = predictor_new(n1, order, eps * eps);
     float *u = falloc(n12 * np);
     for (int i3 = 0; i3 < n3; i3++) {
         spray2(P, din + i3 * n12, dip + i3 * n12, n1, n2, ns, u);
-        for (int i = 0; i < n2; i++)
-            slot_median_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2,
-                            out + i3 * n12 + (size_t)i * n1);
+        for (int i = 0; i < n2; i++) {
+            if (option == 1) slot_median_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2, out + i3 * n12 + (size_t)i * n1);
+            else             svmf_row(u + (size_t)i * np * n1, n1, np, nmf, (np - 1) / 2, out + i3 * n12 + (size_t)i * n1);
+        }
     }
     free(u); predictor_free(P);
     return 0;

@@ -211,6 +211,21 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
     return out.reshape(n1, n2, n3, order="F")
 
 
+def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=1, ctx=None):
+    """2-D interpolation of sparse data by shaping-regularised CG with the 2-D plane-wave smoother (reference
+    pyseistr/sint.py:61-94 -> csint2d, soint2d_cfuns.c).  csint2d is csint3d on an (n1, n2, 1) volume with no xline
+    smoothing (ns2 = 0, zero xline slope), bit for bit on the compiled reference (tests/test_oracle.py::
+    test_ref_sint2d_is_sint3d_with_one_plane), so it runs through pst_sint3d."""
+    din = np.asarray(din)
+    if din.ndim != 2:
+        raise ValueError("sint2dc expects a 2-D panel")
+    n1, n2 = din.shape
+    r3 = lambda a: np.float32(a).reshape(n1, n2, 1)
+    out = sint3dc(r3(din), r3(mask), r3(dip), np.zeros((n1, n2, 1), np.float32), niter=niter, eps=eps, ns1=ns, ns2=0,
+                  order1=order, order2=order, verb=verb, ctx=ctx)
+    return out.reshape(n1, n2)
+
+
 def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=1, ctx=None):
     """N-D triangle / box smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf, dip_cfuns.c:2006-2123),
     same defaults as the reference (note adj=1).  adj=0 is ps_smooth2 (the operator inside dip3d's shaping CG, here the

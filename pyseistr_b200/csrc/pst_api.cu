@@ -122,6 +122,8 @@ static int ctx_init(pst_ctx *c, int device)
     PST_CUDA(cudaMalloc((void **)&c->d_partial, (size_t)c->max_blocks * PST_RED_SLOTS * sizeof(double)));
     PST_CUDA(cudaMalloc((void **)&c->d_red, 64 * PST_RED_SLOTS * sizeof(double)));
     PST_CUDA(cudaMallocHost((void **)&c->h_red, 64 * PST_RED_SLOTS * sizeof(double)));
+    PST_CUDA(cudaMalloc(&c->d_cgctl, 256));
+    PST_CUDA(cudaMallocHost((void **)&c->h_cgstop, 64));
     return PST_OK;
 }
 
@@ -150,6 +152,8 @@ extern "C" void pst_ctx_destroy(pst_ctx *c)
     if (c->d_partial) cudaFree(c->d_partial);
     if (c->d_red) cudaFree(c->d_red);
     if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->d_cgctl) cudaFree(c->d_cgctl);
+    if (c->h_cgstop) cudaFreeHost((void *)c->h_cgstop);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->tm0) cudaEventDestroy(c->tm0);

@@ -56,6 +56,9 @@ struct pst_ctx {
     double *d_red = nullptr;         // [64 * PST_RED_SLOTS] ring of records
     double *h_red = nullptr;         // pinned mirror
     int max_blocks = 0;
+    // device-resident control block of the shaping CG (pst_dip.cu: CgCtl) + pinned mirror of its stop flag
+    void *d_cgctl = nullptr;
+    volatile int *h_cgstop = nullptr;
     // simple bump arena over one big device allocation, reset per call
     char *arena = nullptr;
     size_t arena_size = 0, arena_used = 0;

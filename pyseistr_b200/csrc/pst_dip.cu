@@ -1187,6 +1187,138 @@ cg_dir4_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
     pst_block_reduce<3>(acc, partial);
 }
 
+// ---- device-resident CG scalars ---------------------------------------------------------------------------------
+// The step lengths of ps_conjgrad (:330-371) are formed ON THE DEVICE from the reduced (and, across ranks, all-reduced)
+// dot products, in the same double arithmetic the host used, and the vector kernels read them from this block: one CG
+// solve is enqueued without a single host synchronisation.  The early exit (:349) raises `stop`; every later kernel of
+// the solve returns at once, and the host -- which polls a pinned copy of the flag without blocking -- stops launching.
+struct CgCtl {
+    double gn, gnp, g0;
+    float alpha_dir;       // gn / gnp of this iteration: s = g + alpha s
+    float a_pending;       // -gn / beta of the last finished iteration: p, x, r += a s (applied by the next head / the tail)
+    int stop, iters;
+};
+
+__global__ void cg_ctl_init_kernel(CgCtl *ctl) { ctl->gn = ctl->gnp = ctl->g0 = 0.; ctl->alpha_dir = ctl->a_pending = 0.f; ctl->stop = 0; ctl->iters = 0; }
+
+// after gn = gp.gp is reduced (:322): g0 on the first iteration, else alpha, dg and the exit test (:331-349)
+__global__ void cg_ctl_gn_kernel(CgCtl *ctl, const double *__restrict__ rec, int iter, float tol)
+{
+    if (ctl->stop) return;
+    const double gn = rec[0];
+    ctl->gn = gn;
+    if (iter == 0) { ctl->g0 = gn; return; }
+    const double alpha = gn / ctl->gnp, dg = gn / ctl->g0;
+    if (alpha < tol || dg < tol) { ctl->stop = 1; return; }
+    ctl->alpha_dir = (float)alpha;
+}
+
+// after sr.sr, sp.sp, sx.sx are reduced (:363-371): beta, the step length, gnp
+__global__ void cg_ctl_beta_kernel(CgCtl *ctl, const double *__restrict__ rec, float eps)
+{
+    if (ctl->stop) return;
+    const double beta = rec[0] + (double)eps * (rec[1] - rec[2]);
+    const double alpha = -ctl->gn / beta;
+    ctl->a_pending = (float)alpha;
+    ctl->gnp = ctl->gn;
+    ctl->iters++;
+}
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(256)
+cg_head4d_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r,
+                 const float *__restrict__ sp, const float *__restrict__ sx,
+                 const float *__restrict__ sr, const float *__restrict__ w, const CgCtl *__restrict__ ctl, float eps,
+                 float *__restrict__ tmp, size_t n)
+{
+    if (ctl->stop) return;
+    const float a = ctl->a_pending;
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+        float4 xv = ld4(x, i), rv = ld4(r, i);
+        const float4 wv = ld4(w, i);
+        if (UPDATE) {
+            float4 pv = ld4(p, i);
+            const float4 spv = ld4(sp, i), sxv = ld4(sx, i), srv = ld4(sr, i);
+            pv.x += a * spv.x; pv.y += a * spv.y; pv.z += a * spv.z; pv.w += a * spv.w;
+            xv.x += a * sxv.x; xv.y += a * sxv.y; xv.z += a * sxv.z; xv.w += a * sxv.w;
+            rv.x += a * srv.x; rv.y += a * srv.y; rv.z += a * srv.z; rv.w += a * srv.w;
+            st4(p, i, pv); st4(x, i, xv); st4(r, i, rv);
+        }
+        float4 g;
+        g.x = -eps * xv.x; g.x += rv.x * wv.x;
+        g.y = -eps * xv.y; g.y += rv.y * wv.y;
+        g.z = -eps * xv.z; g.z += rv.z * wv.z;
+        g.w = -eps * xv.w; g.w += rv.w * wv.w;
+        st4(tmp, i, g);
+    }
+}
+
+// scalar fall-back of the same (n % 4 != 0 or unaligned vectors)
+template <bool UPDATE>
+__global__ void __launch_bounds__(256)
+cg_headd_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r,
+                const float *__restrict__ sp, const float *__restrict__ sx,
+                const float *__restrict__ sr, const float *__restrict__ w, const CgCtl *__restrict__ ctl, float eps,
+                float *__restrict__ tmp, size_t n)
+{
+    if (ctl->stop) return;
+    const float a = ctl->a_pending;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float xi = x[i], ri = r[i];
+        if (UPDATE) {
+            p[i] += a * sp[i];
+            xi += a * sx[i];
+            ri += a * sr[i];
+            x[i] = xi;
+            r[i] = ri;
+        }
+        float g = -eps * xi;
+        g += ri * w[i];
+        tmp[i] = g;
+    }
+}
+
+template <bool FIRST, bool VEC>
+__global__ void __launch_bounds__(256)
+cg_dird_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
+               const float *__restrict__ w, float *__restrict__ sp, float *__restrict__ sx,
+               float *__restrict__ sr, const CgCtl *__restrict__ ctl, size_t n, double *__restrict__ partial)
+{
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (!ctl->stop) {
+        const float alpha = ctl->alpha_dir;
+        if (VEC) {
+            for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+                const float4 g = ld4(gp, i), t = ld4(tmp, i), wv = ld4(w, i);
+                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1;
+                if (!FIRST) { s1 = ld4(sp, i); s2 = ld4(sx, i); s3 = ld4(sr, i); }
+                float4 a, b, c;
+                cg_dir_one<FIRST>(g.x, t.x, wv.x, s1.x, s2.x, s3.x, alpha, a.x, b.x, c.x, acc);
+                cg_dir_one<FIRST>(g.y, t.y, wv.y, s1.y, s2.y, s3.y, alpha, a.y, b.y, c.y, acc);
+                cg_dir_one<FIRST>(g.z, t.z, wv.z, s1.z, s2.z, s3.z, alpha, a.z, b.z, c.z, acc);
+                cg_dir_one<FIRST>(g.w, t.w, wv.w, s1.w, s2.w, s3.w, alpha, a.w, b.w, c.w, acc);
+                st4(sp, i, a); st4(sx, i, b); st4(sr, i, c);
+            }
+        } else {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+                float a, b, c;
+                cg_dir_one<FIRST>(gp[i], tmp[i], w[i], FIRST ? 0.f : sp[i], FIRST ? 0.f : sx[i], FIRST ? 0.f : sr[i], alpha, a, b, c, acc);
+                sp[i] = a; sx[i] = b; sr[i] = c;
+            }
+        }
+    }
+    pst_block_reduce<3>(acc, partial);
+}
+
+__global__ void __launch_bounds__(256)
+cg_taild_kernel(float *__restrict__ x, const float *__restrict__ sx, const CgCtl *__restrict__ ctl, size_t n)
+{
+    if (ctl->stop) return;                      // early exit: the last step was applied by the head of the stopped iteration
+    const float a = ctl->a_pending;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] += a * sx[i];
+}
+
 __global__ void fill_kernel(float *__restrict__ x, float v, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
@@ -1985,6 +2117,50 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     const bool vec4 = vec_on && (n % 4 == 0) && a16(w.p) && a16(rat) && a16(w.r) && a16(w.sp) && a16(w.sx) && a16(w.sr) &&
                       a16(den) && a16(w.tmp) && a16(w.gp);
     const int grid4 = pst_grid_for(c, n / 4 + 1, threads, 2);
+    // default: CG scalars stay on the device (no host synchronisation inside the solve).  PST_CG_DEVSCALARS=0 or one
+    // of the fused-epilogue experiments selects the host-scalar loop below.
+    static const bool dev_scalars = []() { const char *e = getenv("PST_CG_DEVSCALARS"); return !(e && e[0] == '0'); }();
+    if (dev_scalars && !fuse && !fuse_gp) {
+        CgCtl *ctl = (CgCtl *)c->d_cgctl;
+        const double *rec1 = c->d_red + (size_t)1 * PST_RED_SLOTS, *rec2 = c->d_red + (size_t)2 * PST_RED_SLOTS;
+        *c->h_cgstop = 0;
+        PST_LAUNCH(c, PST_K_OTHER, (cg_ctl_init_kernel<<<1, 1, 0, c->stream>>>(ctl)));
+        int launched = 0;
+        for (int iter = 0; iter < liter; iter++) {
+            if (*c->h_cgstop) break;                 // the device left the solve (pinned copy, refreshed every iteration)
+            PST_LAUNCHB(c, PST_K_CGHEAD, (iter ? 44.0 : 16.0) * (double)n,
+                if (vec4 && iter) cg_head4d_kernel<true><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
+                else if (vec4)    cg_head4d_kernel<false><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
+                else if (iter)    cg_headd_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
+                else              cg_headd_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n));
+            PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, nullptr, nullptr, nullptr, nullptr));
+            PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n,
+                if (vec4) cg_gp4_kernel<<<grid4, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial);
+                else cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial));
+            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 1, 1));
+            PST_LAUNCH(c, PST_K_OTHER, (cg_ctl_gn_kernel<<<1, 1, 0, c->stream>>>(ctl, rec1, iter, tol)));
+            PST_CUDA(cudaMemcpyAsync((void *)c->h_cgstop, &ctl->stop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            PST_TRY(pst_shape_apply(c, g, w.gp, w.tmp, w.scr, nullptr, nullptr, nullptr, nullptr));
+            PST_LAUNCHB(c, PST_K_CGDIR, (iter ? 36.0 : 24.0) * (double)n,
+                if (iter == 0 && vec4) cg_dird_kernel<true, true><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
+                else if (iter == 0)    cg_dird_kernel<true, false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
+                else if (vec4)         cg_dird_kernel<false, true><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
+                else                   cg_dird_kernel<false, false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial));
+            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 3, 2));
+            PST_LAUNCH(c, PST_K_OTHER, (cg_ctl_beta_kernel<<<1, 1, 0, c->stream>>>(ctl, rec2, eps)));
+            launched++;
+        }
+        if (launched > 0)      // only the model x (= rat) is consumed after the last iteration
+            PST_LAUNCHB(c, PST_K_CGHEAD, 12.0 * (double)n, (cg_taild_kernel<<<grid, threads, 0, c->stream>>>(rat, w.sx, ctl, n)));
+        // executed iterations (statistics, iteration-count parity tests): the one host synchronisation of the solve
+        PST_CUDA(cudaMemcpyAsync((void *)(c->h_cgstop + 1), &ctl->iters, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        const int done = c->h_cgstop[1];
+        c->stats.cg_iterations += done;
+        if (iters_run) *iters_run = done;
+        PST_CUDA(cudaGetLastError());
+        return PST_OK;
+    }
     CgLate L{c, 0., 0., 0., tol, 0, false, 0.f};
     float a_pending = 0.f;
     bool pending = false;

@@ -438,6 +438,64 @@ slot_median_kernel(SlotPtrs S, int nmf_rt, float *__restrict__ out, long zoff_ou
     }
 }
 
+// exact q-th order statistic of n values (sf_quantile :1058-1084 returns the same VALUE) by rank counting
+template <int MAXN>
+__device__ __forceinline__ float select_rank(const float (&v)[MAXN], int n, int q)
+{
+    float res = v[0];
+    for (int s = 0; s < n; s++) {
+        int lt = 0, le = 0;
+        for (int t = 0; t < n; t++) { lt += (v[t] < v[s]); le += (v[t] <= v[s]); }
+        if (lt <= q && q < le) res = v[s];
+    }
+    return res;
+}
+
+// Space-varying median filter over the slot axis (svmf, sof3d_cfuns.c:1110-1136,:1254-1352; sof_cfuns.c:1190-1216,
+// :1334-1431; `option=2`), centre row kept.  One thread = one output trace: (1) the median of length nfw+2 of EVERY slot
+// row and sample, its magnitudes summed sequentially in float in the reference's row-major order -> panel average;
+// (2) per sample the window length nfw+2 / nfw / nfw-2 / nfw-4 from |x| against avg/2, avg, 2 avg, and the median of
+// that length around the centre slot.  Slot rows outside [0, np) are edge replicas (boundary(), ifbound = 1).
+// DEFINED-BEHAVIOUR VARIANT: the reference's first pass reads one row past its extended panel for the last slot row
+// (:1283), so heap contents enter its panel average; here that row is the edge replica as well.
+template <int MAXN>
+__global__ void __launch_bounds__(128)
+slot_svmf_kernel(SlotPtrs S, int np, int nfw, int n1, int n2, int planes, float *__restrict__ out, long zoff_out, long zoff_slot)
+{
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int zl = blockIdx.y;
+    if (i2 >= n2 || zl >= planes) return;
+    const long base = (long)zl * n1 * n2 + i2;
+    const int nfilter = nfw + 2, m = (nfilter - 1) / 2, m2 = (nfw - 1) / 2, keep = (np - 1) / 2;
+    float win[MAXN];
+    float sum = 0.f;
+    for (int i = 0; i < np; i++)
+        for (int j = 0; j < n1; j++) {
+            const long e = zoff_slot + base + (long)j * n2;
+            for (int k = 0; k < nfilter; k++) {
+                int s = i + k - m2;                                  // (m + i + k - m2) - m
+                s = s < 0 ? 0 : (s > np - 1 ? np - 1 : s);
+                win[k] = S.p[s][e];
+            }
+            sum = sum + fabsf(select_rank<MAXN>(win, nfilter, m));
+        }
+    const float avg = sum / (float)(n1 * np);
+    for (int j = 0; j < n1; j++) {
+        const long e = zoff_slot + base + (long)j * n2;
+        const float x = fabsf(S.p[keep][e]);
+        int wl;
+        if (x < avg) wl = (x < avg / 2) ? nfw + 2 : nfw;
+        else         wl = (x > avg * 2) ? nfw - 4 : nfw - 2;
+        const int h = (wl - 1) / 2;
+        for (int k = 0; k < wl; k++) {
+            int s = keep + k - h;
+            s = s < 0 ? 0 : (s > np - 1 ? np - 1 : s);
+            win[k] = S.p[s][e];
+        }
+        out[zoff_out + base + (long)j * n2] = select_rank<MAXN>(win, wl, h);
+    }
+}
+
 // pwsmooth_lop forward (sof_cfuns.c:1099-1108): out = sum_is u_is * w_is * ws, is ascending;
 // MODE 0: ws = 1 and out -> t (normalisation spray of ones); MODE 1: ws = (t != 0 ? 1/t : 0)
 template <int MODE>
@@ -670,6 +728,22 @@ static int reduce_median(pst_ctx *c, void *user, const SprayPlan &P, float *cons
     return PST_OK;
 }
 
+static int reduce_svmf(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0, int z0, int z1)
+{
+    ReduceOut *R = (ReduceOut *)user;
+    const long plane = (long)P.n1 * P.n2;
+    SlotPtrs S{};
+    for (int s = 0; s < P.np; s++) S.p[s] = slot[s];
+    const int threads = P.n2 >= 128 ? 128 : (P.n2 >= 64 ? 64 : 32);
+    dim3 grid((P.n2 + threads - 1) / threads, z1 - z0);
+    const long zo = plane * (z0 - P.zt0), zs = plane * (z0 - ze0);
+    PST_LAUNCH(c, PST_K_SLOTRED,
+        if (R->nmf + 2 <= 13) slot_svmf_kernel<13><<<grid, threads, 0, c->stream>>>(S, P.np, R->nmf, P.n1, P.n2, z1 - z0, R->outT, zo, zs);
+        else                  slot_svmf_kernel<PST_MAXSLOT + 2><<<grid, threads, 0, c->stream>>>(S, P.np, R->nmf, P.n1, P.n2, z1 - z0, R->outT, zo, zs));
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
 static int reduce_wsum(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0, int z0, int z1)
 {
     ReduceOut *R = (ReduceOut *)user;
@@ -720,7 +794,10 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     P.zs0 = std::max(0, z0 - ns3); P.zs1 = std::min(n3, z1 + ns3);
     const int ne = P.zs1 - P.zs0;                       // stored planes (slab + halos)
     const int cen = (P.np - 1) / 2;
-    for (int s = 0; s < P.np; s++) P.live[s] = (kind == 0 || kind == 2);
+    for (int s = 0; s < P.np; s++) P.live[s] = (kind == 0 || kind == 2 || kind == 4 || kind == 5);   // SVMF: every slot row
+    if (kind == 4 || kind == 5) {
+        if (nmf < 5 || nmf + 2 > PST_MAXSLOT + 2 || (nmf % 2) == 0) { pst_set_error("SVMF: median length nmf=%d unsupported (odd, >= 5: the shortest window is nmf-4)", nmf); return PST_EUNSUP; }
+    }
     if (kind == 1 || kind == 3) {
         if (nmf < 1 || nmf > PST_MAXSLOT || (nmf % 2) == 0) { pst_set_error("median length nmf=%d unsupported (odd, <= %d)", nmf, PST_MAXSLOT); return PST_EUNSUP; }
         const int m = (nmf - 1) / 2;
@@ -765,6 +842,7 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
     ReduceOut R{outT, nmf, nullptr, 0};
     if (kind == 0) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_mean, &R, &io));
     else if (kind == 1 || kind == 3) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_median, &R, &io));
+    else if (kind == 4 || kind == 5) PST_TRY(spray_run(c, P, dT, piT, pxT, reduce_svmf, &R, &io));
     else {
         // pwsmooth_set (sof_cfuns.c:1113-1132): normalisation = smooth of a volume of ones
         PST_TRY(pst_arena_get(c, n, &tnorm));
@@ -797,9 +875,9 @@ extern "C" int pst_somf3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_spray_args(n1, n2, n3, ns2, ns3, order));
-    if (option != 1) { pst_set_error("somf3d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
+    if (option != 1 && option != 2) { pst_set_error("somf3d: option=%d unknown (1 = MF, 2 = SVMF)", option); return PST_EINVAL; }
     const float eps = 0.01;                       // sof3d_cfuns.c:1586
-    return spray_filter_dev(c, 1, d_din, d_dipi, d_dipx, n1, n2, n3, ns2, ns3, nmf, order, eps * eps, d_out);
+    return spray_filter_dev(c, option == 1 ? 1 : 4, d_din, d_dipi, d_dipx, n1, n2, n3, ns2, ns3, nmf, order, eps * eps, d_out);
 }
 
 int pst_somean2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
@@ -815,8 +893,8 @@ int pst_somf2d_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, i
 {
     if (!c) { pst_set_error("null context"); return PST_EINVAL; }
     PST_TRY(check_spray_args(n1, n2, n3, ns, 0, order));
-    if (option != 1) { pst_set_error("somf2d: option=%d (SVMF) not implemented on the GPU path; option=1 (MF) only", option); return PST_EUNSUP; }
-    return spray_filter_dev(c, 3, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, nmf, order, eps * eps, d_out);
+    if (option != 1 && option != 2) { pst_set_error("somf2d: option=%d unknown (1 = MF, 2 = SVMF)", option); return PST_EINVAL; }
+    return spray_filter_dev(c, option == 1 ? 3 : 5, d_din, d_dip, nullptr, n1, n2, n3, ns, 0, nmf, order, eps * eps, d_out);
 }
 
 // =======================================================================================

@@ -43,6 +43,12 @@ def main():
                                      out=ref.somean3dc(de, di, dx, r1, r2, 0.01, order))
         g["somf3d_" + name] = dict(dn=de, dipi=di, dipx=dx, r1=r1, r2=r2, order=order,
                                    out=ref.somf3dc(de, di, dx, r1, r2, 0.01, order))
+    # ---- SVMF (option = 2).  The compiled reference reads one row past its extended panel (sof3d_cfuns.c:1283); its
+    # output therefore depends on heap contents in principle.  These fixtures are what it returned here; the oracle's
+    # defined-behaviour restatement reproduces them bit for bit (tests/test_oracle.py).
+    for name, (r1, r2, order) in {"r22o2": (2, 2, 2), "r21o2": (2, 1, 2), "r31o1": (3, 1, 1)}.items():
+        g["svmf3d_" + name] = dict(dn=de, dipi=di, dipx=dx, r1=r1, r2=r2, order=order,
+                                   out=ref.somf3dc(de, di, dx, r1, r2, 0.01, order, option=2))
     # ---- soint3d (PWD-residual CG interpolation of 50 % missing traces)
     dc = synth.cube(40, 16, 8, seed=11, noise=0.0)
     pi_, px_ = ref.dip3dc(dc)
@@ -70,6 +76,9 @@ def main():
                                    out=ref.somf2dc(d2e, p2, ns, order, eps))
         g["somean2d_" + name] = dict(dn=d2e, dip=p2, ns=ns, order=order, eps=eps,
                                      out=ref.somean2dc(d2e, p2, ns, order, eps))
+    for name, (ns, order, eps) in {"ns3o2": (3, 2, 0.01), "ns8o2": (8, 2, 0.01)}.items():
+        g["svmf2d_" + name] = dict(dn=d2e, dip=p2, ns=ns, order=order, eps=eps,
+                                   out=ref.somf2dc(d2e, p2, ns, order, eps, option=2))
     g["somean2dadj_ns3o2"] = dict(dn=d2e, dip=p2, ns=3, order=2, eps=0.01, out=ref.somean2dc(d2e, p2, 3, 2, 0.01, adj=1))
     g["somean2dadj_ns2o1"] = dict(dn=d2e, dip=p2, ns=2, order=1, eps=0.05, out=ref.somean2dc(d2e, p2, 2, 1, 0.05, adj=1))
     # ---- soint2d default path (one slope field, no preconditioner): csoint2d of the reference

@@ -228,12 +228,32 @@ def test_spray_on_2d_input_like_reference(ctx, port):
     assert np.array_equal(got, port.somf3dc(d, p, z, 2, 2, 0.01, 2))
 
 
-def test_somf3d_option2_is_refused_not_faked(ctx):
+@pytest.mark.parametrize("name", golden_names("svmf3d_") + golden_names("svmf2d_"))
+def test_svmf_golden_bit_exact(ctx, name):
+    """somf3dc / somf2dc with option=2 (space-varying median filter) against what the compiled reference returned, in
+    the defined-behaviour variant of its one-row over-read."""
     import pyseistr_b200 as ps
-    d = synth.cube(20, 6, 4, seed=65)
-    with pytest.raises(ps.PstError) as e:
-        ps.somf3dc(d, 0 * d, 0 * d, 1, 1, 0.01, 1, option=2, verb=0, ctx=ctx)
+    g = golden(name)
+    if name.startswith("svmf3d"):
+        out = ps.somf3dc(g["dn"], g["dipi"], g["dipx"], int(g["r1"]), int(g["r2"]), 0.01, int(g["order"]), option=2, verb=0, ctx=ctx)
+    else:
+        out = ps.somf2dc(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]), option=2, verb=0, ctx=ctx)
+    assert np.array_equal(out, g["out"]), rel_l2(out, g["out"])
+
+
+def test_svmf_vs_oracle_and_short_windows_refused(ctx, port):
+    import pyseistr_b200 as ps
+    d = synth.erratic(synth.cube(60, 21, 7, seed=66), ntraces=8)
+    di, dx = synth.smooth_dips(60, 21, 7, seed=66)
+    for r1, r2, order in ((2, 2, 2), (1, 2, 1), (2, 3, 1)):
+        got = ps.somf3dc(d, di, dx, r1, r2, 0.01, order, option=2, verb=0, ctx=ctx)
+        assert np.array_equal(got, port.somf3dc(d, di, dx, r1, r2, 0.01, order, option=2)), (r1, r2, order)
+    with pytest.raises(ps.PstError) as e:             # nmf = 3: the reference's shortest window would have length -1
+        ps.somf3dc(d, di, dx, 1, 1, 0.01, 1, option=2, verb=0, ctx=ctx)
     assert e.value.code == -5
+    with pytest.raises(ps.PstError) as e:
+        ps.somf3dc(d, di, dx, 2, 2, 0.01, 2, option=3, verb=0, ctx=ctx)
+    assert e.value.code == -1
 
 
 @pytest.mark.parametrize("name", golden_names("somean2dadj_"))
@@ -504,3 +524,19 @@ def test_das_panel_upscaled_30000x1280(ctx, port):
     assert dev <= max(TOL, 3.0 * (noise or 0.0)), (dev, noise)
     f = ps.somf2dc(d, po, 8, 2, 0.01, verb=0, ctx=ctx)
     assert np.array_equal(f, port.somf2dc(d, po, 8, 2, 0.01))
+
+
+def test_sint2d_through_one_plane_sint3d(ctx, port):
+    """sint2dc (reference sint.py:61-94) = sint3dc on an (n1, n2, 1) volume without xline smoothing: the one-trace-per-panel
+    spray path, against the oracle's csint2d restatement (itself pinned to the compiled reference)."""
+    import pyseistr_b200 as ps
+    d = np.asarray(synth.cube(96, 40, 1, seed=97, noise=0.0)).reshape(96, 40)
+    p2 = port.dip2dc(d, 2, 10, 2, 0.01, 1, 1e-6, [7, 7, 1])
+    keep = np.random.default_rng(98).random(40) > 0.5
+    mask = np.zeros_like(d)
+    mask[:, keep] = 1
+    for ns, order, niter in ((1, 1, 6), (2, 2, 8), (3, 1, 5)):
+        got = ps.sint2dc(d * mask, mask, p2, niter=niter, eps=0.01, ns=ns, order=order, verb=0, ctx=ctx)
+        want = port.sint2dc(d * mask, mask, p2, niter=niter, eps=0.01, ns=ns, order=order)
+        assert got.shape == (96, 40)
+        assert rel_l2(got, want) <= TOL, (ns, order, rel_l2(got, want))
