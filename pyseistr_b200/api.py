@@ -111,7 +111,9 @@ def somean3dc(dn, dipi, dipx, r1, r2, eps, order, verb=0, ctx=None):
 def somf3dc(dn, dipi, dipx, r1, r2, eps, order, option=1, verb=1, ctx=None):
     """3-D structure-oriented median (reference pyseistr/somf3d.py:54-97 -> csomf3d,
     sof3d_cfuns.c:1554).  The median runs over nmf = 2*r1*r2+1 slots along the flattened slot
-    axis around the centre slot.  option=1 (MF); option=2 (SVMF) raises."""
+    axis around the centre slot.  option=1: median filter (MF); option=2: space-varying median filter
+    (SVMF, sof3d_cfuns.c:1254-1352) in the defined-behaviour variant of the reference's one-row over-read (DESIGN.md
+    section 1; needs nmf >= 5)."""
     dn = np.asarray(dn)
     n1, n2, n3 = _shape3(dn)
     c = _ctx(ctx)
@@ -142,7 +144,7 @@ def somean2dc(dn, dip, ns, order, eps, adj=0, verb=1, ctx=None):
 
 def somf2dc(dn, dip, ns, order, eps, option=1, verb=1, ctx=None):
     """2-D structure-oriented median over the 2*ns+1 sprayed slots (reference
-    pyseistr/somf2d.py:60-105 -> csomf2d, sof_cfuns.c:1534)."""
+    pyseistr/somf2d.py:60-105 -> csomf2d, sof_cfuns.c:1534).  option=1: MF, option=2: SVMF (see somf3dc)."""
     dn = np.asarray(dn)
     n1, n2, n3 = _shape3(dn)
     c = _ctx(ctx)

@@ -97,7 +97,7 @@ struct PredArgs {
     long sg1_off, sg2_off;      // slope location shift (0 = target, else = parent shift)
     int forw1, forw2;
     float *out;                 // slot volume being produced
-    float *scr;                 // factor scratch [plane][k][NB+2][i2]
+    float *scr;                 // factor scratch [plane][k][NB+1][i2]: b/d, o[0..NB)
     int n1, n2, n3;
     int ze0;                    // global index of chunk-local plane 0
     int zla, zlb;               // chunk-local plane range to produce
@@ -115,7 +115,7 @@ template <int NW, bool TWO>
 __global__ void __launch_bounds__(128)
 predict_kernel(const PredArgs A)
 {
-    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 2;
+    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 1;
     const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int zl = A.zla + blockIdx.y;
     if (i2 >= A.n2) return;
@@ -297,12 +297,12 @@ predict_kernel(const PredArgs A)
 #pragma unroll
             for (int m = 0; m < NB; m++)
                 if (m < i) bk -= O[m][m] * Bh[m];
-            // ---- spill column to scratch
+            // ---- spill column to scratch: the back substitution needs b_k / d_k (formed here: same operands, same
+            // division) and o[.][k], not d_k and b_k separately
             float *sc = scr + (long)i * NC * n2;
-            sc[0] = dk;
+            sc[0] = bk / dk;
 #pragma unroll
             for (int q = 0; q < NB; q++) sc[(long)(1 + q) * n2] = ok[q];
-            sc[(long)(NB + 1) * n2] = bk;
             // ---- shift LDL history
 #pragma unroll
             for (int h = NB - 1; h > 0; h--) {
@@ -352,8 +352,7 @@ predict_kernel(const PredArgs A)
 #pragma unroll
             for (int q = 0; q < NC; q++) cq[u][q] = (kn >= 0) ? scr[((long)kn * NC + q) * n2] : 1.f;
         }
-        const float dk = col[0];
-        float t = col[NB + 1] / dk;
+        float t = col[0];
 #pragma unroll
         for (int m = 0; m < NB; m++)
             if (m < n1 - k - 1) t -= col[1 + m] * Y[m];
@@ -556,7 +555,7 @@ static void plan_close_parents(SprayPlan &P)
 // decides it: the arena reservation and spray_run must agree.
 static void spray_chunk_planes(const SprayPlan &P, int nlive, int *cz, int *nzl)
 {
-    const int NC = 2 * P.nw + 2;
+    const int NC = 2 * P.nw + 1;
     const double bytes_per_plane = (double)P.n1 * P.n2 * 4.0 * (nlive + NC);
     int z = (int)(spray_chunk_bytes() / bytes_per_plane) - 2 * P.ns3;
     if (z < 1) z = 1;
@@ -623,7 +622,7 @@ static int spray_run(pst_ctx *c, const SprayPlan &P, const float *dT, const floa
     const long plane = (long)n1 * n2;
     int nlive = 0;
     for (int s = 0; s < P.np; s++) nlive += P.live[s] ? 1 : 0;
-    const int NC = 2 * nw + 2;
+    const int NC = 2 * nw + 1;
     // chunk height: bound slot + scratch memory to ~6 GB
     int cz, nzl_max;
     spray_chunk_planes(P, nlive, &cz, &nzl_max);
@@ -810,7 +809,7 @@ static int spray_filter_dev(pst_ctx *c, int kind, const float *d_din, const floa
 
     const long plane = (long)n1 * n2;
     const size_t n = (size_t)plane * nz, nex = (size_t)plane * ne;
-    const int NC = 2 * order + 2;
+    const int NC = 2 * order + 1;
     int cz_, nzl_;
     spray_chunk_planes(P, nlive, &cz_, &nzl_);
     const size_t nzl = (size_t)nzl_;
@@ -949,7 +948,7 @@ struct AdjArgs {
     const float *data;         // data-side volume ("out" of pwsmooth_lop), same layout
     const float *tnorm;        // normalisation t; ws = (t != 0 ? 1/t : 0)
     const float *sg;           // slopes, same layout
-    float *scr;                // factor scratch [panel in launch][k][NB+2][i2]
+    float *scr;                // factor scratch [panel in launch][k][NB+1][i2]
     float wslot;               // triangle weight of the slot feeding this level
     int shift;                 // data trace ip = i + shift
     int sg_shift;              // slope trace = i + sg_shift
@@ -967,7 +966,7 @@ template <int NW>
 __global__ void __launch_bounds__(128)
 predict_adj_kernel(const AdjArgs A)
 {
-    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 2;
+    constexpr int NA = 2 * NW + 1, NB = 2 * NW, NC = NB + 1;
     const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
     if (i2 >= A.n2) return;
     const int ip = i2 + A.shift, ipg = ip + A.t_off;
@@ -1080,10 +1079,9 @@ predict_adj_kernel(const AdjArgs A)
             for (int m = 0; m < NB; m++)
                 if (m < i) bk -= O[m][m] * Bh[m];
             float *sc = scr + (long)i * NC * n2;
-            sc[0] = dk;
+            sc[0] = bk / dk;
 #pragma unroll
             for (int q = 0; q < NB; q++) sc[(long)(1 + q) * n2] = ok[q];
-            sc[(long)(NB + 1) * n2] = bk;
 #pragma unroll
             for (int h = NB - 1; h > 0; h--) {
                 D[h] = D[h - 1]; Bh[h] = Bh[h - 1];
@@ -1126,8 +1124,7 @@ predict_adj_kernel(const AdjArgs A)
 #pragma unroll
             for (int q = 0; q < NC; q++) cq[u][q] = (kn >= 0) ? scr[((long)kn * NC + q) * n2] : 1.f;
         }
-        const float dk = col[0];
-        float t = col[NB + 1] / dk;
+        float t = col[0];
 #pragma unroll
         for (int m = 0; m < NB; m++)
             if (m < n1 - k - 1) t -= col[1 + m] * Y[m];
@@ -1251,7 +1248,7 @@ static int smoother_set(pst_ctx *c, Smoother2 &S, float *ones_scratch)
 static int smoother_adj(pst_ctx *c, const Smoother2 &S, float *in, const float *data, bool add, float *trP, float *trM)
 {
     const size_t plane = (size_t)S.n1 * S.nt, n = plane * S.npanel;
-    const int NC = 2 * S.nw + 2;
+    const int NC = 2 * S.nw + 1;
     PST_CUDA(cudaMemsetAsync(trP, 0, n * sizeof(float), c->stream));
     PST_CUDA(cudaMemsetAsync(trM, 0, n * sizeof(float), c->stream));
     const size_t mark = c->arena_used;
@@ -1409,7 +1406,7 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     const size_t plane = (size_t)n1 * n2;
     const size_t n = plane * nz, nex = plane * nzl;               // slab / slab + halos
     const double nglob = (double)plane * n3;
-    const int NCmax = 2 * std::max(order1, order2) + 2, nsmax = std::max(ns1, ns2);
+    const int NCmax = 2 * std::max(order1, order2) + 1, nsmax = std::max(ns1, ns2);
     // 9 CG vectors + 2 dips + 2 norms + 5 work volumes + mask + spray slots/scratch (bounded chunks)
     const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * nex, (double)nex * 4.0 * (2 * nsmax + 1 + NCmax));
     PST_TRY(pst_arena_reserve(c, (size_t)((11 * n + 9 * nex) * sizeof(float) + n + chunk + 3.0e9 + 64 * 4096)));
@@ -1533,7 +1530,7 @@ int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int
     // distributed contexts: n3 is the global plane count; the (n1 x n2) panels are independent, each rank smooths its own
     if (c->comm && c->nranks > 1) n3 = (int)(((long)n3 * (c->rank + 1)) / c->nranks) - (int)(((long)n3 * c->rank) / c->nranks);
     const size_t n = (size_t)n1 * n2 * n3;
-    const int NC = 2 * order + 2;
+    const int NC = 2 * order + 1;
     const double chunk = std::min<double>(spray_chunk_bytes() + 2.0 * 4.0 * n, (double)n * 4.0 * (2 * ns + 1 + NC));
     PST_TRY(pst_arena_reserve(c, (size_t)(7 * n * sizeof(float) + chunk + 3.0e9 + 64 * 4096)));
     pst_arena_reset(c);
