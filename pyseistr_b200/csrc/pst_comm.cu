@@ -81,6 +81,10 @@ struct pst_comm {
     char *mbox_next = nullptr;       // rank+1's mailbox, mapped (null on the last rank)
     size_t mbox_L = 0, mbox_bytes = 0;
     unsigned epoch = 0;
+    // neighbours' workspace arenas mapped with CUDA IPC (peer-memory halos of the axis-3 smoothing taps)
+    char *arena_prev = nullptr, *arena_next = nullptr;
+    char *arena_mapped_for = nullptr;      // my arena pointer at the time of the exchange
+    size_t arena_mapped_size = 0;
 };
 
 int pst_comm_allreduce_record(pst_ctx *c, double *d_rec, int nv)
@@ -137,6 +141,8 @@ int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_h
 void pst_comm_destroy(pst_ctx *c)
 {
     if (c->comm) {
+        if (c->comm->arena_prev) cudaIpcCloseMemHandle(c->comm->arena_prev);
+        if (c->comm->arena_next) cudaIpcCloseMemHandle(c->comm->arena_next);
         if (c->comm->mbox_prev) cudaIpcCloseMemHandle(c->comm->mbox_prev);
         if (c->comm->mbox_next) cudaIpcCloseMemHandle(c->comm->mbox_next);
         if (c->comm->mbox) cudaFree(c->comm->mbox);
@@ -260,7 +266,52 @@ int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v)
     v->ff_out = m->mbox_next ? (unsigned *)(m->mbox_next + off) : nullptr;
     v->cb_out = m->mbox_prev ? (float *)(m->mbox_prev + ocb) : nullptr;
     v->fb_out = m->mbox_prev ? (unsigned *)(m->mbox_prev + ofb) : nullptr;
+    v->hr_in_prev = (unsigned *)(m->mbox + oerr + 16);
+    v->hr_in_next = (unsigned *)(m->mbox + oerr + 32);
+    v->hr_out_prev = m->mbox_prev ? (unsigned *)(m->mbox_prev + oerr + 32) : nullptr;   // I am the previous rank's "next"
+    v->hr_out_next = m->mbox_next ? (unsigned *)(m->mbox_next + oerr + 16) : nullptr;   // and the next rank's "previous"
     v->epoch = ++m->epoch;
+    return PST_OK;
+}
+
+// Collective: map the neighbours' workspace arenas (CUDA IPC) so that kernels can read halo planes straight from peer
+// memory.  The arenas are re-exchanged whenever ANY rank's arena moved since the last exchange (decided with an
+// all-reduce, so that every rank takes the same branch).  *prev / *next: mapped bases (null on the edge ranks).
+int pst_comm_map_arenas(pst_ctx *c, char **prev, char **next)
+{
+    pst_comm *m = c->comm;
+    *prev = *next = nullptr;
+    if (!m || !c->arena) return PST_OK;
+    int *d_flag = nullptr;
+    PST_CUDA(cudaMalloc((void **)&d_flag, 64 + sizeof(cudaIpcMemHandle_t) * (size_t)(c->nranks + 1)));
+    int changed = (m->arena_mapped_for != c->arena || m->arena_mapped_size != c->arena_size) ? 1 : 0;
+    PST_CUDA(cudaMemcpy(d_flag, &changed, sizeof(int), cudaMemcpyHostToDevice));
+    PST_CUDA(cudaDeviceSynchronize());
+    PST_NCCL(g_nccl.AllReduce(d_flag, d_flag, 1, 2 /* ncclInt32 */, 2 /* ncclMax */, m->comm, c->stream));
+    PST_CUDA(cudaStreamSynchronize(c->stream));
+    PST_CUDA(cudaMemcpy(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (changed) {
+        if (m->arena_prev) { cudaIpcCloseMemHandle(m->arena_prev); m->arena_prev = nullptr; }
+        if (m->arena_next) { cudaIpcCloseMemHandle(m->arena_next); m->arena_next = nullptr; }
+        cudaIpcMemHandle_t mine;
+        PST_CUDA(cudaIpcGetMemHandle(&mine, c->arena));
+        char *d_h = (char *)d_flag + 64;                     // (the allocation is 256-byte aligned)
+        PST_CUDA(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        PST_CUDA(cudaDeviceSynchronize());
+        PST_NCCL(g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0 /* ncclInt8 */, m->comm, c->stream));
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+        PST_CUDA(cudaMemcpy(all.data(), d_h + sizeof(mine), sizeof(mine) * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+        if (c->rank > 0)
+            PST_CUDA(cudaIpcOpenMemHandle((void **)&m->arena_prev, all[(size_t)c->rank - 1], cudaIpcMemLazyEnablePeerAccess));
+        if (c->rank < c->nranks - 1)
+            PST_CUDA(cudaIpcOpenMemHandle((void **)&m->arena_next, all[(size_t)c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
+        m->arena_mapped_for = c->arena;
+        m->arena_mapped_size = c->arena_size;
+    }
+    PST_CUDA(cudaFree(d_flag));
+    *prev = m->arena_prev;
+    *next = m->arena_next;
     return PST_OK;
 }
 

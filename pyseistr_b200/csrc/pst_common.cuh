@@ -44,6 +44,9 @@ struct pst_mailbox_view {
     unsigned epoch;
     // tile kernels: self-validating 8-byte {carry bits, epoch} pairs, one per line (no fence, no flag)
     uint2 *pf_in, *pb_in, *pf_out, *pb_out;
+    // peer-memory halos of the axis-3 taps: "my current input is complete" flags (value = epoch).  hr_in_*: in my
+    // mailbox, raised by the previous / next rank; hr_out_*: the slots I raise in theirs
+    unsigned *hr_in_prev, *hr_in_next, *hr_out_prev, *hr_out_next;
 };
 
 struct pst_ctx {

@@ -1337,6 +1337,8 @@ struct DipGeom {
     // work buffers of the distributed axis-3 pass (arena): halo planes before / after the slab,
     // carry planes (in / out), see smooth_axis3_dist
     float *hb = nullptr, *ha = nullptr, *cin = nullptr, *cout = nullptr;
+    // neighbours' arenas mapped with CUDA IPC (equal slabs only: identical arena layouts), see smooth_axis3_dist
+    char *peer_prev = nullptr, *peer_next = nullptr;
 };
 static DipGeom make_geom(int n1, int n2, int n3, int r1, int r2, int r3)
 {
@@ -1378,6 +1380,8 @@ static int slab_geom(pst_ctx *c, const char *who, int n1, int n2, int n3, int r1
     return PST_OK;
 }
 
+int pst_comm_map_arenas(pst_ctx *c, char **prev, char **next);                       // pst_comm.cu
+
 // floats slab_halos() takes from the arena
 static size_t slab_halo_floats(const DipGeom &g)
 {
@@ -1393,6 +1397,7 @@ static int slab_halos(pst_ctx *c, DipGeom *g)
     PST_TRY(pst_arena_get(c, plane * (size_t)std::max(g->r3, 1), &g->ha));
     PST_TRY(pst_arena_get(c, plane, &g->cin));
     PST_TRY(pst_arena_get(c, plane, &g->cout));
+    if (g->r3 > 1 && g->n3g % c->nranks == 0) PST_TRY(pst_comm_map_arenas(c, &g->peer_prev, &g->peer_next));   // collective
     return PST_OK;
 }
 
@@ -1431,6 +1436,9 @@ struct Tri3Args {
     float *cout; unsigned *fout;
     const uint2 *pin; uint2 *pout;   // tile kernels: {carry, epoch} pairs (mine, incoming) / (neighbour's, outgoing)
     unsigned *err; unsigned epoch;
+    // peer-memory halos: hb / ha point INTO the neighbours' slabs (CUDA IPC); the kernel first waits for the flags the
+    // neighbours raise (in my mailbox) once their current input is complete.  Null = halos were copied by NCCL.
+    const unsigned *hr_prev, *hr_next;
     float *dst;            // fold output [nz][L]
     long L, l0, l1;        // lines per plane, chunk [l0, l1)
     int n3g, z0, nz, nb, K0, K1;
@@ -1464,6 +1472,36 @@ __device__ __forceinline__ void tri3_pair_send(uint2 *p, float v, unsigned epoch
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
 
+// peer-memory halos: one thread waits until both neighbours have announced that their current input is complete
+__device__ __forceinline__ void tri3_wait_halos(const Tri3Args &A)
+{
+    if (A.hr_prev == nullptr && A.hr_next == nullptr) return;        // uniform
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        const unsigned *fl[2] = {A.hr_prev, A.hr_next};
+        for (int q = 0; q < 2; q++) {
+            if (!fl[q]) continue;
+            unsigned v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl[q]) : "memory");
+                if (v == A.epoch) break;
+                if (clock64() - t0 > 20000000000LL) { *A.err = 1u; break; }
+                __nanosleep(100);
+            }
+        }
+    }
+    __syncthreads();
+}
+// raised on the stream right after the kernel that produced the input of an axis-3 pass
+__global__ void tri3_halo_ready_kernel(unsigned *to_prev, unsigned *to_next, unsigned epoch)
+{
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (to_prev) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(to_prev), "r"(epoch) : "memory");
+        if (to_next) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(to_next), "r"(epoch) : "memory");
+    }
+}
+
 // line kernels (tall slabs): one flag per CTA (one polling thread); measured at 2 GPUs the per-thread pair
 // polling of the tile kernels costs more here (303K resident pollers per GPU)
 // consumer side of the carry hand-off: one thread spins (acquire, system scope) on this CTA's
@@ -1494,6 +1532,7 @@ __global__ void __launch_bounds__(128)
 tri3_dist_fwd_kernel(const Tri3Args A)
 {
     const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    tri3_wait_halos(A);
     if (A.cin) tri3_wait(A.fin + blockIdx.x, A.epoch, A.err);
     const bool live = l < A.L;
     const float wm = -A.wt;
@@ -1602,6 +1641,7 @@ tri3_tile_fwd_kernel(const Tri3Args A)
     // ---- burst load: row r <-> global plane j = K0 - 2nb + r
     constexpr int CPR = W / 4;                                 // 16-byte chunks per row
     float s = 0.f;
+    tri3_wait_halos(A);
     {
         for (int idx = tid; idx < R * CPR; idx += 128) {
             const int r = idx / CPR, ch = idx - r * CPR;
@@ -1797,12 +1837,30 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     const int nb = g.r3, nz = g.n3, n3g = g.n3g;
     const long L = (long)g.n1 * g.n2;
     const bool first = c->rank == 0, last = c->rank == c->nranks - 1;
-    // nb-plane halos of the CURRENT input (it changes every pass)
-    PST_TRY(pst_comm_halo_exchange(c, src, src + (size_t)(nz - nb) * L, g.hb, g.ha, (size_t)nb * L));
     pst_mailbox_view mb;
     PST_TRY(pst_comm_mailbox(c, (size_t)L, &mb));
     Tri3Args A{};
-    A.x = src; A.hb = g.hb; A.ha = g.ha; A.F = scr; A.dst = dst; A.L = L; A.l0 = 0; A.l1 = L;
+    // nb-plane halos of the CURRENT input (it changes every pass).  Equal slabs give every rank the same arena layout:
+    // the kernels then read the halo planes straight from the neighbours' slabs over NVLink (peer memory), after
+    // each rank has announced "my input is complete" with one flag store per neighbour -- no copy, no NCCL call.
+    // WAR safety: a neighbour overwrites those planes only in or after ITS backward kernel, which cannot start before
+    // its forward kernel has received the carries of all my forward CTAs, i.e. after they have read their halos.
+    const char *sp = (const char *)src;
+    const bool in_arena = sp >= c->arena && sp + g.n * sizeof(float) <= c->arena + c->arena_size;
+    static const bool peer_on = []() { const char *e = getenv("PST_TRI3_PEERHALO"); return !(e && e[0] == '0'); }();
+    const bool peer = peer_on && in_arena && (first || g.peer_prev) && (last || g.peer_next) && (n3g % c->nranks == 0);
+    if (peer) {
+        const size_t off = (size_t)(sp - c->arena);
+        A.hb = first ? nullptr : (const float *)(g.peer_prev + off) + (size_t)(nz - nb) * L;
+        A.ha = last ? nullptr : (const float *)(g.peer_next + off);
+        A.hr_prev = first ? nullptr : mb.hr_in_prev;
+        A.hr_next = last ? nullptr : mb.hr_in_next;
+        PST_LAUNCH(c, PST_K_OTHER, (tri3_halo_ready_kernel<<<1, 32, 0, c->stream>>>(mb.hr_out_prev, mb.hr_out_next, mb.epoch)));
+    } else {
+        PST_TRY(pst_comm_halo_exchange(c, src, src + (size_t)(nz - nb) * L, g.hb, g.ha, (size_t)nb * L));
+        A.hb = g.hb; A.ha = g.ha;
+    }
+    A.x = src; A.F = scr; A.dst = dst; A.L = L; A.l0 = 0; A.l1 = L;
     A.n3g = n3g; A.z0 = g.z0; A.nz = nz; A.nb = nb;
     A.K0 = first ? 0 : g.z0 + nb;
     A.K1 = last ? n3g + 2 * nb : g.z0 + nz + nb;
@@ -1812,7 +1870,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     // tile kernels (burst-loaded shared-memory tiles, short CTA latency) when they fit; the tile width
     // must be the same on every rank (the carry flags are per CTA): derived from the tallest slab
     const int nz_max = (n3g + c->nranks - 1) / c->nranks;
-    const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, g.hb, g.ha);
+    const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, A.hb, A.ha);
     const unsigned blocks = (unsigned)((L + (W ? W : 128) - 1) / (W ? W : 128));
     const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
     // forward sums: carries flow rank -> rank+1, CTA by CTA, through the neighbour's mailbox

@@ -13,7 +13,7 @@
 //     128 contiguous bytes, lane = column; contiguous axis: box = 32 lines x 128 bytes with the 128-byte swizzle, so
 //     that "lane = line" 128-bit shared-memory reads are conflict-free;
 //   * pass A streams the tile upwards once (HBM), pass B streams it downwards again -- 3 to 6 warps per SM x 148 SMs
-//     x 128 KB per tile = 57 - 114 MB in flight, so the second read hits L2 (pass-A loads carry an evict-last policy,
+//     x up to 128 KB per tile (64 KB on average over a tile's life) in flight, so the second read hits L2 (pass-A loads carry an evict-last policy,
 //     pass-B loads and the stores evict-first) and HBM sees the compulsory 8 B per sample;
 //   * outputs leave as aligned 32 x 32 boxes through TMA stores (bulk groups), zero-clipped at the volume edges.
 // The per-line arithmetic is pst_tri_l2_core.h (host-testable, tests/test_tri_l2_core.py).
@@ -66,6 +66,12 @@ __device__ __forceinline__ uint64_t policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t policy_evict_first()
 {
     uint64_t p;
@@ -97,66 +103,79 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 constexpr int BOX = 32 * 32;                 // floats per box (4 KB)
-constexpr int MAXBLK = 72;                   // checkpoints per lane: lines up to 72 * 32 - 2 nb samples
+constexpr int MAXBLK = 160;                  // checkpoints per lane: lines up to 160 * 32 - 2 nb samples
 
 struct Args {
+    float *dst;            // strided axes: outputs are stored directly (coalesced 128-byte rows)
+    long d, sb;            // strided axes: element stride along the line, slab stride
     long ntiles;
     int tilesA;            // strided: tiles along the fast index (per slab); contiguous: unused
+    int na;                // strided: extent of the fast index
     int nx;
     int nld, nrel;         // blocks per tile loaded in pass A / again in pass B
+    int nblk;              // checkpoints per line
     int nslot;             // ring slots per warp
     int hints;             // bit 0: evict-last on pass-A loads, bit 1: evict-first on pass-B loads, bit 2: on stores
     float wm, w2;
 };
 
-// The block transport of one warp: ring of TMA boxes in, two staging boxes out.  Every member function is called by
-// all 32 lanes (warp-uniform control flow); lane 0 issues the TMA operations.
+// The block transport of one warp: ring of TMA boxes in; out: coalesced rows (strided axes) or TMA boxes through two
+// staging boxes (contiguous axis).  Every member function is called by all 32 lanes (warp-uniform control flow); lane 0
+// issues the TMA operations.  All ring / stream positions are advanced incrementally (no divisions in the loop).
 template <bool CONTIG>
 struct WarpIO {
     const CUtensorMap *tin, *tout;
     float *ring, *stage;
     mbar_t *full;
     const Args *A;
-    long tile_first, tile_step, ntiles_mine;   // this warp's tiles: tile_first + p * tile_step
-    long q_issue, q_take, q_total;             // positions in the warp's whole block stream (all of its tiles)
-    int per_tile;                              // blocks per tile in the stream
+    long tile_step;
+    long left_issue;                            // loads still to issue over all of this warp's tiles
+    // issue side: next load = block stream position i_ql of tile i_tile
+    long i_tile; int i_ql, i_slot, i_c0, i_slab;
+    // take side
+    int t_slot; unsigned t_phase;
+    int per_tile;                               // blocks per tile in the stream
     int lane;
     int nstore;
     uint64_t polA, polB, polS;
-    // tile coordinates of the tile being computed (for the stores)
+    // tile being computed (for the stores)
     int cur_c0, cur_slab;
 
     __device__ __forceinline__ void coords(long tile, int &c0, int &slab) const
     {
-        if (CONTIG) { c0 = (int)(tile * 32); slab = 0; }
-        else { slab = (int)(tile / A->tilesA); c0 = (int)(tile - (long)slab * A->tilesA) * 32; }
+        if (CONTIG) { c0 = (int)tile * 32; slab = 0; }
+        else { slab = (int)tile / A->tilesA; c0 = ((int)tile - slab * A->tilesA) * 32; }
     }
-    // lane 0: put the load of stream position q in flight
-    __device__ __forceinline__ void issue(long q)
+    // put the next load of the stream in flight (TMA by lane 0; every lane advances the position)
+    __device__ __forceinline__ void issue()
     {
-        const long p = q / per_tile;
-        const int ql = (int)(q - p * per_tile);
-        const int m = ql < A->nld ? ql : (A->nrel - 1) - (ql - A->nld);
-        const uint64_t pol = ql < A->nld ? polA : polB;
-        int c0, slab;
-        coords(tile_first + p * tile_step, c0, slab);
-        const int s = (int)(q % A->nslot);
-        mbar_expect_tx(full + s, BOX * 4);
-        if (CONTIG) tma_load_2d(ring + (size_t)s * BOX, tin, m * 32, c0, full + s, pol);
-        else tma_load_3d(ring + (size_t)s * BOX, tin, c0, m * 32, slab, full + s, pol);
+        const int m = i_ql < A->nld ? i_ql : (A->nrel - 1) - (i_ql - A->nld);
+        if (lane == 0) {
+            const uint64_t pol = i_ql < A->nld ? polA : polB;
+            mbar_expect_tx(full + i_slot, BOX * 4);
+            if (CONTIG) tma_load_2d(ring + (size_t)i_slot * BOX, tin, m * 32, i_c0, full + i_slot, pol);
+            else tma_load_3d(ring + (size_t)i_slot * BOX, tin, i_c0, m * 32, i_slab, full + i_slot, pol);
+        }
+        left_issue--;
+        if (++i_slot == A->nslot) i_slot = 0;
+        if (++i_ql == per_tile) {
+            i_ql = 0;
+            i_tile += tile_step;
+            coords(i_tile, i_c0, i_slab);
+        }
     }
-    __device__ __forceinline__ void start()
+    __device__ __forceinline__ void start(long tile_first, long ntiles_mine)
     {
-        q_take = 0; q_issue = 0;
-        if (lane == 0)
-            for (; q_issue < q_total && q_issue < A->nslot; q_issue++) issue(q_issue);
-        q_issue = q_total < A->nslot ? q_total : A->nslot;
+        left_issue = ntiles_mine * per_tile;
+        i_tile = tile_first; i_ql = 0; i_slot = 0;
+        coords(i_tile, i_c0, i_slab);
+        t_slot = 0; t_phase = 0;
+        for (int s = 0; s < A->nslot && left_issue > 0; s++) issue();
     }
     __device__ __forceinline__ void load(float *x)
     {
-        const int s = (int)(q_take % A->nslot);
-        mbar_wait(full + s, (unsigned)((q_take / A->nslot) & 1));
-        const float *b = ring + (size_t)s * BOX;
+        mbar_wait(full + t_slot, t_phase);
+        const float *b = ring + (size_t)t_slot * BOX;
         if (CONTIG) {
             // box = [line][32 samples], 16-byte chunks XOR-swizzled by (line & 7)
             const float4 *row = reinterpret_cast<const float4 *>(b + lane * 32);
@@ -170,49 +189,61 @@ struct WarpIO {
             for (int j = 0; j < 32; j++) x[j] = b[j * 32 + lane];
         }
         __syncwarp();                                   // every lane has read the slot: it may be refilled
-        q_take++;
-        if (q_issue < q_total) {
-            if (lane == 0) issue(q_issue);
-            q_issue++;
-        }
+        if (++t_slot == A->nslot) { t_slot = 0; t_phase ^= 1u; }
+        if (left_issue > 0) issue();                    // refills the slot just read (issue and take advance in step)
     }
     __device__ __forceinline__ void store(const float *v, int i0)
     {
-        float *st = stage + (size_t)(nstore & 1) * BOX;
-        if (lane == 0) bulk_wait_read_1();              // the store that used this staging box two windows ago has read it
-        __syncwarp();
         if (CONTIG) {
+            float *st = stage + (size_t)(nstore & 1) * BOX;
+            if (lane == 0) bulk_wait_read_1();          // the store that used this staging box two windows ago has read it
+            __syncwarp();
             float4 *row = reinterpret_cast<float4 *>(st + lane * 32);
 #pragma unroll
             for (int c = 0; c < 8; c++) row[c ^ (lane & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            fence_async();                              // my generic-proxy writes before the TMA unit reads the box
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tout, st, i0, cur_c0, polS);
+                bulk_commit();
+            }
+            nstore++;
         } else {
+            // lane = fast index: every row of the window is one 128-byte store of the warp
+            const int col = cur_c0 + lane;
+            if (col < A->na) {
+                float *q = A->dst + (long)cur_slab * A->sb + col + (long)i0 * A->d;
+                const long db = A->d;
+                if (i0 + 32 <= A->nx) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) st[j * 32 + lane] = v[j];
+                    for (int j = 0; j < 32; j++) { __stcs(q, v[j]); q += db; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) { if (i0 + j < A->nx) __stcs(q, v[j]); q += db; }
+                }
+            }
         }
-        fence_async();                                  // my generic-proxy writes before the TMA unit reads the box
-        __syncwarp();
-        if (lane == 0) {
-            if (CONTIG) tma_store_2d(tout, st, i0, cur_c0, polS);
-            else tma_store_3d(tout, st, cur_c0, i0, cur_slab, polS);
-            bulk_commit();
-        }
-        nstore++;
     }
 };
 
+// per-warp shared memory: ring [nslot][BOX] | stage [2][BOX] (contiguous axis) | checkpoints [nblk][32] | barriers
+__host__ __device__ inline size_t per_warp_bytes(bool contig, int nslot, int nblk)
+{
+    size_t b = ((size_t)(nslot + (contig ? 2 : 0)) * BOX + (size_t)nblk * 32) * 4 + 16 * sizeof(mbar_t);
+    return (b + 1023) & ~(size_t)1023;
+}
+
 template <bool CONTIG, int NB>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(256, 1)
 tri_l2_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout, const Args A)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    // per warp: ring [nslot][BOX] | stage [2][BOX] | checkpoints [MAXBLK][32] | barriers [nslot]
-    const size_t per_warp = ((size_t)(A.nslot + 2) * BOX + MAXBLK * 32) * 4 + 1024;
-    unsigned char *base = smem_raw + (size_t)warp * per_warp;
+    unsigned char *base = smem_raw + (size_t)warp * per_warp_bytes(CONTIG, A.nslot, A.nblk);
     float *ring = reinterpret_cast<float *>(base);
     float *stage = ring + (size_t)A.nslot * BOX;
-    float *ck = stage + 2 * BOX;
-    mbar_t *full = reinterpret_cast<mbar_t *>(ck + MAXBLK * 32);
+    float *ck = stage + (CONTIG ? 2 * BOX : 0);
+    mbar_t *full = reinterpret_cast<mbar_t *>(ck + (size_t)A.nblk * 32);
     if (lane == 0) {
         for (int s = 0; s < A.nslot; s++) mbar_init(full + s, 1);
         fence_init();
@@ -221,26 +252,25 @@ tri_l2_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ C
 
     WarpIO<CONTIG> io;
     io.tin = &tin; io.tout = &tout; io.ring = ring; io.stage = stage; io.full = full; io.A = &A; io.lane = lane;
-    io.tile_first = (long)blockIdx.x * nwarp + warp;
+    const long tile_first = (long)blockIdx.x * nwarp + warp;
     io.tile_step = (long)gridDim.x * nwarp;
-    io.ntiles_mine = io.tile_first < A.ntiles ? (A.ntiles - io.tile_first + io.tile_step - 1) / io.tile_step : 0;
+    const long ntiles_mine = tile_first < A.ntiles ? (A.ntiles - tile_first + io.tile_step - 1) / io.tile_step : 0;
     io.per_tile = A.nld + A.nrel;
-    io.q_total = io.ntiles_mine * io.per_tile;
     io.nstore = 0;
-    io.polA = (A.hints & 1) ? policy_evict_last() : 0;
-    io.polB = (A.hints & 2) ? policy_evict_first() : 0;
-    io.polS = (A.hints & 4) ? policy_evict_first() : 0;
-    if ((A.hints & 1) == 0) { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); io.polA = p; }
-    if ((A.hints & 2) == 0) { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); io.polB = p; }
-    if ((A.hints & 4) == 0) { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); io.polS = p; }
-    if (io.ntiles_mine == 0) return;
-    io.start();
-    for (long p = 0; p < io.ntiles_mine; p++) {
-        io.coords(io.tile_first + p * io.tile_step, io.cur_c0, io.cur_slab);
+    io.polA = (A.hints & 1) ? policy_evict_last() : policy_evict_normal();
+    io.polB = (A.hints & 2) ? policy_evict_first() : policy_evict_normal();
+    io.polS = (A.hints & 4) ? policy_evict_first() : policy_evict_normal();
+    if (ntiles_mine == 0) return;
+    io.start(tile_first, ntiles_mine);
+    long tile = tile_first;
+    for (long p = 0; p < ntiles_mine; p++, tile += io.tile_step) {
+        io.coords(tile, io.cur_c0, io.cur_slab);
         tri_l2::smooth_line<NB>(io, A.nx, A.wm, A.w2, ck + lane, 32);
     }
-    if (lane == 0) bulk_wait_all();                     // the staging boxes must outlive their stores
-    __syncwarp();
+    if (CONTIG) {
+        if (lane == 0) bulk_wait_all();                 // the staging boxes must outlive their stores
+        __syncwarp();
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -264,8 +294,8 @@ EncodeTiledFn get_encode()
 
 struct Plan {
     bool ok;
-    int nx, nb, nld, nrel, tilesA;
-    long ntiles, na;
+    int nx, nb, nld, nrel, nblk, tilesA;
+    long ntiles, na, d, sb;
     float wm, w2;
 };
 
@@ -279,18 +309,21 @@ Plan make_plan(int axis, int n1, int n2, int n3, int nb)
     P.nx = nn[axis]; P.nb = nb;
     if (!nb_built(nb) || nb > P.nx) return P;
     if (n1 % 4 != 0) return P;                                   // TMA: global strides are multiples of 16 bytes
-    const int nblk = (P.nx + 2 * nb + 31) / 32;
-    if (nblk > MAXBLK) return P;
+    P.nblk = (P.nx + 2 * nb + 31) / 32;
+    if (P.nblk > MAXBLK) return P;
     P.nld = (P.nx + 31) / 32;
     P.nrel = tri_l2::reload_count(P.nx, nb);
     if (axis == 0) {
         P.na = (long)n2 * n3;
         P.tilesA = 0;
         P.ntiles = (P.na + 31) / 32;
+        P.d = 1; P.sb = 0;
     } else {
         P.na = axis == 1 ? n1 : (long)n1 * n2;
         P.tilesA = (int)((P.na + 31) / 32);
         P.ntiles = (long)P.tilesA * (axis == 1 ? n3 : 1);
+        P.d = P.na;
+        P.sb = axis == 1 ? (long)n1 * n2 : 0;
     }
     if (P.na >= (1L << 31) || P.ntiles * 32 >= (1L << 31)) return P;
     const float wt = (float)(1.0 / ((double)nb * nb));          // ps_triangle_init dip_cfuns.c:421
@@ -362,20 +395,21 @@ int pst_tri_l2_launch(cudaStream_t stream, int sm_count, int axis, const float *
     if (!P.ok) return -1;
     EncodeTiledFn enc = get_encode();
     if (!enc) return -2;
-    static const int warps_env = env_int("PST_TRI_L2_WARPS", 4);
+    static const int warps_env = env_int("PST_TRI_L2_WARPS", 8);
     static const int slots_env = env_int("PST_TRI_L2_SLOTS", 0);
     static const int hints_env = env_int("PST_TRI_L2_HINTS", 7);
-    int warps = warps_env < 1 ? 1 : (warps_env > 6 ? 6 : warps_env);
+    const bool contig = axis == 0;
+    int warps = warps_env < 1 ? 1 : (warps_env > 8 ? 8 : warps_env);
     const size_t budget = 227 * 1024;
-    const size_t fixed = ((size_t)2 * BOX + MAXBLK * 32) * 4 + 1024;
-    int nslot = (int)((budget / warps - fixed) / (BOX * 4));
-    if (slots_env > 0 && slots_env < nslot) nslot = slots_env;
+    int nslot = slots_env > 0 ? slots_env : 4;
     if (nslot > 16) nslot = 16;
-    if (nslot < 2) return -1;
-    const size_t per_warp = ((size_t)(nslot + 2) * BOX + MAXBLK * 32) * 4 + 1024;
-    const size_t smem = per_warp * warps;
+    while (nslot > 2 && per_warp_bytes(contig, nslot, P.nblk) * warps > budget) nslot--;
+    while (warps > 1 && per_warp_bytes(contig, nslot, P.nblk) * warps > budget) warps--;
+    if (per_warp_bytes(contig, nslot, P.nblk) * warps > budget) return -1;
+    const size_t smem = per_warp_bytes(contig, nslot, P.nblk) * warps;
     Args A{};
-    A.ntiles = P.ntiles; A.tilesA = P.tilesA; A.nx = P.nx; A.nld = P.nld; A.nrel = P.nrel; A.nslot = nslot;
+    A.dst = dst; A.d = P.d; A.sb = P.sb; A.na = (int)(P.na < (1L << 31) ? P.na : 0);
+    A.ntiles = P.ntiles; A.tilesA = P.tilesA; A.nx = P.nx; A.nld = P.nld; A.nrel = P.nrel; A.nblk = P.nblk; A.nslot = nslot;
     A.hints = hints_env; A.wm = P.wm; A.w2 = P.w2;
     CUtensorMap ti, to;
     if (encode_map(enc, &ti, axis, src, n1, n2, n3) || encode_map(enc, &to, axis, dst, n1, n2, n3)) return -3;
