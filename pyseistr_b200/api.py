@@ -216,7 +216,7 @@ def sint3dc(din, mask, dipi, dipx, niter=100, eps=0.01, ns1=1, ns2=1, order1=1, 
 def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=1, ctx=None):
     """2-D interpolation of sparse data by shaping-regularised CG with the 2-D plane-wave smoother (reference
     pyseistr/sint.py:61-94 -> csint2d, soint2d_cfuns.c).  csint2d is csint3d on an (n1, n2, 1) volume with no xline
-    smoothing (ns2 = 0, zero xline slope), bit for bit on the compiled reference (tests/test_oracle.py::
+    smoothing (ns2 = 0, zero xline slope), bit for bit on the compiled reference (CPU test suite:
     test_ref_sint2d_is_sint3d_with_one_plane), so it runs through pst_sint3d."""
     din = np.asarray(din)
     if din.ndim != 2:

@@ -19,6 +19,7 @@
 // Arithmetic follows the reference operation by operation (no FMA), so every sprayed
 // value is bit-identical and the median selection is exact.
 #include "pst_common.cuh"
+#include "pst_predict_core.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -35,78 +36,6 @@ static double spray_chunk_bytes()
     return v;
 }
 
-struct BTabS { double b[PST_MAXTAP]; };
-
-static BTabS make_btab_s(int nw)     // apfilt_init sof3d_cfuns.c:286-303
-{
-    BTabS t{};
-    const int nf = 2 * nw;
-    for (int k = 0; k <= nf; k++) {
-        double bk = 1.0;
-        for (int j = 0; j < nf; j++) {
-            if (j < nf - k) bk *= (k + j + 1.0) / (2 * (2 * j + 1) * (j + 1));
-            else            bk *= 1.0 / (2 * (2 * j + 1));
-        }
-        t.b[k] = bk;
-    }
-    return t;
-}
-
-// passfilter (sof3d_cfuns.c:311-329), taps reversed when forw (pwd_define :414-424)
-template <int NW>
-__device__ __forceinline__ void spray_taps(const BTabS &tb, float p, bool forw, float (&a)[2 * NW + 1])
-{
-    constexpr int NF = 2 * NW;
-    float t[2 * NW + 1];
-#pragma unroll
-    for (int k = 0; k <= NF; k++) {
-        double ak = tb.b[k];
-#pragma unroll
-        for (int j = 0; j < NF; j++) {
-            const float f = (j < NF - k) ? ((float)(NF - j) - p) : ((p + (float)j) + 1.0f);
-            ak *= (double)f;
-        }
-        t[k] = (float)ak;
-    }
-#pragma unroll
-    for (int k = 0; k <= NF; k++) a[k] = forw ? t[NF - k] : t[k];
-}
-
-// regularisation constants in the reference's float/double placement (regularization :548-565)
-struct RegC { float d_in, d_e0, d_e1, o0_in, o0_e, o1, eps2; };
-
-static RegC make_reg(float eps)
-{
-    RegC r;
-    const float eps2 = eps;
-    r.d_in = 6. * eps;
-    r.d_e0 = eps2 + eps;
-    r.d_e1 = eps2 + 5. * eps;
-    r.o0_in = -4. * eps;
-    r.o0_e = -2. * eps;
-    r.o1 = eps;
-    r.eps2 = eps2;
-    return r;
-}
-
-struct PredArgs {
-    // all volumes are chunk-local, trace-minor: elem(zl,k,i2) = (zl*n1 + k)*n2 + i2
-    const float *in1, *in2;     // parent slot volumes
-    const float *sg1, *sg2;     // slope volumes
-    long in1_off, in2_off;      // parent location shift, in elements (+-1 or +-n1*n2)
-    long sg1_off, sg2_off;      // slope location shift (0 = target, else = parent shift)
-    int forw1, forw2;
-    float *out;                 // slot volume being produced
-    float *scr;                 // factor scratch [plane][k][NB+1][i2]: b/d, o[0..NB)
-    int n1, n2, n3;
-    int ze0;                    // global index of chunk-local plane 0
-    int zla, zlb;               // chunk-local plane range to produce
-    int a, b;                   // slot offsets: source = target - (a,b)
-    int t_off, ntg;             // traces of a panel cut over ranks (distributed xline smoother of sint3d): global index
-                                // of local trace 0 and global trace count; whole panels: 0, n2
-    RegC reg;
-    BTabS tb;
-};
 
 // One thread = one target trace.  Forward sweep: taps -> W'W bands (+regularisation) ->
 // LDL' column k -> rhs -> forward substitution; (d, o[0..NB), b) go to scratch.  Backward
@@ -364,6 +293,17 @@ predict_kernel(const PredArgs A)
     }
 }
 
+// predict_fast_kernel: see pst_predict_core.h (the per-trace body is a host/device header so that
+// tests/test_predict_core.py can run it on the host against the CPU restatement)
+template <int NW, bool TWO, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+predict_fast_kernel(const PredArgs A)
+{
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i2 >= A.n2) return;
+    predict_fast_trace<NW, TWO>(A, i2, A.zla + (int)blockIdx.y, (int)blockIdx.y);
+}
+
 // ---------------------------------------------------------------------------------------
 // layout changes: [i3][i2][i1] (reference order, i1 fastest) <-> [i3][i1][i2] (trace-minor)
 __global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int rows,
@@ -569,11 +509,17 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
 {
     const int threads = A.n2 >= 128 ? 128 : (A.n2 >= 64 ? 64 : 32);
     dim3 grid((A.n2 + threads - 1) / threads, A.zlb - A.zla);
+    // PST_PREDICT_FAST=0: the first formulation of the kernel; =2: two-parent kernel with 192 registers and 2 CTAs per
+    // SM instead of 168 (a few spills) and 3 (A/B measurements; same results)
+    static const int fast = []() { const char *e = getenv("PST_PREDICT_FAST"); return e ? atoi(e) : 1; }();
     // algorithmic flops per predicted sample: predict1 47 (nw=1) / 116 (nw=2), predict2 78 / 187
     const double fl = NW == 1 ? (two ? 78.0 : 47.0) : (two ? 187.0 : 116.0);
     PST_LAUNCHBF(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * A.n2 * (A.zlb - A.zla), fl * (double)A.n1 * A.n2 * (A.zlb - A.zla),
-        if (two) predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
-        else     predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A));
+        if (fast == 2 && two) predict_fast_kernel<NW, true, 2><<<grid, threads, 0, c->stream>>>(A);
+        else if (fast && two) predict_fast_kernel<NW, true, 3><<<grid, threads, 0, c->stream>>>(A);
+        else if (fast)        predict_fast_kernel<NW, false, 3><<<grid, threads, 0, c->stream>>>(A);
+        else if (two)    predict_kernel<NW, true><<<grid, threads, 0, c->stream>>>(A);
+        else             predict_kernel<NW, false><<<grid, threads, 0, c->stream>>>(A));
 }
 
 typedef int (*chunk_reduce_fn)(pst_ctx *c, void *user, const SprayPlan &P, float *const *slot, int ze0,

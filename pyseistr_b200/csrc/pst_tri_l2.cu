@@ -395,13 +395,16 @@ int pst_tri_l2_launch(cudaStream_t stream, int sm_count, int axis, const float *
     if (!P.ok) return -1;
     EncodeTiledFn enc = get_encode();
     if (!enc) return -2;
-    static const int warps_env = env_int("PST_TRI_L2_WARPS", 8);
+    // measured on B200, 1000x1024x1024 (profiles/r02_tri_ncu_summary.md): contiguous axis 6 warps x 4 slots (2.07 ms per
+    // pass), strided axes 8 warps x 2 slots (2.05 - 2.29 ms); more warps in flight miss the L2 on the second read
+    static const int warps_env = env_int("PST_TRI_L2_WARPS", 0);
     static const int slots_env = env_int("PST_TRI_L2_SLOTS", 0);
     static const int hints_env = env_int("PST_TRI_L2_HINTS", 7);
     const bool contig = axis == 0;
-    int warps = warps_env < 1 ? 1 : (warps_env > 8 ? 8 : warps_env);
+    int warps = warps_env > 0 ? warps_env : (contig ? 6 : 8);
+    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
     const size_t budget = 227 * 1024;
-    int nslot = slots_env > 0 ? slots_env : 4;
+    int nslot = slots_env > 0 ? slots_env : (contig ? 4 : 2);
     if (nslot > 16) nslot = 16;
     while (nslot > 2 && per_warp_bytes(contig, nslot, P.nblk) * warps > budget) nslot--;
     while (warps > 1 && per_warp_bytes(contig, nslot, P.nblk) * warps > budget) warps--;

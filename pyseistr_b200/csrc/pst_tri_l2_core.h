@@ -22,7 +22,7 @@
 // IO is the caller's block transport (warp-uniform on the GPU):
 //   load(x)            the next block of the stream above, as 32 values of this line (zero beyond nx)
 //   store(v, i0)       y[i0 + j] = v[j] for j in [0, 32), i0 + j < nx
-// The header compiles for the host too (tests/test_tri_l2_core.py checks it against the oracle).
+// The header compiles for the host too (tests/test_tri_l2_core.py checks it against the CPU restatement).
 #pragma once
 
 #ifdef __CUDACC__
