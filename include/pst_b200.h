@@ -156,6 +156,15 @@ int pst_sint3d_dev(pst_ctx *ctx, const float *d_din, const float *d_dipi, const 
                    const float *d_mask, int n1, int n2, int n3, int niter, int ns1, int ns2,
                    int order1, int order2, int verb, float eps, float *d_out);
 
+/* ---- plane-wave painting.  Replaces paint2dcfun.cpaint2d / cpaint3d (pyseistr/src/paint_cfuns.c:1861-2024,
+ * "OOiiiifi": dip, trace, n1, n2, order, i0, eps, verb; the two reference entries are the same code); called by pwpaintc
+ * and rgt (pyseistr/rgt.py).  The seed trace (n1 floats) sits at trace i0 and is predicted outwards trace by trace with
+ * regularisation eps*eps: one dependent chain of n2 - 1 predictions.  out: n1*n2 floats.  Single-GPU contexts. */
+int pst_paint2d(pst_ctx *ctx, const float *dip, const float *seed, int n1, int n2, int order, int i0, float eps,
+                int verb, float *out);
+int pst_paint2d_dev(pst_ctx *ctx, const float *d_dip, const float *d_seed, int n1, int n2, int order, int i0,
+                    float eps, float *d_out);
+
 /* ---- building blocks exposed for parity tests and for the smoothing wrapper (SURVEY §8f
  * rank 1: dipcfun.smoothcf, dip_cfuns.c:2006-2123 with adj=0).  Device pointers. */
 int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1, int n2, int n3,

@@ -210,3 +210,14 @@ def predict_adj(trace, sig, nw, forw, eps=1e-4):
     s = _F(sig)
     lib().pso_predict_adj(t.size, int(nw), ctypes.c_float(eps), int(forw), _p(t), _p(s))
     return t
+
+
+def pwpaintc(dip, trace, order=1, i0=0, eps=0.01, verb=False):
+    """plane-wave painting (reference pyseistr/rgt.py:pwpaintc -> cpaint2d, paint_cfuns.c:1861)"""
+    n1, n2 = dip.shape
+    d, t = _F(dip), _F(trace)
+    out = np.zeros_like(d)
+    rc = lib().pso_paint2d(_p(d), _p(t), n1, n2, int(order), int(i0), ctypes.c_float(eps), _p(out))
+    if rc:
+        raise ValueError("oracle: bad painting arguments")
+    return out.reshape(n1, n2, order="F")

@@ -872,6 +872,30 @@ int pso_somf2d(const float *din, const float *dip, int n1, int n2, int n3, int n
     return 0;
 }
 
+/* cpaint2d / cpaint3d paint_cfuns.c:1861-2024 (the two entries are the same code): plane-wave painting -- the seed
+ * trace sits at trace i0 and is predicted outwards trace by trace, leftwards with the target-location slope
+ * (predict_step(false, false, trace, pp[i2])), rightwards with the parent-location slope and reversed taps
+ * (predict_step(false, true, trace, pp[i2-1])). */
+int pso_paint2d(const float *dip, const float *seed, int n1, int n2, int order, int i0, float eps, float *out)
+{
+    if (i0 < 0 || i0 >= n2) return -1;
+    predictor *P = predictor_new(n1, order, eps * eps);
+    float *tr = falloc(n1);
+    memcpy(tr, seed, n1 * sizeof(float));
+    memcpy(out + (size_t)i0 * n1, seed, n1 * sizeof(float));
+    for (int i2 = i0 - 1; i2 >= 0; i2--) {
+        predict_one(P, 0, tr, dip + (size_t)i2 * n1, tr);
+        memcpy(out + (size_t)i2 * n1, tr, n1 * sizeof(float));
+    }
+    memcpy(tr, seed, n1 * sizeof(float));
+    for (int i2 = i0 + 1; i2 < n2; i2++) {
+        predict_one(P, 1, tr, dip + (size_t)(i2 - 1) * n1, tr);
+        memcpy(out + (size_t)i2 * n1, tr, n1 * sizeof(float));
+    }
+    free(tr); predictor_free(P);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ PWD-residual interpolation */
 
 /* allpass3_lop :625-729 (drift=false, nj=1): y[0:N] = inline PWD of x, y[N:2N] = xline PWD;

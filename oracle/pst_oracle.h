@@ -90,6 +90,8 @@ int pso_somean2d_adj(const float *din, const float *dip, int n1, int n2, int n3,
 /* csint2d soint2d_cfuns.c:2421-2530 (oracle groundwork, no GPU counterpart yet) */
 int pso_sint2d(const float *din, const float *dip, const float *mask, int n1, int n2, int niter, int ns, int order,
                float eps, float *out);
+/* cpaint2d / cpaint3d paint_cfuns.c:1861-2024: plane-wave painting of a seed trace */
+int pso_paint2d(const float *dip, const float *seed, int n1, int n2, int order, int i0, float eps, float *out);
 /* one adjoint prediction step in place (unit-test hook): predict_step(adj=true) :1777-1804 */
 void pso_predict_adj(int n1, int nw, float eps, int forw, float *trace, const float *sig);
 

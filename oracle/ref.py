@@ -174,3 +174,11 @@ def smoothc(x, rect, adj=0, repeat=1, diff=(0, 0, 0), box=(0, 0, 0)):
         y = module("dipcfun").smoothcf(_F(x), n1, n2, n3, int(repeat), int(adj), rect[0], rect[1], rect[2],
                                        int(diff[0]), int(diff[1]), int(diff[2]), int(box[0]), int(box[1]), int(box[2]))
     return np.asarray(y, dtype=np.float32).reshape(n1, n2, n3, order="F")
+
+
+def pwpaintc(dip, trace, order=1, i0=0, eps=0.01, verb=False):
+    """reference pyseistr/rgt.py:pwpaintc (the reshaping glue around paint2dcfun.cpaint2d)"""
+    n1, n2 = dip.shape
+    with quiet():
+        out = module("paint2dcfun").cpaint2d(_F(dip), _F(trace), n1, n2, int(order), int(i0), float(eps), int(verb))
+    return np.asarray(out, np.float32).reshape(n1, n2, order="F")

@@ -76,6 +76,8 @@ SIGNATURES = {
     "pst_soint3d_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "pst_sint3d": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _fp]),
     "pst_sint3d_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "pst_paint2d": (_i, [_vp, _fp, _fp, _i, _i, _i, _i, _f, _i, _fp]),
+    "pst_paint2d_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pst_allpass_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pst_smooth3_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "pst_divne_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),

@@ -228,6 +228,30 @@ def sint2dc(din, mask, dip, niter=100, eps=0.01, ns=1, order=1, verb=1, ctx=None
     return out.reshape(n1, n2)
 
 
+def pwpaintc(dip, trace, order=1, i0=0, eps=0.01, verb=False, ctx=None):
+    """Plane-wave painting: the seed `trace` placed at trace i0 is spread along the slope field `dip` (n1, n2) by
+    successive plane-wave predictions (reference pyseistr/rgt.py:pwpaintc -> paint2dcfun.cpaint2d, paint_cfuns.c:1861).
+    Returns float32 (n1, n2)."""
+    dip = np.asarray(dip)
+    if dip.ndim != 2:
+        raise ValueError("pwpaintc expects a 2-D slope field (n1, n2)")
+    n1, n2 = dip.shape
+    c = _ctx(ctx)
+    d, t = _F(dip), _F(trace)
+    if t.size != n1:
+        raise ValueError("the seed trace must have n1 samples")
+    out = np.empty_like(d)
+    _lib.check(c.lib.pst_paint2d(c.handle, _p(d), _p(t), n1, n2, int(order), int(i0), float(eps), int(bool(verb)), _p(out)))
+    return out.reshape(n1, n2, order="F")
+
+
+def rgt(dip, o1=0, d1=0.004, order=1, i0=0, eps=0.01, verb=False, ctx=None):
+    """Relative geological time: the time axis painted along the slopes (reference pyseistr/rgt.py:rgt)."""
+    n1 = np.asarray(dip).shape[0]
+    trace = np.linspace(0, d1 * (n1 - 1), n1) + o1
+    return pwpaintc(dip, trace, order=order, i0=i0, eps=eps, verb=verb, ctx=ctx)
+
+
 def smoothc(din, rect=[1, 1, 1], diff=[0, 0, 0], box=[0, 0, 0], repeat=1, adj=1, ctx=None):
     """N-D triangle / box smoothing (reference pyseistr/smooth.py:115-183 -> dipcfun.smoothcf, dip_cfuns.c:2006-2123),
     same defaults as the reference (note adj=1).  adj=0 is ps_smooth2 (the operator inside dip3d's shaping CG, here the

@@ -601,6 +601,25 @@ extern "C" int pst_smoothcf(pst_ctx *c, const float *x, int n1, int n2, int n3, 
     return PST_OK;
 }
 
+extern "C" int pst_paint2d(pst_ctx *c, const float *dip, const float *seed, int n1, int n2, int order, int i0, float eps,
+                           int verb, float *out)
+{
+    (void)verb;
+    PST_ENTRY(c);
+    if (!dip || !seed || !out || n1 < 1 || n2 < 1) { pst_set_error("paint2d: null pointer or bad shape"); return PST_EINVAL; }
+    if (c->nranks > 1) { pst_set_error("paint2d: single-GPU contexts only (one dependent chain of trace predictions)"); return PST_EUNSUP; }
+    const size_t n = (size_t)n1 * n2;
+    CallTimer t(c);
+    DevBuf d, s, o;
+    PST_TRY(up(c, d, dip, n));
+    PST_TRY(up(c, s, seed, (size_t)n1));
+    PST_TRY(o.alloc(n * sizeof(float)));
+    PST_TRY(pst_paint2d_dev(c, d.f(), s.f(), n1, n2, order, i0, eps, o.f()));
+    PST_TRY(down(c, out, o, n));
+    t.stop();
+    return PST_OK;
+}
+
 extern "C" int pst_sint3d(pst_ctx *c, const float *din, const float *dipi, const float *dipx, const float *mask,
                           int n1, int n2, int n3, int niter, int ns1, int ns2, int order1, int order2, int verb,
                           float eps, float *out)

@@ -1570,6 +1570,56 @@ tri3_dist_fwd_kernel(const Tri3Args A)
     if (A.cout) tri3_signal(A.fout + blockIdx.x, A.epoch);
 }
 
+// The same forward kernel with the (-1, 2, -1) window of every line held in registers (radius as a template parameter):
+// one global load per step instead of three -- the two delayed taps of the kernel above are re-reads of planes that are
+// nb and 2 nb planes (tens of MB) behind, i.e. mostly HBM traffic again (measured at 2 GPUs, 512-plane slabs: 2.8 ms per
+// pass pair = 3.0 TB/s of the 16 B/voxel the pair should move).
+template <int NB>
+__global__ void __launch_bounds__(128)
+tri3_dist_fwd_win_kernel(const Tri3Args A)
+{
+    const long l = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    tri3_wait_halos(A);
+    if (A.cin) tri3_wait(A.fin + blockIdx.x, A.epoch, A.err);
+    const bool live = l < A.L;
+    const float wm = -A.wt;
+    float s = 0.f;
+    if (live) {
+        if (A.cin) s = __ldcv(A.cin + l);
+        constexpr int U = 8;
+        float win[2 * NB + U];                                   // x of planes k0 - 2nb .. k0 + U - 1 (0 outside the cube)
+#pragma unroll
+        for (int i = 0; i < 2 * NB; i++) {
+            const int j = A.K0 - 2 * NB + i;
+            win[i] = (j >= 0 && j < A.n3g) ? tri3_x(A, j, l) : 0.f;
+        }
+        float *Fo = A.F + l;
+        for (int k0 = A.K0; k0 < A.K1; k0 += U) {
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                const int k = k0 + q;
+                win[2 * NB + q] = (k < A.K1 && k < A.n3g) ? tri3_x(A, k, l) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < U; q++) {
+                const int k = k0 + q;
+                if (k < A.K1) {
+                    float t = 0.f;
+                    t = t + wm * win[2 * NB + q];
+                    t = t + A.w2 * win[NB + q];
+                    t = t + wm * win[q];
+                    s += t;
+                    Fo[(long)(k - A.K0) * A.L] = s;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2 * NB; i++) win[i] = win[i + U];
+        }
+        if (A.cout) A.cout[l] = s;
+    }
+    if (A.cout) tri3_signal(A.fout + blockIdx.x, A.epoch);
+}
+
 // backward sum fused with fold2 (:458-484): y_i = (B_{i+nb} + B_{nb+n3g+(n3g-1-i)}[i >= n3g-nb])
 // + B_{nb-1-i}[i < nb].  Every term lives on the owning rank (slab height >= 2nb): the right-pad
 // values (last rank, visited first) are parked in their target rows, the left-pad values
@@ -1894,7 +1944,20 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
             else if (W == 64) tri3_tile_fwd_kernel<64><<<blocks, 128, smem_f, c->stream>>>(A);
             else tri3_tile_fwd_kernel<32><<<blocks, 128, smem_f, c->stream>>>(A));
     } else {
-        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
+        static const bool win_on = []() { const char *e = getenv("PST_TRI3_WIN"); return !(e && e[0] == '0'); }();
+        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
+            if (!win_on) tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A);
+            else switch (nb) {
+                case 2: tri3_dist_fwd_win_kernel<2><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 3: tri3_dist_fwd_win_kernel<3><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 4: tri3_dist_fwd_win_kernel<4><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 5: tri3_dist_fwd_win_kernel<5><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 6: tri3_dist_fwd_win_kernel<6><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 7: tri3_dist_fwd_win_kernel<7><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 8: tri3_dist_fwd_win_kernel<8><<<blocks, 128, 0, c->stream>>>(A); break;
+                case 10: tri3_dist_fwd_win_kernel<10><<<blocks, 128, 0, c->stream>>>(A); break;
+                default: tri3_dist_fwd_kernel<<<blocks, 128, 0, c->stream>>>(A); break;
+            });
     }
     // backward sums (+ fold): carries flow rank -> rank-1
     A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;

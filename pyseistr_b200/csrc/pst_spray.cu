@@ -1467,6 +1467,45 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     return PST_OK;
 }
 
+// cpaint2d / cpaint3d (reference pyseistr/src/paint_cfuns.c:1861-2024; the two entries are the same code): plane-wave
+// painting.  The seed trace sits at trace i0 and is predicted outwards one trace at a time -- leftwards
+// predict_step(false, false, trace, pp[i2]), rightwards predict_step(false, true, trace, pp[i2-1]) -- so the whole
+// operator is ONE dependent chain of n2 - 1 trace predictions: a launch of the prediction kernel per trace, one thread
+// each.  Latency-bound by construction; provided for completeness of the predict_step consumers.
+extern "C" int pst_paint2d_dev(pst_ctx *c, const float *d_dip, const float *d_seed, int n1, int n2, int order, int i0,
+                               float eps, float *d_out)
+{
+    if (!c) { pst_set_error("null context"); return PST_EINVAL; }
+    if (!d_dip || !d_seed || !d_out) { pst_set_error("paint2d: null pointer"); return PST_EINVAL; }
+    PST_TRY(check_spray_args(n1, n2, 1, 0, 0, order));
+    if (i0 < 0 || i0 >= n2) { pst_set_error("paint2d: reference trace i0=%d outside [0, %d)", i0, n2); return PST_EINVAL; }
+    PST_CUDA(cudaSetDevice(c->device));
+    const int NC = 2 * order + 1;
+    PST_TRY(pst_arena_reserve(c, (size_t)n1 * NC * sizeof(float) + 4096));
+    pst_arena_reset(c);
+    float *scr;
+    PST_TRY(pst_arena_get(c, (size_t)n1 * NC, &scr));
+    PST_CUDA(cudaMemcpyAsync(d_out + (size_t)i0 * n1, d_seed, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    PredArgs A{};
+    A.n1 = n1; A.n2 = 1; A.n3 = 1; A.ze0 = 0; A.zla = 0; A.zlb = 1; A.a = 0; A.b = 0; A.t_off = 0; A.ntg = 1;
+    A.reg = make_reg(eps * eps); A.tb = make_btab_s(order); A.scr = scr;
+    for (int side = 0; side < 2; side++) {
+        const int step = side == 0 ? -1 : 1;
+        for (int i2 = i0 + step; i2 >= 0 && i2 < n2; i2 += step) {
+            A.in1 = d_out + (size_t)(i2 - step) * n1;
+            A.sg1 = d_dip + (size_t)(side == 0 ? i2 : i2 - 1) * n1;
+            A.forw1 = side;
+            A.out = d_out + (size_t)i2 * n1;
+            PST_LAUNCHBF(c, PST_K_PREDICT, 12.0 * n1, (order == 1 ? 47.0 : 116.0) * n1,
+                if (order == 1) predict_fast_kernel<1, false, 3><<<1, 32, 0, c->stream>>>(A);
+                else            predict_fast_kernel<2, false, 3><<<1, 32, 0, c->stream>>>(A));
+            c->stats.predictions++;
+        }
+    }
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
 // csomean2d with adj = 1 (sof_cfuns.c:1503-1508): out = S' din per slice
 int pst_somean2d_adj_dev(pst_ctx *c, const float *d_din, const float *d_dip, int n1, int n2, int n3, int ns,
                          int order, float eps, float *d_out)

@@ -90,6 +90,10 @@ def main():
     for name, (order, niter, njs, hasmask) in {"o1n12": (1, 12, (1, 1), 1), "o2n10": (2, 10, (1, 1), 1), "o1n8nj2": (1, 8, (2, 1), 1)}.items():
         g["soint2d_" + name] = dict(din=d2c * mk2, mask=mk2, dip=p2c, order=order, niter=niter, njs=list(njs), hasmask=hasmask,
                                     out=ref.soint2dc(d2c * mk2, mk2, p2c, order=order, niter=niter, njs=njs, hasmask=hasmask))
+    # ---- plane-wave painting (cpaint2d), seed = a time axis like rgt()
+    for name, (order, i0, eps) in {"o1i0": (1, 0, 0.01), "o2i11": (2, 11, 0.1)}.items():
+        seed = (np.linspace(0, 0.004 * 63, 64) - 0.1).astype(np.float32)
+        g["paint2d_" + name] = dict(dip=p2, trace=seed, order=order, i0=i0, eps=eps, out=ref.pwpaintc(p2, seed, order, i0, eps))
     # ---- smoothing (ps_smooth2 through smoothcf adj=0), incl. a radius larger than an axis
     xs = synth.cube(30, 12, 6, seed=13)
     g["smooth_534"] = dict(x=xs, rect=[5, 3, 4], out=ref.smoothc(xs, [5, 3, 4]))

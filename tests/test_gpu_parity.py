@@ -540,3 +540,21 @@ def test_sint2d_through_one_plane_sint3d(ctx, port):
         want = port.sint2dc(d * mask, mask, p2, niter=niter, eps=0.01, ns=ns, order=order)
         assert got.shape == (96, 40)
         assert rel_l2(got, want) <= TOL, (ns, order, rel_l2(got, want))
+
+
+@pytest.mark.parametrize("name", golden_names("paint2d_"))
+def test_paint2d_golden_bit_exact(ctx, name):
+    """pwpaintc (plane-wave painting, reference rgt.py -> cpaint2d): one dependent chain of trace predictions."""
+    import pyseistr_b200 as ps
+    g = golden(name)
+    out = ps.pwpaintc(g["dip"], g["trace"], order=int(g["order"]), i0=int(g["i0"]), eps=float(g["eps"]), ctx=ctx)
+    assert np.array_equal(out, g["out"]), rel_l2(out, g["out"])
+
+
+def test_rgt_vs_oracle(ctx, port):
+    import pyseistr_b200 as ps
+    p = synth.smooth_dips(150, 37, 1, seed=41)[0]
+    for order, i0 in ((1, 0), (2, 18), (2, 36)):
+        t = ps.rgt(p, o1=-0.2, d1=0.004, order=order, i0=i0, eps=0.1, ctx=ctx)
+        seed = np.linspace(0, 0.004 * 149, 150) - 0.2
+        assert np.array_equal(t, port.pwpaintc(p, seed, order, i0, 0.1)), (order, i0)

@@ -295,3 +295,22 @@ def test_port_svmf_defined_behaviour_matches_compiled_reference(port):
     for name in golden_names("svmf2d_"):
         g = golden(name)
         assert np.array_equal(port.somf2dc(g["dn"], g["dip"], int(g["ns"]), int(g["order"]), float(g["eps"]), option=2), g["out"])
+
+
+@pytest.mark.parametrize("name", golden_names("paint2d_"))
+def test_port_paint2d_matches_golden(port, name):
+    g = golden(name)
+    out = port.pwpaintc(g["dip"], g["trace"], int(g["order"]), int(g["i0"]), float(g["eps"]))
+    assert np.array_equal(out, g["out"])
+
+
+def test_port_paint2d_matches_compiled_reference(port):
+    ref = _ref_or_skip()
+    try:
+        ref.module("paint2dcfun")
+    except ImportError:
+        pytest.skip("oracle/_ref/paint2dcfun not built")
+    for seed, (n1, n2), order, i0, eps in ((1, (120, 40), 1, 0, 0.01), (2, (200, 64), 2, 30, 0.1), (3, (64, 20), 2, 19, 0.01)):
+        p = synth.smooth_dips(n1, n2, 1, seed=seed)[0]
+        tr = np.linspace(0, 0.004 * (n1 - 1), n1).astype(np.float32)
+        assert np.array_equal(port.pwpaintc(p, tr, order, i0, eps), ref.pwpaintc(p, tr, order, i0, eps))
