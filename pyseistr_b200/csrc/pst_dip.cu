@@ -1439,6 +1439,10 @@ struct Tri3Args {
     // peer-memory halos: hb / ha point INTO the neighbours' slabs (CUDA IPC); the kernel first waits for the flags the
     // neighbours raise (in my mailbox) once their current input is complete.  Null = halos were copied by NCCL.
     const unsigned *hr_prev, *hr_next;
+    // recompute variant of the tile kernels: the forward kernel stores no F, only each line's incoming carry (csave) and
+    // -- with peer halos -- a local copy of the planes it read from the NEXT rank (ha_keep): that rank overwrites them
+    // in its backward kernel, which runs before mine
+    float *csave, *ha_keep;
     float *dst;            // fold output [nz][L]
     long L, l0, l1;        // lines per plane, chunk [l0, l1)
     int n3g, z0, nz, nb, K0, K1;
@@ -1679,7 +1683,7 @@ tri3_dist_bwd_kernel(const Tri3Args A)
 // (~10 instructions per sample) instead of a chain of dependent global loads.
 //   forward : rows = x planes [K0-2nb, K1) (zero outside the cube) -> F rows [K0, K1) to scratch
 //   backward: rows = F rows [K0, K1) -> fold2 -> dst; parked reflections live in the consumed rows
-template <int W>
+template <int W, bool STOREF>
 __global__ void __launch_bounds__(128)
 tri3_tile_fwd_kernel(const Tri3Args A)
 {
@@ -1713,24 +1717,37 @@ tri3_tile_fwd_kernel(const Tri3Args A)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (!STOREF && A.ha_keep) {
+        // keep the planes read from the next rank (rows of planes [z1, K1)) for my backward kernel
+        const int r0 = A.z0 + A.nz - (A.K0 - 2 * nb);
+        for (int idx = tid; idx < (R - r0) * CPR; idx += 128) {
+            const int r = r0 + idx / CPR, ch = idx % CPR;
+            const long lc = l0 + 4 * ch;
+            if (lc < A.L) *reinterpret_cast<float4 *>(A.ha_keep + (long)(r - r0) * A.L + lc) = *reinterpret_cast<const float4 *>(t3s + (size_t)r * W + 4 * ch);
+        }
+    }
     if (live) {
         const float wm = -A.wt, w2 = A.w2;
         const float *xc = t3s + tid;                           // x_{k-2nb} of step k = K0 + i at row i
         float *Fo = A.F + l;
         const int n = A.K1 - A.K0;
+        if (!STOREF) A.csave[l] = s;
 #pragma unroll 4
         for (int i = 0; i < n; i++) {
             float t = wm * xc[(size_t)(i + 2 * nb) * W];
             t = t + w2 * xc[(size_t)(i + nb) * W];
             t = t + wm * xc[(size_t)i * W];
             s += t;
-            Fo[(long)i * A.L] = s;
+            if (STOREF) Fo[(long)i * A.L] = s;
         }
         if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
     }
 }
 
-template <int W>
+// RCMP: the tile holds x (rows of planes [K0 - 2nb, K1), like the forward kernel's) and F is recomputed in place from the
+// saved incoming carry -- the same additions in the same order -- before the backward carry is needed: the pass moves
+// 4 (forward read) + 4 + 4 bytes per voxel instead of 16, and the forward kernel stores nothing.
+template <int W, bool RCMP>
 __global__ void __launch_bounds__(128)
 tri3_tile_bwd_kernel(const Tri3Args A)
 {
@@ -1741,7 +1758,7 @@ tri3_tile_bwd_kernel(const Tri3Args A)
     const bool live = tid < W && l < A.L;
     constexpr int CPR = W / 4;
     float s = 0.f;
-    {
+    if (!RCMP) {
         for (int idx = tid; idx < R * CPR; idx += 128) {
             const int r = idx / CPR, ch = idx - r * CPR;
             const long lc = l0 + 4 * ch;
@@ -1750,8 +1767,44 @@ tri3_tile_bwd_kernel(const Tri3Args A)
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (A.pin && live) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    } else {
+        // (no halo flags to wait for: the forward kernel of this pass already did, and the planes of the previous rank
+        // stay untouched until its backward kernel, which waits for my carries)
+        const int RX = R + 2 * nb;
+        for (int idx = tid; idx < RX * CPR; idx += 128) {
+            const int r = idx / CPR, ch = idx - r * CPR;
+            const int j = A.K0 - 2 * nb + r;
+            const long lc = l0 + 4 * ch;
+            float *dsts = t3s + (size_t)r * W + 4 * ch;
+            if (j < 0 || j >= n3g || lc >= A.L) {
+                *reinterpret_cast<float4 *>(dsts) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float *srcp;
+                if (j >= A.z0 && j < A.z0 + A.nz) srcp = A.x + (long)(j - A.z0) * A.L + lc;
+                else if (j < A.z0) srcp = A.hb + (long)(j - (A.z0 - nb)) * A.L + lc;
+                else srcp = (A.ha_keep ? A.ha_keep : A.ha) + (long)(j - (A.z0 + A.nz)) * A.L + lc;
+                cp_async16(dsts, srcp);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        float sf = live ? A.csave[l] : 0.f;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (live) {
+            const float wm = -A.wt, w2 = A.w2;
+            float *xc = t3s + tid;                             // x_{k-2nb} of step k = K0 + i at row i; F_k replaces it
+#pragma unroll 4
+            for (int i = 0; i < R; i++) {
+                float t = wm * xc[(size_t)(i + 2 * nb) * W];
+                t = t + w2 * xc[(size_t)(i + nb) * W];
+                t = t + wm * xc[(size_t)i * W];
+                sf += t;
+                xc[(size_t)i * W] = sf;
+            }
+            if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+        }
     }
-    __syncthreads();
     if (live) {
         float *Fc = t3s + tid;                                 // row (k - K0); consumed rows are reused as parking slots
         float *dl = A.dst + l;
@@ -1922,6 +1975,11 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     const int nz_max = (n3g + c->nranks - 1) / c->nranks;
     const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, A.hb, A.ha);
     const unsigned blocks = (unsigned)((L + (W ? W : 128) - 1) / (W ? W : 128));
+    // tile kernels: recompute F in the backward kernel instead of staging it through HBM (12 instead of 16 B per voxel)
+    static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return !(e && e[0] == '0'); }();
+    const bool rcmp = rcmp_on && W > 0;
+    A.csave = g.cin;
+    A.ha_keep = (rcmp && peer && !last) ? g.ha : nullptr;
     const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
     // forward sums: carries flow rank -> rank+1, CTA by CTA, through the neighbour's mailbox
     A.cin = first ? nullptr : mb.cf_in;  A.fin = mb.ff_in;
@@ -1931,18 +1989,24 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
         static bool attr_dev[64] = {};                       // per-device function attribute
         bool &attr_done = attr_dev[c->device & 63];
         if (!attr_done) {
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-            PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+#define PST_T3_ATTR(K) PST_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024))
+            PST_T3_ATTR((tri3_tile_fwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, true>));
+            PST_T3_ATTR((tri3_tile_fwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, false>));
+            PST_T3_ATTR((tri3_tile_bwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, true>));
+            PST_T3_ATTR((tri3_tile_bwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, false>));
+#undef PST_T3_ATTR
             attr_done = true;
         }
         PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
-            if (W == 128) tri3_tile_fwd_kernel<128><<<blocks, 128, smem_f, c->stream>>>(A);
-            else if (W == 64) tri3_tile_fwd_kernel<64><<<blocks, 128, smem_f, c->stream>>>(A);
-            else tri3_tile_fwd_kernel<32><<<blocks, 128, smem_f, c->stream>>>(A));
+            if (rcmp) {
+                if (W == 128) tri3_tile_fwd_kernel<128, false><<<blocks, 128, smem_f, c->stream>>>(A);
+                else if (W == 64) tri3_tile_fwd_kernel<64, false><<<blocks, 128, smem_f, c->stream>>>(A);
+                else tri3_tile_fwd_kernel<32, false><<<blocks, 128, smem_f, c->stream>>>(A);
+            } else {
+                if (W == 128) tri3_tile_fwd_kernel<128, true><<<blocks, 128, smem_f, c->stream>>>(A);
+                else if (W == 64) tri3_tile_fwd_kernel<64, true><<<blocks, 128, smem_f, c->stream>>>(A);
+                else tri3_tile_fwd_kernel<32, true><<<blocks, 128, smem_f, c->stream>>>(A);
+            });
     } else {
         static const bool win_on = []() { const char *e = getenv("PST_TRI3_WIN"); return !(e && e[0] == '0'); }();
         PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
@@ -1966,9 +2030,15 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? 11 : PST_K_TRI3; }();
     if (W) {
         PST_LAUNCHB(c, bwd_cls, 8.0 * (double)g.n,
-            if (W == 128) tri3_tile_bwd_kernel<128><<<blocks, 128, smem_b, c->stream>>>(A);
-            else if (W == 64) tri3_tile_bwd_kernel<64><<<blocks, 128, smem_b, c->stream>>>(A);
-            else tri3_tile_bwd_kernel<32><<<blocks, 128, smem_b, c->stream>>>(A));
+            if (rcmp) {
+                if (W == 128) tri3_tile_bwd_kernel<128, true><<<blocks, 128, smem_f, c->stream>>>(A);
+                else if (W == 64) tri3_tile_bwd_kernel<64, true><<<blocks, 128, smem_f, c->stream>>>(A);
+                else tri3_tile_bwd_kernel<32, true><<<blocks, 128, smem_f, c->stream>>>(A);
+            } else {
+                if (W == 128) tri3_tile_bwd_kernel<128, false><<<blocks, 128, smem_b, c->stream>>>(A);
+                else if (W == 64) tri3_tile_bwd_kernel<64, false><<<blocks, 128, smem_b, c->stream>>>(A);
+                else tri3_tile_bwd_kernel<32, false><<<blocks, 128, smem_b, c->stream>>>(A);
+            });
     } else {
         PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
     }
@@ -2005,12 +2075,12 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
             static bool ad_dev[64] = {};
             bool &ad = ad_dev[c->device & 63];
             if (!ad) {
-                PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-                PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
                 ad = true;
             }
-            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_fwd_kernel<128><<<blocks, 128, (size_t)(A.K1 + 2 * nb) * 128 * 4, c->stream>>>(A)));
-            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_bwd_kernel<128><<<blocks, 128, (size_t)A.K1 * 128 * 4, c->stream>>>(A)));
+            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_fwd_kernel<128, true><<<blocks, 128, (size_t)(A.K1 + 2 * nb) * 128 * 4, c->stream>>>(A)));
+            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_bwd_kernel<128, false><<<blocks, 128, (size_t)A.K1 * 128 * 4, c->stream>>>(A)));
             PST_CUDA(cudaGetLastError());
             return PST_OK;
         }
