@@ -1975,8 +1975,11 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     const int nz_max = (n3g + c->nranks - 1) / c->nranks;
     const int W = tri3_tile_width(nz_max + 3 * nb, L, src, dst, scr, A.hb, A.ha);
     const unsigned blocks = (unsigned)((L + (W ? W : 128) - 1) / (W ? W : 128));
-    // tile kernels: recompute F in the backward kernel instead of staging it through HBM (12 instead of 16 B per voxel)
-    static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return !(e && e[0] == '0'); }();
+    // tile kernels, PST_TRI3_RC=1: recompute F in the backward kernel instead of staging it through HBM (12 instead of 16 B
+    // per voxel).  Measured SLOWER on B200 (2 ranks, 128-plane slabs: 0.55 against 0.45 ms per pass; 256-plane slabs: 1.54
+    // against 1.16 ms): these kernels are bound by the serial per-thread chains of their CTAs, not by HBM, and the
+    // recomputation lengthens exactly that.  Off by default.
+    static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return e && e[0] == '1'; }();
     const bool rcmp = rcmp_on && W > 0;
     A.csave = g.cin;
     A.ha_keep = (rcmp && peer && !last) ? g.ha : nullptr;

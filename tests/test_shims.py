@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 ARITY = {"dipcfun": {"dipc": 15, "smoothcf": 15}, "sof3dcfun": {"csomean3d": 11, "csomf3d": 13},
          "sofcfun": {"csomean2d": 10, "csomf2d": 11}, "soint3dcfun": {"csoint3d": 16, "csint3d": 14},
-         "soint2dcfun": {"csoint2d": 15, "csint2d": 10}}
+         "soint2dcfun": {"csoint2d": 15, "csint2d": 10}, "paint2dcfun": {"cpaint2d": 8, "cpaint3d": 8}}
 
 
 @pytest.fixture(scope="module")
