@@ -2682,8 +2682,12 @@ pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[5] = {0., 0., 0., 0., 0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int i1 = (int)(i % n1), i2 = (int)((i / n1) % n2), i3 = (int)(i / pl);
+    // one block walks traces (grid-stride), its threads walk i1: the indices come without a division per voxel
+    const long ntr = (long)n2 * n3;
+    for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
+      const int i2 = (int)(tr % n2), i3 = (int)(tr / n2);
+      for (int i1 = threadIdx.x; i1 < n1; i1 += blockDim.x) {
+        const size_t i = (size_t)tr * n1 + i1;
         float yi = ADD ? y[i] : 0.f, yx = ADD ? y[i + n] : 0.f;
         // shifts (w - NW) * nj on rows [NW*nj, n1 - NW*nj)  (allpass3_lop soint3d_cfuns.c:640-662,684-706)
         if (i1 >= NW * nj1 && i1 < n1 - NW * nj1 && i2 < n2 - 1) {
@@ -2705,6 +2709,7 @@ pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const
             acc[3] += (double)yi * r0 + (double)yx * r1;          // gg.rr
             acc[4] += (double)s0 * r0 + (double)s1 * r1;          // Ss.rr
         }
+      }
     }
     if (DOTS) pst_block_reduce<5>(acc, partial);
 }
@@ -2721,8 +2726,11 @@ pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, cons
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[1] = {0.};
-    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
-        const int j1 = (int)(j % n1), j2 = (int)((j / n1) % n2), j3 = (int)(j / pl);
+    const long ntr = (long)n2 * n3;
+    for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
+      const int j2 = (int)(tr % n2), j3 = (int)(tr / n2);
+      for (int j1 = threadIdx.x; j1 < n1; j1 += blockDim.x) {
+        const size_t j = (size_t)tr * n1 + j1;
         float v = 0.f;
         // inline operator: "+" targets of sources in trace j2-1 (source index ascending = shift descending)
         if (j2 >= 1) {
@@ -2763,6 +2771,7 @@ pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, cons
         if (known[j]) v = 0.0f;
         g[j] = v;
         acc[0] += (double)v * v;
+      }
     }
     pst_block_reduce<1>(acc, partial);
 }

@@ -20,6 +20,7 @@
 // value is bit-identical and the median selection is exact.
 #include "pst_common.cuh"
 #include "pst_predict_core.h"
+#include "pst_predict_warp.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -304,6 +305,36 @@ predict_fast_kernel(const PredArgs A)
     predict_fast_trace<NW, TWO>(A, i2, A.zla + (int)blockIdx.y, (int)blockIdx.y);
 }
 
+// predict_warp_kernel: one WARP per target trace (pst_predict_warp.h) for launches with few traces -- 2-D panels (860 -
+// 1280 traces per spray level), painting (one trace), small cubes -- where the thread-per-trace kernel leaves the GPU
+// with ~1000 threads.  Same bits.  The factor scratch of a trace is [band+1][n1] here.
+template <int NW, bool TWO>
+__global__ void __launch_bounds__(128)
+predict_warp_kernel(const PredArgs A)
+{
+    __shared__ PredWarpWS<NW, TWO> ws[4];
+    constexpr int NC = 2 * NW + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i2 = blockIdx.x * 4 + warp;
+    const int zl = A.zla + blockIdx.y;
+    if (i2 >= A.n2) return;                                   // the whole warp
+    const int n1 = A.n1;
+    const long n2 = A.n2;
+    const long base = (long)zl * n1 * n2 + i2;
+    float *out = A.out + base;
+    const int s2 = i2 - A.a, s3 = (A.ze0 + zl) - A.b, s2g = s2 + A.t_off;
+    if (s2 < 0 || s2 >= A.n2 || s2g < 0 || s2g >= A.ntg || s3 < 0 || s3 >= A.n3) {
+        for (int k = lane; k < n1; k += 32) out[(long)k * n2] = 0.f;
+        return;
+    }
+    const float *x1 = A.in1 + base + A.in1_off;
+    const float *g1 = A.sg1 + base + A.sg1_off;
+    const float *x2 = TWO ? A.in2 + base + A.in2_off : nullptr;
+    const float *g2 = TWO ? A.sg2 + base + A.sg2_off : nullptr;
+    float *scr = A.scr + ((long)blockIdx.y * n2 + i2) * (long)NC * n1;
+    predict_warp_trace<NW, TWO>(ws[warp], x1, g1, x2, g2, n2, A.forw1 != 0, A.forw2 != 0, A.reg, A.tb, n1, scr, out);
+}
+
 // ---------------------------------------------------------------------------------------
 // layout changes: [i3][i2][i1] (reference order, i1 fastest) <-> [i3][i1][i2] (trace-minor)
 __global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int rows,
@@ -514,6 +545,17 @@ static void launch_predict(pst_ctx *c, const PredArgs &A, bool two)
     static const int fast = []() { const char *e = getenv("PST_PREDICT_FAST"); return e ? atoi(e) : 1; }();
     // algorithmic flops per predicted sample: predict1 47 (nw=1) / 116 (nw=2), predict2 78 / 187
     const double fl = NW == 1 ? (two ? 78.0 : 47.0) : (two ? 187.0 : 116.0);
+    // few traces: one warp per trace (break-even against one thread per trace measured / modelled at ~8000 traces).
+    // PST_PREDICT_WARP=0: never, =1: always (tests), unset: by the trace count of the launch
+    static const int warp_mode = []() { const char *e = getenv("PST_PREDICT_WARP"); return e ? atoi(e) : -1; }();
+    const long traces = (long)A.n2 * (A.zlb - A.zla);
+    if (warp_mode == 1 || (warp_mode < 0 && traces <= 6000)) {
+        dim3 wgrid((A.n2 + 3) / 4, A.zlb - A.zla);
+        PST_LAUNCHBF(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * traces, fl * (double)A.n1 * traces,
+            if (two) predict_warp_kernel<NW, true><<<wgrid, 128, 0, c->stream>>>(A);
+            else     predict_warp_kernel<NW, false><<<wgrid, 128, 0, c->stream>>>(A));
+        return;
+    }
     PST_LAUNCHBF(c, PST_K_PREDICT, (two ? 20.0 : 12.0) * (double)A.n1 * A.n2 * (A.zlb - A.zla), fl * (double)A.n1 * A.n2 * (A.zlb - A.zla),
         if (fast == 2 && two) predict_fast_kernel<NW, true, 2><<<grid, threads, 0, c->stream>>>(A);
         else if (fast && two) predict_fast_kernel<NW, true, 3><<<grid, threads, 0, c->stream>>>(A);
@@ -1497,8 +1539,8 @@ extern "C" int pst_paint2d_dev(pst_ctx *c, const float *d_dip, const float *d_se
             A.forw1 = side;
             A.out = d_out + (size_t)i2 * n1;
             PST_LAUNCHBF(c, PST_K_PREDICT, 12.0 * n1, (order == 1 ? 47.0 : 116.0) * n1,
-                if (order == 1) predict_fast_kernel<1, false, 3><<<1, 32, 0, c->stream>>>(A);
-                else            predict_fast_kernel<2, false, 3><<<1, 32, 0, c->stream>>>(A));
+                if (order == 1) predict_warp_kernel<1, false><<<1, 128, 0, c->stream>>>(A);
+                else            predict_warp_kernel<2, false><<<1, 128, 0, c->stream>>>(A));
             c->stats.predictions++;
         }
     }

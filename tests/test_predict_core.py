@@ -21,6 +21,8 @@ def host(tmp_path_factory):
     lib = ctypes.CDLL(so)
     lib.predict_host.restype = ctypes.c_int
     lib.predict_host.argtypes = [_fp, _fp, _fp, _fp] + [ctypes.c_int] * 6 + [ctypes.c_float, _fp]
+    lib.predict_warp_host.restype = ctypes.c_int
+    lib.predict_warp_host.argtypes = lib.predict_host.argtypes
     return lib
 
 
@@ -35,12 +37,15 @@ def _p(a):
     return a.ctypes.data_as(_fp)
 
 
+@pytest.mark.parametrize("fn", ["predict_host", "predict_warp_host"])
 @pytest.mark.parametrize("nw", [1, 2])
 @pytest.mark.parametrize("two", [0, 1])
-def test_core_matches_oracle(host, port, nw, two):
+def test_core_matches_oracle(host, port, nw, two, fn):
+    """predict_host: the thread-per-trace core (pst_predict_core.h); predict_warp_host: the warp-per-trace core
+    (pst_predict_warp.h), lanes emulated phase by phase."""
     rng = np.random.default_rng(10 * nw + two)
     ntr = 7
-    for n1 in (2 * nw + 2, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 20, 21, 24, 25, 26, 31, 50, 64, 101, 200):
+    for n1 in (2 * nw + 2, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 20, 21, 24, 25, 26, 30, 31, 32, 33, 34, 35, 50, 62, 63, 64, 65, 66, 67, 95, 96, 97, 101, 200):
         if n1 < 2 * nw + 2:
             continue
         for forw1, forw2 in ((0, 0), (1, 0), (0, 1), (1, 1)):
@@ -50,7 +55,7 @@ def test_core_matches_oracle(host, port, nw, two):
             g2 = rng.uniform(-1.2, 1.2, (n1, ntr)).astype(np.float32)
             x1[rng.random(x1.shape) < 0.1] = 0.0
             out = np.full((n1, ntr), 7.0, np.float32)
-            rc = host.predict_host(_p(x1), _p(g1), _p(x2), _p(g2), n1, ntr, nw, two, forw1, forw2, ctypes.c_float(1e-4), _p(out))
+            rc = getattr(host, fn)(_p(x1), _p(g1), _p(x2), _p(g2), n1, ntr, nw, two, forw1, forw2, ctypes.c_float(1e-4), _p(out))
             assert rc == 0
             for t in range(ntr):
                 if two:
