@@ -17,8 +17,7 @@ _fp = ctypes.POINTER(ctypes.c_float)
 
 def _F(a):
     """float32 1-D array in Fortran order (the reference's ``np.float32(x).flatten(order='F')``).  An array that already
-    is float32 and Fortran-contiguous is passed as a VIEW: no host copy, and the library sees the caller's own buffer, so
-    that volumes handed from one call to the next (dip3dc -> somf3dc) can be recognised and kept on the GPU."""
+    is float32 and Fortran-contiguous is passed as a VIEW (no host copy)."""
     a = np.asarray(a)
     if a.dtype == np.float32 and a.flags.f_contiguous:
         return a.reshape(-1, order="F")

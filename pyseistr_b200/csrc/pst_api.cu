@@ -27,8 +27,6 @@ extern "C" int pst_device_count(void)
     return n;
 }
 
-void resident_clear(pst_ctx *c);
-
 // ---- arena -----------------------------------------------------------------------------
 int pst_arena_reserve(pst_ctx *c, size_t bytes)
 {
@@ -36,11 +34,6 @@ int pst_arena_reserve(pst_ctx *c, size_t bytes)
     if (c->arena && c->arena_size >= bytes) return PST_OK;
     if (c->arena) { cudaStreamSynchronize(c->stream); cudaFree(c->arena); c->arena = nullptr; c->arena_size = 0; }
     cudaError_t e = cudaMalloc((void **)&c->arena, bytes);
-    if (e != cudaSuccess && !c->resident.empty()) {           // the cached device copies are the first thing to give up
-        cudaGetLastError();
-        resident_clear(c);
-        e = cudaMalloc((void **)&c->arena, bytes);
-    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         pst_set_error("device workspace of %.2f GB unavailable: %s", bytes / 1e9, cudaGetErrorString(e));
@@ -137,7 +130,6 @@ static int ctx_init(pst_ctx *c, int device)
 void pst_comm_destroy(pst_ctx *c);   // pst_comm.cu
 
 extern "C" void pst_ctx_destroy(pst_ctx *c);
-void resident_clear(pst_ctx *c);
 
 extern "C" int pst_ctx_create(int device, pst_ctx **out)
 {
@@ -156,7 +148,6 @@ extern "C" void pst_ctx_destroy(pst_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) pst_comm_destroy(c);
-    resident_clear(c);
     if (c->arena) cudaFree(c->arena);
     if (c->d_partial) cudaFree(c->d_partial);
     if (c->d_red) cudaFree(c->d_red);
@@ -313,7 +304,6 @@ struct DevBuf {
         return PST_OK;
     }
     float *f() { return (float *)p; }
-    void *release() { void *q = p; p = nullptr; return q; }
 };
 
 struct CallTimer {
@@ -416,75 +406,6 @@ struct PipeGuard {           // an error return must not leave a stale pipe behi
     ~PipeGuard() { if (c->pipe.on) { c->pipe.on = false; cudaStreamSynchronize(c->stream); if (c->s_in) cudaStreamSynchronize(c->s_in); if (c->s_out) cudaStreamSynchronize(c->s_out); } }
 };
 
-// ---- resident device copies of host volumes ---------------------------------------------------------------------
-// dip3dc -> somf3dc hands the cube and the two dips straight back: 12.6 GB of uploads at the headline size for 0.25 s of
-// kernels.  The last host-pointer call leaves its device copies in the context, keyed by host pointer and length; the
-// next call re-uses a copy only after a SAMPLE of the host array (one float in every 1021, at pseudo-random offsets, plus
-// both ends) has been compared with it on the device -- an array that was rescaled, clipped, smoothed or refilled in
-// between is uploaded again.  An in-place edit that touches fewer than ~1000 floats can escape the sample: callers that
-// make such edits between calls switch the cache off (PST_RESIDENT=0) or use the *_dev entry points.
-static bool resident_enabled()
-{
-    static const bool on = []() { const char *e = getenv("PST_RESIDENT"); return !(e && e[0] == '0'); }();
-    return on;
-}
-
-void resident_clear(pst_ctx *c)
-{
-    std::vector<void *> freed;
-    for (auto &r : c->resident) {
-        bool seen = false;
-        for (void *b : freed) seen = seen || b == r.base;
-        if (!seen) { cudaFree(r.base); freed.push_back(r.base); }
-    }
-    c->resident.clear();
-}
-
-__global__ void resident_check_kernel(const float *__restrict__ dev, const unsigned *__restrict__ samples, size_t n, size_t stride,
-                                      size_t count, int *__restrict__ mismatch)
-{
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-        size_t pos = i * stride + (size_t)((unsigned)(i * 2654435761u) % (unsigned)stride);
-        if (i == count - 1 || pos >= n) pos = n - 1;
-        if (__float_as_uint(dev[pos]) != samples[i]) *mismatch = 1;
-    }
-}
-
-// the device copy of host array h[0..n) when one is cached AND a sample of h still matches it; else nullptr
-static float *resident_find(pst_ctx *c, const float *h, size_t n)
-{
-    if (!resident_enabled() || n < 4096) return nullptr;
-    for (auto &r : c->resident) {
-        if (r.h != h || r.n != n) continue;
-        const size_t stride = 1021, count = n / stride + 2;
-        unsigned *hs = nullptr, *ds = nullptr;
-        int *dflag = nullptr, hflag = 1;
-        if (cudaMallocHost((void **)&hs, count * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        const unsigned *hu = reinterpret_cast<const unsigned *>(h);
-        for (size_t i = 0; i < count; i++) {
-            size_t pos = i * stride + (size_t)((unsigned)(i * 2654435761u) % (unsigned)stride);
-            if (i == count - 1 || pos >= n) pos = n - 1;
-            hs[i] = hu[pos];
-        }
-        bool ok = cudaMalloc((void **)&ds, count * sizeof(unsigned) + 256) == cudaSuccess;
-        if (ok) {
-            dflag = reinterpret_cast<int *>(reinterpret_cast<char *>(ds) + ((count * sizeof(unsigned) + 127) & ~(size_t)127));
-            ok = cudaMemcpyAsync(ds, hs, count * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-                 cudaMemsetAsync(dflag, 0, sizeof(int), c->stream) == cudaSuccess;
-        }
-        if (ok) {
-            resident_check_kernel<<<256, 256, 0, c->stream>>>(r.d, ds, n, stride, count, dflag);
-            ok = cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-                 cudaStreamSynchronize(c->stream) == cudaSuccess;
-        }
-        if (ds) cudaFree(ds);
-        cudaFreeHost(hs);
-        if (!ok) { cudaGetLastError(); return nullptr; }
-        return hflag == 0 ? r.d : nullptr;
-    }
-    return nullptr;
-}
-
 static int up(pst_ctx *c, DevBuf &b, const float *h, size_t n)
 {
     PST_TRY(b.alloc(n * sizeof(float)));
@@ -521,7 +442,6 @@ extern "C" int pst_dip(pst_ctx *c, const float *din, const float *mask, int n1, 
     const int nz = slab_planes(c, n3);
     const size_t plane = (size_t)n1 * n2, n = plane * nz;      /* n = this rank's slab */
     CallTimer t(c);
-    resident_clear(c);
     DevBuf d, m, o;
     PST_TRY(d.alloc(n * sizeof(float)));
     if (mask) PST_TRY(m.alloc(n * sizeof(float)));
@@ -538,15 +458,6 @@ extern "C" int pst_dip(pst_ctx *c, const float *din, const float *mask, int n1, 
     else         PST_TRY(pst_pipe_emit(c, o.f(), nz, 2 * nz));
     PST_TRY(pipe_finish(c));
     t.stop();
-    // the cube and the dips usually come straight back (somf3dc / somean3dc / soint3dc): keep the device copies
-    resident_clear(c);
-    if (resident_enabled()) {
-        float *dd = d.f(), *oo = o.f();
-        void *bd = d.release(), *bo = o.release();
-        c->resident.push_back({din, n, dd, bd});
-        c->resident.push_back({dip_out, n, oo, bo});
-        if (n3 != 1) c->resident.push_back({dip_out + n, n, oo + n, bo});
-    }
     return PST_OK;
 }
 
@@ -558,21 +469,13 @@ static int spray3d_host(pst_ctx *c, int median, const float *din, const float *d
     const int nz = slab_planes(c, n3);
     const size_t plane = (size_t)n1 * n2, n = plane * nz;
     CallTimer t(c);
-    // inputs an earlier host-pointer call left on the device (verified against a sample of the host array) are not
-    // uploaded again; the others go up in plane chunks under the kernels
-    const float *src_all[3] = {din, dipi, dipx};
-    float *dev[3];
     DevBuf own[3], o;
-    float *dst[3];
-    const float *src[3];
-    int nup = 0;
+    float *dev[3], *dst[3];
+    const float *src[3] = {din, dipi, dipx};
+    const int nup = 3;
     for (int v = 0; v < 3; v++) {
-        dev[v] = resident_find(c, src_all[v], n);
-        if (!dev[v]) {
-            PST_TRY(own[v].alloc(n * sizeof(float)));
-            dev[v] = own[v].f();
-            dst[nup] = dev[v]; src[nup] = src_all[v]; nup++;
-        }
+        PST_TRY(own[v].alloc(n * sizeof(float)));
+        dev[v] = dst[v] = own[v].f();
     }
     PST_TRY(o.alloc(n * sizeof(float)));
     PipeGuard guard{c};

@@ -79,11 +79,6 @@ struct pst_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    // Device copies of host volumes the last host-pointer call moved (inputs it uploaded, outputs it downloaded): a
-    // following call that is handed the same host pointer and size re-uses the device copy after checking a sample of the
-    // host contents against it (pst_api.cu: resident_*; PST_RESIDENT=0 disables).  dip3dc -> somf3dc is that pattern.
-    struct Resident { const float *h; size_t n; float *d; void *base; };
-    std::vector<Resident> resident;
     struct Pipe {
         bool on = false;
         std::vector<int> up_planes;            // planes [0, up_planes[k]) of every input volume are uploaded once ...

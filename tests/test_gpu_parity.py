@@ -558,24 +558,3 @@ def test_rgt_vs_oracle(ctx, port):
         t = ps.rgt(p, o1=-0.2, d1=0.004, order=order, i0=i0, eps=0.1, ctx=ctx)
         seed = np.linspace(0, 0.004 * 149, 150) - 0.2
         assert np.array_equal(t, port.pwpaintc(p, seed, order, i0, 0.1)), (order, i0)
-
-
-def test_resident_copies_between_calls_are_verified(ctx):
-    """dip3dc -> somf3dc on the caller's own F-ordered float32 arrays: the second call finds the device copies the first
-    one left (no upload) -- and must notice when the host arrays were changed in between."""
-    import pyseistr_b200 as ps
-    n1, n2, n3 = 96, 40, 24
-    d = np.asfortranarray(synth.erratic(synth.cube(n1, n2, n3, seed=51), ntraces=12))
-    di, dx = ps.dip3dc(d, 2, 4, verb=0, ctx=ctx)
-    a = ps.somf3dc(d, di, dx, 2, 2, 0.01, 2, verb=0, ctx=ctx)                        # same buffers: resident copies
-    h2d_hit = ctx.stats()["h2d_bytes"]
-    b = ps.somf3dc(d.copy(order="F"), di.copy(order="F"), dx.copy(order="F"), 2, 2, 0.01, 2, verb=0, ctx=ctx)   # fresh buffers: uploads
-    h2d_miss = ctx.stats()["h2d_bytes"]
-    assert np.array_equal(a, b)
-    assert h2d_miss >= 3 * d.nbytes
-    di2, dx2 = ps.dip3dc(d, 2, 4, verb=0, ctx=ctx)
-    d *= np.float32(0.5)                                                             # edited in place after the dip call
-    c1 = ps.somf3dc(d, di2, dx2, 2, 2, 0.01, 2, verb=0, ctx=ctx)
-    c2 = ps.somf3dc(d.copy(order="F"), di2.copy(order="F"), dx2.copy(order="F"), 2, 2, 0.01, 2, verb=0, ctx=ctx)
-    assert np.array_equal(c1, c2)
-    print(f"[resident] h2d bytes of somf3dc: {h2d_hit:.0f} with the cube and dips resident, {h2d_miss:.0f} with fresh buffers")
