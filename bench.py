@@ -753,9 +753,9 @@ def _main(real_stdout):
     cls_f = dict(zip(names, st["class_flops"]))
     # kernels, not classes: the three smoothing classes are ONE kernel (the classes only split its launches by axis),
     # every other class is one kernel family
-    groups = {"tri_smooth": ("tri_axis1", "tri_axis2", "tri_axis3")}
+    groups = {"tri_smooth": ("tri_axis1", "tri_axis2", "tri_axis3", "tri_axis3_bwd")}
     for k in names:
-        if k not in groups["tri_smooth"] and k not in ("other", "slot_reduce", "reserved"):
+        if k not in groups["tri_smooth"] and k not in ("other", "slot_reduce"):
             groups[k] = (k,)
     g_ms = {g: sum(cls_ms[k] for k in ks) for g, ks in groups.items()}
     g_n = {g: sum(cls_n[k] for k in ks) for g, ks in groups.items()}
@@ -764,11 +764,11 @@ def _main(real_stdout):
     live = [g for g in groups if g_n[g] > 0 and (g_b[g] > 0 or g_f[g] > 0)]
     dom = max(live, key=lambda g: g_ms[g])
     total_cls = sum(cls_ms.values()) or 1.0
-    tri_kernel = os.environ.get("PST_TRI_KERNEL_NAME", "tri_stream_kernel<CONTIG,NB> (axes 1-3; distributed axis 3: tri3_tile_fwd/bwd_kernel)")
+    tri_kernel = os.environ.get("PST_TRI_KERNEL_NAME", "tri_l2_kernel<CONTIG,NB> (axis 1), tri_sys_kernel<CONTIG,NB,..> (axes 2-3); distributed axis 3: tri3_tile_fwd/bwd_kernel")
     kernel_names = {"tri_smooth": tri_kernel,
-                    "cg_head": "cg_head4_kernel", "cg_dir": "cg_dir4_kernel", "cg_gp": "cg_gp4_kernel",
+                    "cg_head": "cg_head4d_kernel", "cg_dir": "cg_dird_kernel", "cg_gp": "cg_gp4_kernel",
                     "allpass": "allpass_kernel", "cg_setup": "divne_prescale/scale_init_kernel / pwd3_*/cgstep kernels",
-                    "predict": "predict_kernel<NW,TWO> / predict_adj_kernel<NW>"}
+                    "predict": "predict_fast_kernel<NW,TWO> / predict_warp_kernel<NW,TWO> / predict_adj_kernel<NW>"}
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = FP32_LANES * 2 * sm_mhz * 1e6 / 1e12           # TFLOP/s at the SM clock sampled during the run
     if dom == "predict":

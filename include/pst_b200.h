@@ -59,6 +59,7 @@ typedef struct pst_stats {
 #define PST_K_CGHEAD    8   /* CG: p,x,r += a*s of the previous iteration + gradient head gx = -eps x + w r */
 #define PST_K_CGGP      9   /* CG: gp = eps p + S(gx), sum gp^2 */
 #define PST_K_CGDIR    10   /* CG: gr = w gx, direction update s = g + alpha s, three dots */
+#define PST_K_TRI3BWD  11   /* distributed axis 3 with PST_TRI3_SPLIT=1: the backward (carry-down) kernels; else part of PST_K_TRI3 */
 #define PST_K_NCLASS   12
 
 const char *pst_last_error(void);

@@ -44,7 +44,7 @@ class Stats(ctypes.Structure):
 
 
 KERNEL_CLASSES = ("allpass", "tri_axis1", "tri_axis2", "tri_axis3", "cg_setup", "predict", "slot_reduce", "other",
-                  "cg_head", "cg_gp", "cg_dir", "reserved")
+                  "cg_head", "cg_gp", "cg_dir", "tri_axis3_bwd")
 
 
 # name -> (restype, argtypes); every symbol include/pst_b200.h declares

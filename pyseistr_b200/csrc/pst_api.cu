@@ -85,6 +85,84 @@ int pst_finish_reduce(pst_ctx *c, int nblocks, int nv, int rec)
     return PST_OK;
 }
 
+// ---- canonical sums (pst_common.cuh) ----
+// one warp per (value, GLOBAL plane): the plane's pieces in lane-strided order + the fixed shuffle tree; +0 for planes
+// of other ranks
+__global__ void plane_sums_kernel(const double *__restrict__ partial, int ppp, int nz, int z0, int nzg, int nv,
+                                  double *__restrict__ planes)
+{
+    const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long)nzg * nv) return;
+    const int q = (int)(w / nzg), zg = (int)(w - (long)q * nzg), z = zg - z0;
+    double s = 0.0;
+    if (z >= 0 && z < nz) {
+        for (int p = lane; p < ppp; p += 32) s += partial[((size_t)z * ppp + p) * PST_RED_SLOTS + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) planes[(size_t)q * nzg + zg] = s;
+}
+
+// one block per value: planes in thread-strided order, lanes by the shuffle tree, warps in index order
+__global__ void __launch_bounds__(256) final_sums_kernel(const double *__restrict__ planes, int nzg, double *__restrict__ rec)
+{
+    __shared__ double sh[8];
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int z = threadIdx.x; z < nzg; z += 256) s += planes[(size_t)q * nzg + z];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) sh[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sh[0];
+        for (int k = 1; k < 8; k++) t += sh[k];
+        rec[q] = t;
+    }
+}
+
+int pst_reserve_partials(pst_ctx *c, size_t nblocks, int nzg)
+{
+    if (nblocks > (size_t)c->max_blocks) {
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_planes) cudaFree(c->d_planes);
+        c->d_partial = nullptr; c->max_blocks = 0;
+        PST_CUDA(cudaMalloc((void **)&c->d_partial, nblocks * PST_RED_SLOTS * sizeof(double)));
+        c->max_blocks = (int)nblocks;
+    }
+    if (nzg > c->planes_cap) {
+        PST_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_planes) cudaFree(c->d_planes);
+        c->d_planes = nullptr; c->planes_cap = 0;
+        PST_CUDA(cudaMalloc((void **)&c->d_planes, (size_t)nzg * PST_RED_SLOTS * sizeof(double)));
+        c->planes_cap = nzg;
+    }
+    return PST_OK;
+}
+
+int pst_finish_reduce_canon(pst_ctx *c, int ppp, int nz, int z0, int nzg, int nv, int rec)
+{
+    if ((size_t)ppp * nz > (size_t)c->max_blocks || nzg > c->planes_cap || nv > PST_RED_SLOTS) {
+        pst_set_error("internal: canonical reduction without pst_reserve_partials");
+        return PST_EINVAL;
+    }
+    {
+        KTimer kt(c, PST_K_OTHER);
+        const long warps = (long)nzg * nv;
+        plane_sums_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, c->stream>>>(c->d_partial, ppp, nz, z0, nzg, nv, c->d_planes);
+    }
+    PST_CUDA(cudaGetLastError());
+    if (c->comm) PST_TRY(pst_comm_allreduce_record(c, c->d_planes, nv * nzg));
+    {
+        KTimer kt(c, PST_K_OTHER);
+        final_sums_kernel<<<nv, 256, 0, c->stream>>>(c->d_planes, nzg, c->d_red + (size_t)rec * PST_RED_SLOTS);
+    }
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
 int pst_fetch_record(pst_ctx *c, int rec, int nv, double *host_out)
 {
     PST_CUDA(cudaMemcpyAsync(c->h_red + (size_t)rec * PST_RED_SLOTS, c->d_red + (size_t)rec * PST_RED_SLOTS,

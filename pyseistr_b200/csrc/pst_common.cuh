@@ -56,6 +56,8 @@ struct pst_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // reduction plumbing: per-block partials -> one record of PST_RED_SLOTS doubles
     double *d_partial = nullptr;     // [max_blocks * PST_RED_SLOTS]
+    double *d_planes = nullptr;      // [PST_RED_SLOTS][planes_cap]: per-plane sums of the canonical reductions
+    int planes_cap = 0;
     double *d_red = nullptr;         // [64 * PST_RED_SLOTS] ring of records
     double *h_red = nullptr;         // pinned mirror
     int max_blocks = 0;
@@ -170,6 +172,39 @@ __device__ __forceinline__ void pst_block_reduce(double (&v)[NV], double *partia
         }
     }
 }
+
+// ---- canonical (partition-independent) sums ---------------------------------------------------------------------
+// A volume [n1 n2][nz] is summed as: elements of one PIECE (PST_RED_CH consecutive elements of ONE n3-plane; block =
+// piece, fixed thread pattern + fixed trees) -> pieces of a plane in index order (pst_plane_sums_kernel) -> planes of
+// the GLOBAL cube in a fixed order (pst_final_sums_kernel).  No step looks at how many planes THIS rank owns, so an
+// n3-slab decomposition over any number of ranks forms every CG / divne / line-search scalar with exactly the
+// additions of the single-GPU run: ranks fill their planes of the [nv][n3 global] table, the others stay +0, and the
+// all-reduce of that table adds only zeros (exact in any order).
+#define PST_RED_CH 32768u
+struct Span { size_t n; unsigned n12, ppp; };     // ppp > 0: block = piece (blockIdx.x % ppp) of plane (blockIdx.x / ppp); 0: grid-stride over n
+inline Span pst_span_canon(size_t n12, int nz)
+{
+    Span S; S.n = n12 * (size_t)nz; S.n12 = (unsigned)n12; S.ppp = (unsigned)((n12 + PST_RED_CH - 1) / PST_RED_CH);
+    return S;
+}
+#ifdef __CUDACC__
+// this thread's elements: i0, i0 + step, ... < i1 (width = elements per thread and step: 1 or 4)
+__device__ __forceinline__ void pst_span(const Span &S, int width, size_t &i0, size_t &i1, size_t &step)
+{
+    if (S.ppp) {
+        const unsigned z = blockIdx.x / S.ppp, p = blockIdx.x - z * S.ppp;
+        const unsigned o = p * PST_RED_CH;
+        const unsigned len = (S.n12 - o < PST_RED_CH) ? S.n12 - o : PST_RED_CH;
+        const size_t base = (size_t)z * S.n12 + o;
+        i0 = base + (size_t)width * threadIdx.x; i1 = base + len; step = (size_t)width * blockDim.x;
+    } else {
+        i0 = (size_t)width * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i1 = S.n; step = (size_t)width * gridDim.x * blockDim.x;
+    }
+}
+#endif
+// pieces [nz][ppp] of c->d_partial -> record `rec`; z0 / nzg place this rank's planes in the global cube
+int pst_finish_reduce_canon(pst_ctx *c, int ppp, int nz, int z0, int nzg, int nv, int rec);
+int pst_reserve_partials(pst_ctx *c, size_t nblocks, int nzg);
 
 // sum the per-block partials into record `rec` (device), optionally fetch to host
 int pst_finish_reduce(pst_ctx *c, int nblocks, int nv, int rec);

@@ -85,19 +85,22 @@ __device__ __forceinline__ void pst_aderfilter(const BTab &tb, float p, float (&
 // (inline) or n1*n2 (xline); zero on the nw border rows and on the last trace / plane.
 // LS variant fuses the line-search update p = p0 + lam*dp (dip3 :1669-1675) in front.
 // Always emits the block partial of sum(y^2) (usum / usum2 of dip3 :1650-1654,:1681-1685).
-// One block walks traces (grid-stride), threads walk i1: fully coalesced.
+// One block walks a group of traces, threads walk i1: fully coalesced.
 template <int NW, bool DER, bool LS>
 __global__ void __launch_bounds__(256)
 allpass_kernel(const float *__restrict__ u, const float *__restrict__ p_in,
                const float *__restrict__ dp, float lam, float *__restrict__ p_out,
                float *__restrict__ y, int n1, int n2, int n3, int xline, int n3_live, BTab tb,
-               double *__restrict__ partial)
+               unsigned gpp, int tg, double *__restrict__ partial)
 {
-    const long ntr = (long)n2 * n3;
     const long ip = xline ? (long)n1 * n2 : (long)n1;
     double acc2[1] = {0.0};
-    for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
-        const int i2 = (int)(tr % n2), i3 = (int)(tr / n2);
+    // block = group (blockIdx.x % gpp) of tg consecutive traces of plane blockIdx.x / gpp: the pieces of the
+    // canonical sums (pst_common.cuh); tg depends on n1 only
+    const int i3 = (int)(blockIdx.x / gpp), t0 = (int)(blockIdx.x - (unsigned)i3 * gpp) * tg;
+    const int t1 = t0 + tg < n2 ? t0 + tg : n2;
+    for (int i2 = t0; i2 < t1; i2++) {
+        const long tr = (long)i3 * n2 + i2;
         const bool live_tr = xline ? (i3 < n3_live) : (i2 < n2 - 1);
         const long base = tr * n1;
         for (int i1 = threadIdx.x; i1 < n1; i1 += blockDim.x) {
@@ -984,11 +987,13 @@ tri_tile_contig_v4_kernel(const TriArgs A)
 // in double; partial of sum(den^2) (:811).
 __global__ void __launch_bounds__(256)
 divne_prescale_kernel(float *__restrict__ num, float *__restrict__ den,
-                      const unsigned char *__restrict__ mask, float eps, size_t n,
+                      const unsigned char *__restrict__ mask, float eps, Span S,
                       double *__restrict__ partial)
 {
     double acc[1] = {0.0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(S, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float a = num[i], b = den[i];
         if (mask && mask[i]) { a = 0.f; b = 0.f; }
         if (eps > 0.0f) {
@@ -1008,10 +1013,12 @@ divne_prescale_kernel(float *__restrict__ num, float *__restrict__ den,
 __global__ void __launch_bounds__(256)
 divne_scale_init_kernel(const float *__restrict__ num, float *__restrict__ den, double norm,
                         float *__restrict__ r, float *__restrict__ p, float *__restrict__ x,
-                        size_t n, double *__restrict__ partial)
+                        Span S, double *__restrict__ partial)
 {
     double acc[1] = {0.0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(S, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         const float a = (float)((double)num[i] * norm);
         den[i] = (float)((double)den[i] * norm);
         const float ri = -a;
@@ -1058,10 +1065,12 @@ cg_tail_kernel(float *__restrict__ x, const float *__restrict__ sx, float a, siz
 // gp = eps*p + S(gx)  (:303,:318); partial gp.gp.  (The second shaping call reads gp out of place.)
 __global__ void __launch_bounds__(256)
 cg_gp_kernel(const float *__restrict__ p, const float *__restrict__ tmp, float *__restrict__ gp,
-             float eps, size_t n, double *__restrict__ partial)
+             float eps, Span S, double *__restrict__ partial)
 {
     double acc[1] = {0.0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(S, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float g = eps * p[i];
         g += tmp[i];
         gp[i] = g;
@@ -1134,10 +1143,12 @@ cg_head4_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict_
 
 __global__ void __launch_bounds__(256)
 cg_gp4_kernel(const float *__restrict__ p, const float *__restrict__ tmp, float *__restrict__ gp,
-              float eps, size_t n, double *__restrict__ partial)
+              float eps, Span S, double *__restrict__ partial)
 {
     double acc[1] = {0.0};
-    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(S, 4, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         const float4 pv = ld4(p, i), tv = ld4(tmp, i);
         float4 g;
         g.x = eps * pv.x; g.x += tv.x;
@@ -1282,13 +1293,15 @@ template <bool FIRST, bool VEC>
 __global__ void __launch_bounds__(256)
 cg_dird_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
                const float *__restrict__ w, float *__restrict__ sp, float *__restrict__ sx,
-               float *__restrict__ sr, const CgCtl *__restrict__ ctl, size_t n, double *__restrict__ partial)
+               float *__restrict__ sr, const CgCtl *__restrict__ ctl, Span S, double *__restrict__ partial)
 {
     double acc[3] = {0.0, 0.0, 0.0};
     if (!ctl->stop) {
         const float alpha = ctl->alpha_dir;
+        size_t i0, i1, step;
+        pst_span(S, VEC ? 4 : 1, i0, i1, step);
         if (VEC) {
-            for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+            for (size_t i = i0; i < i1; i += step) {
                 const float4 g = ld4(gp, i), t = ld4(tmp, i), wv = ld4(w, i);
                 float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1;
                 if (!FIRST) { s1 = ld4(sp, i); s2 = ld4(sx, i); s3 = ld4(sr, i); }
@@ -1300,7 +1313,7 @@ cg_dird_kernel(const float *__restrict__ gp, const float *__restrict__ tmp,
                 st4(sp, i, a); st4(sx, i, b); st4(sr, i, c);
             }
         } else {
-            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            for (size_t i = i0; i < i1; i += step) {
                 float a, b, c;
                 cg_dir_one<FIRST>(gp[i], tmp[i], w[i], FIRST ? 0.f : sp[i], FIRST ? 0.f : sx[i], FIRST ? 0.f : sr[i], alpha, a, b, c, acc);
                 sp[i] = a; sx[i] = b; sr[i] = c;
@@ -1447,6 +1460,7 @@ struct Tri3Args {
     long L, l0, l1;        // lines per plane, chunk [l0, l1)
     int n3g, z0, nz, nb, K0, K1;
     float wt, w2;
+    int rev;               // tile kernels, backward: visit the tiles in descending order (the F tiles written last are still in L2)
 };
 
 __device__ __forceinline__ float tri3_x(const Tri3Args &A, int j, long l)
@@ -1753,7 +1767,7 @@ tri3_tile_bwd_kernel(const Tri3Args A)
 {
     extern __shared__ __align__(16) float t3s[];
     const int nb = A.nb, n3g = A.n3g, R = A.K1 - A.K0, tid = threadIdx.x;
-    const long l0 = (long)blockIdx.x * W;
+    const long l0 = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * W;
     const long l = l0 + tid;
     const bool live = tid < W && l < A.L;
     constexpr int CPR = W / 4;
@@ -1841,8 +1855,9 @@ static int tri3_tile_width(int rows_max, long L, const void *a, const void *b, c
     if (!on) return 0;
     // narrower tiles leave too few chain threads per SM: measured at 2 GPUs (527 rows, W = 32) the tile
     // kernels take 2.6 ms per launch against 1.4 ms for the line kernels, so tall slabs keep the latter
+    static const int wmax = []() { const char *v = getenv("PST_TRI3_WMAX"); return v ? atoi(v) : 128; }();   // A/B: cap the tile width
     const int ws[2] = {128, 64};
-    for (int w : ws) if ((size_t)rows_max * w * 4 <= 75 * 1024) return w;
+    for (int w : ws) if (w <= wmax && (size_t)rows_max * w * 4 <= 75 * 1024) return w;
     return 0;
 }
 
@@ -2030,7 +2045,9 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;
     A.cout = first ? nullptr : mb.cb_out; A.fout = mb.fb_out;
     A.pin = last ? nullptr : mb.pb_in; A.pout = first ? nullptr : mb.pb_out;
-    static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? 11 : PST_K_TRI3; }();
+    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
+    A.rev = rev_on ? 1 : 0;
+    static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? PST_K_TRI3BWD : PST_K_TRI3; }();
     if (W) {
         PST_LAUNCHB(c, bwd_cls, 8.0 * (double)g.n,
             if (rcmp) {
@@ -2221,23 +2238,23 @@ int pst_smooth3_inplace(pst_ctx *c, float *x, float *scr, int n1, int n2, int n3
 template <int NW>
 static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, const float *dp, float lam,
                              float *p_out, float *y, int n1, int n2, int n3, int xline, bool der,
-                             bool ls, int rec, int n3_live)
+                             bool ls, int rec, int n3_live, int z0, int n3g)
 {
     static const BTab tb = make_btab(NW);
-    const long ntr = (long)n2 * n3;
-    long blocks = ntr;
-    const long cap = (long)c->sm_count * 8;
-    if (blocks > cap) blocks = cap;
+    const int tg = n1 >= (int)PST_RED_CH ? 1 : (int)(PST_RED_CH / (unsigned)n1);     // traces per piece: a function of n1 only
+    const unsigned gpp = (unsigned)((n2 + tg - 1) / tg);
+    const long blocks = (long)gpp * n3;
+    PST_TRY(pst_reserve_partials(c, (size_t)blocks, n3g));
     const int threads = n1 >= 256 ? 256 : (n1 >= 128 ? 128 : 64);
     PST_LAUNCHB(c, PST_K_ALLPASS, (ls ? 20.0 : 12.0) * (double)n1 * n2 * n3,
         if (ls)
-            allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, n3_live, tb, c->d_partial);
+            allpass_kernel<NW, false, true><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, n3_live, tb, gpp, tg, c->d_partial);
         else if (der)
-            allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, c->d_partial);
+            allpass_kernel<NW, true, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, gpp, tg, c->d_partial);
         else
-            allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, c->d_partial));
+            allpass_kernel<NW, false, false><<<(unsigned)blocks, threads, 0, c->stream>>>(u, p_in, nullptr, 0.f, nullptr, y, n1, n2, n3, xline, n3_live, tb, gpp, tg, c->d_partial));
     PST_CUDA(cudaGetLastError());
-    return pst_finish_reduce(c, (int)blocks, 1, rec);
+    return pst_finish_reduce_canon(c, (int)gpp, n3, z0, n3g, 1, rec);
 }
 
 // n3_live: planes whose next plane exists (xline stencil); -1 = n3 - 1 (whole cube on this GPU).
@@ -2245,11 +2262,12 @@ static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, cons
 // the last rank.
 int pst_allpass_launch(pst_ctx *c, const float *u, const float *p_in, const float *dp, float lam,
                        float *p_out, float *y, int n1, int n2, int n3, int nw, int xline, bool der,
-                       bool ls, int rec, int n3_live = -1)
+                       bool ls, int rec, int n3_live = -1, int z0 = 0, int n3g = -1)
 {
     if (n3_live < 0) n3_live = n3 - 1;
-    if (nw == 1) return allpass_launch_nw<1>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live);
-    if (nw == 2) return allpass_launch_nw<2>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live);
+    if (n3g < 0) n3g = n3;
+    if (nw == 1) return allpass_launch_nw<1>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live, z0, n3g);
+    if (nw == 2) return allpass_launch_nw<2>(c, u, p_in, dp, lam, p_out, y, n1, n2, n3, xline, der, ls, rec, n3_live, z0, n3g);
     pst_set_error("order=%d unsupported (1 or 2)", nw);
     return PST_EUNSUP;
 }
@@ -2284,19 +2302,24 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     const float eps = 1.f * 1.f, tol = 1.e-6f;
     const int threads = 256;
     const int grid = pst_grid_for(c, n, threads);
+    // every sum of the solve is canonical (pst_common.cuh): the scalars do not depend on the slab decomposition
+    const Span S = pst_span_canon((size_t)g.n1 * g.n2, g.n3);
+    const unsigned gridc = S.ppp * (unsigned)g.n3;
+    PST_TRY(pst_reserve_partials(c, gridc, g.n3g));
+    auto finish = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)S.ppp, g.n3, g.z0, g.n3g, nv, rec); };
     double h[PST_RED_SLOTS];
     if (iters_run) *iters_run = 0;
 
-    PST_LAUNCHB(c, PST_K_CGVEC, 16.0 * (double)n, (divne_prescale_kernel<<<grid, threads, 0, c->stream>>>(num, den, mask, eps_div, n, c->d_partial)));
-    PST_TRY(pst_finish_reduce(c, grid, 1, 0));
+    PST_LAUNCHB(c, PST_K_CGVEC, 16.0 * (double)n, (divne_prescale_kernel<<<gridc, threads, 0, c->stream>>>(num, den, mask, eps_div, S, c->d_partial)));
+    PST_TRY(finish(1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) {
         PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rat, 0.f, n)));
         return PST_OK;
     }
     const double norm = sqrt(g.nglob / h[0]);
-    PST_LAUNCHB(c, PST_K_CGVEC, 24.0 * (double)n, (divne_scale_init_kernel<<<grid, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, n, c->d_partial)));
-    PST_TRY(pst_finish_reduce(c, grid, 1, 0));
+    PST_LAUNCHB(c, PST_K_CGVEC, 24.0 * (double)n, (divne_scale_init_kernel<<<gridc, threads, 0, c->stream>>>(num, den, norm, w.r, w.p, rat, S, c->d_partial)));
+    PST_TRY(finish(1, 0));
     PST_TRY(pst_fetch_record(c, 0, 1, h));
     if (h[0] == 0.0) return PST_OK;               // zero residual: p = x = 0 (:299-303)
 
@@ -2308,7 +2331,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     // 16-byte kernels when every vector is 16-byte aligned and n % 4 == 0
     auto a16 = [](const void *q) { return (((uintptr_t)q) & 15) == 0; };
     static const bool vec_on = []() { const char *e = getenv("PST_CG_VEC4"); return !(e && e[0] == '0'); }();
-    const bool vec4 = vec_on && (n % 4 == 0) && a16(w.p) && a16(rat) && a16(w.r) && a16(w.sp) && a16(w.sx) && a16(w.sr) &&
+    const bool vec4 = vec_on && (S.n12 % 4 == 0) && a16(w.p) && a16(rat) && a16(w.r) && a16(w.sp) && a16(w.sx) && a16(w.sr) &&
                       a16(den) && a16(w.tmp) && a16(w.gp);
     const int grid4 = pst_grid_for(c, n / 4 + 1, threads, 2);
     // default: CG scalars stay on the device (no host synchronisation inside the solve).  PST_CG_DEVSCALARS=0 or one
@@ -2329,18 +2352,18 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
                 else              cg_headd_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n));
             PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, nullptr, nullptr, nullptr, nullptr));
             PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n,
-                if (vec4) cg_gp4_kernel<<<grid4, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial);
-                else cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial));
-            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 1, 1));
+                if (vec4) cg_gp4_kernel<<<gridc, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, S, c->d_partial);
+                else cg_gp_kernel<<<gridc, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, S, c->d_partial));
+            PST_TRY(finish(1, 1));
             PST_LAUNCH(c, PST_K_OTHER, (cg_ctl_gn_kernel<<<1, 1, 0, c->stream>>>(ctl, rec1, iter, tol)));
             PST_CUDA(cudaMemcpyAsync((void *)c->h_cgstop, &ctl->stop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             PST_TRY(pst_shape_apply(c, g, w.gp, w.tmp, w.scr, nullptr, nullptr, nullptr, nullptr));
             PST_LAUNCHB(c, PST_K_CGDIR, (iter ? 36.0 : 24.0) * (double)n,
-                if (iter == 0 && vec4) cg_dird_kernel<true, true><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
-                else if (iter == 0)    cg_dird_kernel<true, false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
-                else if (vec4)         cg_dird_kernel<false, true><<<grid4, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial);
-                else                   cg_dird_kernel<false, false><<<grid, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, n, c->d_partial));
-            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 3, 2));
+                if (iter == 0 && vec4) cg_dird_kernel<true, true><<<gridc, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, S, c->d_partial);
+                else if (iter == 0)    cg_dird_kernel<true, false><<<gridc, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, S, c->d_partial);
+                else if (vec4)         cg_dird_kernel<false, true><<<gridc, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, S, c->d_partial);
+                else                   cg_dird_kernel<false, false><<<gridc, threads, 0, c->stream>>>(w.gp, w.tmp, den, w.sp, w.sx, w.sr, ctl, S, c->d_partial));
+            PST_TRY(finish(3, 2));
             PST_LAUNCH(c, PST_K_OTHER, (cg_ctl_beta_kernel<<<1, 1, 0, c->stream>>>(ctl, rec2, eps)));
             launched++;
         }
@@ -2378,9 +2401,9 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, fuse_gp ? &e1 : nullptr, nullptr, nullptr, &fused));
         if (!fused) {
             PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n,
-                if (vec4) cg_gp4_kernel<<<grid4, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial);
-                else cg_gp_kernel<<<grid, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, n, c->d_partial));
-            PST_TRY(pst_finish_reduce(c, vec4 ? grid4 : grid, 1, 1));
+                if (vec4) cg_gp4_kernel<<<gridc, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, S, c->d_partial);
+                else cg_gp_kernel<<<gridc, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, S, c->d_partial));
+            PST_TRY(finish(1, 1));
         }
         // gx = S(gp); direction update fused into the last axis once alpha is known
         EpiSpec e2;
@@ -2424,18 +2447,18 @@ static int gauss_newton(pst_ctx *c, const DipGeom &g, const float *u, float *p, 
 {
     double h[PST_RED_SLOTS];
     float *pcur = p, *pnext = ptrial;
-    PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u2, g.n1, g.n2, g.n3, nw, xline, false, false, 3, n3_live));
+    PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u2, g.n1, g.n2, g.n3, nw, xline, false, false, 3, n3_live, g.z0, g.n3g));
     PST_TRY(pst_fetch_record(c, 3, 1, h));
     double usum = h[0];
     for (int iter = 0; iter < niter; iter++) {
-        PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u1, g.n1, g.n2, g.n3, nw, xline, true, false, 4, n3_live));
+        PST_TRY(pst_allpass_launch(c, u, pcur, nullptr, 0.f, nullptr, u1, g.n1, g.n2, g.n3, nw, xline, true, false, 4, n3_live, g.z0, g.n3g));
         int its = 0;
         PST_TRY(pst_divne_run(c, g, u2, u1, dp, mask, w, liter, 1.0f, &its));
         float lam = 1.f;
         double usum2 = 0.;
         int k;
         for (k = 0; k < 8; k++) {
-            PST_TRY(pst_allpass_launch(c, u, pcur, dp, lam, pnext, u2, g.n1, g.n2, g.n3, nw, xline, false, true, 3, n3_live));
+            PST_TRY(pst_allpass_launch(c, u, pcur, dp, lam, pnext, u2, g.n1, g.n2, g.n3, nw, xline, false, true, 3, n3_live, g.z0, g.n3g));
             PST_TRY(pst_fetch_record(c, 3, 1, h));
             c->stats.linesearch_evals++;
             usum2 = h[0];

@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 
 import torch.distributed as dist  # noqa: E402
 
+import pyseistr_b200 as ps  # noqa: E402
 from pyseistr_b200 import dist as pd, synth  # noqa: E402
 
 
@@ -30,6 +31,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     ctx = pd.context_from_torch(dist, local)
     ok = True
+    solo = ps.Context(local) if rank == 0 else None
     for (shape, kw) in [((60, 24, 12 * world), dict(niter=3, liter=6, order=2, rect=(5, 5, 5))),
                         ((40, 17, 10 * world + 3), dict(niter=2, liter=5, order=1, rect=(3, 4, 4))),
                         # tall slabs: the axis-3 tile kernels run with 64-line tiles (rows x 128 lines > 75 KB)
@@ -61,9 +63,13 @@ def main():
             of = port.somf3dc(noisy, DI, DX, 2, 2, 0.01, kw["order"])
             om = port.somean3dc(noisy, DI, DX, 2, 2, 0.01, kw["order"])
             bf, bm = bool(np.array_equal(F, of)), bool(np.array_equal(M, om))
+            # the same cube on ONE GPU (a second, single-GPU context on this rank's device): every sum of the dip
+            # solve is canonical (pst_common.cuh), so the slab run must return the same bits
+            si, sx = ps.dip3dc(cube, ctx=solo, verb=0, **kw)
+            b1 = bool(np.array_equal(DI, si) and np.array_equal(DX, sx))
             print(f"[dist_check] world={world} shape={shape}: dip rel-L2 {e1:.2e}/{e2:.2e} "
-                  f"somf bit-exact={bf} somean bit-exact={bm}", flush=True)
-            ok = ok and e1 <= 1e-5 and e2 <= 1e-5 and bf and bm
+                  f"somf bit-exact={bf} somean bit-exact={bm} dips == single-GPU run: {b1}", flush=True)
+            ok = ok and e1 <= 1e-5 and e2 <= 1e-5 and bf and bm and b1
     # ---- dip3dc with mask= across slabs (the mask footprint of the xline stencil needs the neighbour's plane too)
     n1, n2, n3 = 40, 16, 6 * world + 1
     cube = synth.cube(n1, n2, n3, seed=80)
