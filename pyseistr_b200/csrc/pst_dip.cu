@@ -1706,28 +1706,36 @@ tri3_tile_fwd_kernel(const Tri3Args A)
     const long l0 = (long)blockIdx.x * W;
     const long l = l0 + tid;
     const bool live = tid < W && l < A.L;
-    // ---- burst load: row r <-> global plane j = K0 - 2nb + r
+    // ---- burst load: row r <-> global plane j = K0 - 2nb + r.  The rows of my own slab go first; the flags of the
+    // neighbours' planes ("my input is complete") are awaited while those loads are in flight, then the halo rows follow.
     constexpr int CPR = W / 4;                                 // 16-byte chunks per row
     float s = 0.f;
-    tri3_wait_halos(A);
     {
-        for (int idx = tid; idx < R * CPR; idx += 128) {
-            const int r = idx / CPR, ch = idx - r * CPR;
-            const int j = A.K0 - 2 * nb + r;
-            const long l = l0 + 4 * ch;
-            float *dsts = t3s + (size_t)r * W + 4 * ch;
-            if (j < 0 || j >= A.n3g || l >= A.L) {
-                *reinterpret_cast<float4 *>(dsts) = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                const float *srcp;
-                if (j >= A.z0 && j < A.z0 + A.nz) srcp = A.x + (long)(j - A.z0) * A.L + l;
-                else if (j < A.z0) srcp = A.hb + (long)(j - (A.z0 - nb)) * A.L + l;
-                else srcp = A.ha + (long)(j - (A.z0 + A.nz)) * A.L + l;
-                cp_async16(dsts, srcp);
+        auto rows = [&](bool halo) {
+            for (int idx = tid; idx < R * CPR; idx += 128) {
+                const int r = idx / CPR, ch = idx - r * CPR;
+                const int j = A.K0 - 2 * nb + r;
+                const long lc = l0 + 4 * ch;
+                float *dsts = t3s + (size_t)r * W + 4 * ch;
+                const bool zero = j < 0 || j >= A.n3g || lc >= A.L;
+                const bool mine = j >= A.z0 && j < A.z0 + A.nz;
+                if (halo ? (zero || mine) : !(zero || mine)) continue;
+                if (zero) {
+                    *reinterpret_cast<float4 *>(dsts) = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const float *srcp;
+                    if (mine) srcp = A.x + (long)(j - A.z0) * A.L + lc;
+                    else if (j < A.z0) srcp = A.hb + (long)(j - (A.z0 - nb)) * A.L + lc;
+                    else srcp = A.ha + (long)(j - (A.z0 + A.nz)) * A.L + lc;
+                    cp_async16(dsts, srcp);
+                }
             }
-        }
+        };
+        rows(false);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (A.pin && live) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);      // polled while the tile is in flight
+        tri3_wait_halos(A);
+        rows(true);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
@@ -1739,19 +1747,28 @@ tri3_tile_fwd_kernel(const Tri3Args A)
             const long lc = l0 + 4 * ch;
             if (lc < A.L) *reinterpret_cast<float4 *>(A.ha_keep + (long)(r - r0) * A.L + lc) = *reinterpret_cast<const float4 *>(t3s + (size_t)r * W + 4 * ch);
         }
+        __syncthreads();                                       // (the stencil values below overwrite rows in place)
     }
     if (live) {
         const float wm = -A.wt, w2 = A.w2;
-        const float *xc = t3s + tid;                           // x_{k-2nb} of step k = K0 + i at row i
+        float *xc = t3s + tid;                                 // x_{k-2nb} of step k = K0 + i at row i
         float *Fo = A.F + l;
         const int n = A.K1 - A.K0;
-        if (!STOREF) A.csave[l] = s;
+        // every downstream rank waits for the latency of this CTA AFTER its carry has arrived: the stencil values
+        // t_k = ((0 + wm x_k) + w2 x_{k-nb}) + wm x_{k-2nb} do not depend on the carry and are formed first (in place: row i
+        // is read by steps i, i - nb and i - 2nb only), so that one addition per sample is left behind the wait
 #pragma unroll 4
         for (int i = 0; i < n; i++) {
             float t = wm * xc[(size_t)(i + 2 * nb) * W];
             t = t + w2 * xc[(size_t)(i + nb) * W];
             t = t + wm * xc[(size_t)i * W];
-            s += t;
+            xc[(size_t)i * W] = t;
+        }
+        if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+        if (!STOREF) A.csave[l] = s;
+#pragma unroll 8
+        for (int i = 0; i < n; i++) {
+            s += xc[(size_t)i * W];
             if (STOREF) Fo[(long)i * A.L] = s;
         }
         if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
@@ -2699,16 +2716,18 @@ __global__ void __launch_bounds__(256)
 pwd3_fwd_kernel(const float *__restrict__ x, const float *__restrict__ fi, const float *__restrict__ fx,
                 float *__restrict__ y, const float *__restrict__ Ss, const float *__restrict__ rr,
                 int n1, int n2, int n3, int nj1, int nj2, int z0, int n3g, const float *__restrict__ xnext,
-                double *__restrict__ partial)
+                unsigned gpp, int tg, double *__restrict__ partial)
 {
     // n3 = planes held here (global planes [z0, z0 + n3) of n3g); xnext = plane z0 + n3 of x (next rank's first)
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[5] = {0., 0., 0., 0., 0.};
-    // one block walks traces (grid-stride), its threads walk i1: the indices come without a division per voxel
-    const long ntr = (long)n2 * n3;
-    for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
-      const int i2 = (int)(tr % n2), i3 = (int)(tr / n2);
+    // one block walks a group of tg traces of one plane (the pieces of the canonical sums, pst_common.cuh), its threads
+    // walk i1: the indices come without a division per voxel
+    const int i3 = (int)(blockIdx.x / gpp), t0 = (int)(blockIdx.x - (unsigned)i3 * gpp) * tg;
+    const int t1 = t0 + tg < n2 ? t0 + tg : n2;
+    for (int i2 = t0; i2 < t1; i2++) {
+      const long tr = (long)i3 * n2 + i2;
       for (int i1 = threadIdx.x; i1 < n1; i1 += blockDim.x) {
         const size_t i = (size_t)tr * n1 + i1;
         float yi = ADD ? y[i] : 0.f, yx = ADD ? y[i + n] : 0.f;
@@ -2743,15 +2762,16 @@ __global__ void __launch_bounds__(256)
 pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, const float *__restrict__ fx,
                 const unsigned char *__restrict__ known, float *__restrict__ g, int n1, int n2, int n3,
                 int nj1, int nj2, int z0, int n3g, const float *__restrict__ yprev, const float *__restrict__ fxprev,
-                double *__restrict__ partial)
+                unsigned gpp, int tg, double *__restrict__ partial)
 {
     // yprev / fxprev: xline residual and xline taps ([w][plane]) of global plane z0 - 1 (previous rank's last)
     const size_t n = (size_t)n1 * n2 * n3;
     const long pl = (long)n1 * n2;
     double acc[1] = {0.};
-    const long ntr = (long)n2 * n3;
-    for (long tr = blockIdx.x; tr < ntr; tr += gridDim.x) {
-      const int j2 = (int)(tr % n2), j3 = (int)(tr / n2);
+    const int j3 = (int)(blockIdx.x / gpp), t0 = (int)(blockIdx.x - (unsigned)j3 * gpp) * tg;
+    const int t1 = t0 + tg < n2 ? t0 + tg : n2;
+    for (int j2 = t0; j2 < t1; j2++) {
+      const long tr = (long)j3 * n2 + j2;
       for (int j1 = threadIdx.x; j1 < n1; j1 += blockDim.x) {
         const size_t j = (size_t)tr * n1 + j1;
         float v = 0.f;
@@ -2803,10 +2823,13 @@ pwd3_adj_kernel(const float *__restrict__ yy, const float *__restrict__ fi, cons
 __global__ void __launch_bounds__(256)
 cgstep_update_kernel(float *__restrict__ x, float *__restrict__ S, const float *__restrict__ g,
                      float *__restrict__ rr, float *__restrict__ Ss, const float *__restrict__ gg,
-                     float alfa, float beta, size_t n, double *__restrict__ partial)
+                     float alfa, float beta, Span Sp, double *__restrict__ partial)
 {
     double acc[1] = {0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = Sp.n;
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float s = S[i];
         s *= beta;
         s += alfa * g[i];
@@ -2828,11 +2851,15 @@ cgstep_update_kernel(float *__restrict__ x, float *__restrict__ S, const float *
 }
 
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float *__restrict__ v, size_t n, double *__restrict__ partial)
+sumsq2_kernel(const float *__restrict__ v, Span Sp, double *__restrict__ partial)      // both components of v[2][n]
 {
     double acc[1] = {0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         acc[0] += (double)v[i] * v[i];
+        acc[0] += (double)v[i + Sp.n] * v[i + Sp.n];
+    }
     pst_block_reduce<1>(acc, partial);
 }
 
@@ -2957,6 +2984,15 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     };
     float *x = d_out;
     const int threads = 256, grid = pst_grid_for(c, n, threads);
+    // canonical sums (pst_common.cuh): pieces = groups of tg traces of one plane (stencil kernels) / PST_RED_CH elements
+    // of one plane (vector kernels); the CG scalars do not depend on the slab decomposition
+    const int tg = n1 >= (int)PST_RED_CH ? 1 : (int)(PST_RED_CH / (unsigned)n1);
+    const unsigned gpp = (unsigned)((n2 + tg - 1) / tg), gridt = gpp * (unsigned)n3;
+    const Span Sp = pst_span_canon(pln, n3);
+    const unsigned gridc = Sp.ppp * (unsigned)n3;
+    PST_TRY(pst_reserve_partials(c, gridt > gridc ? gridt : gridc, n3g));
+    auto finish_t = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)gpp, n3, z0, n3g, nv, rec); };
+    auto finish_c = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)Sp.ppp, n3, z0, n3g, nv, rec); };
     double h[PST_RED_SLOTS];
     PST_LAUNCHB(c, PST_K_OTHER, 48.0 * (double)n, (pwd3_taps_kernel<NW><<<grid, threads, 0, c->stream>>>(d_pp, d_qq, fi, fx, n, tb)));
     for (int w = 0; dist && w < NA; w++) PST_TRY(halo_prev(fx + (size_t)w * n, fxprev + (size_t)w * pln));   // once: taps are fixed
@@ -2967,12 +3003,12 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     else PST_LAUNCH(c, PST_K_OTHER, (fill_kernel<<<grid, threads, 0, c->stream>>>(rr, -0.0f, 2 * n)));
     PST_TRY(halo_next(x));
     PST_LAUNCHB(c, PST_K_ALLPASS, 60.0 * (double)n,
-                (pwd3_fwd_kernel<NW, true, false><<<grid, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, c->d_partial)));
+                (pwd3_fwd_kernel<NW, true, false><<<gridt, threads, 0, c->stream>>>(x, fi, fx, rr, nullptr, nullptr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, gpp, tg, c->d_partial)));
     PST_CUDA(cudaMemsetAsync(S, 0, n * sizeof(float), c->stream));
     PST_CUDA(cudaMemsetAsync(Ss, 0, 2 * n * sizeof(float), c->stream));
     // dpr0 = rr.rr (:1042)
-    PST_LAUNCH(c, PST_K_OTHER, (sumsq_kernel<<<grid, threads, 0, c->stream>>>(rr, 2 * n, c->d_partial)));
-    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_LAUNCH(c, PST_K_OTHER, (sumsq2_kernel<<<gridc, threads, 0, c->stream>>>(rr, Sp, c->d_partial)));
+    PST_TRY(finish_c(1, 8));
     PST_TRY(pst_fetch_record(c, 8, 1, h));
     const double dpr0 = h[0];
     double dpg0 = 1., rr2 = dpr0;
@@ -2980,12 +3016,12 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     for (int iter = 0; iter < niter; iter++) {
         PST_TRY(halo_prev(rr + n, yprev));
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 13.0) * (double)n,
-                    (pwd3_adj_kernel<NW><<<grid, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, nj1, nj2, z0, n3g, yprev, fxprev, c->d_partial)));
-        PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+                    (pwd3_adj_kernel<NW><<<gridt, threads, 0, c->stream>>>(rr, fi, fx, known, g, n1, n2, n3, nj1, nj2, z0, n3g, yprev, fxprev, gpp, tg, c->d_partial)));
+        PST_TRY(finish_t(1, 8));
         PST_TRY(halo_next(g));
         PST_LAUNCHB(c, PST_K_ALLPASS, (8.0 * NA + 28.0) * (double)n,
-                    (pwd3_fwd_kernel<NW, false, true><<<grid, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, c->d_partial)));
-        PST_TRY(pst_finish_reduce(c, grid, 5, 9));
+                    (pwd3_fwd_kernel<NW, false, true><<<gridt, threads, 0, c->stream>>>(g, fi, fx, gg, Ss, rr, n1, n2, n3, nj1, nj2, z0, n3g, xnext, gpp, tg, c->d_partial)));
+        PST_TRY(finish_t(5, 9));
         PST_TRY(pst_fetch_record(c, 8, 1, h));
         const double g2 = h[0];
         double dpr, dpg;
@@ -3011,8 +3047,8 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
             beta = (-gds * gdr + gdg * sdr) / determ;
         }
         PST_LAUNCHB(c, PST_K_CGDIR, 60.0 * (double)n,
-                    (cgstep_update_kernel<<<grid, threads, 0, c->stream>>>(x, S, g, rr, Ss, gg, (float)alfa, (float)beta, n, c->d_partial)));
-        PST_TRY(pst_finish_reduce(c, grid, 1, 10));
+                    (cgstep_update_kernel<<<gridc, threads, 0, c->stream>>>(x, S, g, rr, Ss, gg, (float)alfa, (float)beta, Sp, c->d_partial)));
+        PST_TRY(finish_c(1, 10));
         PST_TRY(pst_fetch_record(c, 10, 1, h));
         rr2 = h[0];
         c->stats.cg_iterations++;

@@ -1284,11 +1284,13 @@ sint_init_kernel(const float *__restrict__ d, float *__restrict__ p, float *__re
 }
 // r += L x (known samples) ; partial r.r
 __global__ void __launch_bounds__(256)
-sint_resid_kernel(float *__restrict__ r, const float *__restrict__ x, const unsigned char *__restrict__ known, size_t n,
+sint_resid_kernel(float *__restrict__ r, const float *__restrict__ x, const unsigned char *__restrict__ known, Span Sp,
                   double *__restrict__ partial)
 {
     double acc[1] = {0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float v = r[i];
         if (known[i]) v += x[i];
         r[i] = v;
@@ -1312,11 +1314,13 @@ sint_grad_kernel(const float *__restrict__ p, const float *__restrict__ x, const
 template <bool FIRST>
 __global__ void __launch_bounds__(256)
 sint_dir_kernel(float *__restrict__ gp, float *__restrict__ gx, const unsigned char *__restrict__ known,
-                float *__restrict__ sp, float *__restrict__ sx, float *__restrict__ sr, float alpha, size_t n,
+                float *__restrict__ sp, float *__restrict__ sx, float *__restrict__ sr, float alpha, Span Sp,
                 double *__restrict__ partial)
 {
     double acc[3] = {0., 0., 0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         const float gpi = gp[i], gxi = gx[i];
         float gri = 0.f;
         if (known[i]) gri += gxi;
@@ -1345,19 +1349,23 @@ sint_update_kernel(float *__restrict__ p, float *__restrict__ x, float *__restri
     }
 }
 __global__ void __launch_bounds__(256)
-sint_sumsq_kernel(const float *__restrict__ v, size_t n, double *__restrict__ partial)
+sint_sumsq_kernel(const float *__restrict__ v, Span Sp, double *__restrict__ partial)
 {
     double acc[1] = {0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step)
         acc[0] += (double)v[i] * v[i];
     pst_block_reduce<1>(acc, partial);
 }
 // known = (mask != 0), partial count
 __global__ void __launch_bounds__(256)
-sint_known_kernel(const float *__restrict__ mask, unsigned char *__restrict__ known, size_t n, double *__restrict__ partial)
+sint_known_kernel(const float *__restrict__ mask, unsigned char *__restrict__ known, Span Sp, double *__restrict__ partial)
 {
     double acc[1] = {0.};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(Sp, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         const unsigned char k = mask[i] != 0.f;
         known[i] = k;
         acc[0] += k;
@@ -1407,6 +1415,11 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     for (float **q : extv) PST_TRY(pst_arena_get(c, nex, q));
     PST_TRY(pst_arena_get(c, n, &known));
     const int threads = 256, grid = pst_grid_for(c, n, threads);
+    // canonical sums (pst_common.cuh): the CG scalars do not depend on the slab decomposition
+    const Span Sp = pst_span_canon(plane, nz);
+    const unsigned gridc = Sp.ppp * (unsigned)nz;
+    PST_TRY(pst_reserve_partials(c, gridc, n3));
+    auto finish = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)Sp.ppp, nz, z0, n3, nv, rec); };
     double h[PST_RED_SLOTS];
     float *const eS = eA + (size_t)offs * plane;                 // the slab inside the extended A volume
 
@@ -1424,8 +1437,8 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     PST_TRY(swap_ab(c, eA, dipB, nzl, n1, n2));
     PST_TRY(transpose_planes(c, d_din, dA, n2, n1, nz));
     PST_TRY(transpose_planes(c, d_mask, wA1, n2, n1, nz));
-    PST_LAUNCH(c, PST_K_OTHER, (sint_known_kernel<<<grid, threads, 0, c->stream>>>(wA1, known, n, c->d_partial)));
-    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_LAUNCH(c, PST_K_OTHER, (sint_known_kernel<<<gridc, threads, 0, c->stream>>>(wA1, known, Sp, c->d_partial)));
+    PST_TRY(finish(1, 8));
     PST_TRY(pst_fetch_record(c, 8, 1, h));
     // "lam += 1." on a float saturates at 2^24 (soint3d_cfuns.c:2583-2592)
     float lam = (float)std::min(h[0], 16777216.0);
@@ -1472,8 +1485,8 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
 
     PST_LAUNCH(c, PST_K_OTHER, (sint_init_kernel<<<grid, threads, 0, c->stream>>>(dA, p, r, n)));
     PST_TRY(S_fwd(p, x));
-    PST_LAUNCH(c, PST_K_OTHER, (sint_resid_kernel<<<grid, threads, 0, c->stream>>>(r, x, known, n, c->d_partial)));
-    PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+    PST_LAUNCH(c, PST_K_OTHER, (sint_resid_kernel<<<gridc, threads, 0, c->stream>>>(r, x, known, Sp, c->d_partial)));
+    PST_TRY(finish(1, 8));
     PST_TRY(pst_fetch_record(c, 8, 1, h));
     if (h[0] != 0.) {
         double gn, gnp = 0., alpha, beta, g0 = 0., dg;
@@ -1481,20 +1494,20 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
             PST_LAUNCH(c, PST_K_CGHEAD, (sint_grad_kernel<<<grid, threads, 0, c->stream>>>(p, x, r, known, ceps, gp, gx, n)));
             PST_TRY(S_adj_add(gp, gx));
             PST_TRY(S_fwd(gp, gx));
-            PST_LAUNCH(c, PST_K_OTHER, (sint_sumsq_kernel<<<grid, threads, 0, c->stream>>>(gp, n, c->d_partial)));
-            PST_TRY(pst_finish_reduce(c, grid, 1, 8));
+            PST_LAUNCH(c, PST_K_OTHER, (sint_sumsq_kernel<<<gridc, threads, 0, c->stream>>>(gp, Sp, c->d_partial)));
+            PST_TRY(finish(1, 8));
             PST_TRY(pst_fetch_record(c, 8, 1, h));
             gn = h[0];
             if (iter == 0) {
                 g0 = gn;
-                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<true><<<grid, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, 0.f, n, c->d_partial)));
+                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<true><<<gridc, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, 0.f, Sp, c->d_partial)));
             } else {
                 alpha = gn / gnp;
                 dg = gn / g0;
                 if (alpha < tol || dg < tol) break;
-                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<false><<<grid, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, (float)alpha, n, c->d_partial)));
+                PST_LAUNCH(c, PST_K_CGDIR, (sint_dir_kernel<false><<<gridc, threads, 0, c->stream>>>(gp, gx, known, sp, sx, sr, (float)alpha, Sp, c->d_partial)));
             }
-            PST_TRY(pst_finish_reduce(c, grid, 3, 9));
+            PST_TRY(finish(3, 9));
             PST_TRY(pst_fetch_record(c, 9, 3, h));
             beta = h[0] + (double)ceps * (h[1] - h[2]);
             alpha = -gn / beta;
