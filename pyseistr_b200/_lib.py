@@ -80,6 +80,7 @@ SIGNATURES = {
     "pst_paint2d_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "pst_allpass_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pst_smooth3_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "pst_selftest_axis3_slabs": (_i, [_vp, _vp, _i, _i, _i, _i, _i]),
     "pst_divne_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),
     "pst_smooth3": (_i, [_vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp]),
     "pst_smoothcf": (_i, [_vp, _fp] + [_i] * 14 + [_fp]),

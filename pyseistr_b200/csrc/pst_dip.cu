@@ -1712,7 +1712,7 @@ tri3_tile_fwd_kernel(const Tri3Args A)
     float s = 0.f;
     {
         auto rows = [&](bool halo) {
-            for (int idx = tid; idx < R * CPR; idx += 128) {
+            for (int idx = tid; idx < R * CPR; idx += blockDim.x) {
                 const int r = idx / CPR, ch = idx - r * CPR;
                 const int j = A.K0 - 2 * nb + r;
                 const long lc = l0 + 4 * ch;
@@ -1742,7 +1742,7 @@ tri3_tile_fwd_kernel(const Tri3Args A)
     if (!STOREF && A.ha_keep) {
         // keep the planes read from the next rank (rows of planes [z1, K1)) for my backward kernel
         const int r0 = A.z0 + A.nz - (A.K0 - 2 * nb);
-        for (int idx = tid; idx < (R - r0) * CPR; idx += 128) {
+        for (int idx = tid; idx < (R - r0) * CPR; idx += blockDim.x) {
             const int r = r0 + idx / CPR, ch = idx % CPR;
             const long lc = l0 + 4 * ch;
             if (lc < A.L) *reinterpret_cast<float4 *>(A.ha_keep + (long)(r - r0) * A.L + lc) = *reinterpret_cast<const float4 *>(t3s + (size_t)r * W + 4 * ch);
@@ -1790,7 +1790,7 @@ tri3_tile_bwd_kernel(const Tri3Args A)
     constexpr int CPR = W / 4;
     float s = 0.f;
     if (!RCMP) {
-        for (int idx = tid; idx < R * CPR; idx += 128) {
+        for (int idx = tid; idx < R * CPR; idx += blockDim.x) {
             const int r = idx / CPR, ch = idx - r * CPR;
             const long lc = l0 + 4 * ch;
             if (lc < A.L) cp_async16(t3s + (size_t)r * W + 4 * ch, A.F + (long)r * A.L + lc);
@@ -1803,7 +1803,7 @@ tri3_tile_bwd_kernel(const Tri3Args A)
         // (no halo flags to wait for: the forward kernel of this pass already did, and the planes of the previous rank
         // stay untouched until its backward kernel, which waits for my carries)
         const int RX = R + 2 * nb;
-        for (int idx = tid; idx < RX * CPR; idx += 128) {
+        for (int idx = tid; idx < RX * CPR; idx += blockDim.x) {
             const int r = idx / CPR, ch = idx - r * CPR;
             const int j = A.K0 - 2 * nb + r;
             const long lc = l0 + 4 * ch;
@@ -1863,6 +1863,164 @@ tri3_tile_bwd_kernel(const Tri3Args A)
     }
 }
 
+// ---- distributed axis 3, register kernels (short slabs: 8 ranks at n3 = 1024) ------------------------------------------
+// One thread owns one line and keeps the line's local rows in REGISTERS (slots, indices known at compile time): no
+// shared memory, no block synchronisation after the halo flags, ~140 independent coalesced loads in flight per thread.
+// The forward kernel forms the stencil values t, waits for its line's carry, adds the t's to it in order and hands the
+// result on; it stores nothing but the incoming carry.  The backward kernel loads the same rows again (4 B per voxel,
+// instead of 4 written + 4 read for a staged F), repeats the forward additions from the saved carry -- same operands,
+// same order, same bits -- while it waits for the backward carry, then runs the backward sum with the fold.  The pass
+// moves 12 B per voxel instead of 16, and one addition per sample is left behind each wait.
+// Slot q <-> local row r = q - off of the x rows (planes K0 - 2nb + r), t / F of step k = K0 + (q - off) replace x in slot q.
+// EDGE: 0 interior rank, 1 first rank (left reflection: the rows at the bottom, off = 0), 2 last rank (right reflection:
+// the rows at the top are aligned with the last slot, off = MAXT - n), so every fold index is a compile-time slot.
+template <int NB, int MAXT, int EDGE>
+__device__ __forceinline__ void tri3_reg_load(const Tri3Args &A, long l, bool live, int off, const float *ha_src,
+                                              float (&v)[MAXT + 2 * NB], bool before_flags)
+{
+    constexpr int MAXS = MAXT + 2 * NB;
+    const int RX = A.K1 - A.K0 + 2 * NB;
+#pragma unroll
+    for (int q = 0; q < MAXS; q++) {
+        const int r = q - off, j = A.K0 - 2 * NB + r;
+        const bool in = live && r >= 0 && r < RX && j >= 0 && j < A.n3g;
+        const bool mine = j >= A.z0 && j < A.z0 + A.nz;
+        if (before_flags) {
+            v[q] = 0.f;
+            if (in && mine) v[q] = __ldcg(A.x + (long)(j - A.z0) * A.L + l);
+        } else if (in && !mine) {
+            v[q] = (j < A.z0) ? __ldcg(A.hb + (long)(j - (A.z0 - NB)) * A.L + l) : __ldcg(ha_src + (long)(j - (A.z0 + A.nz)) * A.L + l);
+        }
+    }
+}
+
+template <int NB, int MAXT>
+__global__ void __launch_bounds__(64)
+tri3_reg_fwd_kernel(const Tri3Args A)
+{
+    constexpr int MAXS = MAXT + 2 * NB;
+    const long l = (long)blockIdx.x * 64 + threadIdx.x;
+    const bool live = l < A.L;
+    const int n = A.K1 - A.K0;
+    float v[MAXS];
+    tri3_reg_load<NB, MAXT, 0>(A, l, live, 0, A.ha, v, true);       // own rows: in flight while the flags are awaited
+    tri3_wait_halos(A);
+    tri3_reg_load<NB, MAXT, 0>(A, l, live, 0, A.ha, v, false);
+    if (!live) return;
+    if (A.ha_keep) {
+        // keep the planes read from the next rank (planes [z1, K1)) for my backward kernel: that rank overwrites them in
+        // its own backward kernel, which runs before mine
+#pragma unroll
+        for (int q = 0; q < MAXS; q++) {
+            const int j = A.K0 - 2 * NB + q;
+            if (j >= A.z0 + A.nz && j < A.K1 && j < A.n3g) A.ha_keep[(long)(j - (A.z0 + A.nz)) * A.L + l] = v[q];
+        }
+    }
+    const float wm = -A.wt, w2 = A.w2;
+#pragma unroll
+    for (int q = 0; q < MAXT; q++) {
+        float t = wm * v[q + 2 * NB];
+        t = t + w2 * v[q + NB];
+        t = t + wm * v[q];
+        v[q] = t;
+    }
+    float s = 0.f;
+    if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    A.csave[l] = s;
+#pragma unroll
+    for (int q = 0; q < MAXT; q++) if (q < n) s += v[q];
+    if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
+}
+
+template <int NB, int MAXT, int EDGE>
+__global__ void __launch_bounds__(64)
+tri3_reg_bwd_kernel(const Tri3Args A)
+{
+    constexpr int MAXS = MAXT + 2 * NB;
+    const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
+    if (l >= A.L) return;
+    const int n = A.K1 - A.K0, off = (EDGE == 2) ? MAXT - n : 0;
+    float v[MAXS];
+    // (no halo flags to wait for: the forward kernel of this pass did, and the previous rank's planes stay untouched until
+    // its backward thread of this line has received the carry sent below)
+    tri3_reg_load<NB, MAXT, EDGE>(A, l, true, off, A.ha_keep ? A.ha_keep : A.ha, v, true);
+    tri3_reg_load<NB, MAXT, EDGE>(A, l, true, off, A.ha_keep ? A.ha_keep : A.ha, v, false);
+    const float wm = -A.wt, w2 = A.w2;
+#pragma unroll
+    for (int q = 0; q < MAXT; q++) {
+        float t = wm * v[q + 2 * NB];
+        t = t + w2 * v[q + NB];
+        t = t + wm * v[q];
+        v[q] = t;
+    }
+    float sf = A.csave[l];
+#pragma unroll
+    for (int q = 0; q < MAXT; q++) if (q >= off && q - off < n) { sf += v[q]; v[q] = sf; }
+    float s = 0.f;
+    if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    float *dl = A.dst + l;
+    float park[NB];                                            // EDGE 2: B of the right pad; EDGE 1: heads awaiting the left pad
+#pragma unroll
+    for (int q = MAXT - 1; q >= 0; q--) {
+        if (q >= off && q - off < n) {
+            s += v[q];
+            const int i = q - off;                             // step k = K0 + i
+            if (EDGE == 2) {
+                // k = K1 - 1 - jt with jt = MAXT - 1 - q;  right pad: k >= nb + n3g <=> jt < nb;  the last nb samples
+                // (gi >= n3g - nb <=> jt in [nb, 2nb)) take B_{nb + n3g + (n3g - 1 - gi)} = the value parked at 2nb - 1 - jt
+                const int jt = MAXT - 1 - q;
+                if (jt < NB) park[jt < NB ? jt : 0] = s;
+                else {
+                    float y = s;
+                    if (jt < 2 * NB) y = y + park[(2 * NB - 1 - jt) >= 0 && (2 * NB - 1 - jt) < NB ? (2 * NB - 1 - jt) : 0];
+                    dl[(long)(A.K0 + i - NB - A.z0) * A.L] = y;
+                }
+            } else if (EDGE == 1) {
+                // K0 = 0, q = k.  k >= 2nb: sample gi = k - nb; k in [nb, 2nb): heads (completed by the left pad);
+                // k < nb: left pad, y_gi = head_gi + B_k with gi = nb - 1 - k
+                if (q >= 2 * NB) dl[(long)(q - NB) * A.L] = s;
+                else if (q >= NB) park[(q - NB) >= 0 && (q - NB) < NB ? (q - NB) : 0] = s;
+                else dl[(long)(NB - 1 - q) * A.L] = park[(NB - 1 - q) >= 0 && (NB - 1 - q) < NB ? (NB - 1 - q) : 0] + s;
+            } else {
+                dl[(long)(A.K0 + i - NB - A.z0) * A.L] = s;
+            }
+        }
+    }
+    if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
+}
+
+// register kernels: radii instantiated, rows per thread
+#define PST_T3_REG_MAXT 136
+static bool tri3_reg_ok(int nb, int rows_max)
+{
+    static const bool on = []() { const char *e = getenv("PST_TRI3_REG"); return !(e && e[0] == '0'); }();
+    return on && rows_max <= PST_T3_REG_MAXT && (nb == 2 || nb == 3 || nb == 4 || nb == 5 || nb == 6 || nb == 8);
+}
+template <int NB>
+static void tri3_reg_launch_nb(const Tri3Args &A, bool fwd, int edge, unsigned blocks, cudaStream_t st)
+{
+    if (fwd) tri3_reg_fwd_kernel<NB, PST_T3_REG_MAXT><<<blocks, 64, 0, st>>>(A);
+    else if (edge == 1) tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 1><<<blocks, 64, 0, st>>>(A);
+    else if (edge == 2) tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 2><<<blocks, 64, 0, st>>>(A);
+    else tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 0><<<blocks, 64, 0, st>>>(A);
+}
+// the forward kernel reads 4 B per voxel, the backward kernel reads 4 and writes 4
+static int tri3_reg_launch(pst_ctx *c, const Tri3Args &A, bool fwd, int edge, size_t nvox, int cls)
+{
+    const unsigned blocks = (unsigned)((A.L + 63) / 64);
+    PST_LAUNCHB(c, cls, (fwd ? 4.0 : 8.0) * (double)nvox,
+        switch (A.nb) {
+            case 2: tri3_reg_launch_nb<2>(A, fwd, edge, blocks, c->stream); break;
+            case 3: tri3_reg_launch_nb<3>(A, fwd, edge, blocks, c->stream); break;
+            case 4: tri3_reg_launch_nb<4>(A, fwd, edge, blocks, c->stream); break;
+            case 5: tri3_reg_launch_nb<5>(A, fwd, edge, blocks, c->stream); break;
+            case 6: tri3_reg_launch_nb<6>(A, fwd, edge, blocks, c->stream); break;
+            default: tri3_reg_launch_nb<8>(A, fwd, edge, blocks, c->stream); break;
+        });
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
 // widest tile (lines per CTA) whose rows fit in shared memory; 0 = use the line kernels
 static int tri3_tile_width(int rows_max, long L, const void *a, const void *b, const void *c2, const void *d, const void *e)
 {
@@ -1873,7 +2031,7 @@ static int tri3_tile_width(int rows_max, long L, const void *a, const void *b, c
     // narrower tiles leave too few chain threads per SM: measured at 2 GPUs (527 rows, W = 32) the tile
     // kernels take 2.6 ms per launch against 1.4 ms for the line kernels, so tall slabs keep the latter
     static const int wmax = []() { const char *v = getenv("PST_TRI3_WMAX"); return v ? atoi(v) : 128; }();   // A/B: cap the tile width
-    const int ws[2] = {128, 64};
+    const int ws[3] = {128, 64, 32};                          // 32 only on request (PST_TRI3_WMAX=32)
     for (int w : ws) if (w <= wmax && (size_t)rows_max * w * 4 <= 75 * 1024) return w;
     return 0;
 }
@@ -1967,6 +2125,88 @@ int pst_comm_halo_exchange(pst_ctx *c, const float *send_lo, const float *send_h
 int pst_comm_mailbox(pst_ctx *c, size_t L, pst_mailbox_view *v);                      // pst_comm.cu
 int pst_comm_check(pst_ctx *c);
 
+// launches of the tile kernels (shared by the distributed pass and the single-GPU short-axis path)
+static int tri3_tiles_attr(pst_ctx *c)
+{
+    static bool attr_dev[64] = {};                       // per-device function attribute
+    bool &attr_done = attr_dev[c->device & 63];
+    if (!attr_done) {
+#define PST_T3_ATTR(K) PST_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024))
+        PST_T3_ATTR((tri3_tile_fwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, true>));
+        PST_T3_ATTR((tri3_tile_fwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, false>));
+        PST_T3_ATTR((tri3_tile_bwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, true>));
+        PST_T3_ATTR((tri3_tile_bwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, false>));
+#undef PST_T3_ATTR
+        attr_done = true;
+    }
+    return PST_OK;
+}
+static int tri3_tiles_fwd(pst_ctx *c, const Tri3Args &A, int W, unsigned blocks, bool rcmp, size_t nvox)
+{
+    PST_TRY(tri3_tiles_attr(c));
+    const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * A.nb) * W * 4;
+    const int T = W < 128 ? (W < 64 ? 32 : 64) : 128;        // threads = lines of the tile
+    PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)nvox,
+        if (rcmp) {
+            if (W == 128) tri3_tile_fwd_kernel<128, false><<<blocks, T, smem_f, c->stream>>>(A);
+            else if (W == 64) tri3_tile_fwd_kernel<64, false><<<blocks, T, smem_f, c->stream>>>(A);
+            else tri3_tile_fwd_kernel<32, false><<<blocks, T, smem_f, c->stream>>>(A);
+        } else {
+            if (W == 128) tri3_tile_fwd_kernel<128, true><<<blocks, T, smem_f, c->stream>>>(A);
+            else if (W == 64) tri3_tile_fwd_kernel<64, true><<<blocks, T, smem_f, c->stream>>>(A);
+            else tri3_tile_fwd_kernel<32, true><<<blocks, T, smem_f, c->stream>>>(A);
+        });
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+static int tri3_tiles_bwd(pst_ctx *c, const Tri3Args &A, int W, unsigned blocks, bool rcmp, size_t nvox, int cls)
+{
+    const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * A.nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
+    const int T = W < 128 ? (W < 64 ? 32 : 64) : 128;
+    PST_LAUNCHB(c, cls, 8.0 * (double)nvox,
+        if (rcmp) {
+            if (W == 128) tri3_tile_bwd_kernel<128, true><<<blocks, T, smem_f, c->stream>>>(A);
+            else if (W == 64) tri3_tile_bwd_kernel<64, true><<<blocks, T, smem_f, c->stream>>>(A);
+            else tri3_tile_bwd_kernel<32, true><<<blocks, T, smem_f, c->stream>>>(A);
+        } else {
+            if (W == 128) tri3_tile_bwd_kernel<128, false><<<blocks, T, smem_b, c->stream>>>(A);
+            else if (W == 64) tri3_tile_bwd_kernel<64, false><<<blocks, T, smem_b, c->stream>>>(A);
+            else tri3_tile_bwd_kernel<32, false><<<blocks, T, smem_b, c->stream>>>(A);
+        });
+    PST_CUDA(cudaGetLastError());
+    return PST_OK;
+}
+
+// Single GPU, short third axis (PST_TRI3_SOLO=1): the tile kernels of the distributed pass on the whole axis (first and
+// last rank at once: no carries, no halos).  Exists to measure and profile those kernels without neighbours.
+static int smooth_axis3_solo(pst_ctx *c, const DipGeom &g, const float *src, float *dst, float *scr, int W)
+{
+    Tri3Args A{};
+    const int nb = g.r3;
+    A.x = src; A.F = scr; A.dst = dst; A.L = (long)g.n1 * g.n2; A.l0 = 0; A.l1 = A.L;
+    A.n3g = g.n3; A.z0 = 0; A.nz = g.n3; A.nb = nb; A.K0 = 0; A.K1 = g.n3 + 2 * nb;
+    A.wt = (float)(1.0 / ((double)nb * nb));
+    A.w2 = (float)(2. * A.wt);
+    A.err = nullptr; A.epoch = 1;                        // (no waits: nothing can time out)
+    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
+    A.rev = rev_on ? 1 : 0;
+    static const bool fake_reg = []() { const char *e = getenv("PST_TRI3_SOLO"); return e && e[0] == '2'; }();
+    if (fake_reg && tri3_reg_ok(nb, g.n3 + nb)) {
+        // TIMING ONLY (wrong numbers): the register kernels as an interior rank would run them, halo rows read from the
+        // volume itself, no carries
+        A.K0 = nb; A.K1 = g.n3 + nb; A.n3g = g.n3 + 1000; A.hb = src; A.ha = src; A.csave = scr;
+        PST_TRY(tri3_reg_launch(c, A, true, 0, g.n, PST_K_TRI3));
+        PST_TRY(tri3_reg_launch(c, A, false, 0, g.n, PST_K_TRI3));
+        c->stats.smooth_passes++;
+        return PST_OK;
+    }
+    const unsigned blocks = (unsigned)((A.L + W - 1) / W);
+    PST_TRY(tri3_tiles_fwd(c, A, W, blocks, false, g.n));
+    PST_TRY(tri3_tiles_bwd(c, A, W, blocks, false, g.n, PST_K_TRI3));
+    c->stats.smooth_passes++;
+    return PST_OK;
+}
+
 static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, float *dst, float *scr)
 {
     const int nb = g.r3, nz = g.n3, n3g = g.n3g;
@@ -2012,36 +2252,20 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     // against 1.16 ms): these kernels are bound by the serial per-thread chains of their CTAs, not by HBM, and the
     // recomputation lengthens exactly that.  Off by default.
     static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return e && e[0] == '1'; }();
-    const bool rcmp = rcmp_on && W > 0;
+    // register kernels (short slabs, first choice): always the recompute scheme
+    const bool reg = c->nranks >= 2 && tri3_reg_ok(nb, nz_max + nb);
+    const int edge = first ? 1 : (last ? 2 : 0);
+    const bool rcmp = (rcmp_on && W > 0) || reg;
     A.csave = g.cin;
     A.ha_keep = (rcmp && peer && !last) ? g.ha : nullptr;
-    const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
     // forward sums: carries flow rank -> rank+1, CTA by CTA, through the neighbour's mailbox
     A.cin = first ? nullptr : mb.cf_in;  A.fin = mb.ff_in;
     A.cout = last ? nullptr : mb.cf_out; A.fout = mb.ff_out;
     A.pin = first ? nullptr : mb.pf_in; A.pout = last ? nullptr : mb.pf_out;
-    if (W) {
-        static bool attr_dev[64] = {};                       // per-device function attribute
-        bool &attr_done = attr_dev[c->device & 63];
-        if (!attr_done) {
-#define PST_T3_ATTR(K) PST_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024))
-            PST_T3_ATTR((tri3_tile_fwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, true>));
-            PST_T3_ATTR((tri3_tile_fwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_fwd_kernel<32, false>));
-            PST_T3_ATTR((tri3_tile_bwd_kernel<128, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, true>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, true>));
-            PST_T3_ATTR((tri3_tile_bwd_kernel<128, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<64, false>)); PST_T3_ATTR((tri3_tile_bwd_kernel<32, false>));
-#undef PST_T3_ATTR
-            attr_done = true;
-        }
-        PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
-            if (rcmp) {
-                if (W == 128) tri3_tile_fwd_kernel<128, false><<<blocks, 128, smem_f, c->stream>>>(A);
-                else if (W == 64) tri3_tile_fwd_kernel<64, false><<<blocks, 128, smem_f, c->stream>>>(A);
-                else tri3_tile_fwd_kernel<32, false><<<blocks, 128, smem_f, c->stream>>>(A);
-            } else {
-                if (W == 128) tri3_tile_fwd_kernel<128, true><<<blocks, 128, smem_f, c->stream>>>(A);
-                else if (W == 64) tri3_tile_fwd_kernel<64, true><<<blocks, 128, smem_f, c->stream>>>(A);
-                else tri3_tile_fwd_kernel<32, true><<<blocks, 128, smem_f, c->stream>>>(A);
-            });
+    if (reg) {
+        PST_TRY(tri3_reg_launch(c, A, true, edge, g.n, PST_K_TRI3));
+    } else if (W) {
+        PST_TRY(tri3_tiles_fwd(c, A, W, blocks, rcmp, g.n));
     } else {
         static const bool win_on = []() { const char *e = getenv("PST_TRI3_WIN"); return !(e && e[0] == '0'); }();
         PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n,
@@ -2065,17 +2289,10 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
     A.rev = rev_on ? 1 : 0;
     static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? PST_K_TRI3BWD : PST_K_TRI3; }();
-    if (W) {
-        PST_LAUNCHB(c, bwd_cls, 8.0 * (double)g.n,
-            if (rcmp) {
-                if (W == 128) tri3_tile_bwd_kernel<128, true><<<blocks, 128, smem_f, c->stream>>>(A);
-                else if (W == 64) tri3_tile_bwd_kernel<64, true><<<blocks, 128, smem_f, c->stream>>>(A);
-                else tri3_tile_bwd_kernel<32, true><<<blocks, 128, smem_f, c->stream>>>(A);
-            } else {
-                if (W == 128) tri3_tile_bwd_kernel<128, false><<<blocks, 128, smem_b, c->stream>>>(A);
-                else if (W == 64) tri3_tile_bwd_kernel<64, false><<<blocks, 128, smem_b, c->stream>>>(A);
-                else tri3_tile_bwd_kernel<32, false><<<blocks, 128, smem_b, c->stream>>>(A);
-            });
+    if (reg) {
+        PST_TRY(tri3_reg_launch(c, A, false, edge, g.n, bwd_cls));
+    } else if (W) {
+        PST_TRY(tri3_tiles_bwd(c, A, W, blocks, rcmp, g.n, bwd_cls));
     } else {
         PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)g.n, (tri3_dist_bwd_kernel<<<blocks, 128, 0, c->stream>>>(A)));
     }
@@ -2092,35 +2309,14 @@ static int smooth_axis(pst_ctx *c, const DipGeom &g, int axis, const float *src,
     const int nx = nn[axis], nb = rr[axis];
     const int cls = axis == 0 ? PST_K_TRI1 : (axis == 1 ? PST_K_TRI2 : PST_K_TRI3);
     if (fused) *fused = false;
+    static const bool solo3 = []() { const char *e = getenv("PST_TRI3_SOLO"); return e && (e[0] == '1' || e[0] == '2'); }();
+    if (axis == 2 && !g.dist && solo3 && nb > 1 && 2 * nb <= g.n3 && !(epi && epi->kind != EPI_NONE)) {
+        const int W = tri3_tile_width(g.n3 + 4 * nb, (long)g.n1 * g.n2, src, dst, scr, nullptr, nullptr);
+        if (W) return smooth_axis3_solo(c, g, src, dst, scr, W);
+    }
     if (axis == 2 && g.dist) {
         c->stats.smooth_passes++;
         return smooth_axis3_dist(c, g, src, dst, scr);
-    }
-    // measurement hook: run the DISTRIBUTED axis-3 tile kernels on one GPU (no neighbours, no carries)
-    // to time them without communication: PST_TRI3_TILE_SELFTEST=1 and a slab-shaped volume
-    static const bool selftest = []() { const char *e = getenv("PST_TRI3_TILE_SELFTEST"); return e && e[0] == '1'; }();
-    if (selftest && axis == 2 && 2 * nb <= g.n3 && !(epi && epi->kind != EPI_NONE)) {
-        const long L = (long)g.n1 * g.n2;
-        const int W = tri3_tile_width(g.n3 + 3 * nb, L, src, dst, scr, nullptr, nullptr);
-        if (W == 128) {
-            c->stats.smooth_passes++;
-            Tri3Args A{};
-            A.x = src; A.F = scr; A.dst = dst; A.L = L; A.l0 = 0; A.l1 = L;
-            A.n3g = g.n3; A.z0 = 0; A.nz = g.n3; A.nb = nb; A.K0 = 0; A.K1 = g.n3 + 2 * nb;
-            A.wt = (float)(1.0 / ((double)nb * nb)); A.w2 = (float)(2. * A.wt);
-            const unsigned blocks = (unsigned)((L + 127) / 128);
-            static bool ad_dev[64] = {};
-            bool &ad = ad_dev[c->device & 63];
-            if (!ad) {
-                PST_CUDA(cudaFuncSetAttribute(tri3_tile_fwd_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-                PST_CUDA(cudaFuncSetAttribute(tri3_tile_bwd_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-                ad = true;
-            }
-            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_fwd_kernel<128, true><<<blocks, 128, (size_t)(A.K1 + 2 * nb) * 128 * 4, c->stream>>>(A)));
-            PST_LAUNCHB(c, cls, 8.0 * (double)g.n, (tri3_tile_bwd_kernel<128, false><<<blocks, 128, (size_t)A.K1 * 128 * 4, c->stream>>>(A)));
-            PST_CUDA(cudaGetLastError());
-            return PST_OK;
-        }
     }
     // 16-byte path: every row/line start must be 16-byte aligned
     auto al16 = [](const void *q) { return q == nullptr || (((uintptr_t)q) & 15) == 0; };
@@ -2646,6 +2842,66 @@ extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, 
     if (g.dist) PST_TRY(pst_comm_check(c));
     PST_CUDA(cudaStreamSynchronize(c->stream));
     return PST_OK;
+}
+
+// Test hook: the register kernels of the distributed axis-3 pass, run RANK AFTER RANK on one GPU over the n3-slabs
+// of d_x (in place), with device buffers standing in for the neighbours' mailboxes -- every kernel variant (first,
+// interior, last rank) is exercised without a second GPU.  The result must equal pst_smooth3_dev(1, 1, r3) bit for bit.
+extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r3, int nranks)
+{
+    if (!c || !d_x) { pst_set_error("selftest_axis3_slabs: null pointer"); return PST_EINVAL; }
+    if (nranks < 2 || n3 / nranks < 2 * r3 || !tri3_reg_ok(r3, (n3 + nranks - 1) / nranks + r3)) {
+        pst_set_error("selftest_axis3_slabs: geometry outside the register kernels (radius 2-6 or 8, slabs of 2*r3 .. %d planes)", PST_T3_REG_MAXT - r3);
+        return PST_EUNSUP;
+    }
+    PST_CUDA(cudaSetDevice(c->device));
+    const long L = (long)n1 * n2;
+    const int nb = r3;
+    struct Bufs { uint2 *pf = nullptr, *pb = nullptr; float *csave = nullptr, *keep = nullptr; };
+    std::vector<Bufs> B(nranks);
+    unsigned *d_err = nullptr;
+    int rc = PST_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == PST_OK) { pst_set_error("selftest_axis3_slabs: %s", cudaGetErrorString(e)); rc = PST_ECUDA; } };
+    fail(cudaMalloc((void **)&d_err, 64));
+    if (rc == PST_OK) fail(cudaMemsetAsync(d_err, 0, 64, c->stream));
+    for (int r = 0; r < nranks && rc == PST_OK; r++) {
+        fail(cudaMalloc((void **)&B[r].pf, L * sizeof(uint2)));
+        fail(cudaMalloc((void **)&B[r].pb, L * sizeof(uint2)));
+        fail(cudaMalloc((void **)&B[r].csave, L * sizeof(float)));
+        fail(cudaMalloc((void **)&B[r].keep, (size_t)nb * L * sizeof(float)));
+        if (rc == PST_OK) { fail(cudaMemsetAsync(B[r].pf, 0, L * sizeof(uint2), c->stream)); fail(cudaMemsetAsync(B[r].pb, 0, L * sizeof(uint2), c->stream)); }
+    }
+    auto args = [&](int r) {
+        Tri3Args A{};
+        const int z0 = (int)(((long)n3 * r) / nranks), z1 = (int)(((long)n3 * (r + 1)) / nranks);
+        const bool first = r == 0, last = r == nranks - 1;
+        A.x = d_x + (size_t)z0 * L; A.dst = d_x + (size_t)z0 * L; A.F = nullptr;
+        A.hb = first ? nullptr : d_x + (size_t)(z0 - nb) * L;
+        A.ha = last ? nullptr : d_x + (size_t)z1 * L;
+        A.csave = B[r].csave; A.ha_keep = last ? nullptr : B[r].keep;
+        A.L = L; A.l0 = 0; A.l1 = L; A.n3g = n3; A.z0 = z0; A.nz = z1 - z0; A.nb = nb;
+        A.K0 = first ? 0 : z0 + nb; A.K1 = last ? n3 + 2 * nb : z1 + nb;
+        A.wt = (float)(1.0 / ((double)nb * nb)); A.w2 = (float)(2. * A.wt);
+        A.err = d_err; A.epoch = 1; A.rev = (r & 1);           // both tile orders
+        return A;
+    };
+    for (int r = 0; r < nranks && rc == PST_OK; r++) {
+        Tri3Args A = args(r);
+        A.pin = r == 0 ? nullptr : B[r].pf; A.pout = r == nranks - 1 ? nullptr : B[r + 1].pf;
+        rc = tri3_reg_launch(c, A, true, 0, (size_t)A.nz * L, PST_K_TRI3);
+    }
+    for (int r = nranks - 1; r >= 0 && rc == PST_OK; r--) {
+        Tri3Args A = args(r);
+        A.pin = r == nranks - 1 ? nullptr : B[r].pb; A.pout = r == 0 ? nullptr : B[r - 1].pb;
+        rc = tri3_reg_launch(c, A, false, r == 0 ? 1 : (r == nranks - 1 ? 2 : 0), (size_t)A.nz * L, PST_K_TRI3);
+    }
+    unsigned h_err = 0;
+    if (rc == PST_OK) fail(cudaMemcpyAsync(&h_err, d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    fail(cudaStreamSynchronize(c->stream));
+    if (rc == PST_OK && h_err) { pst_set_error("selftest_axis3_slabs: a carry never arrived"); rc = PST_ECOMM; }
+    for (auto &b : B) { cudaFree(b.pf); cudaFree(b.pb); cudaFree(b.csave); cudaFree(b.keep); }
+    cudaFree(d_err);
+    return rc;
 }
 
 extern "C" int pst_smooth3_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj)
