@@ -1448,6 +1448,7 @@ struct Tri3Args {
     const float *cin; const unsigned *fin;
     float *cout; unsigned *fout;
     const uint2 *pin; uint2 *pout;   // tile kernels: {carry, epoch} pairs (mine, incoming) / (neighbour's, outgoing)
+    uint2 *pself;                    // register kernels, last rank: its own (otherwise unused) backward mailbox, see tri3_reg_bwd_kernel
     unsigned *err; unsigned epoch;
     // peer-memory halos: hb / ha point INTO the neighbours' slabs (CUDA IPC); the kernel first waits for the flags the
     // neighbours raise (in my mailbox) once their current input is complete.  Null = halos were copied by NCCL.
@@ -1863,146 +1864,155 @@ tri3_tile_bwd_kernel(const Tri3Args A)
     }
 }
 
-// ---- distributed axis 3, register kernels (short slabs: 8 ranks at n3 = 1024) ------------------------------------------
-// One thread owns one line and keeps the line's local rows in REGISTERS (slots, indices known at compile time): no
-// shared memory, no block synchronisation after the halo flags, ~140 independent coalesced loads in flight per thread.
-// The forward kernel forms the stencil values t, waits for its line's carry, adds the t's to it in order and hands the
-// result on; it stores nothing but the incoming carry.  The backward kernel loads the same rows again (4 B per voxel,
-// instead of 4 written + 4 read for a staged F), repeats the forward additions from the saved carry -- same operands,
-// same order, same bits -- while it waits for the backward carry, then runs the backward sum with the fold.  The pass
-// moves 12 B per voxel instead of 16, and one addition per sample is left behind each wait.
-// Slot q <-> local row r = q - off of the x rows (planes K0 - 2nb + r), t / F of step k = K0 + (q - off) replace x in slot q.
-// EDGE: 0 interior rank, 1 first rank (left reflection: the rows at the bottom, off = 0), 2 last rank (right reflection:
-// the rows at the top are aligned with the last slot, off = MAXT - n), so every fold index is a compile-time slot.
-template <int NB, int MAXT, int EDGE>
-__device__ __forceinline__ void tri3_reg_load(const Tri3Args &A, long l, bool live, int off, const float *ha_src,
-                                              float (&v)[MAXT + 2 * NB], bool before_flags)
-{
-    constexpr int MAXS = MAXT + 2 * NB;
-    const int RX = A.K1 - A.K0 + 2 * NB;
+// ---- distributed axis 3, register kernels (equal slabs of exactly NZ planes: 8 ranks at n3 = 1024) ---------------------
+// One thread owns one line and keeps the line's local rows in REGISTERS; the slab height is a template parameter, so every
+// row index, every fold index and the role of every row (own plane / neighbour's plane / outside the cube) is known at
+// compile time: no shared memory, no block synchronisation after the halo flags, ~140 independent coalesced loads in flight
+// per thread, ~10 instructions per sample and pass.  The forward kernel forms the stencil values t, waits for its line's
+// carry, adds the t's to it in order and hands the result on; it stores nothing but the incoming carry.  The backward
+// kernel loads the same rows again (4 B per voxel, instead of 4 written + 4 read for a staged F), repeats the forward
+// additions from the saved carry -- same operands, same order, same bits -- while it waits for the backward carry, then
+// runs the backward sum with the fold.  The pass moves 12 B per voxel instead of 16, and one addition per sample is left
+// behind each wait.
+// EDGE: 0 interior rank (steps k = z0 + nb + q, q < NZ), 1 first rank (k = q < NZ + nb; left reflection), 2 last rank
+// (k = z0 + nb + q, q < NZ + nb; right reflection).  Slot q holds plane k - 2nb of x, then t_k, then F_k.
+template <int NB, int NZ, int EDGE>
+struct Tri3Reg {
+    static constexpr int N = (EDGE == 0) ? NZ : NZ + NB;       // steps
+    static constexpr int S = N + 2 * NB;                       // x rows
+    static constexpr int OWN0 = (EDGE == 1) ? 2 * NB : NB;     // slots [OWN0, OWN0 + NZ): planes of my slab
+    // x rows -> registers.  PART 0: my planes; PART 1: the neighbours' planes (after their flags)
+    template <int PART>
+    static __device__ __forceinline__ void load(const Tri3Args &A, long l, const float *ha_src, float (&v)[S])
+    {
 #pragma unroll
-    for (int q = 0; q < MAXS; q++) {
-        const int r = q - off, j = A.K0 - 2 * NB + r;
-        const bool in = live && r >= 0 && r < RX && j >= 0 && j < A.n3g;
-        const bool mine = j >= A.z0 && j < A.z0 + A.nz;
-        if (before_flags) {
-            v[q] = 0.f;
-            if (in && mine) v[q] = __ldcg(A.x + (long)(j - A.z0) * A.L + l);
-        } else if (in && !mine) {
-            v[q] = (j < A.z0) ? __ldcg(A.hb + (long)(j - (A.z0 - NB)) * A.L + l) : __ldcg(ha_src + (long)(j - (A.z0 + A.nz)) * A.L + l);
-        }
-    }
-}
-
-template <int NB, int MAXT>
-__global__ void __launch_bounds__(64)
-tri3_reg_fwd_kernel(const Tri3Args A)
-{
-    constexpr int MAXS = MAXT + 2 * NB;
-    const long l = (long)blockIdx.x * 64 + threadIdx.x;
-    const bool live = l < A.L;
-    const int n = A.K1 - A.K0;
-    float v[MAXS];
-    tri3_reg_load<NB, MAXT, 0>(A, l, live, 0, A.ha, v, true);       // own rows: in flight while the flags are awaited
-    tri3_wait_halos(A);
-    tri3_reg_load<NB, MAXT, 0>(A, l, live, 0, A.ha, v, false);
-    if (!live) return;
-    if (A.ha_keep) {
-        // keep the planes read from the next rank (planes [z1, K1)) for my backward kernel: that rank overwrites them in
-        // its own backward kernel, which runs before mine
-#pragma unroll
-        for (int q = 0; q < MAXS; q++) {
-            const int j = A.K0 - 2 * NB + q;
-            if (j >= A.z0 + A.nz && j < A.K1 && j < A.n3g) A.ha_keep[(long)(j - (A.z0 + A.nz)) * A.L + l] = v[q];
-        }
-    }
-    const float wm = -A.wt, w2 = A.w2;
-#pragma unroll
-    for (int q = 0; q < MAXT; q++) {
-        float t = wm * v[q + 2 * NB];
-        t = t + w2 * v[q + NB];
-        t = t + wm * v[q];
-        v[q] = t;
-    }
-    float s = 0.f;
-    if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    A.csave[l] = s;
-#pragma unroll
-    for (int q = 0; q < MAXT; q++) if (q < n) s += v[q];
-    if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
-}
-
-template <int NB, int MAXT, int EDGE>
-__global__ void __launch_bounds__(64)
-tri3_reg_bwd_kernel(const Tri3Args A)
-{
-    constexpr int MAXS = MAXT + 2 * NB;
-    const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
-    if (l >= A.L) return;
-    const int n = A.K1 - A.K0, off = (EDGE == 2) ? MAXT - n : 0;
-    float v[MAXS];
-    // (no halo flags to wait for: the forward kernel of this pass did, and the previous rank's planes stay untouched until
-    // its backward thread of this line has received the carry sent below)
-    tri3_reg_load<NB, MAXT, EDGE>(A, l, true, off, A.ha_keep ? A.ha_keep : A.ha, v, true);
-    tri3_reg_load<NB, MAXT, EDGE>(A, l, true, off, A.ha_keep ? A.ha_keep : A.ha, v, false);
-    const float wm = -A.wt, w2 = A.w2;
-#pragma unroll
-    for (int q = 0; q < MAXT; q++) {
-        float t = wm * v[q + 2 * NB];
-        t = t + w2 * v[q + NB];
-        t = t + wm * v[q];
-        v[q] = t;
-    }
-    float sf = A.csave[l];
-#pragma unroll
-    for (int q = 0; q < MAXT; q++) if (q >= off && q - off < n) { sf += v[q]; v[q] = sf; }
-    float s = 0.f;
-    if (A.pin) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    float *dl = A.dst + l;
-    float park[NB];                                            // EDGE 2: B of the right pad; EDGE 1: heads awaiting the left pad
-#pragma unroll
-    for (int q = MAXT - 1; q >= 0; q--) {
-        if (q >= off && q - off < n) {
-            s += v[q];
-            const int i = q - off;                             // step k = K0 + i
-            if (EDGE == 2) {
-                // k = K1 - 1 - jt with jt = MAXT - 1 - q;  right pad: k >= nb + n3g <=> jt < nb;  the last nb samples
-                // (gi >= n3g - nb <=> jt in [nb, 2nb)) take B_{nb + n3g + (n3g - 1 - gi)} = the value parked at 2nb - 1 - jt
-                const int jt = MAXT - 1 - q;
-                if (jt < NB) park[jt < NB ? jt : 0] = s;
-                else {
-                    float y = s;
-                    if (jt < 2 * NB) y = y + park[(2 * NB - 1 - jt) >= 0 && (2 * NB - 1 - jt) < NB ? (2 * NB - 1 - jt) : 0];
-                    dl[(long)(A.K0 + i - NB - A.z0) * A.L] = y;
-                }
-            } else if (EDGE == 1) {
-                // K0 = 0, q = k.  k >= 2nb: sample gi = k - nb; k in [nb, 2nb): heads (completed by the left pad);
-                // k < nb: left pad, y_gi = head_gi + B_k with gi = nb - 1 - k
-                if (q >= 2 * NB) dl[(long)(q - NB) * A.L] = s;
-                else if (q >= NB) park[(q - NB) >= 0 && (q - NB) < NB ? (q - NB) : 0] = s;
-                else dl[(long)(NB - 1 - q) * A.L] = park[(NB - 1 - q) >= 0 && (NB - 1 - q) < NB ? (NB - 1 - q) : 0] + s;
+        for (int q = 0; q < S; q++) {
+            if (q >= OWN0 && q < OWN0 + NZ) {
+                if (PART == 0) v[q] = __ldcg(A.x + (long)(q - OWN0) * A.L + l);
+            } else if (q < OWN0) {
+                if (EDGE == 1) { if (PART == 0) v[q] = 0.f; }                              // planes < 0
+                else if (PART == 1) v[q] = __ldcg(A.hb + (long)q * A.L + l);              // planes [z0 - nb, z0)
             } else {
-                dl[(long)(A.K0 + i - NB - A.z0) * A.L] = s;
+                if (EDGE == 2) { if (PART == 0) v[q] = 0.f; }                              // planes >= n3g
+                else if (PART == 1) v[q] = __ldcg(ha_src + (long)(q - OWN0 - NZ) * A.L + l);   // planes [z1, z1 + nb)
             }
         }
     }
-    if (A.pout) tri3_pair_send(A.pout + l, s, A.epoch);
+    static __device__ __forceinline__ void stencil(const Tri3Args &A, float (&v)[S])
+    {
+        const float wm = -A.wt, w2 = A.w2;
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            float t = wm * v[q + 2 * NB];
+            t = t + w2 * v[q + NB];
+            t = t + wm * v[q];
+            v[q] = t;
+        }
+    }
+};
+
+template <int NB, int NZ, int EDGE>
+__global__ void __launch_bounds__(64)
+tri3_reg_fwd_kernel(const Tri3Args A)
+{
+    using R = Tri3Reg<NB, NZ, EDGE>;
+    const long l = (long)blockIdx.x * 64 + threadIdx.x;
+    const bool live = l < A.L;
+    float v[R::S];
+    if (live) R::template load<0>(A, l, A.ha, v);              // my planes: in flight while the flags are awaited
+    tri3_wait_halos(A);
+    if (!live) return;
+    R::template load<1>(A, l, A.ha, v);
+    if (EDGE != 2 && A.ha_keep) {
+        // keep the planes read from the next rank for my backward kernel: that rank overwrites them in its own backward
+        // kernel, which runs before mine
+#pragma unroll
+        for (int a = 0; a < NB; a++) A.ha_keep[(long)a * A.L + l] = v[R::OWN0 + NZ + a];
+    }
+    R::stencil(A, v);
+    float s = 0.f;
+    if (EDGE != 1) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    A.csave[l] = s;
+#pragma unroll
+    for (int q = 0; q < R::N; q++) s += v[q];
+    if (EDGE != 2) tri3_pair_send(A.pout + l, s, A.epoch);
+    else tri3_pair_send(A.pself + l, 0.f, A.epoch);            // the last rank's backward carry: +0, through its own mailbox
 }
 
-// register kernels: radii instantiated, rows per thread
-#define PST_T3_REG_MAXT 136
-static bool tri3_reg_ok(int nb, int rows_max)
+template <int NB, int NZ, int EDGE>
+__global__ void __launch_bounds__(64)
+tri3_reg_bwd_kernel(const Tri3Args A)
+{
+    using R = Tri3Reg<NB, NZ, EDGE>;
+    constexpr int N = R::N;
+    const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
+    if (l >= A.L) return;
+    float v[R::S];
+    // (no halo flags to wait for: the forward kernel of this pass did, and the previous rank's planes stay untouched until
+    // its backward thread of this line has received the carry sent below)
+    const float *ha_src = A.ha_keep ? A.ha_keep : A.ha;
+    R::template load<0>(A, l, ha_src, v);
+    R::template load<1>(A, l, ha_src, v);
+    R::stencil(A, v);
+    float sf = A.csave[l];
+#pragma unroll
+    for (int q = 0; q < N; q++) { sf += v[q]; v[q] = sf; }
+    // (the last rank receives the +0 its forward kernel left in its own mailbox: with no wait loop at all ptxas gives
+    // this straight-line kernel 32 registers and spills the whole line)
+    float s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    float *dl = A.dst + l;                                     // local row of sample gi = k - nb: q (EDGE 0, 2), q - nb (EDGE 1)
+    float park[NB];                                            // EDGE 2: B of the right pad; EDGE 1: heads awaiting the left pad
+#pragma unroll
+    for (int q = N - 1; q >= 0; q--) {
+        s += v[q];
+        if (EDGE == 2) {
+            // right pad: k >= nb + n3g <=> q >= NZ: parked.  The last nb samples (q in [NZ - nb, NZ)) take
+            // B_{nb + n3g + (n3g - 1 - gi)}, the value parked by step q' = 2 NZ - 1 - q
+            if (q >= NZ) park[q >= NZ ? q - NZ : 0] = s;
+            else {
+                float y = s;
+                if (q >= NZ - NB) y = y + park[q >= NZ - NB ? NZ - 1 - q : 0];
+                dl[(long)q * A.L] = y;
+            }
+        } else if (EDGE == 1) {
+            // k = q.  k >= 2nb: sample gi = k - nb; k in [nb, 2nb): heads (completed by the left pad); k < nb: left pad,
+            // y_gi = head_gi + B_k with gi = nb - 1 - k
+            if (q >= 2 * NB) dl[(long)(q - NB) * A.L] = s;
+            else if (q >= NB) park[q >= NB && q < 2 * NB ? q - NB : 0] = s;
+            else dl[(long)(NB - 1 - q) * A.L] = park[q < NB ? NB - 1 - q : 0] + s;
+        } else {
+            dl[(long)q * A.L] = s;
+        }
+    }
+    if (EDGE != 1) tri3_pair_send(A.pout + l, s, A.epoch);
+}
+
+// register kernels: radii and slab heights instantiated
+static bool tri3_reg_ok(int nb, int n3g, int nranks)
 {
     static const bool on = []() { const char *e = getenv("PST_TRI3_REG"); return !(e && e[0] == '0'); }();
-    return on && rows_max <= PST_T3_REG_MAXT && (nb == 2 || nb == 3 || nb == 4 || nb == 5 || nb == 6 || nb == 8);
+    if (!on || nranks < 2 || n3g % nranks != 0) return false;
+    const int nz = n3g / nranks;
+    return (nz == 128 || nz == 32) && nz >= 2 * nb && (nb == 2 || nb == 3 || nb == 4 || nb == 5 || nb == 6 || nb == 8);
+}
+template <int NB, int NZ>
+static void tri3_reg_launch_z(const Tri3Args &A, bool fwd, int edge, unsigned blocks, cudaStream_t st)
+{
+    if (fwd) {
+        if (edge == 1) tri3_reg_fwd_kernel<NB, NZ, 1><<<blocks, 64, 0, st>>>(A);
+        else if (edge == 2) tri3_reg_fwd_kernel<NB, NZ, 2><<<blocks, 64, 0, st>>>(A);
+        else tri3_reg_fwd_kernel<NB, NZ, 0><<<blocks, 64, 0, st>>>(A);
+    } else {
+        if (edge == 1) tri3_reg_bwd_kernel<NB, NZ, 1><<<blocks, 64, 0, st>>>(A);
+        else if (edge == 2) tri3_reg_bwd_kernel<NB, NZ, 2><<<blocks, 64, 0, st>>>(A);
+        else tri3_reg_bwd_kernel<NB, NZ, 0><<<blocks, 64, 0, st>>>(A);
+    }
 }
 template <int NB>
 static void tri3_reg_launch_nb(const Tri3Args &A, bool fwd, int edge, unsigned blocks, cudaStream_t st)
 {
-    if (fwd) tri3_reg_fwd_kernel<NB, PST_T3_REG_MAXT><<<blocks, 64, 0, st>>>(A);
-    else if (edge == 1) tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 1><<<blocks, 64, 0, st>>>(A);
-    else if (edge == 2) tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 2><<<blocks, 64, 0, st>>>(A);
-    else tri3_reg_bwd_kernel<NB, PST_T3_REG_MAXT, 0><<<blocks, 64, 0, st>>>(A);
+    if (A.nz == 128) tri3_reg_launch_z<NB, 128>(A, fwd, edge, blocks, st);
+    else tri3_reg_launch_z<NB, 32>(A, fwd, edge, blocks, st);
 }
 // the forward kernel reads 4 B per voxel, the backward kernel reads 4 and writes 4
 static int tri3_reg_launch(pst_ctx *c, const Tri3Args &A, bool fwd, int edge, size_t nvox, int cls)
@@ -2191,10 +2201,16 @@ static int smooth_axis3_solo(pst_ctx *c, const DipGeom &g, const float *src, flo
     static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
     A.rev = rev_on ? 1 : 0;
     static const bool fake_reg = []() { const char *e = getenv("PST_TRI3_SOLO"); return e && e[0] == '2'; }();
-    if (fake_reg && tri3_reg_ok(nb, g.n3 + nb)) {
+    if (fake_reg && tri3_reg_ok(nb, 2 * g.n3, 2)) {
         // TIMING ONLY (wrong numbers): the register kernels as an interior rank would run them, halo rows read from the
         // volume itself, no carries
         A.K0 = nb; A.K1 = g.n3 + nb; A.n3g = g.n3 + 1000; A.hb = src; A.ha = src; A.csave = scr;
+        // carries: a mailbox whose every word already reads 0x01010101 (= the epoch), and one to send into
+        uint2 *in = (uint2 *)(scr + A.L), *out = in + A.L;
+        A.epoch = 0x01010101u; A.err = (unsigned *)(out + A.L);
+        PST_CUDA(cudaMemsetAsync(in, 0x01, (size_t)A.L * sizeof(uint2), c->stream));
+        PST_CUDA(cudaMemsetAsync(A.err, 0, 64, c->stream));
+        A.pin = in; A.pout = out;
         PST_TRY(tri3_reg_launch(c, A, true, 0, g.n, PST_K_TRI3));
         PST_TRY(tri3_reg_launch(c, A, false, 0, g.n, PST_K_TRI3));
         c->stats.smooth_passes++;
@@ -2253,7 +2269,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     // recomputation lengthens exactly that.  Off by default.
     static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return e && e[0] == '1'; }();
     // register kernels (short slabs, first choice): always the recompute scheme
-    const bool reg = c->nranks >= 2 && tri3_reg_ok(nb, nz_max + nb);
+    const bool reg = tri3_reg_ok(nb, n3g, c->nranks);
     const int edge = first ? 1 : (last ? 2 : 0);
     const bool rcmp = (rcmp_on && W > 0) || reg;
     A.csave = g.cin;
@@ -2262,6 +2278,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.cin = first ? nullptr : mb.cf_in;  A.fin = mb.ff_in;
     A.cout = last ? nullptr : mb.cf_out; A.fout = mb.ff_out;
     A.pin = first ? nullptr : mb.pf_in; A.pout = last ? nullptr : mb.pf_out;
+    A.pself = (uint2 *)mb.pb_in;
     if (reg) {
         PST_TRY(tri3_reg_launch(c, A, true, edge, g.n, PST_K_TRI3));
     } else if (W) {
@@ -2285,7 +2302,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     // backward sums (+ fold): carries flow rank -> rank-1
     A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;
     A.cout = first ? nullptr : mb.cb_out; A.fout = mb.fb_out;
-    A.pin = last ? nullptr : mb.pb_in; A.pout = first ? nullptr : mb.pb_out;
+    A.pin = (last && !reg) ? nullptr : mb.pb_in; A.pout = first ? nullptr : mb.pb_out;
     static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
     A.rev = rev_on ? 1 : 0;
     static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? PST_K_TRI3BWD : PST_K_TRI3; }();
@@ -2850,8 +2867,8 @@ extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, 
 extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r3, int nranks)
 {
     if (!c || !d_x) { pst_set_error("selftest_axis3_slabs: null pointer"); return PST_EINVAL; }
-    if (nranks < 2 || n3 / nranks < 2 * r3 || !tri3_reg_ok(r3, (n3 + nranks - 1) / nranks + r3)) {
-        pst_set_error("selftest_axis3_slabs: geometry outside the register kernels (radius 2-6 or 8, slabs of 2*r3 .. %d planes)", PST_T3_REG_MAXT - r3);
+    if (!tri3_reg_ok(r3, n3, nranks)) {
+        pst_set_error("selftest_axis3_slabs: geometry outside the register kernels (radius 2-6 or 8, equal slabs of 32 or 128 planes, nranks >= 2)");
         return PST_EUNSUP;
     }
     PST_CUDA(cudaSetDevice(c->device));
@@ -2887,12 +2904,12 @@ extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, 
     };
     for (int r = 0; r < nranks && rc == PST_OK; r++) {
         Tri3Args A = args(r);
-        A.pin = r == 0 ? nullptr : B[r].pf; A.pout = r == nranks - 1 ? nullptr : B[r + 1].pf;
-        rc = tri3_reg_launch(c, A, true, 0, (size_t)A.nz * L, PST_K_TRI3);
+        A.pin = r == 0 ? nullptr : B[r].pf; A.pout = r == nranks - 1 ? nullptr : B[r + 1].pf; A.pself = B[r].pb;
+        rc = tri3_reg_launch(c, A, true, r == 0 ? 1 : (r == nranks - 1 ? 2 : 0), (size_t)A.nz * L, PST_K_TRI3);
     }
     for (int r = nranks - 1; r >= 0 && rc == PST_OK; r--) {
         Tri3Args A = args(r);
-        A.pin = r == nranks - 1 ? nullptr : B[r].pb; A.pout = r == 0 ? nullptr : B[r - 1].pb;
+        A.pin = B[r].pb; A.pout = r == 0 ? nullptr : B[r - 1].pb;
         rc = tri3_reg_launch(c, A, false, r == 0 ? 1 : (r == nranks - 1 ? 2 : 0), (size_t)A.nz * L, PST_K_TRI3);
     }
     unsigned h_err = 0;

@@ -81,14 +81,15 @@ def test_smooth3_bit_exact(ctx, port, shape, rect):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("shape,r3,nranks", [((20, 13, 64), 5, 2), ((20, 13, 67), 5, 3), ((8, 40, 1024), 5, 8), ((37, 3, 90), 2, 7),
-                                             ((16, 8, 250), 8, 2), ((12, 6, 96), 3, 4), ((12, 6, 97), 6, 5), ((9, 7, 203), 4, 2)])
+@pytest.mark.parametrize("shape,r3,nranks", [((20, 13, 64), 5, 2), ((20, 13, 96), 5, 3), ((8, 40, 1024), 5, 8), ((37, 3, 224), 2, 7),
+                                             ((16, 8, 256), 8, 2), ((12, 6, 128), 3, 4), ((12, 6, 160), 6, 5), ((9, 7, 384), 4, 3)])
 def test_multi_gpu_axis3_kernels_on_one_gpu(ctx, port, shape, r3, nranks):
     """The register kernels of the distributed axis-3 pass (first / interior / last rank variants, both tile orders),
     run rank after rank on one GPU over the n3-slabs of the volume: bit-identical to ps_smooth2 along axis 3."""
     n1, n2, n3 = shape
     x = synth.cube(n1, n2, n3, seed=41)
     d = Dev(ctx, x)
+    from pyseistr_b200 import _lib
     _lib.check(ctx.lib.pst_selftest_axis3_slabs(ctx.handle, d.p, n1, n2, n3, r3, nranks))
     got = d.get(shape)
     want = port.smooth3(x, (1, 1, r3)).reshape(x.shape, order="F")

@@ -30,7 +30,7 @@ def run(solo):
     for _ in range(passes):
         _lib.check(lib.pst_smoothcf_dev(ctx.handle, d, n1, n2, n3, 1, 0, 1, 1, r3, 0, 0, 0, 0, 0, 0))
     ctx.sync()
-    st = ctx.stats().as_dict()
+    st = ctx.stats()
     i = _lib.KERNEL_CLASSES.index("tri_axis3")
     ms, nl = st["class_ms"][i], st["class_launches"][i]
     print(f"solo={solo} {n1}x{n2}x{n3} r3={r3}: {ms / passes:.3f} ms per pass ({nl // passes} launches), "
