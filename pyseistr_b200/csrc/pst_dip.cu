@@ -2198,7 +2198,7 @@ static int smooth_axis3_solo(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.wt = (float)(1.0 / ((double)nb * nb));
     A.w2 = (float)(2. * A.wt);
     A.err = nullptr; A.epoch = 1;                        // (no waits: nothing can time out)
-    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
+    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return !(e && e[0] == '0'); }();
     A.rev = rev_on ? 1 : 0;
     static const bool fake_reg = []() { const char *e = getenv("PST_TRI3_SOLO"); return e && e[0] == '2'; }();
     if (fake_reg && tri3_reg_ok(nb, 2 * g.n3, 2)) {
@@ -2303,7 +2303,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.cin = last ? nullptr : mb.cb_in;    A.fin = mb.fb_in;
     A.cout = first ? nullptr : mb.cb_out; A.fout = mb.fb_out;
     A.pin = (last && !reg) ? nullptr : mb.pb_in; A.pout = first ? nullptr : mb.pb_out;
-    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return e && e[0] == '1'; }();
+    static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return !(e && e[0] == '0'); }();
     A.rev = rev_on ? 1 : 0;
     static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? PST_K_TRI3BWD : PST_K_TRI3; }();
     if (reg) {

@@ -36,8 +36,10 @@ def main():
                         ((40, 17, 10 * world + 3), dict(niter=2, liter=5, order=1, rect=(3, 4, 4))),
                         # tall slabs: the axis-3 tile kernels run with 64-line tiles (rows x 128 lines > 75 KB)
                         ((16, 12, 200 * world + 1), dict(niter=2, liter=4, order=2, rect=(3, 3, 6))),
-                        # 128-plane slabs, default radii: the geometry of the headline cube on 8 GPUs (128-line tiles)
+                        # 128-plane slabs, default radii: the geometry of the headline cube on 8 GPUs (register kernels of the axis-3 pass)
                         ((16, 12, 128 * world), dict(niter=2, liter=4, order=2, rect=(5, 5, 5))),
+                        # 32-plane slabs: the register kernels of the axis-3 pass, small instantiation
+                        ((24, 10, 32 * world), dict(niter=2, liter=4, order=1, rect=(3, 3, 6))),
                         # slabs too tall for the tile kernels: the line kernels (register-window forward kernel), the
                         # geometry of the headline cube on 2 GPUs
                         ((8, 4, 330 * world), dict(niter=2, liter=3, order=1, rect=(2, 2, 5)))]:
