@@ -402,6 +402,19 @@ int pst_tri_l2_launch(cudaStream_t stream, int sm_count, int axis, const float *
     static const int hints_env = env_int("PST_TRI_L2_HINTS", 7);
     const bool contig = axis == 0;
     int warps = warps_env > 0 ? warps_env : (contig ? 6 : 8);
+    if (warps_env <= 0 && contig) {
+        // tiles are dealt to the warps round-robin: with few tiles per warp (a slab of a multi-GPU run: 4096 tiles over
+        // 148 x 6 warps = 4.6 rounds) the last, partial round costs a whole one.  Pick the warp count with the cheapest
+        // rounds x warps, weighted by the steady-state cost per tile measured at 5 / 6 / 7 / 8 warps (2.176 / 2.073 /
+        // 2.135 / 2.158 ms per pass at 1000x1024x1024).
+        const double f[4] = {1.050, 1.000, 1.030, 1.041};
+        double best = 0.;
+        for (int w = 5; w <= 8; w++) {
+            const double rounds = (double)((P.ntiles + (long)sm_count * w - 1) / ((long)sm_count * w));
+            const double cost = rounds * w * f[w - 5];
+            if (best == 0. || cost < best - 1e-9) { best = cost; warps = w; }
+        }
+    }
     warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
     const size_t budget = 227 * 1024;
     int nslot = slots_env > 0 ? slots_env : (contig ? 4 : 2);

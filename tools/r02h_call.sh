@@ -25,6 +25,6 @@ p=29560
 for w in dip3d_somf3d soint3d sint3d; do
     p=$((p+1))
     steps=3; [ $w = sint3d ] && steps=2
-    timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $p bench.py --gpus $N --workload $w --steps $steps --warmup 3 > $O/r02h_bench_${w}_n$N.json 2> $O/r02h_bench_${w}_n$N.err
+    PST_TRI3_SPLIT=1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $p bench.py --gpus $N --workload $w --steps $steps --warmup 3 > $O/r02h_bench_${w}_n$N.json 2> $O/r02h_bench_${w}_n$N.err
     echo "$w N=$N rc $?: $(line $O/r02h_bench_${w}_n$N.json)" | tee -a $S
 done
