@@ -174,17 +174,19 @@ __device__ __forceinline__ void pst_block_reduce(double (&v)[NV], double *partia
 }
 
 // ---- canonical (partition-independent) sums ---------------------------------------------------------------------
-// A volume [n1 n2][nz] is summed as: elements of one PIECE (PST_RED_CH consecutive elements of ONE n3-plane; block =
+// A volume [n1 n2][nz] is summed as: elements of one PIECE (pst_red_ch() consecutive elements of ONE n3-plane; block =
 // piece, fixed thread pattern + fixed trees) -> pieces of a plane in index order (pst_plane_sums_kernel) -> planes of
 // the GLOBAL cube in a fixed order (pst_final_sums_kernel).  No step looks at how many planes THIS rank owns, so an
 // n3-slab decomposition over any number of ranks forms every CG / divne / line-search scalar with exactly the
 // additions of the single-GPU run: ranks fill their planes of the [nv][n3 global] table, the others stay +0, and the
 // all-reduce of that table adds only zeros (exact in any order).
-#define PST_RED_CH 32768u
-struct Span { size_t n; unsigned n12, ppp; };     // ppp > 0: block = piece (blockIdx.x % ppp) of plane (blockIdx.x / ppp); 0: grid-stride over n
-inline Span pst_span_canon(size_t n12, int nz)
+// piece length: a function of the GLOBAL volume only (never of the slab): big volumes take big pieces (fewer, fatter
+// blocks stream faster), small ones small pieces (a 64-plane slab of 500x512x512 must still fill 148 SMs)
+inline unsigned pst_red_ch(size_t n12, int nzg) { return n12 * (size_t)nzg >= ((size_t)1 << 29) ? 32768u : 8192u; }
+struct Span { size_t n; unsigned n12, ppp, ch; };  // ppp > 0: block = piece (blockIdx.x % ppp) of plane (blockIdx.x / ppp); 0: grid-stride over n
+inline Span pst_span_canon(size_t n12, int nz, int nzg)
 {
-    Span S; S.n = n12 * (size_t)nz; S.n12 = (unsigned)n12; S.ppp = (unsigned)((n12 + PST_RED_CH - 1) / PST_RED_CH);
+    Span S; S.n = n12 * (size_t)nz; S.n12 = (unsigned)n12; S.ch = pst_red_ch(n12, nzg); S.ppp = (unsigned)((n12 + S.ch - 1) / S.ch);
     return S;
 }
 #ifdef __CUDACC__
@@ -193,8 +195,8 @@ __device__ __forceinline__ void pst_span(const Span &S, int width, size_t &i0, s
 {
     if (S.ppp) {
         const unsigned z = blockIdx.x / S.ppp, p = blockIdx.x - z * S.ppp;
-        const unsigned o = p * PST_RED_CH;
-        const unsigned len = (S.n12 - o < PST_RED_CH) ? S.n12 - o : PST_RED_CH;
+        const unsigned o = p * S.ch;
+        const unsigned len = (S.n12 - o < S.ch) ? S.n12 - o : S.ch;
         const size_t base = (size_t)z * S.n12 + o;
         i0 = base + (size_t)width * threadIdx.x; i1 = base + len; step = (size_t)width * blockDim.x;
     } else {

@@ -2471,7 +2471,8 @@ static int allpass_launch_nw(pst_ctx *c, const float *u, const float *p_in, cons
                              bool ls, int rec, int n3_live, int z0, int n3g)
 {
     static const BTab tb = make_btab(NW);
-    const int tg = n1 >= (int)PST_RED_CH ? 1 : (int)(PST_RED_CH / (unsigned)n1);     // traces per piece: a function of n1 only
+    const unsigned ch = pst_red_ch((size_t)n1 * n2, n3g);
+    const int tg = n1 >= (int)ch ? 1 : (int)(ch / (unsigned)n1);     // traces per piece: a function of the global shape only
     const unsigned gpp = (unsigned)((n2 + tg - 1) / tg);
     const long blocks = (long)gpp * n3;
     PST_TRY(pst_reserve_partials(c, (size_t)blocks, n3g));
@@ -2533,7 +2534,7 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
     const int threads = 256;
     const int grid = pst_grid_for(c, n, threads);
     // every sum of the solve is canonical (pst_common.cuh): the scalars do not depend on the slab decomposition
-    const Span S = pst_span_canon((size_t)g.n1 * g.n2, g.n3);
+    const Span S = pst_span_canon((size_t)g.n1 * g.n2, g.n3, g.n3g);
     const unsigned gridc = S.ppp * (unsigned)g.n3;
     PST_TRY(pst_reserve_partials(c, gridc, g.n3g));
     auto finish = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)S.ppp, g.n3, g.z0, g.n3g, nv, rec); };
@@ -3257,11 +3258,12 @@ static int soint3d_run(pst_ctx *c, const float *d_din, const float *d_mask, cons
     };
     float *x = d_out;
     const int threads = 256, grid = pst_grid_for(c, n, threads);
-    // canonical sums (pst_common.cuh): pieces = groups of tg traces of one plane (stencil kernels) / PST_RED_CH elements
+    // canonical sums (pst_common.cuh): pieces = groups of tg traces of one plane (stencil kernels) / pst_red_ch() elements
     // of one plane (vector kernels); the CG scalars do not depend on the slab decomposition
-    const int tg = n1 >= (int)PST_RED_CH ? 1 : (int)(PST_RED_CH / (unsigned)n1);
+    const unsigned ch = pst_red_ch(pln, n3g);
+    const int tg = n1 >= (int)ch ? 1 : (int)(ch / (unsigned)n1);
     const unsigned gpp = (unsigned)((n2 + tg - 1) / tg), gridt = gpp * (unsigned)n3;
-    const Span Sp = pst_span_canon(pln, n3);
+    const Span Sp = pst_span_canon(pln, n3, n3g);
     const unsigned gridc = Sp.ppp * (unsigned)n3;
     PST_TRY(pst_reserve_partials(c, gridt > gridc ? gridt : gridc, n3g));
     auto finish_t = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)gpp, n3, z0, n3g, nv, rec); };

@@ -1416,7 +1416,7 @@ extern "C" int pst_sint3d_dev(pst_ctx *c, const float *d_din, const float *d_dip
     PST_TRY(pst_arena_get(c, n, &known));
     const int threads = 256, grid = pst_grid_for(c, n, threads);
     // canonical sums (pst_common.cuh): the CG scalars do not depend on the slab decomposition
-    const Span Sp = pst_span_canon(plane, nz);
+    const Span Sp = pst_span_canon(plane, nz, n3);
     const unsigned gridc = Sp.ppp * (unsigned)nz;
     PST_TRY(pst_reserve_partials(c, gridc, n3));
     auto finish = [&](int nv, int rec) { return pst_finish_reduce_canon(c, (int)Sp.ppp, nz, z0, n3, nv, rec); };

@@ -22,7 +22,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 grep "dist_check" $O/r02h_dist_check_n$N.log | sort -u | tee -a $S
 echo "== bench.py at N = $N" | tee -a $S
 p=29560
-for w in dip3d_somf3d soint3d sint3d; do
+for w in ${WORKLOADS:-dip3d_somf3d soint3d sint3d}; do
     p=$((p+1))
     steps=3; [ $w = sint3d ] && steps=2
     PST_TRI3_SPLIT=1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $p bench.py --gpus $N --workload $w --steps $steps --warmup 3 > $O/r02h_bench_${w}_n$N.json 2> $O/r02h_bench_${w}_n$N.err
