@@ -173,7 +173,7 @@ int pst_allpass_dev(pst_ctx *ctx, const float *d_u, const float *d_sigma, int n1
 int pst_smooth3_dev(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int r1, int r2, int r3, int repeat, int adj);
 /* Test hook: the kernels of the MULTI-GPU axis-3 smoothing pass (pst_ctx_create_dist contexts, short n3-slabs) run rank
  * after rank on one GPU over the nranks n3-slabs of d_x, in place; equals pst_smooth3_dev(.., 1, 1, r3, 1, 0) bit for bit.
- * PST_EUNSUP outside those kernels' geometry (radius 2-6 or 8, n3 = nranks x 32 or nranks x 128 planes, nranks >= 2). */
+ * PST_EUNSUP outside those kernels' geometry (radius 2-6 or 8, nranks >= 2 equal slabs of 32, 64, 96 or k x 128 planes). */
 int pst_selftest_axis3_slabs(pst_ctx *ctx, float *d_x, int n1, int n2, int n3, int r3, int nranks);
 int pst_divne_dev(pst_ctx *ctx, float *d_num, float *d_den, float *d_rat, int n1, int n2, int n3,
                   int r1, int r2, int r3, int liter, int *iters_run);

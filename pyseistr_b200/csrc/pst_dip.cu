@@ -1398,7 +1398,7 @@ int pst_comm_map_arenas(pst_ctx *c, char **prev, char **next);                  
 // floats slab_halos() takes from the arena
 static size_t slab_halo_floats(const DipGeom &g)
 {
-    return g.dist ? (size_t)g.n1 * g.n2 * (size_t)(2 * std::max(g.r3, 1) + 2) + 4 * 64 : 0;
+    return g.dist ? (size_t)g.n1 * g.n2 * (size_t)(2 * std::max(g.r3, 1) + 1 + (g.n3 / 128 + 3)) + 4 * 64 : 0;
 }
 
 // work planes of the distributed axis-3 pass (smooth_axis3_dist): r3-plane halos either side + carry planes
@@ -1408,7 +1408,7 @@ static int slab_halos(pst_ctx *c, DipGeom *g)
     const size_t plane = (size_t)g->n1 * g->n2;
     PST_TRY(pst_arena_get(c, plane * (size_t)std::max(g->r3, 1), &g->hb));
     PST_TRY(pst_arena_get(c, plane * (size_t)std::max(g->r3, 1), &g->ha));
-    PST_TRY(pst_arena_get(c, plane, &g->cin));
+    PST_TRY(pst_arena_get(c, plane * (size_t)(g->n3 / 128 + 3), &g->cin));   // carry plane in / the running sum before every chunk (register kernels)
     PST_TRY(pst_arena_get(c, plane, &g->cout));
     if (g->r3 > 1 && g->n3g % c->nranks == 0) PST_TRY(pst_comm_map_arenas(c, &g->peer_prev, &g->peer_next));   // collective
     return PST_OK;
@@ -1864,43 +1864,45 @@ tri3_tile_bwd_kernel(const Tri3Args A)
     }
 }
 
-// ---- distributed axis 3, register kernels (equal slabs of exactly NZ planes: 8 ranks at n3 = 1024) ---------------------
-// One thread owns one line and keeps the line's local rows in REGISTERS; the slab height is a template parameter, so every
-// row index, every fold index and the role of every row (own plane / neighbour's plane / outside the cube) is known at
-// compile time: no shared memory, no block synchronisation after the halo flags, ~140 independent coalesced loads in flight
-// per thread, ~10 instructions per sample and pass.  The forward kernel forms the stencil values t, waits for its line's
-// carry, adds the t's to it in order and hands the result on; it stores nothing but the incoming carry.  The backward
-// kernel loads the same rows again (4 B per voxel, instead of 4 written + 4 read for a staged F), repeats the forward
-// additions from the saved carry -- same operands, same order, same bits -- while it waits for the backward carry, then
-// runs the backward sum with the fold.  The pass moves 12 B per voxel instead of 16, and one addition per sample is left
-// behind each wait.
-// EDGE: 0 interior rank (steps k = z0 + nb + q, q < NZ), 1 first rank (k = q < NZ + nb; left reflection), 2 last rank
-// (k = z0 + nb + q, q < NZ + nb; right reflection).  Slot q holds plane k - 2nb of x, then t_k, then F_k.
+// ---- distributed axis 3, register kernels (equal slabs of v x NZ planes: 2, 4, 8 ranks at n3 = 1024) --------------------
+// One thread owns one line and walks the line's local rows in CHUNKS of NZ planes held in REGISTERS; NZ and the role of a
+// chunk (first of the cube / interior / last of the cube) are template parameters, so the role of every row (own plane,
+// neighbouring plane, outside the cube) and every fold index is known at compile time: no shared memory, no block
+// synchronisation after the halo flags, ~140 independent coalesced loads in flight per thread and chunk, 11 (forward) and
+// 18 (backward) instructions per sample.  The forward kernel forms the stencil values t of its first chunk, waits for its
+// line's carry, adds the t's to it in order, chunk after chunk, and hands the result on; it stores nothing but the running
+// sum before every chunk.  The backward kernel walks the chunks downwards: it loads the same rows again (4 B per voxel,
+// instead of 4 written + 4 read for a staged F), repeats the forward additions from the saved sum -- same operands, same
+// order, same bits -- (for its top chunk: WHILE the backward carry is on its way), then runs the backward sum with the
+// fold.  The pass moves 12 B per voxel instead of 16.
+// EDGE: 0 interior chunk (steps k = zc + nb + q, q < NZ), 1 first chunk of the cube (k = q < NZ + nb; left reflection),
+// 2 last chunk of the cube (k = zc + nb + q, q < NZ + nb; right reflection).  Slot q holds plane k - 2nb of x, then t_k,
+// then F_k.
 template <int NB, int NZ, int EDGE>
 struct Tri3Reg {
     static constexpr int N = (EDGE == 0) ? NZ : NZ + NB;       // steps
     static constexpr int S = N + 2 * NB;                       // x rows
-    static constexpr int OWN0 = (EDGE == 1) ? 2 * NB : NB;     // slots [OWN0, OWN0 + NZ): planes of my slab
-    // x rows -> registers.  PART 0: my planes; PART 1: the neighbours' planes (after their flags)
+    static constexpr int OWN0 = (EDGE == 1) ? 2 * NB : NB;     // slots [OWN0, OWN0 + NZ): planes of the chunk
+    // own: the chunk's first plane; before: plane zc - nb (previous chunk or previous rank); after: plane zc + NZ (next chunk
+    // or next rank / its kept copy).  PART 0: the chunk's planes, 1: the planes around it, 2: both
     template <int PART>
-    static __device__ __forceinline__ void load(const Tri3Args &A, long l, const float *ha_src, float (&v)[S])
+    static __device__ __forceinline__ void load(const float *own, const float *before, const float *after, long L, float (&v)[S])
     {
 #pragma unroll
         for (int q = 0; q < S; q++) {
             if (q >= OWN0 && q < OWN0 + NZ) {
-                if (PART == 0) v[q] = __ldcg(A.x + (long)(q - OWN0) * A.L + l);
+                if (PART != 1) v[q] = __ldcg(own + (long)(q - OWN0) * L);
             } else if (q < OWN0) {
-                if (EDGE == 1) { if (PART == 0) v[q] = 0.f; }                              // planes < 0
-                else if (PART == 1) v[q] = __ldcg(A.hb + (long)q * A.L + l);              // planes [z0 - nb, z0)
+                if (EDGE == 1) { if (PART != 1) v[q] = 0.f; }                             // planes < 0
+                else if (PART != 0) v[q] = __ldcg(before + (long)q * L);
             } else {
-                if (EDGE == 2) { if (PART == 0) v[q] = 0.f; }                              // planes >= n3g
-                else if (PART == 1) v[q] = __ldcg(ha_src + (long)(q - OWN0 - NZ) * A.L + l);   // planes [z1, z1 + nb)
+                if (EDGE == 2) { if (PART != 1) v[q] = 0.f; }                             // planes >= n3g
+                else if (PART != 0 && after) v[q] = __ldcg(after + (long)(q - OWN0 - NZ) * L);
             }
         }
     }
-    static __device__ __forceinline__ void stencil(const Tri3Args &A, float (&v)[S])
+    static __device__ __forceinline__ void stencil(float wm, float w2, float (&v)[S])
     {
-        const float wm = -A.wt, w2 = A.w2;
 #pragma unroll
         for (int q = 0; q < N; q++) {
             float t = wm * v[q + 2 * NB];
@@ -1911,56 +1913,88 @@ struct Tri3Reg {
     }
 };
 
+// one chunk of the forward kernel; returns the running sum after the chunk
 template <int NB, int NZ, int EDGE>
-__global__ void __launch_bounds__(64)
-tri3_reg_fwd_kernel(const Tri3Args A)
+__device__ __forceinline__ float tri3_reg_fwd_chunk(const Tri3Args &A, long l, bool live, int j, int nch, bool head, float s)
 {
     using R = Tri3Reg<NB, NZ, EDGE>;
-    const long l = (long)blockIdx.x * 64 + threadIdx.x;
-    const bool live = l < A.L;
     float v[R::S];
-    if (live) R::template load<0>(A, l, A.ha, v);              // my planes: in flight while the flags are awaited
-    tri3_wait_halos(A);
-    if (!live) return;
-    R::template load<1>(A, l, A.ha, v);
-    if (EDGE != 2 && A.ha_keep) {
+    const float *own = A.x + (long)j * NZ * A.L + l;
+    const float *before = j > 0 ? own - (long)NB * A.L : A.hb + l;
+    const float *after = j < nch - 1 ? own + (long)NZ * A.L : A.ha + l;
+    if (head) {
+        // first chunk: its own planes are in flight while the neighbours' flags are awaited; then its carry
+        if (live) R::template load<0>(own, before, after, A.L, v);
+        tri3_wait_halos(A);
+        if (!live) return 0.f;
+        R::template load<1>(own, before, after, A.L, v);
+    } else {
+        R::template load<2>(own, before, after, A.L, v);
+    }
+    if (EDGE != 2 && j == nch - 1 && A.ha_keep) {
         // keep the planes read from the next rank for my backward kernel: that rank overwrites them in its own backward
         // kernel, which runs before mine
 #pragma unroll
         for (int a = 0; a < NB; a++) A.ha_keep[(long)a * A.L + l] = v[R::OWN0 + NZ + a];
     }
-    R::stencil(A, v);
-    float s = 0.f;
-    if (EDGE != 1) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    A.csave[l] = s;
+    R::stencil(-A.wt, A.w2, v);
+    if (head && EDGE != 1) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    A.csave[(long)j * A.L + l] = s;
 #pragma unroll
     for (int q = 0; q < R::N; q++) s += v[q];
-    if (EDGE != 2) tri3_pair_send(A.pout + l, s, A.epoch);
+    return s;
+}
+
+template <int NB, int NZ>
+__global__ void __launch_bounds__(64)
+tri3_reg_fwd_kernel(const Tri3Args A)
+{
+    const long l = (long)blockIdx.x * 64 + threadIdx.x;
+    const bool live = l < A.L;
+    const int nch = A.nz / NZ;
+    const bool first = A.K0 == 0, last = A.K1 == A.n3g + 2 * NB;
+    float s = 0.f;
+    // chunk 0 (block-uniform role)
+    if (first) s = tri3_reg_fwd_chunk<NB, NZ, 1>(A, l, live, 0, nch, true, s);
+    else if (last && nch == 1) s = tri3_reg_fwd_chunk<NB, NZ, 2>(A, l, live, 0, nch, true, s);
+    else s = tri3_reg_fwd_chunk<NB, NZ, 0>(A, l, live, 0, nch, true, s);
+    if (!live) return;
+    for (int j = 1; j < nch; j++) {
+        if (last && j == nch - 1) s = tri3_reg_fwd_chunk<NB, NZ, 2>(A, l, true, j, nch, false, s);
+        else s = tri3_reg_fwd_chunk<NB, NZ, 0>(A, l, true, j, nch, false, s);
+    }
+    if (!last) tri3_pair_send(A.pout + l, s, A.epoch);
     else tri3_pair_send(A.pself + l, 0.f, A.epoch);            // the last rank's backward carry: +0, through its own mailbox
 }
 
+// one chunk of the backward kernel.  keep[]: x of the first nb planes of the chunk above (this thread has already
+// overwritten them with outputs); on return: those of this chunk.  Returns the backward running sum below the chunk.
 template <int NB, int NZ, int EDGE>
-__global__ void __launch_bounds__(64)
-tri3_reg_bwd_kernel(const Tri3Args A)
+__device__ __forceinline__ float tri3_reg_bwd_chunk(const Tri3Args &A, long l, int j, int nch, const float *ha_src, float (&keep)[NB], float s)
 {
     using R = Tri3Reg<NB, NZ, EDGE>;
     constexpr int N = R::N;
-    const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
-    if (l >= A.L) return;
     float v[R::S];
+    const float *own = A.x + (long)j * NZ * A.L + l;
+    const float *before = j > 0 ? own - (long)NB * A.L : A.hb + l;
+    const bool top = j == nch - 1;
     // (no halo flags to wait for: the forward kernel of this pass did, and the previous rank's planes stay untouched until
-    // its backward thread of this line has received the carry sent below)
-    const float *ha_src = A.ha_keep ? A.ha_keep : A.ha;
-    R::template load<0>(A, l, ha_src, v);
-    R::template load<1>(A, l, ha_src, v);
-    R::stencil(A, v);
-    float sf = A.csave[l];
+    // its backward thread of this line has received the carry sent at the end)
+    R::template load<2>(own, before, top ? ha_src + l : nullptr, A.L, v);
+    if (EDGE != 2 && !top) {
+#pragma unroll
+        for (int a = 0; a < NB; a++) v[R::OWN0 + NZ + a] = keep[a];
+    }
+#pragma unroll
+    for (int a = 0; a < NB; a++) keep[a] = v[R::OWN0 + a];
+    R::stencil(-A.wt, A.w2, v);
+    float sf = A.csave[(long)j * A.L + l];
 #pragma unroll
     for (int q = 0; q < N; q++) { sf += v[q]; v[q] = sf; }
     // (the last rank receives the +0 its forward kernel left in its own mailbox: with no wait loop at all ptxas gives
-    // this straight-line kernel 32 registers and spills the whole line)
-    float s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    float *dl = A.dst + l;                                     // local row of sample gi = k - nb: q (EDGE 0, 2), q - nb (EDGE 1)
+    // this straight-line code 32 registers and spills the whole line)
+    if (top) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
+    float *dl = A.dst + (long)j * NZ * A.L + l;                // local row of sample gi = k - nb: q (EDGE 0, 2), q - nb (EDGE 1)
     float park[NB];                                            // EDGE 2: B of the right pad; EDGE 1: heads awaiting the left pad
 #pragma unroll
     for (int q = N - 1; q >= 0; q--) {
@@ -1984,48 +2018,64 @@ tri3_reg_bwd_kernel(const Tri3Args A)
             dl[(long)q * A.L] = s;
         }
     }
-    if (EDGE != 1) tri3_pair_send(A.pout + l, s, A.epoch);
+    return s;
 }
 
-// register kernels: radii and slab heights instantiated
-static bool tri3_reg_ok(int nb, int n3g, int nranks)
+template <int NB, int NZ>
+__global__ void __launch_bounds__(64)
+tri3_reg_bwd_kernel(const Tri3Args A)
+{
+    const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
+    if (l >= A.L) return;
+    const int nch = A.nz / NZ;
+    const bool first = A.K0 == 0, last = A.K1 == A.n3g + 2 * NB;
+    const float *ha_src = A.ha_keep ? A.ha_keep : A.ha;
+    float keep[NB];
+#pragma unroll
+    for (int a = 0; a < NB; a++) keep[a] = 0.f;
+    float s = 0.f;
+    for (int j = nch - 1; j >= 0; j--) {
+        if (first && j == 0) s = tri3_reg_bwd_chunk<NB, NZ, 1>(A, l, j, nch, ha_src, keep, s);
+        else if (last && j == nch - 1) s = tri3_reg_bwd_chunk<NB, NZ, 2>(A, l, j, nch, ha_src, keep, s);
+        else s = tri3_reg_bwd_chunk<NB, NZ, 0>(A, l, j, nch, ha_src, keep, s);
+    }
+    if (!first) tri3_pair_send(A.pout + l, s, A.epoch);
+}
+
+// register kernels: radii and chunk heights instantiated; equal slabs of whole chunks
+static int tri3_reg_chunk(int nb, int n3g, int nranks)
 {
     static const bool on = []() { const char *e = getenv("PST_TRI3_REG"); return !(e && e[0] == '0'); }();
-    if (!on || nranks < 2 || n3g % nranks != 0) return false;
+    if (!on || nranks < 2 || n3g % nranks != 0) return 0;
+    if (!(nb == 2 || nb == 3 || nb == 4 || nb == 5 || nb == 6 || nb == 8)) return 0;
     const int nz = n3g / nranks;
-    return (nz == 128 || nz == 32) && nz >= 2 * nb && (nb == 2 || nb == 3 || nb == 4 || nb == 5 || nb == 6 || nb == 8);
+    const int NZ = nz % 128 == 0 ? 128 : ((nz % 32 == 0 && nz <= 96) ? 32 : 0);
+    return (NZ && NZ >= 2 * nb) ? NZ : 0;
 }
-template <int NB, int NZ>
-static void tri3_reg_launch_z(const Tri3Args &A, bool fwd, int edge, unsigned blocks, cudaStream_t st)
+static bool tri3_reg_ok(int nb, int n3g, int nranks) { return tri3_reg_chunk(nb, n3g, nranks) != 0; }
+template <int NB>
+static void tri3_reg_launch_nb(const Tri3Args &A, bool fwd, int NZ, unsigned blocks, cudaStream_t st)
 {
     if (fwd) {
-        if (edge == 1) tri3_reg_fwd_kernel<NB, NZ, 1><<<blocks, 64, 0, st>>>(A);
-        else if (edge == 2) tri3_reg_fwd_kernel<NB, NZ, 2><<<blocks, 64, 0, st>>>(A);
-        else tri3_reg_fwd_kernel<NB, NZ, 0><<<blocks, 64, 0, st>>>(A);
+        if (NZ == 128) tri3_reg_fwd_kernel<NB, 128><<<blocks, 64, 0, st>>>(A);
+        else tri3_reg_fwd_kernel<NB, 32><<<blocks, 64, 0, st>>>(A);
     } else {
-        if (edge == 1) tri3_reg_bwd_kernel<NB, NZ, 1><<<blocks, 64, 0, st>>>(A);
-        else if (edge == 2) tri3_reg_bwd_kernel<NB, NZ, 2><<<blocks, 64, 0, st>>>(A);
-        else tri3_reg_bwd_kernel<NB, NZ, 0><<<blocks, 64, 0, st>>>(A);
+        if (NZ == 128) tri3_reg_bwd_kernel<NB, 128><<<blocks, 64, 0, st>>>(A);
+        else tri3_reg_bwd_kernel<NB, 32><<<blocks, 64, 0, st>>>(A);
     }
 }
-template <int NB>
-static void tri3_reg_launch_nb(const Tri3Args &A, bool fwd, int edge, unsigned blocks, cudaStream_t st)
-{
-    if (A.nz == 128) tri3_reg_launch_z<NB, 128>(A, fwd, edge, blocks, st);
-    else tri3_reg_launch_z<NB, 32>(A, fwd, edge, blocks, st);
-}
 // the forward kernel reads 4 B per voxel, the backward kernel reads 4 and writes 4
-static int tri3_reg_launch(pst_ctx *c, const Tri3Args &A, bool fwd, int edge, size_t nvox, int cls)
+static int tri3_reg_launch(pst_ctx *c, const Tri3Args &A, bool fwd, int NZ, size_t nvox, int cls)
 {
     const unsigned blocks = (unsigned)((A.L + 63) / 64);
     PST_LAUNCHB(c, cls, (fwd ? 4.0 : 8.0) * (double)nvox,
         switch (A.nb) {
-            case 2: tri3_reg_launch_nb<2>(A, fwd, edge, blocks, c->stream); break;
-            case 3: tri3_reg_launch_nb<3>(A, fwd, edge, blocks, c->stream); break;
-            case 4: tri3_reg_launch_nb<4>(A, fwd, edge, blocks, c->stream); break;
-            case 5: tri3_reg_launch_nb<5>(A, fwd, edge, blocks, c->stream); break;
-            case 6: tri3_reg_launch_nb<6>(A, fwd, edge, blocks, c->stream); break;
-            default: tri3_reg_launch_nb<8>(A, fwd, edge, blocks, c->stream); break;
+            case 2: tri3_reg_launch_nb<2>(A, fwd, NZ, blocks, c->stream); break;
+            case 3: tri3_reg_launch_nb<3>(A, fwd, NZ, blocks, c->stream); break;
+            case 4: tri3_reg_launch_nb<4>(A, fwd, NZ, blocks, c->stream); break;
+            case 5: tri3_reg_launch_nb<5>(A, fwd, NZ, blocks, c->stream); break;
+            case 6: tri3_reg_launch_nb<6>(A, fwd, NZ, blocks, c->stream); break;
+            default: tri3_reg_launch_nb<8>(A, fwd, NZ, blocks, c->stream); break;
         });
     PST_CUDA(cudaGetLastError());
     return PST_OK;
@@ -2155,7 +2205,10 @@ static int tri3_tiles_fwd(pst_ctx *c, const Tri3Args &A, int W, unsigned blocks,
 {
     PST_TRY(tri3_tiles_attr(c));
     const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * A.nb) * W * 4;
-    const int T = W < 128 ? (W < 64 ? 32 : 64) : 128;        // threads = lines of the tile
+    // 128 threads whatever the tile width: the narrower tiles keep their burst-load issue rate (measured: 64-line tiles
+    // with 64 threads 110 ms per step against 95 with 128, 2 ranks x 128-plane slabs)
+    static const int T_env = []() { const char *e = getenv("PST_TRI3_THREADS"); const int v = e ? atoi(e) : 128; return v == 64 || v == 32 ? v : 128; }();
+    const int T = T_env > W ? T_env : W;
     PST_LAUNCHB(c, PST_K_TRI3, 8.0 * (double)nvox,
         if (rcmp) {
             if (W == 128) tri3_tile_fwd_kernel<128, false><<<blocks, T, smem_f, c->stream>>>(A);
@@ -2172,7 +2225,8 @@ static int tri3_tiles_fwd(pst_ctx *c, const Tri3Args &A, int W, unsigned blocks,
 static int tri3_tiles_bwd(pst_ctx *c, const Tri3Args &A, int W, unsigned blocks, bool rcmp, size_t nvox, int cls)
 {
     const size_t smem_f = (size_t)(A.K1 - A.K0 + 2 * A.nb) * W * 4, smem_b = (size_t)(A.K1 - A.K0) * W * 4;
-    const int T = W < 128 ? (W < 64 ? 32 : 64) : 128;
+    static const int T_env = []() { const char *e = getenv("PST_TRI3_THREADS"); const int v = e ? atoi(e) : 128; return v == 64 || v == 32 ? v : 128; }();
+    const int T = T_env > W ? T_env : W;
     PST_LAUNCHB(c, cls, 8.0 * (double)nvox,
         if (rcmp) {
             if (W == 128) tri3_tile_bwd_kernel<128, true><<<blocks, T, smem_f, c->stream>>>(A);
@@ -2201,7 +2255,8 @@ static int smooth_axis3_solo(pst_ctx *c, const DipGeom &g, const float *src, flo
     static const bool rev_on = []() { const char *e = getenv("PST_TRI3_REV"); return !(e && e[0] == '0'); }();
     A.rev = rev_on ? 1 : 0;
     static const bool fake_reg = []() { const char *e = getenv("PST_TRI3_SOLO"); return e && e[0] == '2'; }();
-    if (fake_reg && tri3_reg_ok(nb, 2 * g.n3, 2)) {
+    const int fakeNZ = tri3_reg_chunk(nb, 2 * g.n3, 2);
+    if (fake_reg && fakeNZ) {
         // TIMING ONLY (wrong numbers): the register kernels as an interior rank would run them, halo rows read from the
         // volume itself, no carries
         A.K0 = nb; A.K1 = g.n3 + nb; A.n3g = g.n3 + 1000; A.hb = src; A.ha = src; A.csave = scr;
@@ -2211,8 +2266,8 @@ static int smooth_axis3_solo(pst_ctx *c, const DipGeom &g, const float *src, flo
         PST_CUDA(cudaMemsetAsync(in, 0x01, (size_t)A.L * sizeof(uint2), c->stream));
         PST_CUDA(cudaMemsetAsync(A.err, 0, 64, c->stream));
         A.pin = in; A.pout = out;
-        PST_TRY(tri3_reg_launch(c, A, true, 0, g.n, PST_K_TRI3));
-        PST_TRY(tri3_reg_launch(c, A, false, 0, g.n, PST_K_TRI3));
+        PST_TRY(tri3_reg_launch(c, A, true, fakeNZ, g.n, PST_K_TRI3));
+        PST_TRY(tri3_reg_launch(c, A, false, fakeNZ, g.n, PST_K_TRI3));
         c->stats.smooth_passes++;
         return PST_OK;
     }
@@ -2269,8 +2324,8 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     // recomputation lengthens exactly that.  Off by default.
     static const bool rcmp_on = []() { const char *e = getenv("PST_TRI3_RC"); return e && e[0] == '1'; }();
     // register kernels (short slabs, first choice): always the recompute scheme
-    const bool reg = tri3_reg_ok(nb, n3g, c->nranks);
-    const int edge = first ? 1 : (last ? 2 : 0);
+    const int regNZ = tri3_reg_chunk(nb, n3g, c->nranks);      // chunk height of the register kernels, 0 = not applicable
+    const bool reg = regNZ != 0;
     const bool rcmp = (rcmp_on && W > 0) || reg;
     A.csave = g.cin;
     A.ha_keep = (rcmp && peer && !last) ? g.ha : nullptr;
@@ -2280,7 +2335,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.pin = first ? nullptr : mb.pf_in; A.pout = last ? nullptr : mb.pf_out;
     A.pself = (uint2 *)mb.pb_in;
     if (reg) {
-        PST_TRY(tri3_reg_launch(c, A, true, edge, g.n, PST_K_TRI3));
+        PST_TRY(tri3_reg_launch(c, A, true, regNZ, g.n, PST_K_TRI3));
     } else if (W) {
         PST_TRY(tri3_tiles_fwd(c, A, W, blocks, rcmp, g.n));
     } else {
@@ -2307,7 +2362,7 @@ static int smooth_axis3_dist(pst_ctx *c, const DipGeom &g, const float *src, flo
     A.rev = rev_on ? 1 : 0;
     static const int bwd_cls = []() { const char *e = getenv("PST_TRI3_SPLIT"); return (e && e[0] == '1') ? PST_K_TRI3BWD : PST_K_TRI3; }();
     if (reg) {
-        PST_TRY(tri3_reg_launch(c, A, false, edge, g.n, bwd_cls));
+        PST_TRY(tri3_reg_launch(c, A, false, regNZ, g.n, bwd_cls));
     } else if (W) {
         PST_TRY(tri3_tiles_bwd(c, A, W, blocks, rcmp, g.n, bwd_cls));
     } else {
@@ -2868,10 +2923,12 @@ extern "C" int pst_smoothcf_dev(pst_ctx *c, float *d_x, int n1, int n2, int n3, 
 extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, int n3, int r3, int nranks)
 {
     if (!c || !d_x) { pst_set_error("selftest_axis3_slabs: null pointer"); return PST_EINVAL; }
-    if (!tri3_reg_ok(r3, n3, nranks)) {
-        pst_set_error("selftest_axis3_slabs: geometry outside the register kernels (radius 2-6 or 8, equal slabs of 32 or 128 planes, nranks >= 2)");
+    const int NZ = tri3_reg_chunk(r3, n3, nranks);
+    if (!NZ) {
+        pst_set_error("selftest_axis3_slabs: geometry outside the register kernels (radius 2-6 or 8, nranks >= 2 equal slabs of 32, 64, 96 or k x 128 planes)");
         return PST_EUNSUP;
     }
+    const int nch = n3 / nranks / NZ;
     PST_CUDA(cudaSetDevice(c->device));
     const long L = (long)n1 * n2;
     const int nb = r3;
@@ -2885,7 +2942,7 @@ extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, 
     for (int r = 0; r < nranks && rc == PST_OK; r++) {
         fail(cudaMalloc((void **)&B[r].pf, L * sizeof(uint2)));
         fail(cudaMalloc((void **)&B[r].pb, L * sizeof(uint2)));
-        fail(cudaMalloc((void **)&B[r].csave, L * sizeof(float)));
+        fail(cudaMalloc((void **)&B[r].csave, (size_t)nch * L * sizeof(float)));
         fail(cudaMalloc((void **)&B[r].keep, (size_t)nb * L * sizeof(float)));
         if (rc == PST_OK) { fail(cudaMemsetAsync(B[r].pf, 0, L * sizeof(uint2), c->stream)); fail(cudaMemsetAsync(B[r].pb, 0, L * sizeof(uint2), c->stream)); }
     }
@@ -2906,12 +2963,12 @@ extern "C" int pst_selftest_axis3_slabs(pst_ctx *c, float *d_x, int n1, int n2, 
     for (int r = 0; r < nranks && rc == PST_OK; r++) {
         Tri3Args A = args(r);
         A.pin = r == 0 ? nullptr : B[r].pf; A.pout = r == nranks - 1 ? nullptr : B[r + 1].pf; A.pself = B[r].pb;
-        rc = tri3_reg_launch(c, A, true, r == 0 ? 1 : (r == nranks - 1 ? 2 : 0), (size_t)A.nz * L, PST_K_TRI3);
+        rc = tri3_reg_launch(c, A, true, NZ, (size_t)A.nz * L, PST_K_TRI3);
     }
     for (int r = nranks - 1; r >= 0 && rc == PST_OK; r--) {
         Tri3Args A = args(r);
         A.pin = B[r].pb; A.pout = r == 0 ? nullptr : B[r - 1].pb;
-        rc = tri3_reg_launch(c, A, false, r == 0 ? 1 : (r == nranks - 1 ? 2 : 0), (size_t)A.nz * L, PST_K_TRI3);
+        rc = tri3_reg_launch(c, A, false, NZ, (size_t)A.nz * L, PST_K_TRI3);
     }
     unsigned h_err = 0;
     if (rc == PST_OK) fail(cudaMemcpyAsync(&h_err, d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));

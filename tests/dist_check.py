@@ -38,6 +38,8 @@ def main():
                         ((16, 12, 200 * world + 1), dict(niter=2, liter=4, order=2, rect=(3, 3, 6))),
                         # 128-plane slabs, default radii: the geometry of the headline cube on 8 GPUs (register kernels of the axis-3 pass)
                         ((16, 12, 128 * world), dict(niter=2, liter=4, order=2, rect=(5, 5, 5))),
+                        # 256-plane slabs: two register chunks per rank (the headline cube on 4 GPUs)
+                        ((16, 12, 256 * world), dict(niter=2, liter=3, order=2, rect=(5, 5, 5))),
                         # 32-plane slabs: the register kernels of the axis-3 pass, small instantiation
                         ((24, 10, 32 * world), dict(niter=2, liter=4, order=1, rect=(3, 3, 6))),
                         # slabs too tall for the tile kernels: the line kernels (register-window forward kernel), the

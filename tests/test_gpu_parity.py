@@ -82,7 +82,10 @@ def test_smooth3_bit_exact(ctx, port, shape, rect):
 
 
 @pytest.mark.parametrize("shape,r3,nranks", [((20, 13, 64), 5, 2), ((20, 13, 96), 5, 3), ((8, 40, 1024), 5, 8), ((37, 3, 224), 2, 7),
-                                             ((16, 8, 256), 8, 2), ((12, 6, 128), 3, 4), ((12, 6, 160), 6, 5), ((9, 7, 384), 4, 3)])
+                                             ((16, 8, 256), 8, 2), ((12, 6, 128), 3, 4), ((12, 6, 160), 6, 5), ((9, 7, 384), 4, 3),
+                                             # slabs of several chunks: 2 x 128 (4 ranks at n3 = 1024), 4 x 128 (2 ranks), 3 x 32, 2 x 32
+                                             ((8, 24, 1024), 5, 4), ((8, 9, 1024), 5, 2), ((10, 7, 288), 3, 3), ((11, 6, 128), 6, 2),
+                                             ((5, 13, 768), 8, 2)])
 def test_multi_gpu_axis3_kernels_on_one_gpu(ctx, port, shape, r3, nranks):
     """The register kernels of the distributed axis-3 pass (first / interior / last rank variants, both tile orders),
     run rank after rank on one GPU over the n3-slabs of the volume: bit-identical to ps_smooth2 along axis 3."""
