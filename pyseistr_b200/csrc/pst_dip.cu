@@ -2090,7 +2090,9 @@ static int tri3_tile_width(int rows_max, long L, const void *a, const void *b, c
     if (!on) return 0;
     // narrower tiles leave too few chain threads per SM: measured at 2 GPUs (527 rows, W = 32) the tile
     // kernels take 2.6 ms per launch against 1.4 ms for the line kernels, so tall slabs keep the latter
-    static const int wmax = []() { const char *v = getenv("PST_TRI3_WMAX"); return v ? atoi(v) : 128; }();   // A/B: cap the tile width
+    // widest tile tried: 64 lines (measured on the 128-plane slab, 128 threads: 0.50 / 0.44 / 0.42 ms per pass at 128 / 64 / 32
+    // lines; 32-line tiles lose on tall slabs).  PST_TRI3_WMAX overrides.
+    static const int wmax = []() { const char *v = getenv("PST_TRI3_WMAX"); return v ? atoi(v) : 64; }();
     const int ws[3] = {128, 64, 32};                          // 32 only on request (PST_TRI3_WMAX=32)
     for (int w : ws) if (w <= wmax && (size_t)rows_max * w * 4 <= 75 * 1024) return w;
     return 0;
