@@ -18,8 +18,10 @@ except Exception as e:
 PY
 }
 echo "== $N GPUs: slab parity against the oracle (tests/dist_check.py at world = $N)" | tee $S
+if [ -z "${SKIP_CHECK:-}" ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tests/dist_check.py > $O/r02h_dist_check_n$N.log 2>&1; echo "dist_check rc $?" | tee -a $S
 grep "dist_check" $O/r02h_dist_check_n$N.log | sort -u | tee -a $S
+fi
 echo "== bench.py at N = $N" | tee -a $S
 p=29560
 for w in ${WORKLOADS:-dip3d_somf3d soint3d sint3d}; do
