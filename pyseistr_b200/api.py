@@ -187,13 +187,23 @@ def soint2dc(din, mask, dip, order=1, niter=100, njs=[1, 1], drift=0, hasmask=1,
     """2-D structure-oriented interpolation (reference pyseistr/soint2d.py:92-141 -> csoint2d, soint2d_cfuns.c:2260).
     The default path of csoint2d (one slope field, no preconditioner: ps_solver on allpass21_lop :296-336) is the
     inline half of allpass3_lop, and is bit-identical to csoint3d on an (n1, n2, 1) volume -- checked on the compiled
-    reference by the CPU test suite -- so it runs through pst_soint3d.  twoplane / prec / drift raise."""
-    if twoplane or prec or drift:
-        raise NotImplementedError("soint2dc on GPU: twoplane=0, prec=0, drift=0 only")
+    reference by the CPU test suite -- so it runs through pst_soint3d.
+    twoplane=1, prec=0: the reference's solver call for two slope fields without preconditioner is commented out
+    (soint2d_cfuns.c:2354-2356, :2389-2391), so csoint2d hands the input back unchanged; so does this (quirk Q7, pinned on
+    the compiled reference by the CPU test suite).  prec=1 (ps_solver_prec over predict_lop / predict2_lop) and drift raise."""
     din = np.asarray(din)
     if din.ndim != 2:
         raise ValueError("soint2dc expects a 2-D panel")
     n1, n2 = din.shape
+    if twoplane and not prec:
+        dip = np.asarray(dip)
+        if dip.ndim != 3 or dip.shape != (n1, n2, 2):
+            raise ValueError("soint2dc(twoplane=1) expects the two slope fields as an (n1, n2, 2) array")
+        if np.asarray(mask).size != din.size:
+            raise ValueError("data and mask must have the same size")
+        return np.array(din, dtype=np.float32, order="F", copy=True)
+    if twoplane or prec or drift:
+        raise NotImplementedError("soint2dc on GPU: prec=0, drift=0 only")
     slope = np.float32(dip).reshape(n1, n2, 1)
     m3 = np.float32(mask).reshape(n1, n2, 1) if mask is not None else None
     out = soint3dc(din.reshape(n1, n2, 1), m3, slope, slope, order=order, niter=niter, njs=njs, drift=0, hasmask=hasmask,

@@ -9,8 +9,12 @@ __all__ = ["csoint2d", "csint2d"]
 
 
 def csoint2d(din, mask, dip1, dip2, n1, n2, nw, nj1, nj2, niter, drift, hasmask, twoplane, prec, verb):
+    if twoplane and not prec:
+        # the reference's two-plane solver call without preconditioner is commented out (soint2d_cfuns.c:2354-2356,
+        # :2389-2391): the input comes back unchanged
+        return np.array(f32(din), copy=True)
     if twoplane or prec or drift:
-        raise NotImplementedError("csoint2d on GPU: twoplane=0, prec=0, drift=0 only")
+        raise NotImplementedError("csoint2d on GPU: prec=0, drift=0 only")
     d, a = f32(din), f32(dip1)
     m = f32(mask) if hasmask else None
     c = ctx()

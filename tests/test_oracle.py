@@ -322,3 +322,30 @@ def test_port_paint2d_matches_compiled_reference(port):
         p = synth.smooth_dips(n1, n2, 1, seed=seed)[0]
         tr = np.linspace(0, 0.004 * (n1 - 1), n1).astype(np.float32)
         assert np.array_equal(port.pwpaintc(p, tr, order, i0, eps), ref.pwpaintc(p, tr, order, i0, eps))
+
+
+def test_soint2dc_twoplane_without_preconditioner_returns_its_input():
+    """csoint2d(twoplane=1, prec=0): the solver call is commented out in the reference (soint2d_cfuns.c:2354-2356,
+    :2389-2391), the model comes back unchanged; the drop-in does the same without touching the GPU."""
+    ref = _ref_or_skip()
+    try:
+        m = ref.module("soint2dcfun")
+    except ImportError:
+        pytest.skip("oracle/_ref/soint2dcfun not built")
+    import pyseistr_b200 as ps
+    n1, n2 = 60, 24
+    clean = np.asarray(synth.cube(n1, n2, 1, seed=5, noise=0.0)).reshape(n1, n2)
+    keep = np.random.default_rng(6).random(n2) > 0.4
+    mask = np.zeros_like(clean)
+    mask[:, keep] = 1
+    gaps = np.float32(clean * mask)
+    dip = np.asarray(synth.smooth_dips(n1, n2, 1, seed=5)[0]).reshape(n1, n2)
+    two = np.stack([dip, 0.5 * dip], axis=2)
+    F = lambda a: np.asfortranarray(np.float32(a)).ravel(order="F")  # noqa: E731
+    with ref.quiet():
+        want = np.asarray(m.csoint2d(F(gaps), F(mask), F(two[:, :, 0]), F(two[:, :, 1]), n1, n2, 1, 1, 1, 20, 0, 1, 1, 0, 0))
+    want = want.reshape(n1, n2, order="F")
+    got = ps.soint2dc(gaps, mask, two, order=1, niter=20, twoplane=1, verb=0)
+    assert np.array_equal(want, gaps) and np.array_equal(got, want) and got is not gaps
+    with pytest.raises(NotImplementedError):
+        ps.soint2dc(gaps, mask, two, twoplane=1, prec=1)
