@@ -10,6 +10,7 @@
 // vectors are bit-identical to the reference's; only the global sums (double tree
 // reductions here, sequential sums there) may differ in the last bits of a double.
 #include "pst_common.cuh"
+#include "pst_tri3_reg_core.h"
 #include "pst_tri_stream.cuh"
 #include "pst_tri_rc.cuh"
 #include "pst_tri_sys.cuh"
@@ -1865,160 +1866,26 @@ tri3_tile_bwd_kernel(const Tri3Args A)
 }
 
 // ---- distributed axis 3, register kernels (equal slabs of v x NZ planes: 2, 4, 8 ranks at n3 = 1024) --------------------
-// One thread owns one line and walks the line's local rows in CHUNKS of NZ planes held in REGISTERS; NZ and the role of a
-// chunk (first of the cube / interior / last of the cube) are template parameters, so the role of every row (own plane,
-// neighbouring plane, outside the cube) and every fold index is known at compile time: no shared memory, no block
-// synchronisation after the halo flags, ~140 independent coalesced loads in flight per thread and chunk, 11 (forward) and
-// 18 (backward) instructions per sample.  The forward kernel forms the stencil values t of its first chunk, waits for its
-// line's carry, adds the t's to it in order, chunk after chunk, and hands the result on; it stores nothing but the running
-// sum before every chunk.  The backward kernel walks the chunks downwards: it loads the same rows again (4 B per voxel,
-// instead of 4 written + 4 read for a staged F), repeats the forward additions from the saved sum -- same operands, same
-// order, same bits -- (for its top chunk: WHILE the backward carry is on its way), then runs the backward sum with the
-// fold.  The pass moves 12 B per voxel instead of 16.
-// EDGE: 0 interior chunk (steps k = zc + nb + q, q < NZ), 1 first chunk of the cube (k = q < NZ + nb; left reflection),
-// 2 last chunk of the cube (k = zc + nb + q, q < NZ + nb; right reflection).  Slot q holds plane k - 2nb of x, then t_k,
-// then F_k.
-template <int NB, int NZ, int EDGE>
-struct Tri3Reg {
-    static constexpr int N = (EDGE == 0) ? NZ : NZ + NB;       // steps
-    static constexpr int S = N + 2 * NB;                       // x rows
-    static constexpr int OWN0 = (EDGE == 1) ? 2 * NB : NB;     // slots [OWN0, OWN0 + NZ): planes of the chunk
-    // own: the chunk's first plane; before: plane zc - nb (previous chunk or previous rank); after: plane zc + NZ (next chunk
-    // or next rank / its kept copy).  PART 0: the chunk's planes, 1: the planes around it, 2: both
-    template <int PART>
-    static __device__ __forceinline__ void load(const float *own, const float *before, const float *after, long L, float (&v)[S])
-    {
-#pragma unroll
-        for (int q = 0; q < S; q++) {
-            if (q >= OWN0 && q < OWN0 + NZ) {
-                if (PART != 1) v[q] = __ldcg(own + (long)(q - OWN0) * L);
-            } else if (q < OWN0) {
-                if (EDGE == 1) { if (PART != 1) v[q] = 0.f; }                             // planes < 0
-                else if (PART != 0) v[q] = __ldcg(before + (long)q * L);
-            } else {
-                if (EDGE == 2) { if (PART != 1) v[q] = 0.f; }                             // planes >= n3g
-                else if (PART != 0 && after) v[q] = __ldcg(after + (long)(q - OWN0 - NZ) * L);
-            }
-        }
-    }
-    static __device__ __forceinline__ void stencil(float wm, float w2, float (&v)[S])
-    {
-#pragma unroll
-        for (int q = 0; q < N; q++) {
-            float t = wm * v[q + 2 * NB];
-            t = t + w2 * v[q + NB];
-            t = t + wm * v[q];
-            v[q] = t;
-        }
-    }
+// One thread owns one line and walks the line's local rows in chunks of NZ planes held in REGISTERS: no shared memory, no
+// block synchronisation after the halo flags, ~140 independent coalesced loads in flight per thread and chunk, 11 (forward)
+// and 18 (backward) instructions per sample; the pass moves 12 B per voxel instead of 16 (F is recomputed, not staged).
+// The per-line arithmetic is pst_tri3_reg_core.h (host-tested); here: the mailboxes and the launch.
+struct Tri3RegIO {
+    const Tri3Args &A;
+    __device__ __forceinline__ void wait_halos() { tri3_wait_halos(A); }
+    __device__ __forceinline__ float recv(long l) { return tri3_pair_recv(A.pin + l, A.epoch, A.err); }
 };
-
-// one chunk of the forward kernel; returns the running sum after the chunk
-template <int NB, int NZ, int EDGE>
-__device__ __forceinline__ float tri3_reg_fwd_chunk(const Tri3Args &A, long l, bool live, int j, int nch, bool head, float s)
-{
-    using R = Tri3Reg<NB, NZ, EDGE>;
-    float v[R::S];
-    const float *own = A.x + (long)j * NZ * A.L + l;
-    const float *before = j > 0 ? own - (long)NB * A.L : A.hb + l;
-    const float *after = j < nch - 1 ? own + (long)NZ * A.L : A.ha + l;
-    if (head) {
-        // first chunk: its own planes are in flight while the neighbours' flags are awaited; then its carry
-        if (live) R::template load<0>(own, before, after, A.L, v);
-        tri3_wait_halos(A);
-        if (!live) return 0.f;
-        R::template load<1>(own, before, after, A.L, v);
-    } else {
-        R::template load<2>(own, before, after, A.L, v);
-    }
-    if (EDGE != 2 && j == nch - 1 && A.ha_keep) {
-        // keep the planes read from the next rank for my backward kernel: that rank overwrites them in its own backward
-        // kernel, which runs before mine
-#pragma unroll
-        for (int a = 0; a < NB; a++) A.ha_keep[(long)a * A.L + l] = v[R::OWN0 + NZ + a];
-    }
-    R::stencil(-A.wt, A.w2, v);
-    if (head && EDGE != 1) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    A.csave[(long)j * A.L + l] = s;
-#pragma unroll
-    for (int q = 0; q < R::N; q++) s += v[q];
-    return s;
-}
 
 template <int NB, int NZ>
 __global__ void __launch_bounds__(64)
 tri3_reg_fwd_kernel(const Tri3Args A)
 {
     const long l = (long)blockIdx.x * 64 + threadIdx.x;
-    const bool live = l < A.L;
-    const int nch = A.nz / NZ;
-    const bool first = A.K0 == 0, last = A.K1 == A.n3g + 2 * NB;
-    float s = 0.f;
-    // chunk 0 (block-uniform role)
-    if (first) s = tri3_reg_fwd_chunk<NB, NZ, 1>(A, l, live, 0, nch, true, s);
-    else if (last && nch == 1) s = tri3_reg_fwd_chunk<NB, NZ, 2>(A, l, live, 0, nch, true, s);
-    else s = tri3_reg_fwd_chunk<NB, NZ, 0>(A, l, live, 0, nch, true, s);
-    if (!live) return;
-    for (int j = 1; j < nch; j++) {
-        if (last && j == nch - 1) s = tri3_reg_fwd_chunk<NB, NZ, 2>(A, l, true, j, nch, false, s);
-        else s = tri3_reg_fwd_chunk<NB, NZ, 0>(A, l, true, j, nch, false, s);
-    }
-    if (!last) tri3_pair_send(A.pout + l, s, A.epoch);
+    Tri3RegIO io{A};
+    float s;
+    if (!tri3_reg::fwd_line<NB, NZ>(A, io, l, l < A.L, &s)) return;
+    if (A.K1 != A.n3g + 2 * NB) tri3_pair_send(A.pout + l, s, A.epoch);
     else tri3_pair_send(A.pself + l, 0.f, A.epoch);            // the last rank's backward carry: +0, through its own mailbox
-}
-
-// one chunk of the backward kernel.  keep[]: x of the first nb planes of the chunk above (this thread has already
-// overwritten them with outputs); on return: those of this chunk.  Returns the backward running sum below the chunk.
-template <int NB, int NZ, int EDGE>
-__device__ __forceinline__ float tri3_reg_bwd_chunk(const Tri3Args &A, long l, int j, int nch, const float *ha_src, float (&keep)[NB], float s)
-{
-    using R = Tri3Reg<NB, NZ, EDGE>;
-    constexpr int N = R::N;
-    float v[R::S];
-    const float *own = A.x + (long)j * NZ * A.L + l;
-    const float *before = j > 0 ? own - (long)NB * A.L : A.hb + l;
-    const bool top = j == nch - 1;
-    // (no halo flags to wait for: the forward kernel of this pass did, and the previous rank's planes stay untouched until
-    // its backward thread of this line has received the carry sent at the end)
-    R::template load<2>(own, before, top ? ha_src + l : nullptr, A.L, v);
-    if (EDGE != 2 && !top) {
-#pragma unroll
-        for (int a = 0; a < NB; a++) v[R::OWN0 + NZ + a] = keep[a];
-    }
-#pragma unroll
-    for (int a = 0; a < NB; a++) keep[a] = v[R::OWN0 + a];
-    R::stencil(-A.wt, A.w2, v);
-    float sf = A.csave[(long)j * A.L + l];
-#pragma unroll
-    for (int q = 0; q < N; q++) { sf += v[q]; v[q] = sf; }
-    // (the last rank receives the +0 its forward kernel left in its own mailbox: with no wait loop at all ptxas gives
-    // this straight-line code 32 registers and spills the whole line)
-    if (top) s = tri3_pair_recv(A.pin + l, A.epoch, A.err);
-    float *dl = A.dst + (long)j * NZ * A.L + l;                // local row of sample gi = k - nb: q (EDGE 0, 2), q - nb (EDGE 1)
-    float park[NB];                                            // EDGE 2: B of the right pad; EDGE 1: heads awaiting the left pad
-#pragma unroll
-    for (int q = N - 1; q >= 0; q--) {
-        s += v[q];
-        if (EDGE == 2) {
-            // right pad: k >= nb + n3g <=> q >= NZ: parked.  The last nb samples (q in [NZ - nb, NZ)) take
-            // B_{nb + n3g + (n3g - 1 - gi)}, the value parked by step q' = 2 NZ - 1 - q
-            if (q >= NZ) park[q >= NZ ? q - NZ : 0] = s;
-            else {
-                float y = s;
-                if (q >= NZ - NB) y = y + park[q >= NZ - NB ? NZ - 1 - q : 0];
-                dl[(long)q * A.L] = y;
-            }
-        } else if (EDGE == 1) {
-            // k = q.  k >= 2nb: sample gi = k - nb; k in [nb, 2nb): heads (completed by the left pad); k < nb: left pad,
-            // y_gi = head_gi + B_k with gi = nb - 1 - k
-            if (q >= 2 * NB) dl[(long)(q - NB) * A.L] = s;
-            else if (q >= NB) park[q >= NB && q < 2 * NB ? q - NB : 0] = s;
-            else dl[(long)(NB - 1 - q) * A.L] = park[q < NB ? NB - 1 - q : 0] + s;
-        } else {
-            dl[(long)q * A.L] = s;
-        }
-    }
-    return s;
 }
 
 template <int NB, int NZ>
@@ -2027,19 +1894,9 @@ tri3_reg_bwd_kernel(const Tri3Args A)
 {
     const long l = (long)(A.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 64 + threadIdx.x;
     if (l >= A.L) return;
-    const int nch = A.nz / NZ;
-    const bool first = A.K0 == 0, last = A.K1 == A.n3g + 2 * NB;
-    const float *ha_src = A.ha_keep ? A.ha_keep : A.ha;
-    float keep[NB];
-#pragma unroll
-    for (int a = 0; a < NB; a++) keep[a] = 0.f;
-    float s = 0.f;
-    for (int j = nch - 1; j >= 0; j--) {
-        if (first && j == 0) s = tri3_reg_bwd_chunk<NB, NZ, 1>(A, l, j, nch, ha_src, keep, s);
-        else if (last && j == nch - 1) s = tri3_reg_bwd_chunk<NB, NZ, 2>(A, l, j, nch, ha_src, keep, s);
-        else s = tri3_reg_bwd_chunk<NB, NZ, 0>(A, l, j, nch, ha_src, keep, s);
-    }
-    if (!first) tri3_pair_send(A.pout + l, s, A.epoch);
+    Tri3RegIO io{A};
+    const float s = tri3_reg::bwd_line<NB, NZ>(A, io, l);
+    if (A.K0 != 0) tri3_pair_send(A.pout + l, s, A.epoch);
 }
 
 // register kernels: radii and chunk heights instantiated; equal slabs of whole chunks
