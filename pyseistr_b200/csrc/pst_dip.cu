@@ -2644,7 +2644,8 @@ extern "C" int pst_dip_dev(pst_ctx *c, const float *d_din, const float *d_mask, 
     const bool dist = g.dist;
     const int nz = g.n3;
     const size_t n = g.n, plane = (size_t)n1 * n2;
-    const size_t extra = dist ? (plane * (size_t)(2 * r3 + 2 + 2) + n + plane + (d_mask ? n + 2 * plane : 0)) : 0;
+    // slabs: halo / carry planes of the axis-3 pass, the data (and mask) slab with the neighbour's first plane appended
+    const size_t extra = dist ? (slab_halo_floats(g) + (n + 2 * plane) + (d_mask ? n + 2 * plane : 0) + 16 * 64) : 0;
     const size_t need = (11 * n + scr + extra) * sizeof(float) + 2 * n + 32 * 256;
     PST_TRY(pst_arena_reserve(c, need));
     pst_arena_reset(c);
