@@ -1241,11 +1241,15 @@ __global__ void __launch_bounds__(256)
 cg_head4d_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r,
                  const float *__restrict__ sp, const float *__restrict__ sx,
                  const float *__restrict__ sr, const float *__restrict__ w, const CgCtl *__restrict__ ctl, float eps,
-                 float *__restrict__ tmp, size_t n)
+                 float *__restrict__ tmp, Span S)
 {
     if (ctl->stop) return;
     const float a = ctl->a_pending;
-    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+    // block = one piece of one plane, like the kernels with sums: contiguous pieces stream faster than a grid-stride walk
+    // (measured on gp / direction when they moved to pieces: 201 -> 186 and 577 -> 547 ms per step)
+    size_t i0, i1, step;
+    pst_span(S, 4, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float4 xv = ld4(x, i), rv = ld4(r, i);
         const float4 wv = ld4(w, i);
         if (UPDATE) {
@@ -1271,11 +1275,13 @@ __global__ void __launch_bounds__(256)
 cg_headd_kernel(float *__restrict__ p, float *__restrict__ x, float *__restrict__ r,
                 const float *__restrict__ sp, const float *__restrict__ sx,
                 const float *__restrict__ sr, const float *__restrict__ w, const CgCtl *__restrict__ ctl, float eps,
-                float *__restrict__ tmp, size_t n)
+                float *__restrict__ tmp, Span S)
 {
     if (ctl->stop) return;
     const float a = ctl->a_pending;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t i0, i1, step;
+    pst_span(S, 1, i0, i1, step);
+    for (size_t i = i0; i < i1; i += step) {
         float xi = x[i], ri = r[i];
         if (UPDATE) {
             p[i] += a * sp[i];
@@ -2491,10 +2497,10 @@ int pst_divne_run(pst_ctx *c, const DipGeom &g, float *num, float *den, float *r
         for (int iter = 0; iter < liter; iter++) {
             if (*c->h_cgstop) break;                 // the device left the solve (pinned copy, refreshed every iteration)
             PST_LAUNCHB(c, PST_K_CGHEAD, (iter ? 44.0 : 16.0) * (double)n,
-                if (vec4 && iter) cg_head4d_kernel<true><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
-                else if (vec4)    cg_head4d_kernel<false><<<grid4, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
-                else if (iter)    cg_headd_kernel<true><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n);
-                else              cg_headd_kernel<false><<<grid, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, n));
+                if (vec4 && iter) cg_head4d_kernel<true><<<gridc, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, S);
+                else if (vec4)    cg_head4d_kernel<false><<<gridc, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, S);
+                else if (iter)    cg_headd_kernel<true><<<gridc, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, S);
+                else              cg_headd_kernel<false><<<gridc, threads, 0, c->stream>>>(w.p, rat, w.r, w.sp, w.sx, w.sr, den, ctl, eps, w.tmp, S));
             PST_TRY(pst_shape_apply(c, g, w.tmp, w.tmp, w.scr, nullptr, nullptr, nullptr, nullptr));
             PST_LAUNCHB(c, PST_K_CGGP, 12.0 * (double)n,
                 if (vec4) cg_gp4_kernel<<<gridc, threads, 0, c->stream>>>(w.p, w.tmp, w.gp, eps, S, c->d_partial);
