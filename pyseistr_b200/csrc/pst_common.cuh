@@ -180,9 +180,16 @@ __device__ __forceinline__ void pst_block_reduce(double (&v)[NV], double *partia
 // n3-slab decomposition over any number of ranks forms every CG / divne / line-search scalar with exactly the
 // additions of the single-GPU run: ranks fill their planes of the [nv][n3 global] table, the others stay +0, and the
 // all-reduce of that table adds only zeros (exact in any order).
-// piece length: a function of the GLOBAL volume only (never of the slab): big volumes take big pieces (fewer, fatter
-// blocks stream faster), small ones small pieces (a 64-plane slab of 500x512x512 must still fill 148 SMs)
-inline unsigned pst_red_ch(size_t n12, int nzg) { return n12 * (size_t)nzg >= ((size_t)1 << 29) ? 32768u : 8192u; }
+// piece length: never a function of the slab.  8192 elements (32 per thread): measured against 32768 at 1000x1024x1024,
+// CG gp / direction / head 186 / 547 / 725 (grid-stride head) -> 181 / 531 / 657 ms per step, and a 64-plane slab of
+// 500x512x512 still fills 148 SMs
+inline unsigned pst_red_ch(size_t n12, int nzg)
+{
+    static const unsigned forced = []() { const char *e = getenv("PST_RED_CH"); const long v = e ? atol(e) : 0; return (v >= 1024 && v % 1024 == 0) ? (unsigned)v : 0u; }();
+    if (forced) return forced;                 // A/B (set it on every rank alike)
+    (void)n12; (void)nzg;
+    return 8192u;
+}
 struct Span { size_t n; unsigned n12, ppp, ch; };  // ppp > 0: block = piece (blockIdx.x % ppp) of plane (blockIdx.x / ppp); 0: grid-stride over n
 inline Span pst_span_canon(size_t n12, int nz, int nzg)
 {
