@@ -809,8 +809,9 @@ def _main(real_stdout):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.label((n1, n2, n3g)),
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} n3-slabs, NCCL: halos (xline stencil, spray), carry planes (axis-3 running sums), "
-                   f"all-reduced CG scalars",
+                   f"{world} n3-slabs; axis-3 running sums: carries and halo planes through peer memory over NVLink, "
+                   f"inside the kernels; NCCL: halos of the xline stencil and the spray, all-reduce of the per-plane sum "
+                   f"tables (partition-independent CG / line-search scalars)",
                    "l2_policy": "inputs (4 B x voxels per volume) are far larger than the 126 MB L2"
                    if 4 * N > 4 * 126e6 else "L2 flushed by the workload itself: every step streams several volumes "
                                               "through scratch buffers whose total exceeds the 126 MB L2",
