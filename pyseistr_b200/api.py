@@ -201,6 +201,7 @@ def soint2dc(din, mask, dip, order=1, niter=100, njs=[1, 1], drift=0, hasmask=1,
             raise ValueError("soint2dc(twoplane=1) expects the two slope fields as an (n1, n2, 2) array")
         if np.asarray(mask).size != din.size:
             raise ValueError("data and mask must have the same size")
+        _ctx(ctx)                       # no CPU-only mode anywhere in this package: without the library / a device this raises too
         return np.array(din, dtype=np.float32, order="F", copy=True)
     if twoplane or prec or drift:
         raise NotImplementedError("soint2dc on GPU: prec=0, drift=0 only")

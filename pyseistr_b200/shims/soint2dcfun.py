@@ -12,6 +12,7 @@ def csoint2d(din, mask, dip1, dip2, n1, n2, nw, nj1, nj2, niter, drift, hasmask,
     if twoplane and not prec:
         # the reference's two-plane solver call without preconditioner is commented out (soint2d_cfuns.c:2354-2356,
         # :2389-2391): the input comes back unchanged
+        ctx()                           # (raises without the library / a device, like every other entry point)
         return np.array(f32(din), copy=True)
     if twoplane or prec or drift:
         raise NotImplementedError("csoint2d on GPU: prec=0, drift=0 only")

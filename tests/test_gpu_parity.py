@@ -576,3 +576,19 @@ def test_rgt_vs_oracle(ctx, port):
         t = ps.rgt(p, o1=-0.2, d1=0.004, order=order, i0=i0, eps=0.1, ctx=ctx)
         seed = np.linspace(0, 0.004 * 149, 150) - 0.2
         assert np.array_equal(t, port.pwpaintc(p, seed, order, i0, 0.1)), (order, i0)
+
+
+def test_soint2dc_twoplane_without_preconditioner_returns_its_input(ctx):
+    """csoint2d(twoplane=1, prec=0) is a no-op in the reference (its solver call is commented out, soint2d_cfuns.c:2354-2356,
+    :2389-2391; pinned on the compiled reference by the CPU suite): the drop-in hands a copy of the input back."""
+    import pyseistr_b200 as ps
+    n1, n2 = 60, 24
+    clean = np.asarray(synth.cube(n1, n2, 1, seed=5, noise=0.0)).reshape(n1, n2)
+    mask = np.zeros_like(clean)
+    mask[:, ::2] = 1
+    gaps = np.float32(clean * mask)
+    dip = np.asarray(synth.smooth_dips(n1, n2, 1, seed=5)[0]).reshape(n1, n2)
+    two = np.stack([dip, 0.5 * dip], axis=2)
+    got = ps.soint2dc(gaps, mask, two, order=1, niter=20, twoplane=1, verb=0, ctx=ctx)
+    assert np.array_equal(got, gaps) and got is not gaps
+

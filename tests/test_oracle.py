@@ -326,7 +326,7 @@ def test_port_paint2d_matches_compiled_reference(port):
 
 def test_soint2dc_twoplane_without_preconditioner_returns_its_input():
     """csoint2d(twoplane=1, prec=0): the solver call is commented out in the reference (soint2d_cfuns.c:2354-2356,
-    :2389-2391), the model comes back unchanged; the drop-in does the same without touching the GPU."""
+    :2389-2391), the model comes back unchanged (the drop-in's side of it: tests/test_gpu_parity.py)."""
     ref = _ref_or_skip()
     try:
         m = ref.module("soint2dcfun")
@@ -345,7 +345,8 @@ def test_soint2dc_twoplane_without_preconditioner_returns_its_input():
     with ref.quiet():
         want = np.asarray(m.csoint2d(F(gaps), F(mask), F(two[:, :, 0]), F(two[:, :, 1]), n1, n2, 1, 1, 1, 20, 0, 1, 1, 0, 0))
     want = want.reshape(n1, n2, order="F")
-    got = ps.soint2dc(gaps, mask, two, order=1, niter=20, twoplane=1, verb=0)
-    assert np.array_equal(want, gaps) and np.array_equal(got, want) and got is not gaps
+    assert np.array_equal(want, gaps)
     with pytest.raises(NotImplementedError):
         ps.soint2dc(gaps, mask, two, twoplane=1, prec=1)
+    with pytest.raises(ValueError):
+        ps.soint2dc(gaps, mask, dip, twoplane=1)           # one slope field where two are announced
